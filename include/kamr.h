@@ -1,0 +1,207 @@
+/*
+ * kamr.h — C-ABI of libkamr, the B200-native replacement for KitAMR.jl's
+ * per-step phase-space path   slope! -> flux! -> iterate!
+ *
+ * Reference seam (there is no FFI in the reference; these are the Julia entry
+ * points a host shim replaces):
+ *   slope!(p4est, ka)     src/Flux/Slope.jl:1047      -> kamr_slope
+ *   flux!(p4est, ka)      src/Flux/Flux.jl:458        -> kamr_flux
+ *   iterate!(p4est, ka)   src/Theory/Iterate.jl:5     -> kamr_iterate
+ *   solve! loop body      src/Solver/Solver.jl:59-67  -> kamr_step (fused)
+ *   amr_recover!          src/Solver/AMR.jl:54        -> kamr_upload_topology (re-flatten trigger)
+ *   data_exchange! etc.   src/Parallel/Ghost.jl:841,896,867 -> internal NCCL halo (kamr_comm_init)
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, non-zero on failure; the message
+ *     is available from kamr_last_error(ctx) (or kamr_last_error(NULL) for
+ *     failures of kamr_create).  No C++ exception crosses this boundary and the
+ *     library never calls back into the host.
+ *   - all pointers are HOST pointers owned by the caller, read (or written, for
+ *     downloads) only during the call.  The library owns all device memory.
+ *   - one context per rank == per GPU; calls on a context are serialised by the
+ *     caller (KitAMR runs one Julia task per MPI rank).
+ *   - indices are 0-based int32 unless stated; reals are fp64.
+ *
+ * Host array layouts (identical to the reference's Julia column-major blocks)
+ *   cell ids: [0,n_local) local cells that own velocity data (fluid, donor and
+ *             solid ghost cells — InsideSolidData placeholders are not listed),
+ *             [n_local, n_local+n_ghost) p4est ghost cells (contiguous per
+ *             source rank, Parallel/Ghost.jl:221-239),
+ *             [n_local+n_ghost, n_cell) SolidNeighbor pseudo-cells
+ *             (Physical_space/Types.jl:28-48).
+ *   per-point state of cell c with n = n(c) points, starting at
+ *   P = vs_off[c] = sum_{c'<c} n(c'):
+ *      df  [ (P*NDF)      + k*n + i ]            == VsData.df[i,k]
+ *      sdf [ (P*NDF*DIM)  + (d*NDF + k)*n + i ]  == VsData.sdf[i,k,d]
+ *      flux[ (P*NDF)      + k*n + i ]            == VsData.flux[i,k]
+ *   per-cell:  w,prim,mflux [c*(DIM+2)+m];  qf [c*DIM+d];  sw [c*(DIM+2)*DIM + d*(DIM+2)+m]
+ *   velocity grids are shared: cell c uses grid g = cell_grid[c]; grid g has
+ *   n_g = grid_off[g+1]-grid_off[g] points at Q = grid_off[g]:
+ *      v_level [Q+i]  (Int8, VsData.level)     v_weight[Q+i] (VsData.weight)
+ *      v_mid   [Q*DIM + d*n_g + i]             == VsData.midpoint[i,d]
+ *   (the host shim may give every cell its own grid; sharing identical grids
+ *    lets the device keep one copy — see DESIGN.md "static dedup").
+ */
+#ifndef KAMR_H
+#define KAMR_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KAMR_VERSION 1
+
+/* flux scheme: Solver.flux (src/Solver/Types.jl:69) */
+enum { KAMR_FLUX_CAIDVM = 0, KAMR_FLUX_DVM = 1 };
+/* time marching: Solver.time_marching (src/Solver/Types.jl:71) */
+enum { KAMR_MARCH_CAIDVM = 0, KAMR_MARCH_CIP = 1, KAMR_MARCH_EULER = 2 };
+/* face kinds (src/Physical_space/Types.jl:157-219, src/Boundary/Types.jl:27-33).
+ * Hanging / BackHanging faces are passed as one record per (here, there) pair,
+ * i.e. one per FluxData (src/Flux/Flux.jl:37-59). */
+enum { KAMR_FACE_DOMAIN = 0, KAMR_FACE_FULL = 1, KAMR_FACE_HANGING = 2, KAMR_FACE_BACKHANGING = 3 };
+/* domain boundary conditions (src/Flux/CAIDVM.jl:4,29,53,71) */
+enum { KAMR_BC_MAXWELLIAN = 0, KAMR_BC_SUPERSONIC_INFLOW = 1, KAMR_BC_UNIFORM_OUTFLOW = 2,
+       KAMR_BC_INTERPOLATED_OUTFLOW = 3 };
+/* download mask bits */
+enum { KAMR_DL_DF = 1, KAMR_DL_SDF = 2, KAMR_DL_FLUX = 4, KAMR_DL_W = 8, KAMR_DL_PRIM = 16,
+       KAMR_DL_QF = 32, KAMR_DL_SW = 64, KAMR_DL_MFLUX = 128 };
+
+typedef struct kamr_ctx kamr_ctx;
+
+typedef struct kamr_config {
+    int32_t dim;          /* 2 or 3 */
+    int32_t ndf;          /* 2 (2D2F) or 1 (3D1F) */
+    int32_t flux_type;    /* KAMR_FLUX_* */
+    int32_t marching;     /* KAMR_MARCH_* */
+    double  K, Pr, gamma, omega, mu_ref;  /* Gas (src/Gas/Types.jl:5-24) */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t rank, nranks; /* MPI rank / size of the owning process */
+    void*   stream;       /* optional cudaStream_t to launch on (NULL: library creates one) */
+} kamr_config;
+
+typedef struct kamr_mesh {
+    /* ---- cells ---- */
+    int32_t n_local, n_ghost, n_solidnbr;
+    const double*  ds;        /* [n_cell*DIM]  PsData.ds */
+    const double*  mid;       /* [n_cell*DIM]  PsData.midpoint */
+    const int32_t* bound_enc; /* [n_cell] 0 fluid, >0 donor, <0 solid (PsData.bound_enc) */
+    const int32_t* ps_level;  /* [n_cell] physical refinement level (cell_level, Slope.jl:825) */
+    const int32_t* cell_grid; /* [n_cell] velocity-grid id */
+    /* ---- velocity grids ---- */
+    int32_t n_grid;
+    const int64_t* grid_off;  /* [n_grid+1] */
+    const int8_t*  v_level;
+    const double*  v_weight;
+    const double*  v_mid;
+    /* ---- slope neighbours of local cells: PsData.neighbor (Mesh/Neighbor.jl:31-63) ----
+     * entry e = c*2*DIM + (faceid-1); state: 0 boundary, 1 same, -1 coarser, 2^(DIM-1) finer */
+    const int32_t* nb_state;  /* [n_local*2*DIM] */
+    const int32_t* nb_off;    /* [n_local*2*DIM+1] */
+    const int32_t* nb_ids;    /* neighbour cell ids (local, ghost or solid-neighbour slots) */
+    int32_t ps_maxlevel;      /* Solver.AMR_PS_MAXLEVEL */
+    int32_t ps_minlevel;      /* min_cell_level(ka) over ALL ranks (Slope.jl:953-967) */
+    /* ---- faces: ka.kdata.field.faces, in the host's order ---- */
+    int32_t n_face;
+    const int32_t* face_kind;   /* KAMR_FACE_* */
+    const int32_t* face_here;   /* local cell id */
+    const int32_t* face_there;  /* cell id, or bc index for domain faces */
+    const int32_t* face_dir;    /* 0-based direction */
+    const double*  face_rot;    /* +1 / -1  (get_rot, Theory/Math.jl:2) */
+    const double*  face_mid;    /* [n_face*DIM] face midpoint */
+    const double*  face_there_mid; /* [n_face*DIM] there_data.midpoint (shifted for periodic aliases) */
+    /* ---- domain boundary conditions ---- */
+    int32_t n_bc;
+    const int32_t* bc_type;     /* KAMR_BC_* */
+    const double*  bc_prim;     /* [n_bc*(DIM+2)] */
+    /* ---- halo (p4est ghost layer, Parallel/Ghost.jl:133-145) ---- */
+    int32_t n_peer;
+    const int32_t* peer_rank;   /* [n_peer] */
+    const int32_t* send_off;    /* [n_peer+1] into send_cells */
+    const int32_t* send_cells;  /* mirror cells (local ids) in mirror_proc_mirrors order */
+    const int32_t* recv_off;    /* [n_peer+1] ghost index ranges (relative to n_local) */
+    /* ---- immersed boundary (Boundary/Immersed_boundary.jl) ---- */
+    const struct kamr_ib* ib;   /* NULL when no immersed boundary */
+} kamr_mesh;
+
+/* Immersed-boundary tables, built by the host at re-flatten time
+ * (initialize_solid_neighbor! :282, initialize_cutted_velocity_cell :226). */
+typedef struct kamr_ib {
+    /* solid ghost cells (bound_enc<0): fluid neighbours used by update_solid_cell! :122 */
+    int32_t n_solid;
+    const int32_t* solid_cell;    /* [n_solid] local cell id */
+    const int32_t* solid_nb_off;  /* [n_solid+1] */
+    const int32_t* solid_nb_ids;  /* fluid neighbour cell ids (first element of each face/corner list) */
+    /* solid neighbours (one per donor cell x solid face) */
+    int32_t n_sn;                 /* == n_solidnbr */
+    const int32_t* sn_donor;      /* [n_sn] donor cell id */
+    const int32_t* sn_solid;      /* [n_sn] solid cell id (local or ghost) */
+    const int32_t* sn_faceid;     /* [n_sn] 0-based face id of the donor */
+    const double*  sn_aux;        /* [n_sn*DIM] wall intersection point */
+    const double*  sn_normal;     /* [n_sn*DIM] */
+    const double*  sn_bc;         /* [n_sn*(DIM+2)] wall prim evaluated at aux point */
+    const int32_t* sn_nb_off;     /* [n_sn+1] donor's fluid neighbours used by image_df :376 */
+    const int32_t* sn_nb_ids;
+    /* cut velocity cells (CuttedVelocityCells, Velocity_space/Types.jl:81-94) */
+    const int32_t* cvc_off;       /* [n_sn+1] */
+    const int32_t* cvc_index;     /* velocity point index within the donor grid */
+    const double*  cvc_gas_w;     /* gas-side weight */
+    const double*  cvc_solid_w;   /* solid-side weight */
+} kamr_ib;
+
+/* lifecycle */
+int  kamr_create(const kamr_config* cfg, kamr_ctx** out);
+int  kamr_destroy(kamr_ctx* ctx);
+const char* kamr_last_error(const kamr_ctx* ctx);
+int  kamr_version(void);
+
+/* multi-GPU: nccl_unique_id points at the 128-byte ncclUniqueId obtained on
+ * rank 0 via kamr_comm_unique_id and distributed by the host (MPI_Bcast in the
+ * Julia shim).  Not needed for nranks == 1. */
+int  kamr_comm_unique_id(void* id128);
+int  kamr_comm_init(kamr_ctx* ctx, const void* id128);
+
+/* re-flatten: after initialize / restart / every amr_recover! (Solver/AMR.jl:54) */
+int  kamr_upload_topology(kamr_ctx* ctx, const kamr_mesh* mesh);
+/* state in host layout; df for all n_cell cells (ghost / solid-neighbour blocks may be anything),
+ * w and prim for local cells [n_local*(DIM+2)].  NULL pointers are skipped. */
+int  kamr_upload_state(kamr_ctx* ctx, const double* df, const double* w, const double* prim);
+/* optional: upload sdf / vs flux / macro flux (restart in the middle of a step) */
+int  kamr_upload_aux(kamr_ctx* ctx, const double* sdf, const double* flux, const double* mflux);
+int  kamr_download_state(kamr_ctx* ctx, uint32_t mask, double* df, double* sdf, double* flux,
+                         double* w, double* prim, double* qf, double* sw, double* mflux);
+
+/* the hot path */
+int  kamr_slope(kamr_ctx* ctx);
+int  kamr_flux(kamr_ctx* ctx, double dt);
+/* res_out: [2*(DIM+2)] = sumRes | sumAvg of residual_check! (Solver/Finalize.jl:5), local to this rank */
+int  kamr_iterate(kamr_ctx* ctx, double dt, int32_t want_residual, double* res_out);
+/* slope + flux + iterate with the flux kept on chip (DESIGN.md "fused step") */
+int  kamr_step(kamr_ctx* ctx, double dt, int32_t want_residual, double* res_out);
+/* halo of df after the update (data_exchange!, Parallel/Ghost.jl:841); called by kamr_iterate/kamr_step
+ * internally, exported for host-driven sequences */
+int  kamr_exchange_df(kamr_ctx* ctx);
+int  kamr_sync(kamr_ctx* ctx);
+
+/* introspection (tests, benchmark accounting) */
+typedef struct kamr_stats {
+    int64_t n_phase_local;     /* sum of vs_num over local fluid cells (IO/Check.jl:98) */
+    int64_t n_points_total;    /* sum of vs_num over all cells */
+    int64_t n_relations;       /* distinct (grid,grid) pair maps built */
+    int64_t n_slots;           /* cell-face slots */
+    int64_t kernel_launches;   /* kernels launched since creation */
+    int64_t device_bytes;      /* device memory owned */
+    int64_t halo_bytes_per_step;
+    int32_t n_levels;          /* slope sweep phases */
+    int32_t fused_cells;       /* cells taking the on-chip flux+update path */
+} kamr_stats;
+int  kamr_get_stats(kamr_ctx* ctx, kamr_stats* out);
+/* pair map of grid ga onto grid gb: start[n_a+1]; returns 1 if identity */
+int  kamr_get_pair_map(kamr_ctx* ctx, int32_t ga, int32_t gb, int32_t* start, int32_t cap);
+/* cell-face slots of a local cell: writes up to cap records {face, sign}; returns count via *n */
+int  kamr_get_cell_slots(kamr_ctx* ctx, int32_t cell, int32_t* face, int32_t* sign, int32_t cap, int32_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KAMR_H */

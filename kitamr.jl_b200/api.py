@@ -1,0 +1,114 @@
+"""Thin object wrapper over the C-ABI (include/kamr.h).  All compute happens in libkamr.so on the GPU;
+this module only marshals numpy arrays across the boundary."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .model import HostMesh, HostState
+
+
+class KamrError(RuntimeError):
+    pass
+
+
+class Context:
+    def __init__(self, cfg: abi.KamrConfig, lib=None):
+        self.lib = lib or abi.load()
+        self.cfg = cfg
+        self.D, self.K, self.M = cfg.dim, cfg.ndf, cfg.dim + 2
+        h = C.c_void_p()
+        rc = self.lib.kamr_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise KamrError(self.lib.kamr_last_error(None).decode())
+        self.h = h
+        self.mesh = None
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise KamrError(self.lib.kamr_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kamr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- multi-GPU -------------------------------------------------------------------------
+    def unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        if self.lib.kamr_comm_unique_id(buf) != 0:
+            raise KamrError(self.lib.kamr_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, uid: bytes):
+        buf = C.create_string_buffer(uid, 128)
+        self._ck(self.lib.kamr_comm_init(self.h, buf))
+
+    # ---- topology / state ------------------------------------------------------------------
+    def upload_topology(self, mesh: HostMesh):
+        self.mesh = mesh
+        m = mesh.c_struct()
+        self._ck(self.lib.kamr_upload_topology(self.h, C.byref(m)))
+
+    def upload_state(self, st: HostState, aux=False):
+        p = lambda a: a.ctypes.data_as(abi.c_f64p)
+        self._ck(self.lib.kamr_upload_state(self.h, p(st.df), p(st.w), p(st.prim)))
+        if aux:
+            self._ck(self.lib.kamr_upload_aux(self.h, p(st.sdf), p(st.flux), p(st.mflux)))
+
+    def download_state(self, st: HostState, mask=0xFF):
+        p = lambda a: a.ctypes.data_as(abi.c_f64p)
+        self._ck(self.lib.kamr_download_state(self.h, mask, p(st.df), p(st.sdf), p(st.flux), p(st.w), p(st.prim),
+                                              p(st.qf), p(st.sw), p(st.mflux)))
+        return st
+
+    # ---- hot path --------------------------------------------------------------------------
+    def slope(self):
+        self._ck(self.lib.kamr_slope(self.h))
+
+    def flux(self, dt):
+        self._ck(self.lib.kamr_flux(self.h, dt))
+
+    def iterate(self, dt, want_residual=False):
+        res = np.zeros(2 * self.M)
+        self._ck(self.lib.kamr_iterate(self.h, dt, int(want_residual), res.ctypes.data_as(abi.c_f64p)))
+        return res
+
+    def step(self, dt, want_residual=False):
+        res = np.zeros(2 * self.M)
+        self._ck(self.lib.kamr_step(self.h, dt, int(want_residual), res.ctypes.data_as(abi.c_f64p)))
+        return res
+
+    def sync(self):
+        self._ck(self.lib.kamr_sync(self.h))
+
+    # ---- introspection ---------------------------------------------------------------------
+    def stats(self) -> abi.KamrStats:
+        s = abi.KamrStats()
+        self._ck(self.lib.kamr_get_stats(self.h, C.byref(s)))
+        return s
+
+    def pair_map(self, ga, gb):
+        n = int(self.mesh.grid_off[ga + 1] - self.mesh.grid_off[ga])
+        start = np.zeros(n + 1, dtype=np.int32)
+        rc = self.lib.kamr_get_pair_map(self.h, ga, gb, start.ctypes.data_as(abi.c_i32p), n + 1)
+        if rc == 1:
+            return None
+        if rc != 0:
+            raise KamrError(self.lib.kamr_last_error(self.h).decode())
+        return start
+
+    def cell_slots(self, cell):
+        face = np.zeros(64, dtype=np.int32); sign = np.zeros(64, dtype=np.int32)
+        n = C.c_int32(0)
+        self._ck(self.lib.kamr_get_cell_slots(self.h, cell, face.ctypes.data_as(abi.c_i32p),
+                                              sign.ctypes.data_as(abi.c_i32p), 64, C.byref(n)))
+        return face[: n.value].copy(), sign[: n.value].copy()

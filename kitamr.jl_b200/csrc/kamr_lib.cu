@@ -1,0 +1,1015 @@
+// kamr_lib.cu — C-ABI of libkamr (include/kamr.h): context, re-flatten (topology build), state
+// transfer, kernel launch sequences and the NCCL halo.
+//
+// Reference seam: slope!/flux!/iterate!(p4est, ka) (Flux/Slope.jl:1047, Flux/Flux.jl:458,
+// Theory/Iterate.jl:5), re-flatten trigger amr_recover! (Solver/AMR.jl:54).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/kamr.h"
+#include "kamr_comm.h"
+#include "kamr_kernels.cuh"
+
+using namespace kamr;
+
+namespace {
+
+std::string g_create_err;
+
+struct Fail : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            throw Fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +         \
+                       std::to_string(__LINE__) + ")");                                                 \
+    } while (0)
+#define NCK(call)                                                                                       \
+    do {                                                                                                \
+        int r_ = (call);                                                                                \
+        if (r_ != 0) throw Fail(std::string(#call) + ": " + nccl().GetErrorString(r_));                 \
+    } while (0)
+
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+};
+
+struct Bin {
+    std::vector<int> cells;
+    int* d_cells = nullptr;
+    size_t smem = 0;  // dynamic shared memory per block (0 => global staging)
+};
+
+struct PeerPlan {
+    int rank;
+    // df exchange
+    std::vector<CopySeg> df_send;
+    CopySeg* d_df_send = nullptr;
+    long long df_send_len = 0;
+    long long df_recv_off = 0, df_recv_len = 0;  // contiguous ghost range in the df array (doubles)
+    // sdf exchange per level
+    struct Lvl {
+        std::vector<CopySeg> send, recv;
+        CopySeg *d_send = nullptr, *d_recv = nullptr;
+        long long send_len = 0, recv_len = 0;
+    };
+    std::map<int, Lvl> sdf;
+    long long send_base = 0, recv_base = 0;  // offsets of this peer's region in the staging buffers
+};
+
+}  // namespace
+
+struct kamr_ctx {
+    kamr_config cfg{};
+    GasPar gas{};
+    std::string err;
+    int D = 0, K = 0, M = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // topology (host copies)
+    int n_local = 0, n_ghost = 0, n_sn = 0, n_cell = 0, n_grid = 0;
+    std::vector<CellInfo> cells;
+    std::vector<Slot> slots;
+    std::vector<long long> host_off;  // unpadded point offset per cell (host layout)
+    std::vector<int> grid_n, grid_np;
+    std::vector<long long> grid_goff, grid_hoff;
+    std::vector<int8_t> h_level;      // host copy of v_level (host layout) for pair maps
+    std::map<std::pair<int, int>, int> rel_id;
+    std::vector<long long> rel_off;
+    std::vector<int> pm_start;
+    std::vector<std::pair<int, std::vector<SlopeTask>>> level_tasks;
+    std::vector<SlopeTask*> d_level_tasks;
+    std::vector<int> fluid_cells;
+    int* d_fluid_cells = nullptr;
+    std::vector<Bin> bins;
+    bool padded = false;
+    long long npts_pad = 0, npts_host = 0;
+    // device
+    std::vector<void*> allocs;
+    long long device_bytes = 0;
+    DevView dv{};
+    double* d_res = nullptr;
+    double* h_res = nullptr;  // pinned
+    double* h_stage = nullptr;  // pinned staging for padded transfers
+    size_t stage_doubles = 0;
+    // halo
+    ncclComm_t comm = nullptr;
+    std::vector<PeerPlan> peers;
+    double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+    long long halo_bytes_step = 0;
+    // stats
+    long long launches = 0;
+    long long n_phase_local = 0;
+    int fused_cells = 0;
+
+    template <class T>
+    T* dalloc(size_t n) {
+        void* p = nullptr;
+        size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+        CK(cudaMalloc(&p, bytes));
+        allocs.push_back(p);
+        device_bytes += (long long)bytes;
+        return (T*)p;
+    }
+    template <class T>
+    T* dupload(const std::vector<T>& v) {
+        T* p = dalloc<T>(v.size());
+        if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        return p;
+    }
+    void free_topology() {
+        if (stream) cudaStreamSynchronize(stream);
+        for (void* p : allocs) cudaFree(p);
+        allocs.clear();
+        device_bytes = 0;
+        cells.clear(); slots.clear(); host_off.clear(); grid_n.clear(); grid_np.clear(); grid_goff.clear();
+        grid_hoff.clear(); h_level.clear(); rel_id.clear(); rel_off.clear(); pm_start.clear();
+        level_tasks.clear(); d_level_tasks.clear(); fluid_cells.clear(); bins.clear(); peers.clear();
+        dv = DevView{};
+        d_res = nullptr; d_sendbuf = d_recvbuf = nullptr; d_fluid_cells = nullptr;
+    }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// pair map of grid a onto grid b: start[i] = first point of b matched with point i of a
+// in the reference's merge-walk (Flux/Slope.jl:29-64).  Integer volume accounting instead of the
+// reference's floating-point `flag` accumulation; tests check it against the oracle's restatement.
+int build_rel(kamr_ctx* c, int ga, int gb) {
+    if (ga == gb) return -1;
+    auto key = std::make_pair(ga, gb);
+    auto it = c->rel_id.find(key);
+    if (it != c->rel_id.end()) return it->second;
+    const int D = c->D;
+    const int na = c->grid_n[ga], nb = c->grid_n[gb];
+    const int8_t* la = c->h_level.data() + c->grid_hoff[ga];
+    const int8_t* lb = c->h_level.data() + c->grid_hoff[gb];
+    int lmax = 0;
+    for (int i = 0; i < na; ++i) lmax = std::max<int>(lmax, la[i]);
+    for (int j = 0; j < nb; ++j) lmax = std::max<int>(lmax, lb[j]);
+    auto vol = [&](int l) { return (long long)1 << (D * (lmax - l)); };
+    const long long off = (long long)c->pm_start.size();
+    c->pm_start.resize(off + na + 1);
+    int* start = c->pm_start.data() + off;
+    int j = 0;
+    long long acc = 0;
+    for (int i = 0; i < na; ++i) {
+        if (j >= nb) throw Fail("velocity grids " + std::to_string(ga) + "/" + std::to_string(gb) +
+                                " do not cover the same domain");
+        start[i] = j;
+        const long long va = vol(la[i]), vb = vol(lb[j]);
+        if (va == vb && acc == 0) {
+            ++j;
+        } else if (va > vb) {
+            long long got = 0;
+            while (got < va) {
+                if (j >= nb) throw Fail("velocity grid walk overran (coarse side)");
+                got += vol(lb[j]);
+                ++j;
+            }
+            if (got != va) throw Fail("velocity grids are not nested");
+        } else {
+            acc += va;
+            if (acc == vb) { ++j; acc = 0; }
+            else if (acc > vb) throw Fail("velocity grids are not nested");
+        }
+    }
+    if (j != nb || acc != 0) throw Fail("velocity grid walk did not consume the neighbour grid");
+    start[na] = nb;
+    const int id = (int)c->rel_off.size();
+    c->rel_off.push_back(off);
+    c->rel_id[key] = id;
+    return id;
+}
+
+double face_area_of(const CellInfo& ci, int D, int dir) {  // Flux/Flux.jl:10-15
+    if (D == 2) return ci.ds[dir == 0 ? 1 : 0];
+    if (dir == 0) return ci.ds[1] * ci.ds[2];
+    if (dir == 1) return ci.ds[0] * ci.ds[2];
+    return ci.ds[0] * ci.ds[1];
+}
+
+struct NbList {
+    int cnt;
+    const int32_t* ids;
+};
+
+// _ps_has_transverse_offset, Flux/Slope.jl:177-201
+bool has_offset(const kamr_ctx* c, int cell, NbList nb, int dir) {
+    const int D = c->D;
+    if (nb.cnt == 0) return false;
+    for (int t = 0; t < D; ++t) {
+        if (t == dir) continue;
+        double avg = 0.0;
+        for (int j = 0; j < nb.cnt; ++j) avg += c->cells[nb.ids[j]].mid[t];
+        avg /= nb.cnt;
+        if (avg != c->cells[cell].mid[t]) return true;
+    }
+    return false;
+}
+
+void fill_side(kamr_ctx* c, int cell, NbList nb, double ds, int dir, int project /*0 no,1 yes*/, SlopeSide& s) {
+    if (nb.cnt > 4) throw Fail("more than 4 neighbours on one face");
+    s.n = nb.cnt;
+    s.ds = ds;
+    for (int a = 0; a < 4; ++a) { s.nbr[a] = 0; s.rel[a] = -1; s.proj[a] = 0; for (int t = 0; t < MAXD; ++t) s.dm[a][t] = 0.0; }
+    for (int a = 0; a < nb.cnt; ++a) {
+        const int nbr = nb.ids[a];
+        s.nbr[a] = nbr;
+        s.rel[a] = build_rel(c, c->cells[cell].grid, c->cells[nbr].grid);
+        if (project) {
+            bool any = false;
+            for (int t = 0; t < c->D; ++t) {
+                s.dm[a][t] = (t == dir) ? 0.0 : (c->cells[cell].mid[t] - c->cells[nbr].mid[t]);
+                any = any || s.dm[a][t] != 0.0;
+            }
+            s.proj[a] = any ? 1 : 0;  // dm == 0 contributes exactly 0 in the reference as well
+        }
+    }
+}
+
+// the 15 update_slope! methods (Flux/Slope.jl:458-771) resolved into a stencil descriptor
+void baseline_dir(kamr_ctx* c, const kamr_mesh* m, int cell, int dir, SlopeDir& out) {
+    const int D = c->D;
+    const int e = cell * 2 * D + 2 * dir;
+    const int sL = m->nb_state[e], sR = m->nb_state[e + 1];
+    NbList L{m->nb_off[e + 1] - m->nb_off[e], m->nb_ids + m->nb_off[e]};
+    NbList R{m->nb_off[e + 2] - m->nb_off[e + 1], m->nb_ids + m->nb_off[e + 1]};
+    const CellInfo& ci = c->cells[cell];
+    auto midd = [&](int id) { return c->cells[id].mid[dir]; };
+    memset(&out, 0, sizeof(out));
+    if (sL == 1 && sR == 1) {
+        const bool solidL = c->cells[L.ids[0]].bound_enc < 0, solidR = c->cells[R.ids[0]].bound_enc < 0;
+        if (solidL && solidR) { out.mode = SLOPE_ZERO; return; }
+        if (solidL) { out.mode = SLOPE_BOUND; fill_side(c, cell, R, ci.mid[dir] - midd(R.ids[0]), dir, 0, out.A); return; }
+        if (solidR) { out.mode = SLOPE_BOUND; fill_side(c, cell, L, ci.mid[dir] - midd(L.ids[0]), dir, 0, out.A); return; }
+        out.mode = SLOPE_INNER;
+        fill_side(c, cell, L, ci.ds[dir], dir, 0, out.A);
+        fill_side(c, cell, R, -ci.ds[dir], dir, 0, out.B);
+        return;
+    }
+    if (sL == 0 && sR == 0) throw Fail("cell with domain boundaries on both sides of one direction (no such "
+                                       "update_slope! method in the reference)");
+    if (sL == 0) { out.mode = SLOPE_BOUND; fill_side(c, cell, R, ci.mid[dir] - midd(R.ids[0]), dir, 0, out.A); return; }
+    if (sR == 0) { out.mode = SLOPE_BOUND; fill_side(c, cell, L, ci.mid[dir] - midd(L.ids[0]), dir, 0, out.A); return; }
+    const double ds = ci.ds[dir];
+    const double dsL = (sL == 1) ? ds : ((sL == -1 ? 1.5 : 0.75) * ds);
+    const double dsR = (sR == 1) ? -ds : (-(sR == -1 ? 1.5 : 0.75) * ds);
+    out.mode = SLOPE_INNER;
+    fill_side(c, cell, L, dsL, dir, 0, out.A);
+    fill_side(c, cell, R, dsR, dir, 0, out.B);
+}
+
+// update_slope_transverse_level!, Flux/Slope.jl:849-945
+void transverse_dir(kamr_ctx* c, const kamr_mesh* m, int cell, int dir, SlopeDir& out) {
+    const int D = c->D;
+    const int e = cell * 2 * D + 2 * dir;
+    const int sL = m->nb_state[e], sR = m->nb_state[e + 1];
+    if (!(sL == -1 || sR == -1)) { baseline_dir(c, m, cell, dir, out); return; }
+    NbList L{m->nb_off[e + 1] - m->nb_off[e], m->nb_ids + m->nb_off[e]};
+    NbList R{m->nb_off[e + 2] - m->nb_off[e + 1], m->nb_ids + m->nb_off[e + 1]};
+    const CellInfo& ci = c->cells[cell];
+    memset(&out, 0, sizeof(out));
+    auto solid = [&](NbList l) { return c->cells[l.ids[0]].bound_enc < 0; };
+    if (sL != 0 && sR != 0) {
+        const double dsL = ci.mid[dir] - c->cells[L.ids[0]].mid[dir];
+        const double dsR = ci.mid[dir] - c->cells[R.ids[0]].mid[dir];
+        if (solid(L)) { out.mode = SLOPE_BOUND; fill_side(c, cell, R, dsR, dir, 1, out.A); return; }
+        if (solid(R)) { out.mode = SLOPE_BOUND; fill_side(c, cell, L, dsL, dir, 1, out.A); return; }
+        out.mode = SLOPE_INNER;
+        fill_side(c, cell, L, dsL, dir, has_offset(c, cell, L, dir) ? 1 : 0, out.A);
+        fill_side(c, cell, R, dsR, dir, has_offset(c, cell, R, dir) ? 1 : 0, out.B);
+    } else if (sR == 0 && sL == -1) {
+        if (solid(L)) { out.mode = SLOPE_KEEP; return; }
+        out.mode = SLOPE_BOUND;
+        fill_side(c, cell, L, ci.mid[dir] - c->cells[L.ids[0]].mid[dir], dir, 1, out.A);
+    } else {
+        if (solid(R)) { out.mode = SLOPE_KEEP; return; }
+        out.mode = SLOPE_BOUND;
+        fill_side(c, cell, R, ci.mid[dir] - c->cells[R.ids[0]].mid[dir], dir, 1, out.A);
+    }
+}
+
+void build_topology(kamr_ctx* c, const kamr_mesh* m) {
+    const int D = c->D, K = c->K, M = c->M;
+    c->free_topology();
+    c->n_local = m->n_local; c->n_ghost = m->n_ghost; c->n_sn = m->n_solidnbr;
+    c->n_cell = m->n_local + m->n_ghost + m->n_solidnbr;
+    c->n_grid = m->n_grid;
+    if (c->n_local <= 0) throw Fail("mesh has no local cells");
+    // ---- grids
+    c->grid_n.resize(m->n_grid); c->grid_np.resize(m->n_grid);
+    c->grid_goff.resize(m->n_grid + 1); c->grid_hoff.resize(m->n_grid + 1);
+    c->grid_goff[0] = 0; c->grid_hoff[0] = 0;
+    bool padded = false;
+    for (int g = 0; g < m->n_grid; ++g) {
+        const long long n = m->grid_off[g + 1] - m->grid_off[g];
+        if (n <= 0 || n > (1ll << 30)) throw Fail("bad velocity grid size");
+        c->grid_n[g] = (int)n;
+        c->grid_np[g] = (int)round_up(n, PAD);
+        padded = padded || (c->grid_np[g] != n);
+        c->grid_hoff[g + 1] = c->grid_hoff[g] + n;
+        c->grid_goff[g + 1] = c->grid_goff[g] + c->grid_np[g];
+    }
+    c->padded = padded;
+    const long long gpts_h = c->grid_hoff[m->n_grid], gpts_d = c->grid_goff[m->n_grid];
+    c->h_level.assign(m->v_level, m->v_level + gpts_h);
+    {
+        std::vector<int8_t> lv(gpts_d, 0);
+        std::vector<double> wt(gpts_d, 0.0), vm((size_t)gpts_d * D, 0.0);
+        for (int g = 0; g < m->n_grid; ++g) {
+            const int n = c->grid_n[g], np = c->grid_np[g];
+            const long long ho = c->grid_hoff[g], go = c->grid_goff[g];
+            memcpy(lv.data() + go, m->v_level + ho, n);
+            memcpy(wt.data() + go, m->v_weight + ho, sizeof(double) * n);
+            for (int d = 0; d < D; ++d)
+                memcpy(vm.data() + go * D + (size_t)d * np, m->v_mid + ho * D + (size_t)d * n, sizeof(double) * n);
+            // padding points replicate the last real point so padded lanes stay finite
+            for (int i = n; i < np; ++i) {
+                lv[go + i] = lv[go + n - 1];
+                for (int d = 0; d < D; ++d) vm[go * D + (size_t)d * np + i] = vm[go * D + (size_t)d * np + n - 1];
+            }
+        }
+        c->dv.v_level = c->dupload(lv);
+        c->dv.v_weight = c->dupload(wt);
+        c->dv.v_mid = c->dupload(vm);
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    // ---- cells
+    c->cells.resize(c->n_cell);
+    c->host_off.resize(c->n_cell + 1);
+    c->host_off[0] = 0;
+    long long doff = 0;
+    c->n_phase_local = 0;
+    for (int i = 0; i < c->n_cell; ++i) {
+        CellInfo& ci = c->cells[i];
+        memset(&ci, 0, sizeof(ci));
+        const int g = m->cell_grid[i];
+        if (g < 0 || g >= m->n_grid) throw Fail("cell_grid out of range");
+        ci.grid = g; ci.n = c->grid_n[g]; ci.np = c->grid_np[g];
+        ci.doff = doff; ci.goff = c->grid_goff[g];
+        ci.bound_enc = m->bound_enc[i];
+        ci.ps_level = m->ps_level[i];
+        ci.vol = 1.0;
+        for (int d = 0; d < D; ++d) {
+            ci.ds[d] = m->ds[(size_t)i * D + d];
+            ci.mid[d] = m->mid[(size_t)i * D + d];
+            ci.vol *= ci.ds[d];  // reduce(*, ps_data.ds), Iterate.jl:106
+        }
+        doff += ci.np;
+        c->host_off[i + 1] = c->host_off[i] + ci.n;
+        if (i < c->n_local && ci.bound_enc >= 0) c->n_phase_local += ci.n;
+    }
+    c->npts_pad = doff; c->npts_host = c->host_off[c->n_cell];
+    // ---- slots (cell-centric view of the face list)
+    std::vector<std::vector<Slot>> per_cell(c->n_local);
+    for (int f = 0; f < m->n_face; ++f) {
+        const int kind = m->face_kind[f], here = m->face_here[f], there = m->face_there[f], dir = m->face_dir[f];
+        const double rot = m->face_rot[f];
+        if (here < 0 || here >= c->n_local) throw Fail("face_here must be a local cell");
+        if (dir < 0 || dir >= D) throw Fail("face_dir out of range");
+        Slot s;
+        memset(&s, 0, sizeof(s));
+        s.dir = dir; s.rot = rot; s.face = f; s.is_here = 1; s.rel = -1;
+        const CellInfo& ch = c->cells[here];
+        for (int t = 0; t < D; ++t) { s.fmid[t] = m->face_mid[(size_t)f * D + t]; s.own_mid[t] = ch.mid[t]; }
+        double area = face_area_of(ch, D, dir);
+        if (kind == KAMR_FACE_DOMAIN) {
+            if (there < 0 || there >= m->n_bc) throw Fail("domain face bc index out of range");
+            s.nbr = -1;
+            s.area = rot * area;
+            switch (m->bc_type[there]) {
+                case KAMR_BC_MAXWELLIAN: s.kind = SLOT_BC_MAXWELL; break;
+                case KAMR_BC_SUPERSONIC_INFLOW: s.kind = SLOT_BC_INFLOW; break;
+                case KAMR_BC_UNIFORM_OUTFLOW: s.kind = SLOT_BC_UNIFORM; break;
+                case KAMR_BC_INTERPOLATED_OUTFLOW:
+                    if (D != 2) throw Fail("InterpolatedOutflow is 2-D only (CAIDVM.jl:71)");
+                    s.kind = SLOT_BC_INTERP; break;
+                default: throw Fail("unknown bc type");
+            }
+            for (int q = 0; q < M; ++q) s.bc[q] = m->bc_prim[(size_t)there * M + q];
+            per_cell[here].push_back(s);
+            continue;
+        }
+        if (there < 0 || there >= c->n_cell) throw Fail("face_there out of range");
+        if (kind == KAMR_FACE_HANGING) area = area / (double)(1 << (D - 1)) * rot;  // Flux.jl:84-86
+        else area = area * rot;                                                     // Flux.jl:87-89
+        const CellInfo& ct = c->cells[there];
+        s.nbr = there;
+        s.kind = (ct.bound_enc < 0) ? SLOT_NBR_SOLID : SLOT_INNER;
+        s.rel = build_rel(c, ch.grid, ct.grid);
+        s.area = area;
+        for (int t = 0; t < D; ++t) s.nbr_mid[t] = m->face_there_mid[(size_t)f * D + t];
+        per_cell[here].push_back(s);
+        if (there < c->n_local && ct.bound_enc >= 0) {  // update_macro_flux!/update_micro_flux! write-back side
+            Slot r = s;
+            r.is_here = 0; r.nbr = here; r.kind = SLOT_INNER;
+            r.rel = build_rel(c, ct.grid, ch.grid);
+            r.area = -area;
+            for (int t = 0; t < D; ++t) { r.own_mid[t] = s.nbr_mid[t]; r.nbr_mid[t] = ch.mid[t]; }
+            per_cell[there].push_back(r);
+        }
+    }
+    for (int i = 0; i < c->n_local; ++i) {
+        if ((int)per_cell[i].size() > MAX_SLOTS) throw Fail("too many faces on one cell");
+        c->cells[i].slot_begin = (int)c->slots.size();
+        c->slots.insert(c->slots.end(), per_cell[i].begin(), per_cell[i].end());
+        c->cells[i].slot_end = (int)c->slots.size();
+    }
+    // ---- slope tasks per level (slope!, Slope.jl:1047-1070)
+    {
+        std::map<int, std::vector<SlopeTask>> by_level;
+        for (int i = 0; i < c->n_local; ++i) {
+            if (c->cells[i].bound_enc < 0) continue;
+            const int L = c->cells[i].ps_level;
+            SlopeTask t;
+            memset(&t, 0, sizeof(t));
+            t.cell = i;
+            for (int d = 0; d < D; ++d) {
+                if (L <= m->ps_minlevel) baseline_dir(c, m, i, d, t.d[d]);
+                else transverse_dir(c, m, i, d, t.d[d]);
+            }
+            by_level[L].push_back(t);
+        }
+        for (auto& kv : by_level) {
+            // heaviest cells first: better tail behaviour of the block scheduler
+            std::stable_sort(kv.second.begin(), kv.second.end(), [&](const SlopeTask& a, const SlopeTask& b) {
+                return c->cells[a.cell].n > c->cells[b.cell].n;
+            });
+            c->d_level_tasks.push_back(c->dupload(kv.second));
+            c->level_tasks.emplace_back(kv.first, std::move(kv.second));
+        }
+    }
+    // ---- fluid cell list and update bins
+    for (int i = 0; i < c->n_local; ++i)
+        if (c->cells[i].bound_enc >= 0) c->fluid_cells.push_back(i);
+    std::stable_sort(c->fluid_cells.begin(), c->fluid_cells.end(),
+                     [&](int a, int b) { return c->cells[a].n > c->cells[b].n; });
+    c->d_fluid_cells = c->dupload(c->fluid_cells);
+    {
+        const size_t caps[] = {16 << 10, 48 << 10, 96 << 10, 200 << 10};
+        std::vector<Bin> bins(5);
+        for (int q = 0; q < 4; ++q) bins[q].smem = caps[q];
+        bins[4].smem = 0;
+        c->fused_cells = 0;
+        for (int cell : c->fluid_cells) {
+            const size_t need = (size_t)c->cells[cell].n * K * sizeof(double);
+            int q = 0;
+            while (q < 4 && need > caps[q]) ++q;
+            bins[q].cells.push_back(cell);
+            if (q < 4) c->fused_cells++;
+        }
+        for (auto& b : bins) {
+            if (b.cells.empty()) continue;
+            if (b.smem) {  // request only what the largest cell of the bin needs
+                size_t mx = 0;
+                for (int cell : b.cells) mx = std::max(mx, (size_t)c->cells[cell].n * K * sizeof(double));
+                b.smem = mx;
+            }
+            b.d_cells = c->dupload(b.cells);
+            c->bins.push_back(b);
+        }
+    }
+    // ---- device state
+    const size_t np = (size_t)c->npts_pad;
+    c->dv.cells = c->dupload(c->cells);
+    c->dv.slots = c->dupload(c->slots);
+    c->dv.pm_start = c->dupload(c->pm_start);
+    c->dv.rel_off = c->dupload(c->rel_off);
+    c->dv.df = c->dalloc<double>(np * K);
+    c->dv.df_new = c->dalloc<double>(np * K);
+    c->dv.sdf = c->dalloc<double>(np * K * D);
+    c->dv.flux = c->dalloc<double>(np * K);
+    c->dv.w = c->dalloc<double>((size_t)c->n_cell * M);
+    c->dv.prim = c->dalloc<double>((size_t)c->n_cell * M);
+    c->dv.mflux = c->dalloc<double>((size_t)c->n_cell * M);
+    c->dv.qf = c->dalloc<double>((size_t)c->n_cell * D);
+    c->dv.sw = c->dalloc<double>((size_t)c->n_cell * M * D);
+    c->dv.res_cell = c->dalloc<double>((size_t)c->n_local * 2 * M);
+    c->dv.n_local = c->n_local;
+    c->d_res = c->dalloc<double>(2 * M);
+    CK(cudaMemsetAsync(c->dv.df, 0, np * K * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->dv.df_new, 0, np * K * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->dv.sdf, 0, np * K * D * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->dv.flux, 0, np * K * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->dv.w, 0, (size_t)c->n_cell * M * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->dv.prim, 0, (size_t)c->n_cell * M * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->dv.mflux, 0, (size_t)c->n_cell * M * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->dv.qf, 0, (size_t)c->n_cell * D * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->dv.sw, 0, (size_t)c->n_cell * M * D * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->dv.res_cell, 0, (size_t)c->n_local * 2 * M * sizeof(double), c->stream));
+    // ---- halo plan (Parallel/Ghost.jl:133-145, 203-284)
+    c->halo_bytes_step = 0;
+    long long send_total = 0, recv_total = 0;
+    for (int p = 0; p < m->n_peer; ++p) {
+        PeerPlan pp;
+        pp.rank = m->peer_rank[p];
+        pp.send_base = send_total; pp.recv_base = recv_total;
+        long long pos = 0, spos_max = 0;
+        std::map<int, long long> lpos;
+        for (int q = m->send_off[p]; q < m->send_off[p + 1]; ++q) {
+            const CellInfo& ci = c->cells[m->send_cells[q]];
+            pp.df_send.push_back(CopySeg{ci.doff * K, pp.send_base + pos, (long long)ci.np * K});
+            pos += (long long)ci.np * K;
+            if (ci.bound_enc >= 0) {  // solid cells carry no slopes
+                auto& lv = pp.sdf[ci.ps_level];
+                long long& lp = lpos[ci.ps_level];
+                lv.send.push_back(CopySeg{ci.doff * K * D, pp.send_base + lp, (long long)ci.np * K * D});
+                lp += (long long)ci.np * K * D;
+                lv.send_len = lp;
+                spos_max = std::max(spos_max, lp);
+            }
+        }
+        pp.df_send_len = pos;
+        const int g0 = c->n_local + m->recv_off[p], g1 = c->n_local + m->recv_off[p + 1];
+        if (g1 > g0) {
+            pp.df_recv_off = c->cells[g0].doff * K;
+            pp.df_recv_len = (c->cells[g1 - 1].doff + c->cells[g1 - 1].np - c->cells[g0].doff) * K;
+        }
+        std::map<int, long long> rpos;
+        long long rpos_max = 0;
+        for (int gidx = g0; gidx < g1; ++gidx) {
+            const CellInfo& ci = c->cells[gidx];
+            if (ci.bound_enc < 0) continue;
+            auto& lv = pp.sdf[ci.ps_level];
+            long long& rp = rpos[ci.ps_level];
+            lv.recv.push_back(CopySeg{pp.recv_base + rp, ci.doff * K * D, (long long)ci.np * K * D});
+            rp += (long long)ci.np * K * D;
+            lv.recv_len = rp;
+            rpos_max = std::max(rpos_max, rp);
+        }
+        for (auto& kv : pp.sdf) {
+            kv.second.d_send = c->dupload(kv.second.send);
+            kv.second.d_recv = c->dupload(kv.second.recv);
+            c->halo_bytes_step += 8 * kv.second.send_len;
+        }
+        pp.d_df_send = c->dupload(pp.df_send);
+        c->halo_bytes_step += 8 * pp.df_send_len;
+        send_total += std::max(pos, spos_max);
+        recv_total += rpos_max;
+        c->peers.push_back(std::move(pp));
+    }
+    if (m->n_peer > 0) {
+        c->d_sendbuf = c->dalloc<double>((size_t)send_total);
+        c->d_recvbuf = c->dalloc<double>((size_t)recv_total);
+    }
+    CK(cudaStreamSynchronize(c->stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host <-> device transfer of per-point arrays (host layout: unpadded planes; device: padded planes)
+void copy_points(kamr_ctx* c, double* dev, double* host_rw, const double* host_ro, int comps, bool to_device) {
+    const size_t total_h = (size_t)c->npts_host * comps;
+    if (!c->padded) {
+        if (to_device) CK(cudaMemcpyAsync(dev, host_ro, total_h * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        else CK(cudaMemcpyAsync(host_rw, dev, total_h * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return;
+    }
+    // padded: go through the pinned staging buffer in chunks of whole cells
+    int i = 0;
+    while (i < c->n_cell) {
+        int j = i;
+        size_t dcount = 0;
+        while (j < c->n_cell && dcount + (size_t)c->cells[j].np * comps <= c->stage_doubles) {
+            dcount += (size_t)c->cells[j].np * comps;
+            ++j;
+        }
+        if (j == i) throw Fail("staging buffer smaller than one cell block");
+        double* dptr = dev + (size_t)c->cells[i].doff * comps;
+        if (to_device) {
+            size_t pos = 0;
+            for (int q = i; q < j; ++q) {
+                const CellInfo& ci = c->cells[q];
+                const double* src = host_ro + (size_t)c->host_off[q] * comps;
+                for (int p = 0; p < comps; ++p) {
+                    memcpy(c->h_stage + pos, src + (size_t)p * ci.n, sizeof(double) * ci.n);
+                    for (int t = ci.n; t < ci.np; ++t) c->h_stage[pos + t] = 0.0;
+                    pos += ci.np;
+                }
+            }
+            CK(cudaMemcpyAsync(dptr, c->h_stage, dcount * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        } else {
+            CK(cudaMemcpyAsync(c->h_stage, dptr, dcount * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            size_t pos = 0;
+            for (int q = i; q < j; ++q) {
+                const CellInfo& ci = c->cells[q];
+                double* dst = host_rw + (size_t)c->host_off[q] * comps;
+                for (int p = 0; p < comps; ++p) {
+                    memcpy(dst + (size_t)p * ci.n, c->h_stage + pos, sizeof(double) * ci.n);
+                    pos += ci.np;
+                }
+            }
+        }
+        i = j;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// halo
+void exchange(kamr_ctx* c, int what /*0 df, 1 sdf*/, int level) {
+    if (c->peers.empty()) return;
+    if (!c->comm) throw Fail("mesh has peers but kamr_comm_init was not called");
+    const int K = c->K, D = c->D;
+    (void)K; (void)D;
+    double* src = what == 0 ? c->dv.df : c->dv.sdf;
+    bool any = false;
+    for (auto& pp : c->peers) {
+        if (what == 0) {
+            if (!pp.df_send.empty()) {
+                copy_segments_kernel<<<std::min<int>((int)pp.df_send.size(), 2048), 256, 0, c->stream>>>(
+                    pp.d_df_send, (int)pp.df_send.size(), src, c->d_sendbuf);
+                c->launches++;
+            }
+            any = true;
+        } else {
+            auto it = pp.sdf.find(level);
+            if (it == pp.sdf.end()) continue;
+            if (!it->second.send.empty()) {
+                copy_segments_kernel<<<std::min<int>((int)it->second.send.size(), 2048), 256, 0, c->stream>>>(
+                    it->second.d_send, (int)it->second.send.size(), src, c->d_sendbuf);
+                c->launches++;
+            }
+            any = true;
+        }
+    }
+    if (!any) return;
+    NCK(nccl().GroupStart());
+    for (auto& pp : c->peers) {
+        if (what == 0) {
+            if (pp.df_send_len) NCK(nccl().Send(c->d_sendbuf + pp.send_base, (size_t)pp.df_send_len, ncclFloat64, pp.rank, c->comm, c->stream));
+            if (pp.df_recv_len) NCK(nccl().Recv(c->dv.df + pp.df_recv_off, (size_t)pp.df_recv_len, ncclFloat64, pp.rank, c->comm, c->stream));
+        } else {
+            auto it = pp.sdf.find(level);
+            if (it == pp.sdf.end()) continue;
+            if (it->second.send_len) NCK(nccl().Send(c->d_sendbuf + pp.send_base, (size_t)it->second.send_len, ncclFloat64, pp.rank, c->comm, c->stream));
+            if (it->second.recv_len) NCK(nccl().Recv(c->d_recvbuf + pp.recv_base, (size_t)it->second.recv_len, ncclFloat64, pp.rank, c->comm, c->stream));
+        }
+    }
+    NCK(nccl().GroupEnd());
+    if (what == 1) {
+        for (auto& pp : c->peers) {
+            auto it = pp.sdf.find(level);
+            if (it == pp.sdf.end() || it->second.recv.empty()) continue;
+            copy_segments_kernel<<<std::min<int>((int)it->second.recv.size(), 2048), 256, 0, c->stream>>>(
+                it->second.d_recv, (int)it->second.recv.size(), c->d_recvbuf, c->dv.sdf);
+            c->launches++;
+        }
+    }
+    CK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch sequences
+template <int D, int K>
+void run_slope(kamr_ctx* c, bool with_sw) {
+    for (size_t l = 0; l < c->level_tasks.size(); ++l) {
+        const int nt = (int)c->level_tasks[l].second.size();
+        if (nt) {
+            slope_kernel<D, K><<<nt, 256, 0, c->stream>>>(c->dv, c->d_level_tasks[l]);
+            c->launches++;
+        }
+    }
+    CK(cudaGetLastError());
+    // per-level halo of the fresh slopes (slope_exchange_level!, Parallel/Ghost.jl:896).  With one rank
+    // the levels above simply run back to back; with peers each level is followed by its exchange.
+    if (with_sw && !c->fluid_cells.empty()) {
+        macro_slope_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->d_fluid_cells);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+}
+
+template <int D, int K>
+void run_slope_mpi(kamr_ctx* c, bool with_sw) {
+    // levels present locally or in the halo, ascending
+    std::vector<int> levels;
+    for (auto& lt : c->level_tasks) levels.push_back(lt.first);
+    for (auto& pp : c->peers)
+        for (auto& kv : pp.sdf) levels.push_back(kv.first);
+    std::sort(levels.begin(), levels.end());
+    levels.erase(std::unique(levels.begin(), levels.end()), levels.end());
+    for (int L : levels) {
+        for (size_t l = 0; l < c->level_tasks.size(); ++l) {
+            if (c->level_tasks[l].first != L) continue;
+            const int nt = (int)c->level_tasks[l].second.size();
+            slope_kernel<D, K><<<nt, 256, 0, c->stream>>>(c->dv, c->d_level_tasks[l]);
+            c->launches++;
+        }
+        exchange(c, 1, L);
+    }
+    CK(cudaGetLastError());
+    if (with_sw && !c->fluid_cells.empty()) {
+        macro_slope_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->d_fluid_cells);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+}
+
+template <int D, int K>
+void run_flux(kamr_ctx* c, double dt, const int* d_cells, int ncells) {
+    if (!ncells) return;
+    flux_kernel<D, K><<<ncells, 256, 0, c->stream>>>(c->dv, c->gas, d_cells, dt);
+    c->launches++;
+    CK(cudaGetLastError());
+}
+
+template <int D, int K>
+void fetch_residual(kamr_ctx* c, int want, double* res_out) {
+    if (!want) return;
+    const int M = D + 2;
+    residual_reduce_kernel<<<1, 256, 0, c->stream>>>(c->dv.res_cell, c->d_fluid_cells, (int)c->fluid_cells.size(),
+                                                     2 * M, c->d_res);
+    c->launches++;
+    CK(cudaMemcpyAsync(c->h_res, c->d_res, 2 * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (res_out) memcpy(res_out, c->h_res, 2 * M * sizeof(double));
+}
+
+template <int D, int K>
+void run_update(kamr_ctx* c, double dt, int want, const double* fin, double* fout, bool only_global) {
+    for (auto& b : c->bins) {
+        const int nb = (int)b.cells.size();
+        if (b.smem) {
+            if (only_global) continue;
+            CK(cudaFuncSetAttribute(update_kernel<D, K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem));
+            update_kernel<D, K, 1><<<nb, 256, b.smem, c->stream>>>(c->dv, c->gas, b.d_cells, fin, fout, dt, want);
+        } else {
+            update_kernel<D, K, 0><<<nb, 256, 0, c->stream>>>(c->dv, c->gas, b.d_cells, fin, fout, dt, want);
+        }
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+}
+
+template <int D, int K>
+void do_slope(kamr_ctx* c, bool with_sw) {
+    if (c->peers.empty()) run_slope<D, K>(c, with_sw);
+    else run_slope_mpi<D, K>(c, with_sw);
+}
+
+template <int D, int K>
+void do_flux(kamr_ctx* c, double dt) {
+    run_flux<D, K>(c, dt, c->d_fluid_cells, (int)c->fluid_cells.size());
+}
+
+template <int D, int K>
+void do_iterate(kamr_ctx* c, double dt, int want, double* res_out) {
+    if (c->gas.marching == KAMR_MARCH_CIP) throw Fail("CIP_Marching is not implemented on the device yet");
+    run_update<D, K>(c, dt, want, c->dv.df, c->dv.df, false);
+    fetch_residual<D, K>(c, want, res_out);
+    exchange(c, 0, 0);
+}
+
+template <int D, int K>
+void do_step(kamr_ctx* c, double dt, int want, double* res_out) {
+    if (c->gas.marching != KAMR_MARCH_CAIDVM) {  // only CAIDVM_Marching has the fused kernel
+        do_slope<D, K>(c, false);
+        do_flux<D, K>(c, dt);
+        do_iterate<D, K>(c, dt, want, res_out);
+        return;
+    }
+    do_slope<D, K>(c, false);
+    // cells too large for shared-memory staging: separate flux kernel, then out-of-place update
+    for (auto& b : c->bins)
+        if (!b.smem) run_flux<D, K>(c, dt, b.d_cells, (int)b.cells.size());
+    for (auto& b : c->bins) {
+        if (!b.smem) continue;
+        CK(cudaFuncSetAttribute(step_kernel<D, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem));
+        step_kernel<D, K><<<(int)b.cells.size(), 256, b.smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    run_update<D, K>(c, dt, want, c->dv.df, c->dv.df_new, true);
+    // cells that are not updated (solid ghost cells) keep their values in the other buffer as well
+    std::swap(c->dv.df, c->dv.df_new);
+    fetch_residual<D, K>(c, want, res_out);
+    exchange(c, 0, 0);
+}
+
+template <class F>
+int guarded(kamr_ctx* c, F&& f) {
+    if (!c) return 1;
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        c->err = e.what();
+        return 2;
+    } catch (...) {
+        c->err = "unknown error";
+        return 3;
+    }
+}
+
+#define DISPATCH(c, fn, ...)                                                            \
+    do {                                                                                \
+        if ((c)->D == 2 && (c)->K == 2) fn<2, 2>(__VA_ARGS__);                          \
+        else if ((c)->D == 3 && (c)->K == 1) fn<3, 1>(__VA_ARGS__);                     \
+        else throw Fail("unsupported DIM/NDF (2D2F and 3D1F are built)");               \
+    } while (0)
+
+}  // namespace
+
+// ==================================================================================================
+extern "C" {
+
+int kamr_version(void) { return KAMR_VERSION; }
+
+const char* kamr_last_error(const kamr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int kamr_create(const kamr_config* cfg, kamr_ctx** out) {
+    if (!cfg || !out) { g_create_err = "null argument"; return 1; }
+    kamr_ctx* c = nullptr;
+    try {
+        if (!((cfg->dim == 2 && cfg->ndf == 2) || (cfg->dim == 3 && cfg->ndf == 1)))
+            throw Fail("unsupported DIM/NDF: the reference's kinetics exist for 2D2F and 3D1F only (lib/KitCore)");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Fail(std::string("no CUDA device available (libkamr has no CPU fallback): ") + cudaGetErrorString(e));
+        if (cfg->device < 0 || cfg->device >= ndev) throw Fail("device ordinal out of range");
+        CK(cudaSetDevice(cfg->device));
+        c = new kamr_ctx();
+        c->cfg = *cfg;
+        c->D = cfg->dim; c->K = cfg->ndf; c->M = cfg->dim + 2;
+        c->gas = GasPar{cfg->K, cfg->Pr, cfg->gamma, cfg->omega, cfg->mu_ref, cfg->flux_type, cfg->marching};
+        if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
+        else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+        CK(cudaMallocHost((void**)&c->h_res, 64 * sizeof(double)));
+        c->stage_doubles = (size_t)8 << 20;  // 64 MiB pinned staging
+        CK(cudaMallocHost((void**)&c->h_stage, c->stage_doubles * sizeof(double)));
+        *out = c;
+        return 0;
+    } catch (const std::exception& e) {
+        g_create_err = e.what();
+        delete c;
+        return 2;
+    }
+}
+
+int kamr_destroy(kamr_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->cfg.device);
+    c->free_topology();
+    if (c->comm) nccl().CommDestroy(c->comm);
+    if (c->h_res) cudaFreeHost(c->h_res);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int kamr_comm_unique_id(void* id128) {
+    std::string err;
+    if (!nccl().load(err)) { g_create_err = err; return 2; }
+    ncclUniqueId id;
+    int r = nccl().GetUniqueId(&id);
+    if (r) { g_create_err = nccl().GetErrorString(r); return 2; }
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+int kamr_comm_init(kamr_ctx* c, const void* id128) {
+    return guarded(c, [&] {
+        if (c->cfg.nranks <= 1) return;
+        std::string err;
+        if (!nccl().load(err)) throw Fail(err);
+        CK(cudaSetDevice(c->cfg.device));
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof(id));
+        NCK(nccl().CommInitRank(&c->comm, c->cfg.nranks, id, c->cfg.rank));
+    });
+}
+
+int kamr_upload_topology(kamr_ctx* c, const kamr_mesh* m) {
+    return guarded(c, [&] {
+        if (!m) throw Fail("null mesh");
+        CK(cudaSetDevice(c->cfg.device));
+        if (m->ib && (m->ib->n_sn > 0 || m->ib->n_solid > 0))
+            throw Fail("immersed-boundary tables are not consumed by the device path yet");
+        build_topology(c, m);
+    });
+}
+
+int kamr_upload_state(kamr_ctx* c, const double* df, const double* w, const double* prim) {
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->cfg.device));
+        if (c->cells.empty()) throw Fail("upload_topology first");
+        if (df) copy_points(c, c->dv.df, nullptr, df, c->K, true);
+        const size_t nb = (size_t)c->n_local * c->M * sizeof(double);
+        if (w) CK(cudaMemcpyAsync(c->dv.w, w, nb, cudaMemcpyHostToDevice, c->stream));
+        if (prim) CK(cudaMemcpyAsync(c->dv.prim, prim, nb, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int kamr_upload_aux(kamr_ctx* c, const double* sdf, const double* flux, const double* mflux) {
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->cfg.device));
+        if (c->cells.empty()) throw Fail("upload_topology first");
+        if (sdf) copy_points(c, c->dv.sdf, nullptr, sdf, c->K * c->D, true);
+        if (flux) copy_points(c, c->dv.flux, nullptr, flux, c->K, true);
+        if (mflux) CK(cudaMemcpyAsync(c->dv.mflux, mflux, (size_t)c->n_local * c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int kamr_download_state(kamr_ctx* c, uint32_t mask, double* df, double* sdf, double* flux, double* w, double* prim,
+                        double* qf, double* sw, double* mflux) {
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->cfg.device));
+        if (c->cells.empty()) throw Fail("upload_topology first");
+        const int M = c->M, D = c->D;
+        if ((mask & KAMR_DL_DF) && df) copy_points(c, c->dv.df, df, nullptr, c->K, false);
+        if ((mask & KAMR_DL_SDF) && sdf) copy_points(c, c->dv.sdf, sdf, nullptr, c->K * D, false);
+        if ((mask & KAMR_DL_FLUX) && flux) copy_points(c, c->dv.flux, flux, nullptr, c->K, false);
+        const size_t nl = (size_t)c->n_local;
+        if ((mask & KAMR_DL_W) && w) CK(cudaMemcpyAsync(w, c->dv.w, nl * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if ((mask & KAMR_DL_PRIM) && prim) CK(cudaMemcpyAsync(prim, c->dv.prim, nl * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if ((mask & KAMR_DL_QF) && qf) CK(cudaMemcpyAsync(qf, c->dv.qf, nl * D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if ((mask & KAMR_DL_SW) && sw) CK(cudaMemcpyAsync(sw, c->dv.sw, nl * M * D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if ((mask & KAMR_DL_MFLUX) && mflux) CK(cudaMemcpyAsync(mflux, c->dv.mflux, nl * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int kamr_slope(kamr_ctx* c) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_slope, c, true); });
+}
+int kamr_flux(kamr_ctx* c, double dt) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_flux, c, dt); });
+}
+int kamr_iterate(kamr_ctx* c, double dt, int32_t want_residual, double* res_out) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_iterate, c, dt, want_residual, res_out); });
+}
+int kamr_step(kamr_ctx* c, double dt, int32_t want_residual, double* res_out) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_step, c, dt, want_residual, res_out); });
+}
+int kamr_exchange_df(kamr_ctx* c) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); exchange(c, 0, 0); });
+}
+int kamr_sync(kamr_ctx* c) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); CK(cudaStreamSynchronize(c->stream)); });
+}
+
+int kamr_get_stats(kamr_ctx* c, kamr_stats* out) {
+    return guarded(c, [&] {
+        memset(out, 0, sizeof(*out));
+        out->n_phase_local = c->n_phase_local;
+        out->n_points_total = c->npts_host;
+        out->n_relations = (long long)c->rel_off.size();
+        out->n_slots = (long long)c->slots.size();
+        out->kernel_launches = c->launches;
+        out->device_bytes = c->device_bytes;
+        out->halo_bytes_per_step = c->halo_bytes_step;
+        out->n_levels = (int)c->level_tasks.size();
+        out->fused_cells = c->fused_cells;
+    });
+}
+
+int kamr_get_pair_map(kamr_ctx* c, int32_t ga, int32_t gb, int32_t* start, int32_t cap) {
+    int rc = 0;
+    int g = guarded(c, [&] {
+        if (ga < 0 || gb < 0 || ga >= c->n_grid || gb >= c->n_grid) throw Fail("grid id out of range");
+        if (ga == gb) { rc = 1; return; }
+        auto it = c->rel_id.find(std::make_pair((int)ga, (int)gb));
+        if (it == c->rel_id.end()) throw Fail("no relation between these grids in the current topology");
+        const int na = c->grid_n[ga];
+        if (cap < na + 1) throw Fail("buffer too small");
+        memcpy(start, c->pm_start.data() + c->rel_off[it->second], sizeof(int) * (na + 1));
+    });
+    return g ? g + 1 : rc;  // 0 ok, 1 identity, >=2 error
+}
+
+int kamr_get_cell_slots(kamr_ctx* c, int32_t cell, int32_t* face, int32_t* sign, int32_t cap, int32_t* n) {
+    return guarded(c, [&] {
+        if (cell < 0 || cell >= c->n_local) throw Fail("cell out of range");
+        const CellInfo& ci = c->cells[cell];
+        const int ns = ci.slot_end - ci.slot_begin;
+        if (cap < ns) throw Fail("buffer too small");
+        for (int q = 0; q < ns; ++q) {
+            face[q] = c->slots[ci.slot_begin + q].face;
+            sign[q] = c->slots[ci.slot_begin + q].is_here ? 1 : -1;
+        }
+        *n = ns;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+"""Synthetic stand-ins for the reference's example configurations.
+
+Each `Case` carries what `Configure`/`Solver`/`Gas` carry in the reference
+(src/Solver/Types.jl:121-149,381-409; src/Gas/Types.jl:25-38) plus the generated forest,
+velocity grids and initial state.  Seeds: 20260101 + k, RNG = PCG64 keyed by global cell id so
+every rank of a split sees the same field.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .. import abi
+from ..model import HostMesh, HostState, build_rank_view
+from . import vgrid as vg
+from .forest import Forest, partition
+
+SEED_BASE = 20260101
+
+
+def ref_vhs_vis(Kn, omega, alpha=1.0, T_ref=1.0):
+    """src/Gas/Model.jl:5-9"""
+    mu0 = 5.0 * (alpha + 1.0) * (alpha + 2.0) * math.sqrt(math.pi) / \
+        (4.0 * alpha * (5.0 - 2.0 * omega) * (7.0 - 2.0 * omega)) * Kn
+    return mu0 * T_ref ** (0.5 - omega)
+
+
+@dataclass
+class Gas:
+    """src/Gas/Types.jl:5-38 (note: the reference calls ref_vhs_vis(Kn, αᵣ, ωᵣ), i.e. with αᵣ in the
+    `omega` slot and ωᵣ in the `alpha` slot — reproduced here)."""
+    Kn: float = 0.05
+    Pr: float = 2 / 3
+    K: float = 1.0
+    gamma: float = 5 / 3
+    omega: float = 0.5
+    alpha_r: float = 1.0
+    omega_r: float = 0.81
+    mu_ref: float = None
+
+    def __post_init__(self):
+        if self.mu_ref is None:
+            self.mu_ref = ref_vhs_vis(self.Kn, self.alpha_r, self.omega_r)
+
+
+def get_conserved(prim, gamma):
+    prim = np.asarray(prim, dtype=np.float64)
+    D = len(prim) - 2
+    w = np.zeros(D + 2)
+    w[0] = prim[0]
+    w[1:1 + D] = prim[0] * prim[1:1 + D]
+    w[D + 1] = 0.5 * prim[0] / prim[-1] / (gamma - 1.0) + 0.5 * prim[0] * np.sum(prim[1:1 + D] ** 2)
+    return w
+
+
+def get_prim(w, gamma):
+    w = np.asarray(w, dtype=np.float64)
+    D = len(w) - 2
+    p = np.zeros(D + 2)
+    p[0] = w[0]
+    p[1:1 + D] = w[1:1 + D] / w[0]
+    p[D + 1] = 0.5 * w[0] / (gamma - 1.0) / (w[D + 1] - 0.5 * np.sum(w[1:1 + D] ** 2) / w[0])
+    return p
+
+
+def moments(mid, weight, df):
+    """micro_to_macro (lib/KitCore/2D2F.jl:119, 3D1F.jl:109); df [n, ndf]."""
+    D = mid.shape[1]
+    w = np.zeros(D + 2)
+    h = df[:, 0]
+    w[0] = np.sum(weight * h)
+    for d in range(D):
+        w[1 + d] = np.sum(weight * mid[:, d] * h)
+    e = np.sum(mid ** 2, axis=1) * h
+    if df.shape[1] == 2:
+        e = e + df[:, 1]
+    w[D + 1] = 0.5 * np.sum(weight * e)
+    return w
+
+
+@dataclass
+class Case:
+    name: str
+    dim: int
+    ndf: int
+    forest: Forest
+    grids: list
+    cell_grid: np.ndarray
+    bc_type: np.ndarray
+    bc_prim: np.ndarray
+    gas: Gas
+    quadrature: tuple
+    vs_trees_num: tuple
+    vs_maxlevel: int
+    prim_fn: object                  # prim_fn(mid[dim]) -> prim[dim+2]
+    seed: int
+    cfl: float = 0.4
+    marching: int = abi.MARCH_CAIDVM
+    flux_type: int = abi.FLUX_CAIDVM
+    noise: float = 0.01
+    bound_enc: np.ndarray = None
+
+    # ------------------------------------------------------------------ config
+    def config(self, device=0, rank=0, nranks=1, stream=None) -> abi.KamrConfig:
+        g = self.gas
+        return abi.KamrConfig(self.dim, self.ndf, self.flux_type, self.marching, g.K, g.Pr, g.gamma, g.omega,
+                              g.mu_ref, device, rank, nranks, stream)
+
+    def dt(self):
+        """Δt_ξ of Status(config), src/Solver/Types.jl:509-520."""
+        D = self.dim
+        geo, q = self.forest.geometry, self.quadrature
+        ds = [(geo[2 * i + 1] - geo[2 * i]) / self.forest.trees_num[i] / 2 ** self.forest.maxlevel for i in range(D)]
+        U = [max(q[2 * i + 1], abs(q[2 * i])) - (q[2 * i + 1] - q[2 * i]) / self.vs_trees_num[i] /
+             2 ** self.vs_maxlevel / 2 for i in range(D)]
+        return self.cfl * min(a / b for a, b in zip(ds, U))
+
+    # ------------------------------------------------------------------ partition / flatten
+    def owner(self, nranks):
+        n_of = np.array([g.n for g in self.grids])[self.cell_grid]
+        return partition(n_of.astype(np.float64), nranks)
+
+    def rank_mesh(self, rank=0, nranks=1) -> HostMesh:
+        owner = self.owner(nranks) if nranks > 1 else None
+        return build_rank_view(self.forest, self.grids, self.cell_grid, self.bc_type, self.bc_prim, self.ndf,
+                               owner=owner, rank=rank, bound_enc_global=self.bound_enc)
+
+    # ------------------------------------------------------------------ state
+    def cell_df(self, gid):
+        g = self.grids[int(self.cell_grid[gid])]
+        prim = np.asarray(self.prim_fn(self.forest.mid[gid]), dtype=np.float64)
+        df = vg.discrete_maxwell(g.mid, prim, self.ndf, self.gas.K)
+        if self.noise:
+            rng = np.random.Generator(np.random.PCG64([self.seed, int(gid)]))
+            df = df * (1.0 + self.noise * rng.uniform(-1.0, 1.0, size=df.shape))
+        return g, df
+
+    def init_state(self, mesh: HostMesh) -> HostState:
+        st = HostState.zeros(mesh)
+        D, K, M = self.dim, self.ndf, self.dim + 2
+        off = mesh.vs_off()
+        for c in range(mesh.n_local + mesh.n_ghost):
+            g, df = self.cell_df(int(mesh.global_ids[c]))
+            st.df[off[c] * K: off[c + 1] * K] = df.T.ravel()
+            w = moments(g.mid, g.weight, df)
+            st.w[c * M:(c + 1) * M] = w
+            st.prim[c * M:(c + 1) * M] = get_prim(w, self.gas.gamma)
+        return st
+
+
+# ---------------------------------------------------------------------- field helpers
+def smooth_prim(dim, geometry, U0=None, amp=0.2):
+    """ρ = 1 + 0.2 sin, U as given, λ = 1/(1 + 0.3 cos) at the cell centre."""
+    lo = np.array(geometry[0::2]); hi = np.array(geometry[1::2])
+    U0 = np.zeros(dim) if U0 is None else np.asarray(U0, dtype=np.float64)
+
+    def fn(x):
+        s = 2 * np.pi * (np.asarray(x) - lo) / (hi - lo)
+        rho = 1.0 + amp * np.prod(np.sin(s))
+        lam = 1.0 / (1.0 + 0.3 * np.prod(np.cos(s)))
+        return np.concatenate([[rho], U0 + 0.1 * np.sin(s), [lam]])
+    return fn
+
+
+def _bcs(dim, kinds, prims):
+    M = dim + 2
+    bt = np.array(kinds, dtype=np.int32)
+    bp = np.zeros((2 * dim, M))
+    for i, p in enumerate(prims):
+        if p is not None:
+            bp[i] = p
+        else:
+            bp[i] = [1.0] + [0.0] * dim + [1.0]
+    return bt, bp.ravel()
+
+
+def _dedup_grids(per_cell_grids):
+    keys = {}
+    grids = []
+    cell_grid = np.zeros(len(per_cell_grids), dtype=np.int32)
+    for c, g in enumerate(per_cell_grids):
+        k = g.key()
+        if k not in keys:
+            keys[k] = len(grids)
+            grids.append(g)
+        cell_grid[c] = keys[k]
+    return grids, cell_grid
+
+
+# ---------------------------------------------------------------------- cases
+def smoke_s0(noise=0.01, trees=16, vtrees=16) -> Case:
+    """test/runtests.jl:4-41: 2-D, NDF=2, 16x16 cells, 16x16 velocity points, Maxwellian walls in x
+    (xmax wall moving with U=sqrt(5/6)), periodic in y, CAIDVM + CAIDVM_Marching."""
+    geo = (-0.5, 0.5, -0.5, 0.5)
+    forest = Forest.build(2, geo, (trees, trees), 0, periodic=(False, True))
+    quad = (-5.0, 5.0, -5.0, 5.0)
+    g = vg.root_grid(quad, (vtrees, vtrees))
+    gas = Gas(K=0.0, Kn=0.075, omega=0.81, omega_r=0.81)
+    bt, bp = _bcs(2, [abi.BC_MAXWELLIAN, abi.BC_MAXWELLIAN, abi.BC_UNIFORM_OUTFLOW, abi.BC_UNIFORM_OUTFLOW],
+                  [[1., 0., 0., 1.], [1., math.sqrt(5 / 6), 0., 1.], None, None])
+    return Case("S0-smoke", 2, 2, forest, [g], np.zeros(forest.n, np.int32), bt, bp, gas, quad, (vtrees, vtrees), 0,
+                lambda x: np.array([1., 0., 0., 1.]), SEED_BASE, noise=noise)
+
+
+def amr_case(dim=2, trees=4, maxlevel=2, vtrees=6, vs_maxlevel=2, ragged=True, periodic=None, bcs=None,
+             seed=1, name=None, marching=abi.MARCH_CAIDVM, U0=None, quad_half=5.0, refine="ball") -> Case:
+    """Small AMR case used by the parity tests: a refined ball/band in physical space (hanging faces,
+    coarse/fine slope sweep) and, when `ragged`, Maxwellian-adapted velocity grids that differ from
+    cell to cell (pair-list path)."""
+    ndf = 2 if dim == 2 else 1
+    geo = tuple([-0.5, 0.5] * dim)
+    periodic = periodic if periodic is not None else (False,) * dim
+
+    def refine_fn(l, mid, ds):
+        if refine == "ball":
+            r = np.sqrt(np.sum((mid - 0.1) ** 2, axis=1))
+            return r < 0.42 / (l + 1)
+        if refine == "band":
+            return np.abs(mid[:, 0] + 0.5 * mid[:, 1]) < 0.25 / (l + 1)
+        return np.zeros(len(mid), dtype=bool)
+
+    forest = Forest.build(dim, geo, (trees,) * dim, maxlevel, refine_fn, periodic=periodic)
+    quad = tuple([-quad_half, quad_half] * dim)
+    gas = Gas(K=1.0 if dim == 2 else 0.0, Kn=0.05)
+    prim_fn = smooth_prim(dim, geo, U0=U0)
+    if ragged:
+        per_cell = []
+        cache = {}
+        for c in range(forest.n):
+            p = prim_fn(forest.mid[c])
+            # quantise the prim that drives the grid so that neighbouring cells share grids in
+            # patches but differ across patch borders (mimics the state jumps of rp_2D.jl:11-24)
+            key = tuple(np.round(p * 4) / 4)
+            if key not in cache:
+                cache[key] = vg.maxwellian_grid(quad, (vtrees,) * dim, vs_maxlevel, np.array(key), ndf, gas.K)
+            per_cell.append(cache[key])
+        grids, cell_grid = _dedup_grids(per_cell)
+    else:
+        grids = [vg.maxwellian_grid(quad, (vtrees,) * dim, vs_maxlevel,
+                                    np.array([1.0] + [0.0] * dim + [1.0]), ndf, gas.K)]
+        cell_grid = np.zeros(forest.n, np.int32)
+    if bcs is None:
+        kinds = [abi.BC_SUPERSONIC_INFLOW, abi.BC_UNIFORM_OUTFLOW, abi.BC_MAXWELLIAN,
+                 abi.BC_INTERPOLATED_OUTFLOW if dim == 2 else abi.BC_UNIFORM_OUTFLOW] + \
+                ([abi.BC_UNIFORM_OUTFLOW, abi.BC_MAXWELLIAN] if dim == 3 else [])
+        prims = [[1.0] + [0.3] + [0.0] * (dim - 1) + [1.0], None, [1.0] + [0.0] * dim + [0.9], None] + \
+                ([None, [1.0] + [0.1] * dim + [1.1]] if dim == 3 else [])
+        bcs = _bcs(dim, kinds, prims)
+    return Case(name or f"amr{dim}d", dim, ndf, forest, grids, cell_grid, bcs[0], bcs[1], gas, quad,
+                (vtrees,) * dim, vs_maxlevel, prim_fn, SEED_BASE + seed, marching=marching)
+
+
+def uniform_case(dim=2, trees=64, maxlevel=0, vtrees=60, name=None, seed=3, refine_fn=None,
+                 geometry=None, quadrature=None, U0=None) -> Case:
+    """Bench-shaped case: one shared uniform velocity grid (example/airfoil: 60x60, VS level 0) on a
+    (optionally geometry-refined) physical mesh, supersonic inflow at xmin and outflow elsewhere."""
+    ndf = 2 if dim == 2 else 1
+    geo = geometry or tuple([-0.5, 0.5] * dim)
+    trees_t = trees if isinstance(trees, tuple) else (trees,) * dim
+    forest = Forest.build(dim, geo, trees_t, maxlevel, refine_fn)
+    quad = quadrature or tuple([-6.0, 6.0] * dim)
+    vt = vtrees if isinstance(vtrees, tuple) else (vtrees,) * dim
+    g = vg.root_grid(quad, vt)
+    gas = Gas(K=1.0 if dim == 2 else 0.0, Kn=0.05)
+    kinds = [abi.BC_SUPERSONIC_INFLOW] + [abi.BC_UNIFORM_OUTFLOW] * (2 * dim - 1)
+    U = [0.5] + [0.0] * (dim - 1) if U0 is None else list(U0)
+    prims = [[1.0] + U + [1.0]] + [None] * (2 * dim - 1)
+    bt, bp = _bcs(dim, kinds, prims)
+    return Case(name or f"uniform{dim}d", dim, ndf, forest, [g], np.zeros(forest.n, np.int32), bt, bp, gas, quad,
+                vt, 0, smooth_prim(dim, geo, U0=U), SEED_BASE + seed)

@@ -1,0 +1,875 @@
+/*
+ * kamr_oracle.c — CPU restatement of KitAMR.jl's per-step phase-space path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (kitamr.jl_b200/,
+ * libkamr) may include, link or call this file; only tests/, the smoke check
+ * in __graft_entry__.py and bench.py's cpu_baseline / --impl reference legs
+ * use it, as the checker or as the timed CPU baseline.
+ *
+ * PARITY UNPINNED: the reference is pure Julia + libp4est + MPI, none of which
+ * exist in this image, and its own test (test/runtests.jl) asserts nothing and
+ * ships no golden vectors.  This file therefore restates
+ * the reference source function by function (citations below, paths relative
+ * to /root/reference) in the same operation order — sequential merge-walks,
+ * divisions where the reference divides, face-loop scatter — and is compiled
+ * with -ffp-contract=off so no FMA is introduced that Julia would not emit.
+ * Reductions are plain left-to-right sums (Julia's `sum` is pairwise/SIMD, so
+ * reductions agree to rounding only).
+ *
+ * Data model: the flat host arrays of include/kamr.h (the drop-in boundary).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include "../include/kamr.h"
+#include "kamr_oracle.h"
+
+#define EPS_KIT 1e-12                   /* src/Abstract/Types.jl:3 */
+#define EPS_MACH 2.220446049250313e-16  /* Julia eps() == 2^-52, Flux/CAIDVM.jl:137 */
+#define MAXD 3
+#define MAXM 5
+
+static const double PI_ = 3.14159265358979323846;
+
+typedef struct {
+    int D, K, M;            /* DIM, NDF, DIM+2 */
+    const kamr_config* cfg;
+    const kamr_mesh* m;
+    int n_cell;
+    int64_t* vs_off;        /* [n_cell+1] */
+} octx;
+
+static inline double pow2i(int e) { return ldexp(1.0, e); }
+
+static int octx_init(octx* o, const kamr_config* cfg, const kamr_mesh* m) {
+    o->D = cfg->dim; o->K = cfg->ndf; o->M = cfg->dim + 2; o->cfg = cfg; o->m = m;
+    o->n_cell = m->n_local + m->n_ghost + m->n_solidnbr;
+    o->vs_off = (int64_t*)malloc(sizeof(int64_t) * (size_t)(o->n_cell + 1));
+    if (!o->vs_off) return 1;
+    o->vs_off[0] = 0;
+    for (int c = 0; c < o->n_cell; ++c) {
+        int g = m->cell_grid[c];
+        o->vs_off[c + 1] = o->vs_off[c] + (m->grid_off[g + 1] - m->grid_off[g]);
+    }
+    return 0;
+}
+static void octx_free(octx* o) { free(o->vs_off); }
+
+static inline int cell_n(const octx* o, int c) {
+    int g = o->m->cell_grid[c];
+    return (int)(o->m->grid_off[g + 1] - o->m->grid_off[g]);
+}
+static inline const int8_t* cell_level(const octx* o, int c) {
+    return o->m->v_level + o->m->grid_off[o->m->cell_grid[c]];
+}
+static inline const double* cell_weight(const octx* o, int c) {
+    return o->m->v_weight + o->m->grid_off[o->m->cell_grid[c]];
+}
+static inline const double* cell_vmid(const octx* o, int c) { /* plane d at +d*n */
+    return o->m->v_mid + o->m->grid_off[o->m->cell_grid[c]] * o->D;
+}
+static inline double* cell_df(const octx* o, orc_state* s, int c) { return s->df + o->vs_off[c] * o->K; }
+static inline double* cell_sdf(const octx* o, orc_state* s, int c) { return s->sdf + o->vs_off[c] * o->K * o->D; }
+static inline double* cell_flux(const octx* o, orc_state* s, int c) { return s->flux + o->vs_off[c] * o->K; }
+
+/* ------------------------------------------------------------------ kinetics */
+
+/* lib/KitCore/2D.jl:9-16, 3D.jl:12-20 */
+void orc_get_prim(int D, const double* w, double gamma, double* prim) {
+    if (D == 2) {
+        prim[0] = w[0];
+        prim[1] = w[1] / w[0];
+        prim[2] = w[2] / w[0];
+        prim[3] = 0.5 * w[0] / (gamma - 1.0) / (w[3] - 0.5 * (w[1] * w[1] + w[2] * w[2]) / w[0]);
+    } else {
+        prim[0] = w[0];
+        prim[1] = w[1] / w[0];
+        prim[2] = w[2] / w[0];
+        prim[3] = w[3] / w[0];
+        prim[4] = 0.5 * w[0] / (gamma - 1.0) /
+                  (w[4] - 0.5 * (w[1] * w[1] + w[2] * w[2] + w[3] * w[3]) / w[0]);
+    }
+}
+/* lib/KitCore/2D.jl:1-8, 3D.jl:1-11 */
+void orc_get_conserved(int D, const double* prim, double gamma, double* w) {
+    if (D == 2) {
+        w[0] = prim[0];
+        w[1] = prim[0] * prim[1];
+        w[2] = prim[0] * prim[2];
+        w[3] = 0.5 * prim[0] / prim[3] / (gamma - 1.0) +
+               0.5 * prim[0] * (prim[1] * prim[1] + prim[2] * prim[2]);
+    } else {
+        w[0] = prim[0];
+        w[1] = prim[0] * prim[1];
+        w[2] = prim[0] * prim[2];
+        w[3] = prim[0] * prim[3];
+        w[4] = 0.5 * prim[0] / prim[4] / (gamma - 1.0) +
+               0.5 * prim[0] * (prim[1] * prim[1] + prim[2] * prim[2] + prim[3] * prim[3]);
+    }
+}
+/* src/Gas/Model.jl:14 */
+double orc_get_tau(int D, const double* prim, double mu, double omega) {
+    return mu * 2.0 * pow(prim[D + 1], 1 - omega) / prim[0];
+}
+/* lib/KitCore/2D2F.jl:14-21 (scalar form), 3D1F.jl:15-23 */
+static inline void maxwell_point(int D, int K, const double* v, const double* prim, double Kin, double* out) {
+    if (D == 2) {
+        double du = v[0] - prim[1], dv = v[1] - prim[2];
+        double h = prim[0] * (prim[3] / PI_) * exp(-prim[3] * (du * du + dv * dv));
+        out[0] = h;
+        if (K > 1) out[1] = h * Kin / (2.0 * prim[3]);
+    } else {
+        double du = v[0] - prim[1], dv = v[1] - prim[2], dw = v[2] - prim[3];
+        out[0] = prim[0] * pow(prim[4] / PI_, 3.0 / 2.0) * exp(-prim[4] * (du * du + dv * dv + dw * dw));
+    }
+}
+/* lib/KitCore/2D2F.jl:45-67, 3D1F.jl:24-40: F+ for one point given H,B (or M) */
+static inline void shakhov_point(int D, int K, const double* v, const double* F, const double* prim,
+                                 const double* qf, double Pr, double Kin, double* out) {
+    if (D == 2) {
+        double du = v[0] - prim[1], dv = v[1] - prim[2];
+        double lam = prim[3];
+        double c0 = 0.8 * (1 - Pr) * lam * lam / prim[0] * (du * qf[0] + dv * qf[1]);
+        out[0] = c0 * (2 * lam * (du * du + dv * dv) + Kin - 5) * F[0];
+        if (K > 1) out[1] = c0 * (2 * lam * (du * du + dv * dv) + Kin - 3) * F[1];
+    } else {
+        double du = v[0] - prim[1], dv = v[1] - prim[2], dw = v[2] - prim[3];
+        double lam = prim[4];
+        out[0] = 0.8 * (1 - Pr) * lam * lam / prim[0] * (du * qf[0] + dv * qf[1] + dw * qf[2]) *
+                 (2 * lam * (du * du + dv * dv + dw * dw) - 5) * F[0];
+    }
+}
+/* micro_to_macro: lib/KitCore/2D2F.jl:119-126, 3D1F.jl:109-124.
+ * df/vmid given as planes with stride n and an optional index list (masked views). */
+static void micro_to_macro_idx(int D, int K, int cnt, const int* idx, const double* micro /*cnt x K, col-major*/,
+                               int n, const double* vmid, const double* weight, double* w) {
+    double s[MAXM] = {0, 0, 0, 0, 0};
+    double sb = 0.0;
+    for (int a = 0; a < cnt; ++a) {
+        int i = idx ? idx[a] : a;
+        double wt = weight[i];
+        double h = micro[a];
+        if (D == 2) {
+            double u = vmid[i], v = vmid[n + i];
+            s[0] += wt * h;
+            s[1] += wt * u * h;
+            s[2] += wt * v * h;
+            double b = (K > 1) ? micro[cnt + a] : 0.0;
+            sb += wt * ((u * u + v * v) * h + b);
+        } else {
+            double u = vmid[i], v = vmid[n + i], ww = vmid[2 * n + i];
+            s[0] += wt * h;
+            s[1] += wt * u * h;
+            s[2] += wt * v * h;
+            s[3] += wt * ww * h;
+            sb += wt * (u * u + v * v + ww * ww) * h;
+        }
+    }
+    for (int d = 0; d <= D; ++d) w[d] = s[d];
+    w[D + 1] = 0.5 * sb;
+}
+/* heat flux: lib/KitCore/2D2F.jl:68-88, 3D1F.jl:41-72 */
+static void heat_flux(int D, int K, int n, const double* vmid, const double* df, const double* prim,
+                      const double* weight, double* q) {
+    if (D == 2) {
+        double a1 = 0, b1 = 0, a2 = 0, b2 = 0;
+        for (int i = 0; i < n; ++i) {
+            double du = vmid[i] - prim[1], dv = vmid[n + i] - prim[2];
+            double c2 = du * du + dv * dv;
+            a1 += weight[i] * du * c2 * df[i];
+            a2 += weight[i] * dv * c2 * df[i];
+            if (K > 1) {
+                b1 += weight[i] * du * df[n + i];
+                b2 += weight[i] * dv * df[n + i];
+            }
+        }
+        q[0] = 0.5 * (a1 + b1);
+        q[1] = 0.5 * (a2 + b2);
+    } else {
+        double a1 = 0, a2 = 0, a3 = 0;
+        for (int i = 0; i < n; ++i) {
+            double du = vmid[i] - prim[1], dv = vmid[n + i] - prim[2], dw = vmid[2 * n + i] - prim[3];
+            double c2 = du * du + dv * dv + dw * dw;
+            a1 += weight[i] * du * c2 * df[i];
+            a2 += weight[i] * dv * c2 * df[i];
+            a3 += weight[i] * dw * c2 * df[i];
+        }
+        q[0] = 0.5 * a1; q[1] = 0.5 * a2; q[2] = 0.5 * a3;
+    }
+}
+
+/* exported point-wise helpers for unit tests */
+void orc_discrete_maxwell(int D, int K, int n, const double* vmid, const double* prim, double Kin, double* F) {
+    for (int i = 0; i < n; ++i) {
+        double v[MAXD], out[2];
+        for (int d = 0; d < D; ++d) v[d] = vmid[d * n + i];
+        maxwell_point(D, K, v, prim, Kin, out);
+        for (int k = 0; k < K; ++k) F[k * n + i] = out[k];
+    }
+}
+void orc_shakhov_part(int D, int K, int n, const double* vmid, const double* F, const double* prim,
+                      const double* qf, double Pr, double Kin, double* Fp) {
+    for (int i = 0; i < n; ++i) {
+        double v[MAXD], f[2], out[2];
+        for (int d = 0; d < D; ++d) v[d] = vmid[d * n + i];
+        for (int k = 0; k < K; ++k) f[k] = F[k * n + i];
+        shakhov_point(D, K, v, f, prim, qf, Pr, Kin, out);
+        for (int k = 0; k < K; ++k) Fp[k * n + i] = out[k];
+    }
+}
+void orc_micro_to_macro(int D, int K, int n, const double* vmid, const double* df, const double* weight, double* w) {
+    micro_to_macro_idx(D, K, n, NULL, df, n, vmid, weight, w);
+}
+void orc_heat_flux(int D, int K, int n, const double* vmid, const double* df, const double* prim,
+                   const double* weight, double* q) {
+    heat_flux(D, K, n, vmid, df, prim, weight, q);
+}
+
+/* ------------------------------------------------------------------ pair map */
+/* Coverage of grid a's points by grid b's points as visited by the reference's
+ * merge-walks (Flux/Slope.jl:29-64, Flux/Flux.jl:155-279): start[i] = first b
+ * index matched with a's point i; start[n_a] = n_b.  Returns 0 ok, 1 if the
+ * walk runs off either grid (grids do not tile the same domain). */
+int orc_pair_map(int D, int n_a, const int8_t* lev_a, int n_b, const int8_t* lev_b, int32_t* start) {
+    int index = 0;
+    double flag = 0.0;
+    for (int i = 0; i < n_a; ++i) {
+        if (index >= n_b) return 1;
+        start[i] = index;
+        if (lev_a[i] == lev_b[index]) {
+            index += 1;
+        } else if (lev_a[i] < lev_b[index]) {
+            while (flag != 1.0) {
+                if (index >= n_b) return 1;
+                flag += 1 / pow2i(D * (lev_b[index] - lev_a[i]));
+                index += 1;
+            }
+            flag = 0.0;
+        } else {
+            flag += 1 / pow2i(D * (lev_a[i] - lev_b[index]));
+            if (flag == 1.0) { index += 1; flag = 0.0; }
+        }
+    }
+    start[n_a] = n_b;
+    return index == n_b ? 0 : 1;
+}
+
+/* ------------------------------------------------------------------ slopes */
+
+/* minmod, Flux/Slope.jl:20-24 */
+static inline double sgn(double x) { return (x > 0) - (x < 0); }
+static inline double minmod(double sL, double sR) {
+    double SL = fabs(sL), SR = fabs(sR);
+    return 0.5 * (sgn(sL) + sgn(sR)) * fmin(SL, SR);
+}
+
+/* diff_vs!, Flux/Slope.jl:29-64 ; diff_vs_transverse!, :278-333 when dm != NULL */
+static void diff_vs(const octx* o, orc_state* st, int c, int cn, double dsL, const double* dm, double* sL) {
+    const int D = o->D, K = o->K;
+    const int n = cell_n(o, c), nn = cell_n(o, cn);
+    const int8_t* level = cell_level(o, c);
+    const int8_t* level_n = cell_level(o, cn);
+    const double* df = cell_df(o, st, c);
+    const double* dfn = cell_df(o, st, cn);
+    const double* sdfn = cell_sdf(o, st, cn);
+    int index = 0;
+    double flag = 0.0;
+    for (int i = 0; i < n; ++i) {
+        if (level[i] == level_n[index]) {
+            for (int j = 0; j < K; ++j) {
+                double proj = dfn[j * nn + index];
+                if (dm) for (int t = 0; t < D; ++t) proj += dm[t] * sdfn[(t * K + j) * nn + index];
+                sL[j * n + i] += (df[j * n + i] - proj) / dsL;
+            }
+            index += 1;
+        } else if (level[i] < level_n[index]) {
+            while (flag != 1.0) {
+                for (int j = 0; j < K; ++j) {
+                    double proj = dfn[j * nn + index];
+                    if (dm) for (int t = 0; t < D; ++t) proj += dm[t] * sdfn[(t * K + j) * nn + index];
+                    sL[j * n + i] += (df[j * n + i] - proj) / pow2i(D * (level_n[index] - level[i])) / dsL;
+                }
+                flag += 1 / pow2i(D * (level_n[index] - level[i]));
+                index += 1;
+            }
+            flag = 0.0;
+        } else {
+            for (int j = 0; j < K; ++j) {
+                double proj = dfn[j * nn + index];
+                if (dm) for (int t = 0; t < D; ++t) proj += dm[t] * sdfn[(t * K + j) * nn + index];
+                sL[j * n + i] += (df[j * n + i] - proj) / dsL;
+            }
+            flag += 1 / pow2i(D * (level[i] - level_n[index]));
+            if (flag == 1.0) { index += 1; flag = 0.0; }
+        }
+    }
+}
+
+typedef struct { int cnt; const int32_t* ids; } nlist;
+static inline nlist nb_list(const octx* o, int c, int face) {
+    const kamr_mesh* m = o->m;
+    int e = c * 2 * o->D + face;
+    nlist l = { m->nb_off[e + 1] - m->nb_off[e], m->nb_ids + m->nb_off[e] };
+    return l;
+}
+
+/* _ps_has_transverse_offset, Flux/Slope.jl:177-201 */
+static int has_transverse_offset(const octx* o, int c, nlist nb, int dir) {
+    const int D = o->D;
+    if (D == 1 || nb.cnt == 0) return 0;
+    for (int t = 0; t < D; ++t) {
+        if (t == dir) continue;
+        double avg = 0.0;
+        for (int j = 0; j < nb.cnt; ++j) avg += o->m->mid[nb.ids[j] * D + t];
+        avg /= nb.cnt;
+        if (avg != o->m->mid[c * D + t]) return 1;
+    }
+    return 0;
+}
+
+/* update_slope_bound_vs!, Slope.jl:68-86 (transverse: :428-452, always projects) */
+static void slope_bound_vs(const octx* o, orc_state* st, int c, nlist nb, double ds, int dir, int transverse,
+                           double* ws) {
+    const int D = o->D, K = o->K, n = cell_n(o, c);
+    memset(ws, 0, sizeof(double) * (size_t)n * K);
+    for (int j = 0; j < nb.cnt; ++j) {
+        if (transverse) {
+            double dm[MAXD];
+            for (int t = 0; t < D; ++t)
+                dm[t] = (t == dir) ? 0.0 : (o->m->mid[c * D + t] - o->m->mid[nb.ids[j] * D + t]);
+            diff_vs(o, st, c, nb.ids[j], ds, dm, ws);
+        } else {
+            diff_vs(o, st, c, nb.ids[j], ds, NULL, ws);
+        }
+    }
+    double* sdf = cell_sdf(o, st, c);
+    for (int k = 0; k < K; ++k)
+        for (int i = 0; i < n; ++i) sdf[(dir * K + k) * n + i] = ws[k * n + i] / nb.cnt;
+}
+
+/* update_slope_inner_vs!, Slope.jl:90-116 (transverse: :339-383, per-side projection) */
+static void slope_inner_vs(const octx* o, orc_state* st, int c, nlist L, nlist R, double dsL, double dsR, int dir,
+                           int transverse, double* wsL, double* wsR) {
+    const int D = o->D, K = o->K, n = cell_n(o, c);
+    memset(wsL, 0, sizeof(double) * (size_t)n * K);
+    memset(wsR, 0, sizeof(double) * (size_t)n * K);
+    int projL = transverse ? has_transverse_offset(o, c, L, dir) : 0;
+    int projR = transverse ? has_transverse_offset(o, c, R, dir) : 0;
+    double dm[MAXD];
+    for (int j = 0; j < L.cnt; ++j) {
+        if (projL) {
+            for (int t = 0; t < D; ++t)
+                dm[t] = (t == dir) ? 0.0 : (o->m->mid[c * D + t] - o->m->mid[L.ids[j] * D + t]);
+            diff_vs(o, st, c, L.ids[j], dsL, dm, wsL);
+        } else diff_vs(o, st, c, L.ids[j], dsL, NULL, wsL);
+    }
+    for (int j = 0; j < R.cnt; ++j) {
+        if (projR) {
+            for (int t = 0; t < D; ++t)
+                dm[t] = (t == dir) ? 0.0 : (o->m->mid[c * D + t] - o->m->mid[R.ids[j] * D + t]);
+            diff_vs(o, st, c, R.ids[j], dsR, dm, wsR);
+        } else diff_vs(o, st, c, R.ids[j], dsR, NULL, wsR);
+    }
+    double* sdf = cell_sdf(o, st, c);
+    for (int k = 0; k < K; ++k)
+        for (int i = 0; i < n; ++i)
+            sdf[(dir * K + k) * n + i] = minmod(wsL[k * n + i] / L.cnt, wsR[k * n + i] / R.cnt);
+}
+
+/* the 15 update_slope! methods, Slope.jl:458-771 */
+static int update_slope(const octx* o, orc_state* st, int c, int dir, double* wsL, double* wsR) {
+    const kamr_mesh* m = o->m;
+    const int D = o->D, K = o->K, n = cell_n(o, c);
+    int sL = m->nb_state[c * 2 * D + 2 * dir], sR = m->nb_state[c * 2 * D + 2 * dir + 1];
+    nlist L = nb_list(o, c, 2 * dir), R = nb_list(o, c, 2 * dir + 1);
+    const double* mid = m->mid;
+    if (sL == 1 && sR == 1) { /* :458-488 */
+        int solidL = m->bound_enc[L.ids[0]] < 0, solidR = m->bound_enc[R.ids[0]] < 0;
+        if (solidL && solidR) {
+            double* sdf = cell_sdf(o, st, c);
+            for (int k = 0; k < K; ++k)
+                for (int i = 0; i < n; ++i) sdf[(dir * K + k) * n + i] = 0.0;
+        } else if (solidL) {
+            double ds = mid[c * D + dir] - mid[R.ids[0] * D + dir];
+            slope_bound_vs(o, st, c, R, ds, dir, 0, wsL);
+        } else if (solidR) {
+            double ds = mid[c * D + dir] - mid[L.ids[0] * D + dir];
+            slope_bound_vs(o, st, c, L, ds, dir, 0, wsL);
+        } else {
+            double ds = m->ds[c * D + dir];
+            slope_inner_vs(o, st, c, L, R, ds, -ds, dir, 0, wsL, wsR);
+        }
+        return 0;
+    }
+    if (sL == 0 && sR == 0) return 1; /* no such method in the reference */
+    if (sL == 0) { /* :653-668, :716-731, :735-750 */
+        double ds = mid[c * D + dir] - mid[R.ids[0] * D + dir];
+        slope_bound_vs(o, st, c, R, ds, dir, 0, wsL);
+        return 0;
+    }
+    if (sR == 0) { /* :672-687, :691-712, :754-771 */
+        double ds = mid[c * D + dir] - mid[L.ids[0] * D + dir];
+        slope_bound_vs(o, st, c, L, ds, dir, 0, wsL);
+        return 0;
+    }
+    /* inner, :492-649: multiplier 1 (same), 0.75 (finer list), 1.5 (coarser) */
+    double ds = m->ds[c * D + dir];
+    double fL = (sL == 1) ? 1.0 : (sL == -1 ? 1.5 : 0.75);
+    double fR = (sR == 1) ? 1.0 : (sR == -1 ? 1.5 : 0.75);
+    double dsL = (sL == 1) ? ds : fL * ds;
+    double dsR = (sR == 1) ? -ds : -fR * ds;
+    slope_inner_vs(o, st, c, L, R, dsL, dsR, dir, 0, wsL, wsR);
+    return 0;
+}
+
+static inline int skip_cell(const octx* o, int c) { return o->m->bound_enc[c] < 0; }
+
+/* update_slope_level!, Slope.jl:977-1019 */
+static int update_slope_level(const octx* o, orc_state* st, int Lv, double* wsL, double* wsR) {
+    for (int c = 0; c < o->m->n_local; ++c) {
+        if (skip_cell(o, c) || o->m->ps_level[c] != Lv) continue;
+        for (int dir = 0; dir < o->D; ++dir)
+            if (update_slope(o, st, c, dir, wsL, wsR)) return 1;
+    }
+    return 0;
+}
+
+/* update_slope_transverse_level!, Slope.jl:849-945 */
+static int update_slope_transverse_level(const octx* o, orc_state* st, int Lv, double* wsL, double* wsR) {
+    const kamr_mesh* m = o->m;
+    const int D = o->D;
+    for (int c = 0; c < m->n_local; ++c) {
+        if (skip_cell(o, c) || m->ps_level[c] != Lv) continue;
+        for (int dir = 0; dir < D; ++dir) { /* pass (1) */
+            int sL = m->nb_state[c * 2 * D + 2 * dir], sR = m->nb_state[c * 2 * D + 2 * dir + 1];
+            if (sL == -1 || sR == -1) continue;
+            if (update_slope(o, st, c, dir, wsL, wsR)) return 1;
+        }
+        if (D == 1) continue;
+        for (int dir = 0; dir < D; ++dir) { /* pass (2) */
+            int sL = m->nb_state[c * 2 * D + 2 * dir], sR = m->nb_state[c * 2 * D + 2 * dir + 1];
+            nlist L = nb_list(o, c, 2 * dir), R = nb_list(o, c, 2 * dir + 1);
+            if (sL != 0 && sR != 0) {
+                if (!(sL == -1 || sR == -1)) continue;
+                double dsL = m->mid[c * D + dir] - m->mid[L.ids[0] * D + dir];
+                double dsR = m->mid[c * D + dir] - m->mid[R.ids[0] * D + dir];
+                slope_inner_vs(o, st, c, L, R, dsL, dsR, dir, 1, wsL, wsR);
+                if (m->bound_enc[L.ids[0]] < 0) slope_bound_vs(o, st, c, R, dsR, dir, 1, wsL);
+                else if (m->bound_enc[R.ids[0]] < 0) slope_bound_vs(o, st, c, L, dsL, dir, 1, wsL);
+            } else if (sR == 0 && sL == -1) {
+                if (m->bound_enc[L.ids[0]] < 0) continue;
+                double dsL = m->mid[c * D + dir] - m->mid[L.ids[0] * D + dir];
+                slope_bound_vs(o, st, c, L, dsL, dir, 1, wsL);
+            } else if (sL == 0 && sR == -1) {
+                if (m->bound_enc[R.ids[0]] < 0) continue;
+                double dsR = m->mid[c * D + dir] - m->mid[R.ids[0] * D + dir];
+                slope_bound_vs(o, st, c, R, dsR, dir, 1, wsL);
+            }
+        }
+    }
+    return 0;
+}
+
+/* update_macro_slope!, Slope.jl:1022-1036 */
+static void update_macro_slope(const octx* o, orc_state* st) {
+    const int D = o->D, K = o->K, M = o->M;
+    for (int c = 0; c < o->m->n_local; ++c) {
+        if (skip_cell(o, c)) continue;
+        int n = cell_n(o, c);
+        for (int dir = 0; dir < D; ++dir)
+            micro_to_macro_idx(D, K, n, NULL, cell_sdf(o, st, c) + (size_t)dir * K * n, n, cell_vmid(o, c),
+                               cell_weight(o, c), st->sw + (size_t)c * M * D + dir * M);
+    }
+}
+
+/* one level of slope! — exported so multi-rank tests can interleave the
+ * per-level halo exchange exactly as Slope.jl:1055-1066 does */
+int orc_slope_level(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, int Lv, int transverse) {
+    octx o;
+    if (octx_init(&o, cfg, m)) return 1;
+    int maxn = 1;
+    for (int c = 0; c < m->n_local; ++c) if (cell_n(&o, c) > maxn) maxn = cell_n(&o, c);
+    double* wsL = (double*)malloc(sizeof(double) * (size_t)maxn * o.K);
+    double* wsR = (double*)malloc(sizeof(double) * (size_t)maxn * o.K);
+    int rc = transverse ? update_slope_transverse_level(&o, st, Lv, wsL, wsR)
+                        : update_slope_level(&o, st, Lv, wsL, wsR);
+    free(wsL); free(wsR);
+    octx_free(&o);
+    return rc;
+}
+int orc_macro_slope(const kamr_config* cfg, const kamr_mesh* m, orc_state* st) {
+    octx o;
+    if (octx_init(&o, cfg, m)) return 1;
+    update_macro_slope(&o, st);
+    octx_free(&o);
+    return 0;
+}
+/* slope!, Slope.jl:1047-1070 (single address space: the exchanges are no-ops) */
+int orc_slope(const kamr_config* cfg, const kamr_mesh* m, orc_state* st) {
+    int rc = orc_slope_level(cfg, m, st, m->ps_minlevel, 0);
+    if (rc) return rc;
+    for (int L = m->ps_minlevel + 1; L <= m->ps_maxlevel; ++L) {
+        rc = orc_slope_level(cfg, m, st, L, 1);
+        if (rc) return rc;
+    }
+    return orc_macro_slope(cfg, m, st);
+}
+
+/* ------------------------------------------------------------------ flux */
+
+/* face_area, Flux/Flux.jl:10-15 */
+static double face_area(const octx* o, int c, int dir) {
+    const double* ds = o->m->ds + (size_t)c * o->D;
+    if (o->D == 2) return ds[dir == 0 ? 1 : 0];
+    if (dir == 0) return ds[1] * ds[2];
+    if (dir == 1) return ds[0] * ds[2];
+    return ds[0] * ds[1];
+}
+
+typedef struct {
+    int cnt; int* idx;       /* masked point indices (ascending) */
+    double* micro;           /* cnt x K col-major */
+} facevs;
+
+/* positivity_preserving_reconstruct, Flux/CAIDVM.jl:127-141; unlimited branch :110-111 */
+static void reconstruct(const octx* o, orc_state* st, int c, const double* ps_mid, const double* fmid, double dt,
+                        int dir, facevs* fv, int mode /*0 limited,1 unlimited,2 none*/) {
+    const int D = o->D, K = o->K, n = cell_n(o, c);
+    const double* vm = cell_vmid(o, c);
+    const double* df = cell_df(o, st, c);
+    const double* sdf = cell_sdf(o, st, c);
+    const double* ds = o->m->ds + (size_t)c * D;
+    for (int a = 0; a < fv->cnt; ++a) {
+        int i = fv->idx[a];
+        double dx[MAXD];
+        for (int j = 0; j < D; ++j) dx[j] = fmid[j] - vm[j * n + i] * dt - ps_mid[j];
+        double vn = vm[dir * n + i];
+        for (int k = 0; k < K; ++k) {
+            double f = df[k * n + i];
+            if (mode == 2) { fv->micro[k * fv->cnt + a] = f * vn; continue; }
+            double s_abs = 0.0, s_dx = 0.0;
+            for (int t = 0; t < D; ++t) {
+                double s = sdf[(t * K + k) * n + i];
+                s_abs += ds[t] * fabs(s);
+                s_dx += dx[t] * s;
+            }
+            if (mode == 1) fv->micro[k * fv->cnt + a] = (f + s_dx) * vn;
+            else fv->micro[k * fv->cnt + a] =
+                     (f + fmin(fabs((f - EPS_MACH) / (0.5 * s_abs + EPS_KIT)), 1.) * s_dx) * vn;
+        }
+    }
+}
+
+/* make_face_vs masks, Flux/Flux.jl:349-424: here rot*v<=0 ; there rot*v>0 */
+static void make_mask(const octx* o, int c, int dir, double rot, int there, facevs* fv) {
+    const int n = cell_n(o, c);
+    const double* vm = cell_vmid(o, c) + (size_t)dir * n;
+    fv->cnt = 0;
+    for (int i = 0; i < n; ++i) {
+        double x = rot * vm[i];
+        int sel = there ? (x > 0.) : (x <= 0.);
+        if (sel) fv->idx[fv->cnt++] = i;
+    }
+}
+
+/* update_micro_flux!, Flux/Flux.jl:151-344 (local there with/without write-back; ghost there) */
+static void update_micro_flux(const octx* o, orc_state* st, int here, int there, const facevs* hv, const facevs* tv,
+                              double area, int write_there) {
+    const int D = o->D, K = o->K;
+    const int n = cell_n(o, here), nn = cell_n(o, there);
+    const int8_t* level = cell_level(o, here);
+    const int8_t* level_n = cell_level(o, there);
+    double* flux = cell_flux(o, st, here);
+    double* flux_n = cell_flux(o, st, there);
+    int index = 0, j = 0, index_n = 0, hp = 0; /* hp walks hv->idx to recover heavi[i] */
+    double flag = 0.;
+#define HM(k) (hv->micro[(k) * hv->cnt + index] * area)
+#define TM(k) (tv->micro[(k) * tv->cnt + index_n] * area)
+    for (int i = 0; i < n; ++i) {
+        int heavi = (hp < hv->cnt && hv->idx[hp] == i);
+        if (heavi) {
+            hp++;
+            for (int ii = 0; ii < K; ++ii) flux[ii * n + i] += HM(ii);
+            if (level[i] == level_n[j]) {
+                if (write_there) for (int ii = 0; ii < K; ++ii) flux_n[ii * nn + j] -= HM(ii);
+                j += 1;
+            } else if (level[i] < level_n[j]) {
+                while (flag != 1.0) {
+                    if (write_there) for (int ii = 0; ii < K; ++ii) flux_n[ii * nn + j] -= HM(ii);
+                    flag += 1 / pow2i(D * (level_n[j] - level[i]));
+                    j += 1;
+                }
+                flag = 0.0;
+            } else {
+                if (write_there)
+                    for (int ii = 0; ii < K; ++ii) flux_n[ii * nn + j] -= HM(ii) / pow2i(D * (level[i] - level_n[j]));
+                flag += 1 / pow2i(D * (level[i] - level_n[j]));
+                if (flag == 1.0) { j += 1; flag = 0.0; }
+            }
+            index += 1;
+        } else {
+            if (level[i] == level_n[j]) {
+                for (int ii = 0; ii < K; ++ii) {
+                    if (write_there) flux_n[ii * nn + j] -= TM(ii);
+                    flux[ii * n + i] += TM(ii);
+                }
+                j += 1; index_n += 1;
+            } else if (level[i] < level_n[j]) {
+                while (flag != 1.0) {
+                    for (int ii = 0; ii < K; ++ii) {
+                        if (write_there) flux_n[ii * nn + j] -= TM(ii);
+                        flux[ii * n + i] += TM(ii) / pow2i(D * (level_n[j] - level[i]));
+                    }
+                    flag += 1 / pow2i(D * (level_n[j] - level[i]));
+                    j += 1; index_n += 1;
+                }
+                flag = 0.0;
+            } else {
+                for (int ii = 0; ii < K; ++ii) flux[ii * n + i] += TM(ii);
+                flag += 1 / pow2i(D * (level[i] - level_n[j]));
+                if (flag == 1.0) {
+                    if (write_there) for (int ii = 0; ii < K; ++ii) flux_n[ii * nn + j] -= TM(ii);
+                    j += 1; index_n += 1; flag = 0.0;
+                }
+            }
+        }
+    }
+#undef HM
+#undef TM
+}
+
+/* flux!(F, face::FullFace|FluxData), Flux/Flux.jl:28-59,94-111 with calc_flux(CAIDVM) CAIDVM.jl:99-121 */
+static void flux_inner_face(const octx* o, orc_state* st, int f, double dt, facevs* hv, facevs* tv) {
+    const kamr_mesh* m = o->m;
+    const int D = o->D, K = o->K, M = o->M;
+    int here = m->face_here[f], there = m->face_there[f], dir = m->face_dir[f], kind = m->face_kind[f];
+    double rot = m->face_rot[f];
+    const double* fmid = m->face_mid + (size_t)f * D;
+    make_mask(o, here, dir, rot, 0, hv);
+    make_mask(o, there, dir, rot, 1, tv);
+    int there_solid = m->bound_enc[there] < 0;
+    reconstruct(o, st, here, m->mid + (size_t)here * D, fmid, dt, dir, hv, there_solid ? 1 : 0);
+    reconstruct(o, st, there, m->face_there_mid + (size_t)f * D, fmid, dt, dir, tv, there_solid ? 2 : 0);
+    double area = face_area(o, here, dir);
+    if (kind == KAMR_FACE_HANGING) area = area / pow2i(D - 1) * rot; /* Flux.jl:84-86 */
+    else area = area * rot;                                          /* Flux.jl:87-89 */
+    if (o->cfg->flux_type == KAMR_FLUX_CAIDVM) {
+        double fw[MAXM], fw2[MAXM];
+        micro_to_macro_idx(D, K, hv->cnt, hv->idx, hv->micro, cell_n(o, here), cell_vmid(o, here),
+                           cell_weight(o, here), fw);
+        micro_to_macro_idx(D, K, tv->cnt, tv->idx, tv->micro, cell_n(o, there), cell_vmid(o, there),
+                           cell_weight(o, there), fw2);
+        /* update_macro_flux!, Flux.jl:116-136 */
+        int there_local_fluid = (there < m->n_local) && m->bound_enc[there] >= 0;
+        for (int q = 0; q < M; ++q) {
+            double v = (fw[q] + fw2[q]) * area;
+            st->mflux[(size_t)here * M + q] += v;
+            if (there_local_fluid) st->mflux[(size_t)there * M + q] -= v;
+        }
+    }
+    int write_there = (there < m->n_local) && m->bound_enc[there] >= 0;
+    update_micro_flux(o, st, here, there, hv, tv, area, write_there);
+}
+
+/* calc_domain_flux(CAIDVM, ...) CAIDVM.jl:4-97 + update_domain_flux! Flux.jl:64-82 */
+static void flux_domain_face(const octx* o, orc_state* st, int f, double dt, facevs* hv, facevs* tv) {
+    const kamr_mesh* m = o->m;
+    const int D = o->D, K = o->K, M = o->M;
+    int c = m->face_here[f], dir = m->face_dir[f], b = m->face_there[f];
+    double rot = m->face_rot[f];
+    const double* fmid = m->face_mid + (size_t)f * D;
+    const double* pmid = m->mid + (size_t)c * D;
+    const int n = cell_n(o, c);
+    const double* vm = cell_vmid(o, c);
+    const double* wt = cell_weight(o, c);
+    const double* df = cell_df(o, st, c);
+    const double* sdf = cell_sdf(o, st, c);
+    int bct = m->bc_type[b];
+    double bc[MAXM];
+    for (int q = 0; q < M; ++q) bc[q] = m->bc_prim[(size_t)b * M + q];
+    make_mask(o, c, dir, rot, 0, hv);
+    /* nheavi = !heavi */
+    tv->cnt = 0;
+    { int hp = 0; for (int i = 0; i < n; ++i) { if (hp < hv->cnt && hv->idx[hp] == i) hp++; else tv->idx[tv->cnt++] = i; } }
+    if (bct == KAMR_BC_UNIFORM_OUTFLOW) { /* CAIDVM.jl:53-67 */
+        reconstruct(o, st, c, pmid, fmid, dt, dir, hv, 2);
+        reconstruct(o, st, c, pmid, fmid, dt, dir, tv, 2);
+    } else if (bct == KAMR_BC_INTERPOLATED_OUTFLOW) { /* CAIDVM.jl:71-97 */
+        double tmid[MAXD];
+        for (int j = 0; j < D; ++j) tmid[j] = 2.0 * fmid[j] - pmid[j];
+        reconstruct(o, st, c, pmid, fmid, dt, dir, hv, 1);
+        for (int a = 0; a < tv->cnt; ++a) {
+            int i = tv->idx[a];
+            double vn = vm[dir * n + i];
+            for (int k = 0; k < K; ++k) {
+                double tdf = df[k * n + i] + (tmid[dir] - pmid[dir]) * sdf[(dir * K + k) * n + i];
+                double s_dx = 0.0;
+                for (int t = 0; t < D; ++t) s_dx += (fmid[t] - vm[t * n + i] * dt - tmid[t]) * sdf[(t * K + k) * n + i];
+                tv->micro[k * tv->cnt + a] = (tdf + s_dx) * vn;
+            }
+        }
+    } else { /* Maxwellian wall :4-25, SuperSonicInflow :29-49 */
+        reconstruct(o, st, c, pmid, fmid, dt, dir, hv, 1);
+        if (bct == KAMR_BC_MAXWELLIAN) { /* calc_ρw, Theory/Math.jl:251-282 */
+            double SF = 0.0, SG = 0.0;
+            for (int a = 0; a < hv->cnt; ++a) {
+                int i = hv->idx[a];
+                double vn = vm[dir * n + i];
+                /* SF uses the reconstructed h component, Theory/Math.jl:261 */
+                double f = df[i], s_dx = 0.0;
+                for (int t = 0; t < D; ++t) s_dx += (fmid[t] - vm[t * n + i] * dt - pmid[t]) * sdf[(t * K + 0) * n + i];
+                SF += wt[i] * vn * (f + s_dx);
+            }
+            for (int a = 0; a < tv->cnt; ++a) {
+                int i = tv->idx[a];
+                double c2 = 0.0;
+                for (int t = 0; t < D; ++t) { double dd = vm[t * n + i] - bc[1 + t]; c2 += dd * dd; }
+                SG += wt[i] * vm[dir * n + i] * exp(-bc[D + 1] * c2);
+            }
+            if (D == 2) SG = bc[3] / PI_ * SG; else SG = pow(bc[4] / PI_, 3.0 / 2.0) * SG;
+            bc[0] = -SF / SG;
+        }
+        for (int a = 0; a < tv->cnt; ++a) {
+            int i = tv->idx[a];
+            double v[MAXD], out[2];
+            for (int t = 0; t < D; ++t) v[t] = vm[t * n + i];
+            maxwell_point(D, K, v, bc, o->cfg->K, out);
+            for (int k = 0; k < K; ++k) tv->micro[k * tv->cnt + a] = out[k] * vm[dir * n + i];
+        }
+    }
+    double area = rot * face_area(o, c, dir);
+    if (o->cfg->flux_type == KAMR_FLUX_CAIDVM) {
+        double fw[MAXM], fw2[MAXM];
+        micro_to_macro_idx(D, K, hv->cnt, hv->idx, hv->micro, n, vm, wt, fw);
+        micro_to_macro_idx(D, K, tv->cnt, tv->idx, tv->micro, n, vm, wt, fw2);
+        for (int q = 0; q < M; ++q) st->mflux[(size_t)c * M + q] += area * (fw[q] + fw2[q]);
+    }
+    double* flux = cell_flux(o, st, c);
+    for (int k = 0; k < K; ++k) {
+        for (int a = 0; a < hv->cnt; ++a) flux[k * n + hv->idx[a]] += area * hv->micro[k * hv->cnt + a];
+        for (int a = 0; a < tv->cnt; ++a) flux[k * n + tv->idx[a]] += area * tv->micro[k * tv->cnt + a];
+    }
+}
+
+/* flux!(p4est, ka), Flux/Flux.jl:458-488 — face loop (IB phases handled by orc_ib_*) */
+int orc_flux(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt) {
+    octx o;
+    if (octx_init(&o, cfg, m)) return 1;
+    int maxn = 1;
+    for (int c = 0; c < o.n_cell; ++c) if (cell_n(&o, c) > maxn) maxn = cell_n(&o, c);
+    facevs hv, tv;
+    hv.idx = (int*)malloc(sizeof(int) * maxn); tv.idx = (int*)malloc(sizeof(int) * maxn);
+    hv.micro = (double*)malloc(sizeof(double) * (size_t)maxn * o.K);
+    tv.micro = (double*)malloc(sizeof(double) * (size_t)maxn * o.K);
+    for (int f = 0; f < m->n_face; ++f) {
+        if (m->face_kind[f] == KAMR_FACE_DOMAIN) flux_domain_face(&o, st, f, dt, &hv, &tv);
+        else flux_inner_face(&o, st, f, dt, &hv, &tv);
+    }
+    free(hv.idx); free(tv.idx); free(hv.micro); free(tv.micro);
+    octx_free(&o);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ update */
+
+/* iterate!(CAIDVM_Marching) Theory/Iterate.jl:96-130 ; iterate!(Euler) :131-162 ;
+ * residual_check! Solver/Finalize.jl:5-11 */
+int orc_iterate(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt, int want_residual,
+                double* res_out) {
+    octx o;
+    if (octx_init(&o, cfg, m)) return 1;
+    const int D = o.D, K = o.K, M = o.M;
+    double sumRes[MAXM] = {0}, sumAvg[MAXM] = {0};
+    for (int c = 0; c < m->n_local; ++c) {
+        if (skip_cell(&o, c)) continue;
+        const int n = cell_n(&o, c);
+        const double* vm = cell_vmid(&o, c);
+        const double* wt = cell_weight(&o, c);
+        double* f = cell_df(&o, st, c);
+        double* vflux = cell_flux(&o, st, c);
+        double* w = st->w + (size_t)c * M;
+        double* mfl = st->mflux + (size_t)c * M;
+        double area = 1.0;
+        for (int d = 0; d < D; ++d) area *= m->ds[(size_t)c * D + d]; /* reduce(*, ds) */
+        double prim_c[MAXM], qf[MAXD];
+        if (cfg->marching == KAMR_MARCH_CAIDVM) {
+            for (int q = 0; q < M; ++q) w[q] += mfl[q] * dt / area;
+            orc_get_prim(D, w, cfg->gamma, prim_c);
+            for (int k = 0; k < K; ++k)
+                for (int i = 0; i < n; ++i) f[k * n + i] += dt / area * vflux[k * n + i];
+            double w0[MAXM], prim[MAXM];
+            micro_to_macro_idx(D, K, n, NULL, f, n, vm, wt, w0);
+            orc_get_prim(D, w0, cfg->gamma, prim);
+            double tau = orc_get_tau(D, prim_c, cfg->mu_ref, cfg->omega);
+            /* f += F_c - F */
+            for (int i = 0; i < n; ++i) {
+                double v[MAXD], Fc[2], F[2];
+                for (int t = 0; t < D; ++t) v[t] = vm[t * n + i];
+                maxwell_point(D, K, v, prim_c, cfg->K, Fc);
+                maxwell_point(D, K, v, prim, cfg->K, F);
+                for (int k = 0; k < K; ++k) f[k * n + i] += Fc[k] - F[k];
+            }
+            heat_flux(D, K, n, vm, f, prim_c, wt, qf);
+            for (int d = 0; d < D; ++d) st->qf[(size_t)c * D + d] = qf[d];
+            for (int i = 0; i < n; ++i) {
+                double v[MAXD], Fc[2], Fp[2];
+                for (int t = 0; t < D; ++t) v[t] = vm[t * n + i];
+                maxwell_point(D, K, v, prim_c, cfg->K, Fc);
+                shakhov_point(D, K, v, Fc, prim_c, qf, cfg->Pr, cfg->K, Fp);
+                for (int k = 0; k < K; ++k) {
+                    Fc[k] += Fp[k];
+                    double x = f[k * n + i];
+                    x *= tau / (tau + dt);
+                    x += dt / (tau + dt) * Fc[k];
+                    f[k * n + i] = x;
+                }
+            }
+        } else if (cfg->marching == KAMR_MARCH_EULER) {
+            for (int q = 0; q < M; ++q) w[q] += mfl[q] * dt / area;
+            orc_get_prim(D, w, cfg->gamma, prim_c);
+            double tau = orc_get_tau(D, prim_c, cfg->mu_ref, cfg->omega);
+            heat_flux(D, K, n, vm, f, prim_c, wt, qf);
+            for (int d = 0; d < D; ++d) st->qf[(size_t)c * D + d] = qf[d];
+            for (int i = 0; i < n; ++i) {
+                double v[MAXD], F[2], Fp[2];
+                for (int t = 0; t < D; ++t) v[t] = vm[t * n + i];
+                maxwell_point(D, K, v, prim_c, cfg->K, F);
+                shakhov_point(D, K, v, F, prim_c, qf, cfg->Pr, cfg->K, Fp);
+                for (int k = 0; k < K; ++k) {
+                    F[k] += Fp[k];
+                    f[k * n + i] = (f[k * n + i] + dt / area * vflux[k * n + i]) * tau / (tau + dt) +
+                                   dt / (tau + dt) * F[k];
+                }
+            }
+        } else {
+            octx_free(&o);
+            return 2; /* CIP_Marching: see orc_iterate_cip */
+        }
+        if (want_residual) {
+            for (int q = 0; q < M; ++q) {
+                double dd = prim_c[q] - st->prim[(size_t)c * M + q];
+                sumRes[q] += dd * dd;
+                sumAvg[q] += fabs(prim_c[q]);
+            }
+        }
+        for (int q = 0; q < M; ++q) { st->prim[(size_t)c * M + q] = prim_c[q]; mfl[q] = 0.0; }
+        memset(vflux, 0, sizeof(double) * (size_t)n * K);
+    }
+    if (want_residual && res_out) {
+        for (int q = 0; q < M; ++q) { res_out[q] = sumRes[q]; res_out[M + q] = sumAvg[q]; }
+    }
+    octx_free(&o);
+    return 0;
+}
+
+/* one whole step of the solve! loop body, Solver/Solver.jl:65-67 */
+int orc_step(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt, int want_residual,
+             double* res_out) {
+    int rc = orc_slope(cfg, m, st);
+    if (rc) return rc;
+    rc = orc_flux(cfg, m, st, dt);
+    if (rc) return rc;
+    return orc_iterate(cfg, m, st, dt, want_residual, res_out);
+}

@@ -1,0 +1,39 @@
+/* kamr_oracle.h — CPU oracle (test infrastructure only; see kamr_oracle.c header). */
+#ifndef KAMR_ORACLE_H
+#define KAMR_ORACLE_H
+#include <stdint.h>
+#include "../include/kamr.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* state in the host layout of include/kamr.h */
+typedef struct orc_state {
+    double *df, *sdf, *flux;      /* per point */
+    double *w, *prim, *mflux;     /* per cell x (DIM+2) */
+    double *qf;                   /* per cell x DIM */
+    double *sw;                   /* per cell x (DIM+2) x DIM */
+} orc_state;
+
+void   orc_get_prim(int D, const double* w, double gamma, double* prim);
+void   orc_get_conserved(int D, const double* prim, double gamma, double* w);
+double orc_get_tau(int D, const double* prim, double mu, double omega);
+void   orc_discrete_maxwell(int D, int K, int n, const double* vmid, const double* prim, double Kin, double* F);
+void   orc_shakhov_part(int D, int K, int n, const double* vmid, const double* F, const double* prim,
+                        const double* qf, double Pr, double Kin, double* Fp);
+void   orc_micro_to_macro(int D, int K, int n, const double* vmid, const double* df, const double* weight, double* w);
+void   orc_heat_flux(int D, int K, int n, const double* vmid, const double* df, const double* prim,
+                     const double* weight, double* q);
+int    orc_pair_map(int D, int n_a, const int8_t* lev_a, int n_b, const int8_t* lev_b, int32_t* start);
+
+int orc_slope_level(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, int Lv, int transverse);
+int orc_macro_slope(const kamr_config* cfg, const kamr_mesh* m, orc_state* st);
+int orc_slope(const kamr_config* cfg, const kamr_mesh* m, orc_state* st);
+int orc_flux(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt);
+int orc_iterate(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt, int want_residual,
+                double* res_out);
+int orc_step(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt, int want_residual,
+             double* res_out);
+#ifdef __cplusplus
+}
+#endif
+#endif

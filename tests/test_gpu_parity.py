@@ -1,0 +1,120 @@
+"""Parity of the CUDA path (through the C-ABI) with the CPU oracle on identical inputs.
+Tolerance (BASELINE.json north_star): fp64 relative L2 <= 1e-12 per step on f and macroscopic
+fields, <= 1e-9 after many steps."""
+import numpy as np
+import pytest
+
+from util import local_pts, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def _cases():
+    from kitamr_jl_b200 import abi
+    from kitamr_jl_b200.synth import cases
+    return {
+        "S0": lambda: cases.smoke_s0(),
+        "amr2d_ragged": lambda: cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=8, vs_maxlevel=2, ragged=True),
+        "amr2d_band_samegrid": lambda: cases.amr_case(dim=2, trees=6, maxlevel=2, vtrees=10, vs_maxlevel=1,
+                                                       ragged=False, refine="band", seed=2),
+        "amr2d_periodic": lambda: cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=6, vs_maxlevel=2, ragged=True,
+                                                  periodic=(True, True), seed=3),
+        "amr3d_ragged": lambda: cases.amr_case(dim=3, trees=3, maxlevel=1, vtrees=4, vs_maxlevel=1, ragged=True,
+                                                seed=4),
+        "amr3d_samegrid_l2": lambda: cases.amr_case(dim=3, trees=2, maxlevel=2, vtrees=6, vs_maxlevel=0,
+                                                     ragged=False, seed=5),
+        "euler2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=1, vtrees=8, vs_maxlevel=1, ragged=True, seed=6,
+                                          marching=abi.MARCH_EULER),
+    }
+
+
+@pytest.fixture(scope="module", params=list(_cases().keys()))
+def setup(request, kamr_lib):
+    from kitamr_jl_b200 import api
+    case = _cases()[request.param]()
+    mesh = case.rank_mesh()
+    st = case.init_state(mesh)
+    cfg = case.config(device=0)
+    ctx = api.Context(cfg)
+    ctx.upload_topology(mesh)
+    yield case, mesh, st, cfg, ctx
+    ctx.close()
+
+
+def test_phases_match_oracle(setup):
+    """slope! -> flux! -> iterate! one phase at a time, each compared with the oracle."""
+    from oracle import orc
+    case, mesh, st0, cfg, ctx = setup
+    D, K = mesh.dim, mesh.ndf
+    dt = case.dt()
+    ref = st0.copy()
+    ctx.upload_state(st0, aux=True)
+    # slopes
+    orc.slope(cfg, mesh, ref)
+    ctx.slope()
+    out = ctx.download_state(st0.copy())
+    assert rel_l2(local_pts(mesh, out.sdf, K * D), local_pts(mesh, ref.sdf, K * D)) <= TOL
+    nl = mesh.n_local
+    assert rel_l2(out.sw[: nl * (D + 2) * D], ref.sw[: nl * (D + 2) * D]) <= 1e-11  # sums of signed slopes
+    # flux
+    orc.flux(cfg, mesh, ref, dt)
+    ctx.flux(dt)
+    out = ctx.download_state(st0.copy())
+    assert rel_l2(local_pts(mesh, out.flux, K), local_pts(mesh, ref.flux, K)) <= TOL
+    assert rel_l2(out.mflux[: nl * (D + 2)], ref.mflux[: nl * (D + 2)]) <= 1e-11
+    # update
+    r_ref = orc.iterate(cfg, mesh, ref, dt, True)
+    r_out = ctx.iterate(dt, True)
+    out = ctx.download_state(st0.copy())
+    assert rel_l2(local_pts(mesh, out.df, K), local_pts(mesh, ref.df, K)) <= TOL
+    assert rel_l2(out.w[: nl * (D + 2)], ref.w[: nl * (D + 2)]) <= TOL
+    assert rel_l2(out.prim[: nl * (D + 2)], ref.prim[: nl * (D + 2)]) <= TOL
+    assert rel_l2(out.qf[: nl * D], ref.qf[: nl * D]) <= 1e-10  # heat flux is a difference of O(1) moments
+    assert rel_l2(r_out, r_ref) <= 1e-10
+    assert np.all(local_pts(mesh, out.flux, K) == 0.0) and np.all(out.mflux[: nl * (D + 2)] == 0.0)
+
+
+def test_fused_step_matches_oracle(setup):
+    """kamr_step (fused flux+update) against slope!+flux!+iterate! of the oracle, 1 and 10 steps."""
+    from kitamr_jl_b200 import abi
+    from oracle import orc
+    case, mesh, st0, cfg, ctx = setup
+    D, K = mesh.dim, mesh.ndf
+    dt = case.dt()
+    nl = mesh.n_local
+    ref = st0.copy()
+    ctx.upload_state(st0, aux=True)
+    for it in range(10):
+        orc.step(cfg, mesh, ref, dt, it == 9)
+        ctx.step(dt, it == 9)
+        if it in (0, 9):
+            out = ctx.download_state(st0.copy(), abi.DL_DF | abi.DL_W | abi.DL_PRIM)
+            tol = TOL if it == 0 else 1e-11
+            assert rel_l2(local_pts(mesh, out.df, K), local_pts(mesh, ref.df, K)) <= tol
+            assert rel_l2(out.w[: nl * (D + 2)], ref.w[: nl * (D + 2)]) <= tol
+            assert rel_l2(out.prim[: nl * (D + 2)], ref.prim[: nl * (D + 2)]) <= tol
+
+
+def test_pair_maps_bit_exact(setup):
+    """pair maps built by the library == the reference merge-walk restated in the oracle (integer, bit-exact)."""
+    from oracle import orc
+    case, mesh, st0, cfg, ctx = setup
+    D = mesh.dim
+    checked = 0
+    for ga in range(mesh.n_grid):
+        for gb in range(mesh.n_grid):
+            if ga == gb:
+                continue
+            try:
+                pm = ctx.pair_map(ga, gb)
+            except Exception:
+                continue  # relation not needed by the topology
+            la = mesh.v_level[mesh.grid_off[ga]: mesh.grid_off[ga + 1]]
+            lb = mesh.v_level[mesh.grid_off[gb]: mesh.grid_off[gb + 1]]
+            rc, start = orc.pair_map(D, np.ascontiguousarray(la), np.ascontiguousarray(lb))
+            assert rc == 0
+            assert np.array_equal(pm, start)
+            checked += 1
+    assert checked == ctx.stats().n_relations
