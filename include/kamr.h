@@ -196,6 +196,16 @@ typedef struct kamr_stats {
     int32_t fused_cells;       /* cells taking the on-chip flux+update path */
 } kamr_stats;
 int  kamr_get_stats(kamr_ctx* ctx, kamr_stats* out);
+/* per-kernel device timing for roofline accounting (bench.py): while enabled, every kernel
+ * launch of the hot path is bracketed by CUDA events on the library's stream.  kamr_profile_read
+ * synchronises, writes one record per kernel class that ran since the last read and resets. */
+typedef struct kamr_kernel_time {
+    char    name[32];
+    int64_t launches;
+    double  total_ms;
+} kamr_kernel_time;
+int  kamr_profile_enable(kamr_ctx* ctx, int32_t on);
+int  kamr_profile_read(kamr_ctx* ctx, kamr_kernel_time* out, int32_t cap, int32_t* n);
 /* pair map of grid ga onto grid gb: start[n_a+1]; returns 1 if identity */
 int  kamr_get_pair_map(kamr_ctx* ctx, int32_t ga, int32_t gb, int32_t* start, int32_t cap);
 /* cell-face slots of a local cell: writes up to cap records {face, sign}; returns count via *n */

@@ -67,6 +67,10 @@ class KamrStats(C.Structure):
     ]
 
 
+class KamrKernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
+
+
 def ptr(a: np.ndarray, ctype):
     """Pointer to a C-contiguous numpy array of the matching dtype (None -> NULL)."""
     if a is None:
@@ -80,7 +84,7 @@ EXPORTS = [
     "kamr_create", "kamr_destroy", "kamr_last_error", "kamr_version", "kamr_comm_unique_id", "kamr_comm_init",
     "kamr_upload_topology", "kamr_upload_state", "kamr_upload_aux", "kamr_download_state",
     "kamr_slope", "kamr_flux", "kamr_iterate", "kamr_step", "kamr_exchange_df", "kamr_sync",
-    "kamr_get_stats", "kamr_get_pair_map", "kamr_get_cell_slots",
+    "kamr_get_stats", "kamr_get_pair_map", "kamr_get_cell_slots", "kamr_profile_enable", "kamr_profile_read",
 ]
 
 _lib = None
@@ -118,6 +122,8 @@ def load(path: str | None = None):
     lib.kamr_get_stats.argtypes = [vp, C.POINTER(KamrStats)]
     lib.kamr_get_pair_map.argtypes = [vp, C.c_int32, C.c_int32, c_i32p, C.c_int32]
     lib.kamr_get_cell_slots.argtypes = [vp, C.c_int32, c_i32p, c_i32p, C.c_int32, c_i32p]
+    lib.kamr_profile_enable.argtypes = [vp, C.c_int32]
+    lib.kamr_profile_read.argtypes = [vp, C.POINTER(KamrKernelTime), C.c_int32, c_i32p]
     for name in EXPORTS:
         if name != "kamr_last_error":
             getattr(lib, name).restype = C.c_int

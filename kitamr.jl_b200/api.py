@@ -87,6 +87,9 @@ class Context:
         self._ck(self.lib.kamr_step(self.h, dt, int(want_residual), res.ctypes.data_as(abi.c_f64p)))
         return res
 
+    def exchange_df(self):
+        self._ck(self.lib.kamr_exchange_df(self.h))
+
     def sync(self):
         self._ck(self.lib.kamr_sync(self.h))
 
@@ -95,6 +98,16 @@ class Context:
         s = abi.KamrStats()
         self._ck(self.lib.kamr_get_stats(self.h, C.byref(s)))
         return s
+
+    def profile(self, on=True):
+        self._ck(self.lib.kamr_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """{kernel name: (launches, total_ms)} since the last read."""
+        buf = (abi.KamrKernelTime * 16)()
+        n = C.c_int32(0)
+        self._ck(self.lib.kamr_profile_read(self.h, buf, 16, C.byref(n)))
+        return {buf[i].name.decode(): (int(buf[i].launches), float(buf[i].total_ms)) for i in range(n.value)}
 
     def pair_map(self, ga, gb):
         n = int(self.mesh.grid_off[ga + 1] - self.mesh.grid_off[ga])

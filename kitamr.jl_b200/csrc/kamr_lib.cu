@@ -53,6 +53,11 @@ struct Bin {
     size_t smem = 0;  // dynamic shared memory per block (0 => global staging)
 };
 
+enum KernelId { KID_SLOPE = 0, KID_MACRO_SLOPE, KID_FLUX, KID_UPDATE, KID_STEP, KID_RESIDUAL, KID_PACK, KID_UNPACK,
+                KID_COUNT };
+const char* const kKernelNames[KID_COUNT] = {"slope_kernel", "macro_slope_kernel", "flux_kernel", "update_kernel",
+                                             "step_kernel", "residual_reduce_kernel", "pack_kernel", "unpack_kernel"};
+
 struct PeerPlan {
     int rank;
     // df exchange
@@ -110,6 +115,11 @@ struct kamr_ctx {
     std::vector<PeerPlan> peers;
     double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
     long long halo_bytes_step = 0;
+    // per-kernel timing (kamr_profile_enable)
+    bool profiling = false;
+    struct ProfRec { int kid; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
     // stats
     long long launches = 0;
     long long n_phase_local = 0;
@@ -144,6 +154,27 @@ struct kamr_ctx {
 };
 
 namespace {
+
+// Counts a kernel launch and, while profiling is on, brackets it with events on the stream.
+struct Launch {
+    kamr_ctx* c;
+    cudaEvent_t b = nullptr;
+    Launch(kamr_ctx* c_, int kid) : c(c_) {
+        c->launches++;
+        if (!c->profiling) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+            else CK(cudaEventCreate(&e));
+            return e;
+        };
+        cudaEvent_t a = get();
+        b = get();
+        CK(cudaEventRecord(a, c->stream));
+        c->prof_recs.push_back({kid, a, b});
+    }
+    ~Launch() { if (b) cudaEventRecord(b, c->stream); }
+};
 
 // ------------------------------------------------------------------------------------------------
 // pair map of grid a onto grid b: start[i] = first point of b matched with point i of a
@@ -633,18 +664,18 @@ void exchange(kamr_ctx* c, int what /*0 df, 1 sdf*/, int level) {
     for (auto& pp : c->peers) {
         if (what == 0) {
             if (!pp.df_send.empty()) {
-                copy_segments_kernel<<<std::min<int>((int)pp.df_send.size(), 2048), 256, 0, c->stream>>>(
-                    pp.d_df_send, (int)pp.df_send.size(), src, c->d_sendbuf);
-                c->launches++;
+                { Launch L_(c, KID_PACK);
+                  copy_segments_kernel<<<std::min<int>((int)pp.df_send.size(), 2048), 256, 0, c->stream>>>(
+                    pp.d_df_send, (int)pp.df_send.size(), src, c->d_sendbuf); }
             }
             any = true;
         } else {
             auto it = pp.sdf.find(level);
             if (it == pp.sdf.end()) continue;
             if (!it->second.send.empty()) {
-                copy_segments_kernel<<<std::min<int>((int)it->second.send.size(), 2048), 256, 0, c->stream>>>(
-                    it->second.d_send, (int)it->second.send.size(), src, c->d_sendbuf);
-                c->launches++;
+                { Launch L_(c, KID_PACK);
+                  copy_segments_kernel<<<std::min<int>((int)it->second.send.size(), 2048), 256, 0, c->stream>>>(
+                    it->second.d_send, (int)it->second.send.size(), src, c->d_sendbuf); }
             }
             any = true;
         }
@@ -667,9 +698,9 @@ void exchange(kamr_ctx* c, int what /*0 df, 1 sdf*/, int level) {
         for (auto& pp : c->peers) {
             auto it = pp.sdf.find(level);
             if (it == pp.sdf.end() || it->second.recv.empty()) continue;
-            copy_segments_kernel<<<std::min<int>((int)it->second.recv.size(), 2048), 256, 0, c->stream>>>(
-                it->second.d_recv, (int)it->second.recv.size(), c->d_recvbuf, c->dv.sdf);
-            c->launches++;
+            { Launch L_(c, KID_UNPACK);
+              copy_segments_kernel<<<std::min<int>((int)it->second.recv.size(), 2048), 256, 0, c->stream>>>(
+                it->second.d_recv, (int)it->second.recv.size(), c->d_recvbuf, c->dv.sdf); }
         }
     }
     CK(cudaGetLastError());
@@ -682,16 +713,16 @@ void run_slope(kamr_ctx* c, bool with_sw) {
     for (size_t l = 0; l < c->level_tasks.size(); ++l) {
         const int nt = (int)c->level_tasks[l].second.size();
         if (nt) {
-            slope_kernel<D, K><<<nt, 256, 0, c->stream>>>(c->dv, c->d_level_tasks[l]);
-            c->launches++;
+            { Launch L_(c, KID_SLOPE);
+              slope_kernel<D, K><<<nt, 256, 0, c->stream>>>(c->dv, c->d_level_tasks[l]); }
         }
     }
     CK(cudaGetLastError());
     // per-level halo of the fresh slopes (slope_exchange_level!, Parallel/Ghost.jl:896).  With one rank
     // the levels above simply run back to back; with peers each level is followed by its exchange.
     if (with_sw && !c->fluid_cells.empty()) {
-        macro_slope_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->d_fluid_cells);
-        c->launches++;
+        { Launch L_(c, KID_MACRO_SLOPE);
+          macro_slope_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->d_fluid_cells); }
         CK(cudaGetLastError());
     }
 }
@@ -709,15 +740,15 @@ void run_slope_mpi(kamr_ctx* c, bool with_sw) {
         for (size_t l = 0; l < c->level_tasks.size(); ++l) {
             if (c->level_tasks[l].first != L) continue;
             const int nt = (int)c->level_tasks[l].second.size();
-            slope_kernel<D, K><<<nt, 256, 0, c->stream>>>(c->dv, c->d_level_tasks[l]);
-            c->launches++;
+            { Launch L_(c, KID_SLOPE);
+              slope_kernel<D, K><<<nt, 256, 0, c->stream>>>(c->dv, c->d_level_tasks[l]); }
         }
         exchange(c, 1, L);
     }
     CK(cudaGetLastError());
     if (with_sw && !c->fluid_cells.empty()) {
-        macro_slope_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->d_fluid_cells);
-        c->launches++;
+        { Launch L_(c, KID_MACRO_SLOPE);
+          macro_slope_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->d_fluid_cells); }
         CK(cudaGetLastError());
     }
 }
@@ -725,8 +756,8 @@ void run_slope_mpi(kamr_ctx* c, bool with_sw) {
 template <int D, int K>
 void run_flux(kamr_ctx* c, double dt, const int* d_cells, int ncells) {
     if (!ncells) return;
-    flux_kernel<D, K><<<ncells, 256, 0, c->stream>>>(c->dv, c->gas, d_cells, dt);
-    c->launches++;
+    { Launch L_(c, KID_FLUX);
+      flux_kernel<D, K><<<ncells, 256, 0, c->stream>>>(c->dv, c->gas, d_cells, dt); }
     CK(cudaGetLastError());
 }
 
@@ -734,9 +765,9 @@ template <int D, int K>
 void fetch_residual(kamr_ctx* c, int want, double* res_out) {
     if (!want) return;
     const int M = D + 2;
-    residual_reduce_kernel<<<1, 256, 0, c->stream>>>(c->dv.res_cell, c->d_fluid_cells, (int)c->fluid_cells.size(),
-                                                     2 * M, c->d_res);
-    c->launches++;
+    { Launch L_(c, KID_RESIDUAL);
+      residual_reduce_kernel<<<1, 256, 0, c->stream>>>(c->dv.res_cell, c->d_fluid_cells, (int)c->fluid_cells.size(),
+                                                     2 * M, c->d_res); }
     CK(cudaMemcpyAsync(c->h_res, c->d_res, 2 * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (res_out) memcpy(res_out, c->h_res, 2 * M * sizeof(double));
@@ -749,11 +780,12 @@ void run_update(kamr_ctx* c, double dt, int want, const double* fin, double* fou
         if (b.smem) {
             if (only_global) continue;
             CK(cudaFuncSetAttribute(update_kernel<D, K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem));
+            Launch L_(c, KID_UPDATE);
             update_kernel<D, K, 1><<<nb, 256, b.smem, c->stream>>>(c->dv, c->gas, b.d_cells, fin, fout, dt, want);
         } else {
+            Launch L_(c, KID_UPDATE);
             update_kernel<D, K, 0><<<nb, 256, 0, c->stream>>>(c->dv, c->gas, b.d_cells, fin, fout, dt, want);
         }
-        c->launches++;
     }
     CK(cudaGetLastError());
 }
@@ -792,8 +824,8 @@ void do_step(kamr_ctx* c, double dt, int want, double* res_out) {
     for (auto& b : c->bins) {
         if (!b.smem) continue;
         CK(cudaFuncSetAttribute(step_kernel<D, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem));
+        Launch L_(c, KID_STEP);
         step_kernel<D, K><<<(int)b.cells.size(), 256, b.smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
-        c->launches++;
     }
     CK(cudaGetLastError());
     run_update<D, K>(c, dt, want, c->dv.df, c->dv.df_new, true);
@@ -868,6 +900,8 @@ int kamr_destroy(kamr_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->cfg.device);
     c->free_topology();
+    for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->comm) nccl().CommDestroy(c->comm);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -981,6 +1015,42 @@ int kamr_get_stats(kamr_ctx* c, kamr_stats* out) {
         out->halo_bytes_per_step = c->halo_bytes_step;
         out->n_levels = (int)c->level_tasks.size();
         out->fused_cells = c->fused_cells;
+    });
+}
+
+int kamr_profile_enable(kamr_ctx* c, int32_t on) {
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->cfg.device));
+        CK(cudaStreamSynchronize(c->stream));
+        for (auto& r : c->prof_recs) { c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b); }
+        c->prof_recs.clear();
+        c->profiling = on != 0;
+    });
+}
+
+int kamr_profile_read(kamr_ctx* c, kamr_kernel_time* out, int32_t cap, int32_t* n) {
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->cfg.device));
+        CK(cudaStreamSynchronize(c->stream));
+        double ms[KID_COUNT] = {0};
+        long long cnt[KID_COUNT] = {0};
+        for (auto& r : c->prof_recs) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, r.a, r.b));
+            ms[r.kid] += t; cnt[r.kid]++;
+            c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
+        }
+        c->prof_recs.clear();
+        int k = 0;
+        for (int q = 0; q < KID_COUNT; ++q) {
+            if (!cnt[q]) continue;
+            if (k >= cap) throw Fail("buffer too small");
+            memset(&out[k], 0, sizeof(out[k]));
+            strncpy(out[k].name, kKernelNames[q], sizeof(out[k].name) - 1);
+            out[k].launches = cnt[q]; out[k].total_ms = ms[q];
+            ++k;
+        }
+        *n = k;
     });
 }
 

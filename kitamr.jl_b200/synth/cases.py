@@ -270,3 +270,67 @@ def uniform_case(dim=2, trees=64, maxlevel=0, vtrees=60, name=None, seed=3, refi
     bt, bp = _bcs(dim, kinds, prims)
     return Case(name or f"uniform{dim}d", dim, ndf, forest, [g], np.zeros(forest.n, np.int32), bt, bp, gas, quad,
                 vt, 0, smooth_prim(dim, geo, U0=U), SEED_BASE + seed)
+
+
+# ---------------------------------------------------------------------- bench workloads
+def cylinder_s2(copies=1, ps_maxlevel=7, box_level=4, vs_maxlevel=3, vtrees=16, trees=25, noise=0.01) -> Case:
+    """S2 cylinder2d (example/cylinder/cylinder.jl:5-47): 25x25 roots on [-16,16]^2, level `box_level`
+    in max-norm(x)<5 (the converged dynamic-AMR region, cylinder_udf.jl:9-15), level `ps_maxlevel`
+    within search_coeffi*ds_min = 4*ds_min of the r=1 circle; velocity grids 16x16 roots on
+    [-10,10]^2 refined to level<=3 by maxwellian_refine_flag of the buffer IC (cylinder_udf.jl:16-27);
+    Ma 5 inflow at xmin, UniformOutflow elsewhere; K=1, Kn=0.1, omega=0.81.
+
+    `copies` > 1 places that many cylinders side by side in x (one connected forest of
+    25*copies x 25 roots): the weak-scaling workload, one cylinder's worth of work per GPU.
+    """
+    W = 32.0
+    geo = (-16.0, -16.0 + W * copies, -16.0, 16.0)
+    centers = np.array([[W * k, 0.0] for k in range(copies)])
+    ds_min = W / trees / 2 ** ps_maxlevel
+    Ma = 5.0
+
+    def rel(mid):
+        d = mid[:, None, :] - centers[None, :, :]
+        k = np.argmin(np.abs(d[:, :, 0]), axis=1)
+        return d[np.arange(len(mid)), k]
+
+    def refine_fn(l, mid, ds):
+        x = rel(mid)
+        r = np.sqrt(np.sum(x ** 2, axis=1))
+        if l < box_level:
+            return np.max(np.abs(x), axis=1) < 5.0
+        half_diag = 0.5 * np.sqrt(np.sum(ds ** 2))
+        return np.abs(r - 1.0) < 4.0 * ds_min + half_diag
+
+    forest = Forest.build(2, geo, (trees * copies, trees), ps_maxlevel, refine_fn)
+    quad = (-10.0, 10.0, -10.0, 10.0)
+    gas = Gas(K=1.0, Kn=0.1, omega=0.81, omega_r=0.81)
+
+    def prim_fn(x):
+        d = np.asarray(x)[None, :] - centers
+        xr = d[np.argmin(np.abs(d[:, 0]))]
+        r = float(np.sqrt(np.sum(xr ** 2)))
+        if r > 2.0:
+            return np.array([1.0, Ma * math.sqrt(5 / 6), 0.0, 1.0])
+        rr = max(r, 1.0)  # cells inside the body (no immersed boundary in this variant) take the wall state
+        return np.array([1.0, (rr - 1.0) * Ma * math.sqrt(5 / 6), 0.0, 1.0])
+
+    cache = {}
+    per_cell = []
+    for c in range(forest.n):
+        p = prim_fn(forest.mid[c])
+        key = (round(float(p[1]), 1),)
+        if key not in cache:
+            cache[key] = vg.maxwellian_grid(quad, (vtrees, vtrees), vs_maxlevel, np.array([1.0, key[0], 0.0, 1.0]),
+                                            2, gas.K)
+        per_cell.append(cache[key])
+    grids, cell_grid = _dedup_grids(per_cell)
+    bt, bp = _bcs(2, [abi.BC_SUPERSONIC_INFLOW] + [abi.BC_UNIFORM_OUTFLOW] * 3,
+                  [[1.0, Ma * math.sqrt(5 / 6), 0.0, 1.0], None, None, None])
+    return Case(f"S2-cylinder2d-x{copies}", 2, 2, forest, grids, cell_grid, bt, bp, gas, quad, (vtrees, vtrees),
+                vs_maxlevel, prim_fn, SEED_BASE + 2, noise=noise)
+
+
+WORKLOADS = {
+    "S2": cylinder_s2,
+}
