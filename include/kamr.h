@@ -171,6 +171,14 @@ int  kamr_upload_aux(kamr_ctx* ctx, const double* sdf, const double* flux, const
 int  kamr_download_state(kamr_ctx* ctx, uint32_t mask, double* df, double* sdf, double* flux,
                          double* w, double* prim, double* qf, double* sw, double* mflux);
 
+/* options.  KAMR_OPT_KEEP_SDF (default 0): kamr_step keeps the limited slopes r*sdf on the device and
+ * writes the reference's raw VsData.sdf only for the cells a kernel reads them from; with the option on,
+ * every step also writes the raw sdf of every cell so that kamr_download_state(KAMR_DL_SDF) is valid after
+ * kamr_step (the host needs sdf before a velocity-space adapt event, Velocity_space/AMR.jl:9-21).
+ * kamr_slope always writes both. */
+enum { KAMR_OPT_KEEP_SDF = 1 };
+int  kamr_set_option(kamr_ctx* ctx, int32_t option, int32_t value);
+
 /* the hot path */
 int  kamr_slope(kamr_ctx* ctx);
 int  kamr_flux(kamr_ctx* ctx, double dt);

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libkamr.so")
 FLUX_CAIDVM, FLUX_DVM = 0, 1
 MARCH_CAIDVM, MARCH_CIP, MARCH_EULER = 0, 1, 2
 BC_MAXWELLIAN, BC_SUPERSONIC_INFLOW, BC_UNIFORM_OUTFLOW, BC_INTERPOLATED_OUTFLOW = 0, 1, 2, 3
+OPT_KEEP_SDF = 1
 DL_DF, DL_SDF, DL_FLUX, DL_W, DL_PRIM, DL_QF, DL_SW, DL_MFLUX = 1, 2, 4, 8, 16, 32, 64, 128
 
 c_i32p = C.POINTER(C.c_int32)
@@ -84,7 +85,7 @@ EXPORTS = [
     "kamr_create", "kamr_destroy", "kamr_last_error", "kamr_version", "kamr_comm_unique_id", "kamr_comm_init",
     "kamr_upload_topology", "kamr_upload_state", "kamr_upload_aux", "kamr_download_state",
     "kamr_slope", "kamr_flux", "kamr_iterate", "kamr_step", "kamr_exchange_df", "kamr_sync",
-    "kamr_get_stats", "kamr_get_pair_map", "kamr_get_cell_slots", "kamr_profile_enable", "kamr_profile_read",
+    "kamr_get_stats", "kamr_get_pair_map", "kamr_get_cell_slots", "kamr_profile_enable", "kamr_profile_read", "kamr_set_option",
 ]
 
 _lib = None
@@ -122,6 +123,7 @@ def load(path: str | None = None):
     lib.kamr_get_stats.argtypes = [vp, C.POINTER(KamrStats)]
     lib.kamr_get_pair_map.argtypes = [vp, C.c_int32, C.c_int32, c_i32p, C.c_int32]
     lib.kamr_get_cell_slots.argtypes = [vp, C.c_int32, c_i32p, c_i32p, C.c_int32, c_i32p]
+    lib.kamr_set_option.argtypes = [vp, C.c_int32, C.c_int32]
     lib.kamr_profile_enable.argtypes = [vp, C.c_int32]
     lib.kamr_profile_read.argtypes = [vp, C.POINTER(KamrKernelTime), C.c_int32, c_i32p]
     for name in EXPORTS:

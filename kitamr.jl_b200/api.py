@@ -99,6 +99,9 @@ class Context:
         self._ck(self.lib.kamr_get_stats(self.h, C.byref(s)))
         return s
 
+    def set_option(self, option, value):
+        self._ck(self.lib.kamr_set_option(self.h, int(option), int(value)))
+
     def profile(self, on=True):
         self._ck(self.lib.kamr_profile_enable(self.h, int(on)))
 

@@ -1,13 +1,15 @@
 // kamr_kernels.cuh — hand-written sm_100a kernels of the phase-space step.
 //
-//   K-a  slope_kernel        Flux/Slope.jl:29-116,278-452 (per-level sweep, limiter, transverse projection)
-//        flux_kernel         Flux/Flux.jl:94-424 + Flux/CAIDVM.jl:4-141 as an atomic-free cell-centric gather
+//   K-a  slope_kernel        Flux/Slope.jl:29-116,278-452 (dependency-wave sweep, minmod, transverse projection)
+//        phase_kernel<FLUX>  Flux/Flux.jl:94-424 + Flux/CAIDVM.jl:4-141 as an atomic-free cell-centric gather
 //   K-b  block_reduce / macro_slope_kernel   Theory/Math.jl:757-762, Slope.jl:1022-1036
-//   K-c  update_kernel       Theory/Iterate.jl:96-162 (CAIDVM_Marching, Euler)
-//        step_kernel         flux + update fused, convected f kept in shared memory
+//   K-c  phase_kernel<UPDATE>  Theory/Iterate.jl:96-130 (CAIDVM_Marching); euler_update_kernel :131-162
+//        phase_kernel<FUSED>   flux + update fused: the face flux of a cell never leaves the SM
 //   K-e  copy_segments       Parallel/Ghost.jl:757-808 (mirror pack / ghost unpack)
 //
-// All arithmetic is fp64; no tensor cores (stencil + segmented reduction, HBM/fp64-pipe bound).
+// All arithmetic is fp64; no tensor cores (stencil + segmented reduction, HBM / fp64-pipe bound).
+// One CTA owns one physical cell; the velocity points of the cell are the contiguous inner dimension
+// (planes of `np` doubles), so every global access of a warp is a run of 32 consecutive doubles.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -72,10 +74,41 @@ __device__ __forceinline__ double c2_of(const double* v, const double* prim) {
     for (int d = 0; d < D; ++d) { const double c = v[d] - prim[1 + d]; c2 += c * c; }
     return c2;
 }
+// exp(x) for x <= 0 (every exponent on this path is -lambda*c^2): Cody-Waite reduction x = n ln2 + r,
+// |r| <= ln2/2, degree-13 Taylor polynomial (truncation 4e-18), exponent-field scaling.  <= 1 ulp like
+// libdevice exp, without its overflow / NaN / large-argument paths.  Results below 2^-1022 go through a
+// two-step scaling so they denormalise gradually.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double MAGIC = 6755399441055744.0;  // 2^52 + 2^51: adding it rounds to nearest integer
+    double t = fma(x, 1.4426950408889634074, MAGIC);
+    const int n = __double2loint(t);
+    t -= MAGIC;
+    double r = fma(t, -6.93147180369123816490e-01, x);
+    r = fma(t, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    if (n >= -1021) return p * __hiloint2double((n + 1023) << 20, 0);
+    if (n < -1100) return 0.0;
+    const int h = n / 2;
+    return (p * __hiloint2double((h + 1023) << 20, 0)) * __hiloint2double((n - h + 1023) << 20, 0);
+}
+
 // discrete_maxwell (2D2F.jl:14-21, 3D1F.jl:15-23)
 template <int D, int K>
 __device__ __forceinline__ void maxwell(const double* v, const double* prim, double coef, double Kin, double* out) {
-    const double h = coef * exp(-prim[D + 1] * c2_of<D>(v, prim));
+    const double h = coef * exp_nonpos(-prim[D + 1] * c2_of<D>(v, prim));
     out[0] = h;
     if (K > 1) out[1] = h * Kin / (2.0 * prim[D + 1]);
 }
@@ -95,7 +128,7 @@ __device__ __forceinline__ void shakhov(const double* v, const double* F, const 
         out[0] = c0 * (2 * lam * c2 - 5) * F[0];
     }
 }
-// add wt * psi(v) * m to the D+2 moment accumulators (micro_to_macro, 2D2F.jl:119, 3D1F.jl:109);
+// add scale * psi(v) * m to the D+2 moment accumulators (micro_to_macro, 2D2F.jl:119, 3D1F.jl:109);
 // the energy slot accumulates the un-halved sum, callers multiply by 0.5 once at the end.
 template <int D, int K>
 __device__ __forceinline__ void add_moments(double* acc, double scale, const double* v, const double* m) {
@@ -107,166 +140,141 @@ __device__ __forceinline__ void add_moments(double* acc, double scale, const dou
     acc[D + 1] += v2 * h + ((K > 1) ? scale * m[1] : 0.0);
 }
 
+// register-resident component select (a runtime index into a local array would go to local memory)
+template <int D>
+__device__ __forceinline__ double pick(const double* a, int d) {
+    if (D == 2) return d == 0 ? a[0] : a[1];
+    return d == 0 ? a[0] : (d == 1 ? a[1] : a[2]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-cell accessors
 template <int D, int K>
 struct CellPtr {
     const double* f;      // df planes
-    const double* s;      // sdf planes
+    const double* s;      // sdf planes (raw slopes, reference semantics)
+    const double* sl;     // limited slopes r*sdf (device-internal, see slope_kernel)
     const double* v;      // midpoint planes
     const double* wt;
     const int8_t* lev;
     int np;
     __device__ __forceinline__ CellPtr(const DevView& g, const CellInfo& c)
-        : f(g.df + c.doff * K), s(g.sdf + c.doff * K * D), v(g.v_mid + c.goff * D), wt(g.v_weight + c.goff),
+        : f(g.df + c.doff * K), s(g.sdf + c.doff * K * D), sl(g.sdl + c.doff * K * D), v(g.v_mid + c.goff * D),
+          wt(g.v_weight + c.goff),
           lev(g.v_level + c.goff), np(c.np) {}
 };
 
-// limiter factor of positivity_preserving_reconstruct (CAIDVM.jl:134-139)
-__device__ __forceinline__ double limiter(double f, double s_abs) {
-    return fmin(fabs((f - EPS_MACH) / (0.5 * s_abs + EPS_KIT)), 1.);
+// dx = x_face - v*dt - x_cell evaluated in the reference's order without FMA contraction (CAIDVM.jl:108-109):
+// face and cell midpoints are O(domain) while dx is O(cell size), so the rounding of the intermediate
+// differences is what the result inherits; keeping the order keeps the bits.
+__device__ __forceinline__ double face_dx(double fmid, double vdt, double mid) {
+    return __dsub_rn(__dsub_rn(fmid, vdt), mid);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Flux gathered by point i of cell `ci` from all of its face slots.
-//   fl[k]   += sum_slots area * micro      (update_micro_flux!, Flux.jl:151-344, gather form)
-//   mac[m]  += sum_slots area * <psi micro> restricted to what this point contributes
-//              (calc_flux fw, CAIDVM.jl:119; update_macro_flux!, Flux.jl:116-136)
+// limiter factor of positivity_preserving_reconstruct (CAIDVM.jl:134-139):
+// min(|(f - eps())/(0.5 s_abs + EPS)|, 1).  The denominator is positive, so the quotient only has to be
+// formed when the limiter is active (|f - eps()| < denominator); otherwise the min is exactly 1.
+__device__ __forceinline__ double limiter(double f, double s_abs) {
+    const double a = fabs(f - EPS_MACH), b = 0.5 * s_abs + EPS_KIT;
+    return (a >= b) ? 1.0 : a / b;
+}
+
+// One point of a pair-mapped (mismatched velocity grids) neighbour-upwind contribution:
+// update_micro_flux!, Flux.jl:151-344 in gather form.
+//   fl[k]  += area * micro (mean over covering finer points / injection from the coarser point)
+//   mac[m] += area * w_j psi(v_j) micro_j      (the neighbour's share of fw, CAIDVM.jl:119)
 template <int D, int K>
-__device__ __forceinline__ void point_flux(const DevView& g, const GasPar& gas, const CellInfo& ci, const Slot* slots,
-                                           int ns, const double* rho_w, int i, double dt, double* fl, double* mac) {
-    const CellPtr<D, K> own(g, ci);
-    double v[D], f[K], s[K][D], r[K];
-#pragma unroll
-    for (int t = 0; t < D; ++t) v[t] = own.v[t * own.np + i];
-    const double wt = own.wt[i];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        f[k] = own.f[k * own.np + i];
-        double s_abs = 0.0;
+__device__ __forceinline__ void pair_flux(const DevView& g, const Slot& sl, double wt, int li, int i, double dt,
+                                          double* fl, double* mac) {
+    const double* nf = g.df + sl.nbr_doff * K;
+    const double* nsl = g.sdl + sl.nbr_doff * K * D;
+    const double* nv = g.v_mid + sl.nbr_goff * D;
+    const double* nwt = g.v_weight + sl.nbr_goff;
+    const int8_t* nlev = g.v_level + sl.nbr_goff;
+    const int np = sl.nbr_np;
+    const int* st = g.pm_start + sl.rel_off;
+    const int j0 = st[i];
+    const int cnt = max(1, st[i + 1] - j0);
+    const double A = sl.area;
+    for (int j = j0; j < j0 + cnt; ++j) {
+        double vj[D], dx[D], m[K];
 #pragma unroll
         for (int t = 0; t < D; ++t) {
-            s[k][t] = own.s[(t * K + k) * own.np + i];
-            s_abs += ci.ds[t] * fabs(s[k][t]);
+            vj[t] = nv[t * np + j];
+            dx[t] = face_dx(sl.fmid[t], __dmul_rn(vj[t], dt), sl.nbr_mid[t]);
         }
-        r[k] = limiter(f[k], s_abs);
-    }
-    for (int q = 0; q < ns; ++q) {
-        const Slot& sl = slots[q];
-        const int dir = sl.dir;
-        const double vn = v[dir];
-        const double x = sl.rot * vn;
-        const bool own_up = sl.is_here ? (x <= 0.) : (x > 0.);
-        const double A = sl.area;
-        double m[K];
-        if (sl.kind <= SLOT_NBR_SOLID) {
-            if (own_up) {
-                double dx[D];
-#pragma unroll
-                for (int t = 0; t < D; ++t) dx[t] = sl.fmid[t] - v[t] * dt - sl.own_mid[t];
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    double s_dx = 0.0;
-#pragma unroll
-                    for (int t = 0; t < D; ++t) s_dx += dx[t] * s[k][t];
-                    m[k] = (sl.kind == SLOT_INNER) ? (f[k] + r[k] * s_dx) * vn : (f[k] + s_dx) * vn;
-                    fl[k] += A * m[k];
-                }
-                add_moments<D, K>(mac, A * wt, v, m);
-            } else {
-                const CellInfo& cn = g.cells[sl.nbr];
-                const CellPtr<D, K> nb(g, cn);
-                int j0 = i, cnt = 1;
-                if (sl.rel >= 0) {
-                    const int* st = g.pm_start + g.rel_off[sl.rel];
-                    j0 = st[i];
-                    cnt = max(1, st[i + 1] - j0);
-                }
-                const int li = own.lev[i];
-                for (int j = j0; j < j0 + cnt; ++j) {
-                    double vj[D];
-                    if (sl.rel >= 0) {
-#pragma unroll
-                        for (int t = 0; t < D; ++t) vj[t] = nb.v[t * nb.np + j];
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < D; ++t) vj[t] = v[t];
-                    }
-                    const double vnj = vj[dir];
-                    double dx[D];
-#pragma unroll
-                    for (int t = 0; t < D; ++t) dx[t] = sl.fmid[t] - vj[t] * dt - sl.nbr_mid[t];
-                    double scale = 1.0, wq = wt;
-                    if (cnt > 1) {
-                        scale = 1.0 / (double)(1 << (D * (nb.lev[j] - li)));
-                        wq = nb.wt[j];
-                    }
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const double fj = nb.f[k * nb.np + j];
-                        if (sl.kind == SLOT_INNER) {
-                            double s_abs = 0.0, s_dx = 0.0;
-#pragma unroll
-                            for (int t = 0; t < D; ++t) {
-                                const double sj = nb.s[(t * K + k) * nb.np + j];
-                                s_abs += cn.ds[t] * fabs(sj);
-                                s_dx += dx[t] * sj;
-                            }
-                            m[k] = (fj + limiter(fj, s_abs) * s_dx) * vnj;
-                        } else {
-                            m[k] = fj * vnj;
-                        }
-                        fl[k] += (A * m[k]) * scale;
-                    }
-                    add_moments<D, K>(mac, A * wq, vj, m);
-                }
-            }
-        } else {
-            // domain faces (calc_domain_flux, CAIDVM.jl:4-97); own_up == heavi (outgoing half)
-            double dx[D];
-#pragma unroll
-            for (int t = 0; t < D; ++t) dx[t] = sl.fmid[t] - v[t] * dt - ci.mid[t];
-            if (sl.kind == SLOT_BC_UNIFORM) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) m[k] = f[k] * vn;
-            } else if (own_up) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    double s_dx = 0.0;
-#pragma unroll
-                    for (int t = 0; t < D; ++t) s_dx += dx[t] * s[k][t];
-                    m[k] = (f[k] + s_dx) * vn;
-                }
-            } else if (sl.kind == SLOT_BC_INTERP) {
-                double tmid[D], ndx[D];
-#pragma unroll
-                for (int t = 0; t < D; ++t) {
-                    tmid[t] = 2.0 * sl.fmid[t] - ci.mid[t];
-                    ndx[t] = sl.fmid[t] - v[t] * dt - tmid[t];
-                }
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const double tdf = f[k] + (tmid[dir] - ci.mid[dir]) * s[k][dir];
-                    double s_dx = 0.0;
-#pragma unroll
-                    for (int t = 0; t < D; ++t) s_dx += ndx[t] * s[k][t];
-                    m[k] = (tdf + s_dx) * vn;
-                }
-            } else {
-                double bc[D + 2];
-#pragma unroll
-                for (int t = 0; t < D + 2; ++t) bc[t] = sl.bc[t];
-                if (sl.kind == SLOT_BC_MAXWELL) bc[0] = rho_w[q];
-                double F[K];
-                maxwell<D, K>(v, bc, maxwell_coef<D>(bc), gas.K, F);
-#pragma unroll
-                for (int k = 0; k < K; ++k) m[k] = F[k] * vn;
-            }
-#pragma unroll
-            for (int k = 0; k < K; ++k) fl[k] += A * m[k];
-            add_moments<D, K>(mac, A * wt, v, m);
+        const double vnj = pick<D>(vj, sl.dir);
+        double scale = 1.0, wq = wt;
+        if (cnt > 1) {
+            scale = 1.0 / (double)(1 << (D * (nlev[j] - li)));
+            wq = nwt[j];
         }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double fj = nf[k * np + j];
+            if (sl.kind == SLOT_INNER) {
+                double s_dx = 0.0;
+#pragma unroll
+                for (int t = 0; t < D; ++t) s_dx += dx[t] * nsl[(t * K + k) * np + j];
+                m[k] = (fj + s_dx) * vnj;
+            } else {
+                m[k] = fj * vnj;
+            }
+            fl[k] += (A * m[k]) * scale;
+        }
+        add_moments<D, K>(mac, A * wq, vj, m);
     }
+}
+
+// domain faces (calc_domain_flux, CAIDVM.jl:4-97); own_up == heavi (outgoing half)
+template <int D, int K>
+__device__ __forceinline__ void domain_flux(const Slot& sl, const CellInfo& ci, const GasPar& gas, const double* v,
+                                            const double* f, const double* s /*[K][D]*/, double rho_w, bool own_up,
+                                            double dt, double* fl) {
+    const int dir = sl.dir;
+    const double vn = pick<D>(v, dir);
+    double m[K], dx[D];
+#pragma unroll
+    for (int t = 0; t < D; ++t) dx[t] = face_dx(sl.fmid[t], __dmul_rn(v[t], dt), ci.mid[t]);
+    if (sl.kind == SLOT_BC_UNIFORM) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) m[k] = f[k] * vn;
+    } else if (own_up) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double s_dx = 0.0;
+#pragma unroll
+            for (int t = 0; t < D; ++t) s_dx += dx[t] * s[k * D + t];
+            m[k] = (f[k] + s_dx) * vn;
+        }
+    } else if (sl.kind == SLOT_BC_INTERP) {
+        double tmid[D], ndx[D];
+#pragma unroll
+        for (int t = 0; t < D; ++t) {
+            tmid[t] = __dsub_rn(2.0 * sl.fmid[t], ci.mid[t]);
+            ndx[t] = face_dx(sl.fmid[t], __dmul_rn(v[t], dt), tmid[t]);
+        }
+        const double dmid = pick<D>(tmid, dir) - pick<D>(ci.mid, dir);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double tdf = f[k] + dmid * pick<D>(s + k * D, dir);
+            double s_dx = 0.0;
+#pragma unroll
+            for (int t = 0; t < D; ++t) s_dx += ndx[t] * s[k * D + t];
+            m[k] = (tdf + s_dx) * vn;
+        }
+    } else {
+        double bc[D + 2];
+#pragma unroll
+        for (int t = 0; t < D + 2; ++t) bc[t] = sl.bc[t];
+        if (sl.kind == SLOT_BC_MAXWELL) bc[0] = rho_w;
+        double F[K];
+        maxwell<D, K>(v, bc, maxwell_coef<D>(bc), gas.K, F);
+#pragma unroll
+        for (int k = 0; k < K; ++k) m[k] = F[k] * vn;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) fl[k] += sl.area * m[k];
 }
 
 // Wall density of Maxwellian domain faces: rho_w = -SF/SG (calc_ρw, Theory/Math.jl:251-282).
@@ -283,12 +291,12 @@ __device__ __forceinline__ void wall_density(const DevView& g, const CellInfo& c
             double v[D];
 #pragma unroll
             for (int t = 0; t < D; ++t) v[t] = own.v[t * own.np + i];
-            const double vn = v[sl.dir], wt = own.wt[i];
+            const double vn = pick<D>(v, sl.dir), wt = own.wt[i];
             if (sl.rot * vn <= 0.) {
                 double s_dx = 0.0;
 #pragma unroll
                 for (int t = 0; t < D; ++t)
-                    s_dx += (sl.fmid[t] - v[t] * dt - ci.mid[t]) * own.s[(t * K + 0) * own.np + i];
+                    s_dx += face_dx(sl.fmid[t], __dmul_rn(v[t], dt), ci.mid[t]) * own.s[(t * K + 0) * own.np + i];
                 acc[0] += wt * vn * (own.f[i] + s_dx);
             } else {
                 acc[1] += wt * vn * exp(-sl.bc[D + 1] * c2_of<D>(v, sl.bc));
@@ -304,291 +312,263 @@ __device__ __forceinline__ void wall_density(const DevView& g, const CellInfo& c
     }
 }
 
-__device__ __forceinline__ void load_slots(const DevView& g, const CellInfo& ci, Slot* sh_slots) {
-    // cooperative copy of the cell's slot records into shared memory (ints)
-    const int ns = ci.slot_end - ci.slot_begin;
-    const int nwords = ns * (int)(sizeof(Slot) / sizeof(int));
-    const int* src = reinterpret_cast<const int*>(g.slots + ci.slot_begin);
-    int* dst = reinterpret_cast<int*>(sh_slots);
+// cooperative copy of `nwords` 4-byte words into shared memory
+__device__ __forceinline__ void copy_words(const void* src_, void* dst_, int nwords) {
+    const int* src = reinterpret_cast<const int*>(src_);
+    int* dst = reinterpret_cast<int*>(dst_);
     for (int t = threadIdx.x; t < nwords; t += blockDim.x) dst[t] = src[t];
 }
 
 // ------------------------------------------------------------------------------------------------
-// flux!(p4est, ka): vs_data.flux += sum over faces, ps_data.flux += macro flux (cell-centric gather)
-template <int D, int K>
-__global__ void __launch_bounds__(256) flux_kernel(DevView g, GasPar gas, const int* __restrict__ cell_list, double dt) {
-    __shared__ Slot sh_slots[MAX_SLOTS];
-    __shared__ double rho_w[MAX_SLOTS];
-    __shared__ double red[(D + 2) * 32];
-    __shared__ CellInfo ci;
-    const int c = cell_list[blockIdx.x];
-    if (threadIdx.x == 0) ci = g.cells[c];
-    __syncthreads();
-    load_slots(g, ci, sh_slots);
-    __syncthreads();
-    const int ns = ci.slot_end - ci.slot_begin;
-    wall_density<D, K>(g, ci, sh_slots, ns, dt, rho_w, red);
-    double mac[D + 2];
-#pragma unroll
-    for (int q = 0; q < D + 2; ++q) mac[q] = 0.0;
-    double* flux = g.flux + ci.doff * K;
-    for (int i = threadIdx.x; i < ci.n; i += blockDim.x) {
-        double fl[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) fl[k] = 0.0;
-        point_flux<D, K>(g, gas, ci, sh_slots, ns, rho_w, i, dt, fl, mac);
-#pragma unroll
-        for (int k = 0; k < K; ++k) flux[k * ci.np + i] += fl[k];
-    }
-    if (gas.flux_type == 0) {
-        block_reduce<D + 2>(mac, red);
-        if (threadIdx.x == 0) {
-            mac[D + 1] *= 0.5;
-#pragma unroll
-            for (int q = 0; q < D + 2; ++q) g.mflux[(size_t)c * (D + 2) + q] += mac[q];
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// one relaxation update of a cell (Theory/Iterate.jl:96-162), f staged in `fs` (shared or global),
-// plane stride `fstride`.  On entry fs holds f^n (Euler) or the convected f (CAIDVM) ...
-// The three phases are separated by two block reductions (moments, heat flux).
-template <int D, int K>
-struct UpdateShared {
-    double prim_c[D + 2], prim[D + 2], qf[D], tau, coef_c, coef;
+// The hot half of the face gather: fluid/fluid slots.  The own-upwind half needs the cell's own data only;
+// the neighbour-upwind half is taken here when the two velocity grids are identical (the neighbour's point
+// i IS this point).  Both use the LIMITED slopes r*sdf the slope kernel left in g.sdl, so the loop has no
+// division: micro = (f + dx . (r s)) v_n  (positivity_preserving_reconstruct, CAIDVM.jl:127-141).
+// Slots arrive sorted by direction, so v_n is a register, not a select.
+template <int D>
+struct HotSlot {
+    const double* nf;     // neighbour df block
+    const double* nsl;    // neighbour limited-slope block
+    int np, flags;        // flags bit0: this cell is the face's here side; bit1: neighbour half handled here
+    double rot, area;
+    double fmid[D], own_mid[D], nbr_mid[D];
 };
 
-// CAIDVM_Marching phases 2+3 and the bookkeeping, given f_conv in fs and the two moment sets reduced.
 template <int D, int K>
-__device__ __forceinline__ void relax_phases(const DevView& g, const GasPar& gas, const CellInfo& ci, int c,
-                                             double* fs, int fstride, double* fout, double dt, const double* w_new,
-                                             const double* w0, double* red, UpdateShared<D, K>* us,
-                                             int want_residual) {
-    const CellPtr<D, K> own(g, ci);
-    if (threadIdx.x == 0) {
-        get_prim<D>(w_new, gas.gamma, us->prim_c);
-        get_prim<D>(w0, gas.gamma, us->prim);
-        us->tau = gas.mu_ref * 2.0 * pow(us->prim_c[D + 1], 1 - gas.omega) / us->prim_c[0];  // Gas/Model.jl:14
-        us->coef_c = maxwell_coef<D>(us->prim_c);
-        us->coef = maxwell_coef<D>(us->prim);
-    }
-    __syncthreads();
-    // phase 2: conservation correction f += M[prim_c] - M[prim]; heat flux of the corrected f about prim_c
-    double q[D];
+__device__ __forceinline__ void hot_flux(const HotSlot<D>* hot, const int* hot_end, int i, double dt,
+                                         const double* v, const double* f, const double* s /*[K][D] limited*/,
+                                         double* fl) {
+    double vdt[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) q[d] = 0.0;
-    for (int i = threadIdx.x; i < ci.n; i += blockDim.x) {
-        double v[D], Fc[K], F[K], f[K];
+    for (int t = 0; t < D; ++t) vdt[t] = __dmul_rn(v[t], dt);
+    int q = 0;
 #pragma unroll
-        for (int t = 0; t < D; ++t) v[t] = own.v[t * own.np + i];
-        maxwell<D, K>(v, us->prim_c, us->coef_c, gas.K, Fc);
-        maxwell<D, K>(v, us->prim, us->coef, gas.K, F);
+    for (int d = 0; d < D; ++d) {
+        const double vn = v[d];
+        const int qe = hot_end[d];
+        for (; q < qe; ++q) {
+            const HotSlot<D>& h = hot[q];
+            const double x = h.rot * vn;
+            const bool own_up = (h.flags & 1) ? (x <= 0.) : (x > 0.);
+            const double Avn = h.area * vn;
+            if (own_up) {
+                double dx[D];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            f[k] = fs[k * fstride + i] + (Fc[k] - F[k]);
-            fs[k * fstride + i] = f[k];
-        }
-        const double wt = own.wt[i];
-        const double c2 = c2_of<D>(v, us->prim_c);
+                for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.own_mid[t]);
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const double cd = v[d] - us->prim_c[1 + d];
-            q[d] += wt * cd * c2 * f[0] + ((K > 1) ? wt * cd * f[1] : 0.0);
-        }
-    }
-    block_reduce<D>(q, red);
-    if (threadIdx.x == 0) {
+                for (int k = 0; k < K; ++k) {
+                    double val = f[k];
 #pragma unroll
-        for (int d = 0; d < D; ++d) { us->qf[d] = 0.5 * q[d]; g.qf[(size_t)c * D + d] = 0.5 * q[d]; }
-    }
-    __syncthreads();
-    // phase 3: f = f*tau/(tau+dt) + dt/(tau+dt)*(M_c + S[M_c])
-    const double tau = us->tau;
-    const double a = tau / (tau + dt), b = dt / (tau + dt);
-    for (int i = threadIdx.x; i < ci.n; i += blockDim.x) {
-        double v[D], Fc[K], Fp[K];
-#pragma unroll
-        for (int t = 0; t < D; ++t) v[t] = own.v[t * own.np + i];
-        maxwell<D, K>(v, us->prim_c, us->coef_c, gas.K, Fc);
-        shakhov<D, K>(v, Fc, us->prim_c, us->qf, gas.Pr, gas.K, Fp);
-#pragma unroll
-        for (int k = 0; k < K; ++k) fout[k * ci.np + i] = fs[k * fstride + i] * a + b * (Fc[k] + Fp[k]);
-    }
-    if (threadIdx.x == 0) {
-        double* prim_old = g.prim + (size_t)c * (D + 2);
-        if (want_residual) {  // residual_check!, Solver/Finalize.jl:5-11
-#pragma unroll
-            for (int m = 0; m < D + 2; ++m) {
-                const double dd = us->prim_c[m] - prim_old[m];
-                g.res_cell[(size_t)c * 2 * (D + 2) + m] = dd * dd;
-                g.res_cell[(size_t)c * 2 * (D + 2) + (D + 2) + m] = fabs(us->prim_c[m]);
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < D + 2; ++m) {
-            g.w[(size_t)c * (D + 2) + m] = w_new[m];
-            prim_old[m] = us->prim_c[m];
-            g.mflux[(size_t)c * (D + 2) + m] = 0.0;
-        }
-    }
-}
-
-// iterate!(CAIDVM_Marching | Euler).  STAGE = 1: convected f staged in dynamic shared memory;
-// STAGE = 0: staged in the output array itself (cells too large for shared memory).
-template <int D, int K, int STAGE>
-__global__ void __launch_bounds__(256) update_kernel(DevView g, GasPar gas, const int* __restrict__ cell_list,
-                                                     const double* __restrict__ fin_base, double* fout_base, double dt,
-                                                     int want_residual) {
-    extern __shared__ double dyn[];
-    __shared__ double red[2 * (D + 2) * 32];
-    __shared__ CellInfo ci;
-    __shared__ UpdateShared<D, K> us;
-    __shared__ double w_new[D + 2], w0s[D + 2];
-    const int c = cell_list[blockIdx.x];
-    if (threadIdx.x == 0) ci = g.cells[c];
-    __syncthreads();
-    const CellPtr<D, K> own(g, ci);
-    const double* fin = fin_base + ci.doff * K;
-    double* fout = fout_base + ci.doff * K;
-    double* vflux = g.flux + ci.doff * K;
-    double* fs = STAGE ? dyn : fout;
-    const int fstride = STAGE ? ci.n : ci.np;
-    const double dtv = dt / ci.vol;
-    if (gas.marching == 0) {
-        // phase 1: convection f += dt/vol*flux ; moments of the convected f
-        double w0[D + 2];
-#pragma unroll
-        for (int m = 0; m < D + 2; ++m) w0[m] = 0.0;
-        for (int i = threadIdx.x; i < ci.n; i += blockDim.x) {
-            double v[D], f[K];
-#pragma unroll
-            for (int t = 0; t < D; ++t) v[t] = own.v[t * own.np + i];
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                f[k] = fin[k * ci.np + i] + dtv * vflux[k * ci.np + i];
-                fs[k * fstride + i] = f[k];
-                vflux[k * ci.np + i] = 0.0;
-            }
-            add_moments<D, K>(w0, own.wt[i], v, f);
-        }
-        block_reduce<D + 2>(w0, red);
-        if (threadIdx.x == 0) {
-            w0[D + 1] *= 0.5;
-#pragma unroll
-            for (int m = 0; m < D + 2; ++m) {
-                w0s[m] = w0[m];
-                w_new[m] = g.w[(size_t)c * (D + 2) + m] + g.mflux[(size_t)c * (D + 2) + m] * dt / ci.vol;
-            }
-        }
-        __syncthreads();
-        relax_phases<D, K>(g, gas, ci, c, fs, fstride, fout, dt, w_new, w0s, red, &us, want_residual);
-    } else {
-        // Euler, Iterate.jl:131-162: qf from the pre-convection f, single relaxation with prim(w^{n+1})
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int m = 0; m < D + 2; ++m)
-                w_new[m] = g.w[(size_t)c * (D + 2) + m] + g.mflux[(size_t)c * (D + 2) + m] * dt / ci.vol;
-            get_prim<D>(w_new, gas.gamma, us.prim_c);
-            us.tau = gas.mu_ref * 2.0 * pow(us.prim_c[D + 1], 1 - gas.omega) / us.prim_c[0];
-            us.coef_c = maxwell_coef<D>(us.prim_c);
-        }
-        __syncthreads();
-        double q[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) q[d] = 0.0;
-        for (int i = threadIdx.x; i < ci.n; i += blockDim.x) {
-            double v[D];
-#pragma unroll
-            for (int t = 0; t < D; ++t) v[t] = own.v[t * own.np + i];
-            const double wt = own.wt[i];
-            const double c2 = c2_of<D>(v, us.prim_c);
-            const double f0 = fin[i];
-            const double f1 = (K > 1) ? fin[ci.np + i] : 0.0;
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const double cd = v[d] - us.prim_c[1 + d];
-                q[d] += wt * cd * c2 * f0 + ((K > 1) ? wt * cd * f1 : 0.0);
-            }
-        }
-        block_reduce<D>(q, red);
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) { us.qf[d] = 0.5 * q[d]; g.qf[(size_t)c * D + d] = 0.5 * q[d]; }
-        }
-        __syncthreads();
-        const double tau = us.tau;
-        const double a = tau / (tau + dt), b = dt / (tau + dt);
-        for (int i = threadIdx.x; i < ci.n; i += blockDim.x) {
-            double v[D], F[K], Fp[K];
-#pragma unroll
-            for (int t = 0; t < D; ++t) v[t] = own.v[t * own.np + i];
-            maxwell<D, K>(v, us.prim_c, us.coef_c, gas.K, F);
-            shakhov<D, K>(v, F, us.prim_c, us.qf, gas.Pr, gas.K, Fp);
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                fout[k * ci.np + i] = (fin[k * ci.np + i] + dtv * vflux[k * ci.np + i]) * a + b * (F[k] + Fp[k]);
-                vflux[k * ci.np + i] = 0.0;
-            }
-        }
-        if (threadIdx.x == 0) {
-            double* prim_old = g.prim + (size_t)c * (D + 2);
-            if (want_residual) {
-#pragma unroll
-                for (int m = 0; m < D + 2; ++m) {
-                    const double dd = us.prim_c[m] - prim_old[m];
-                    g.res_cell[(size_t)c * 2 * (D + 2) + m] = dd * dd;
-                    g.res_cell[(size_t)c * 2 * (D + 2) + (D + 2) + m] = fabs(us.prim_c[m]);
+                    for (int t = 0; t < D; ++t) val += dx[t] * s[k * D + t];
+                    fl[k] += val * Avn;
                 }
-            }
+            } else if (h.flags & 2) {
+                const double* __restrict__ nf = h.nf + i;
+                const double* __restrict__ nsl = h.nsl + i;
+                const int np = h.np;
+                double dx[D];
 #pragma unroll
-            for (int m = 0; m < D + 2; ++m) {
-                g.w[(size_t)c * (D + 2) + m] = w_new[m];
-                prim_old[m] = us.prim_c[m];
-                g.mflux[(size_t)c * (D + 2) + m] = 0.0;
+                for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.nbr_mid[t]);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    double val = nf[k * np];
+#pragma unroll
+                    for (int t = 0; t < D; ++t) val += dx[t] * nsl[(t * K + k) * np];
+                    fl[k] += val * Avn;
+                }
             }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused flux! + iterate!(CAIDVM_Marching): the face flux of a cell never leaves the SM — the
-// convected f is staged in shared memory, the result goes to the second df buffer.
+// phase_kernel: the per-cell pipeline
+//   MODE_FUSED   flux! + iterate!(CAIDVM_Marching): gather face fluxes, convect, moments, relax; reads
+//                g.df (+ neighbours), writes g.df_new.  The vs flux never exists in memory.
+//   MODE_FLUX    flux!(p4est, ka): vs_data.flux += gathered flux, ps_data.flux += macro flux
+//   MODE_UPDATE  iterate!(CAIDVM_Marching) from stored vs_data.flux / ps_data.flux, in place
+// STAGE_SMEM: the convected f (K planes) and the h-component of M[prim_c] (1 plane) are staged in dynamic
+// shared memory; otherwise (cells larger than shared memory) in the output array, M[prim_c] recomputed.
+//
+// Pass A gathers the hot slots for every point; pass B (cells on the domain edge or with a neighbour on
+// a different velocity grid only) adds the remaining contributions.  Splitting them keeps the hot loop
+// free of the rare paths' registers.
+enum PhaseMode : int { MODE_FUSED = 0, MODE_FLUX = 1, MODE_UPDATE = 2 };
+
 template <int D, int K>
-__global__ void __launch_bounds__(256) step_kernel(DevView g, GasPar gas, const int* __restrict__ cell_list, double dt,
-                                                   int want_residual) {
-    extern __shared__ double dyn[];  // n*K convected f
-    __shared__ Slot sh_slots[MAX_SLOTS];
-    __shared__ double rho_w[MAX_SLOTS];
+struct UpdateShared {
+    double prim_c[D + 2], prim[D + 2], qf[D], tau, coef_c, coef, cb_c, cb;
+};
+
+// M[prim] at one point with the per-cell constants hoisted: h = coef e^{-lambda c^2}, b = h K/(2 lambda)
+template <int D, int K>
+__device__ __forceinline__ void maxwell_c(const double* v, const double* prim, double coef, double cb, double* out) {
+    const double h = coef * exp_nonpos(-prim[D + 1] * c2_of<D>(v, prim));
+    out[0] = h;
+    if (K > 1) out[1] = h * cb;
+}
+
+template <int D, int K, int MODE, bool STAGE_SMEM, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+    phase_kernel(DevView g, GasPar gas, const int* __restrict__ cell_list, double dt, int want_residual) {
+    extern __shared__ double dyn[];
+    constexpr int NSLOT = (MODE == MODE_UPDATE) ? 1 : MaxSlots<D>::value;
+    __shared__ Slot sh_slots[NSLOT];
+    __shared__ HotSlot<D> hot[NSLOT];
+    __shared__ int rare[NSLOT];
+    __shared__ int hot_end[D + 1];  // [d]: end of direction d's hot slots; [D]: number of rare slots
+    __shared__ double rho_w[NSLOT];
     __shared__ double red[2 * (D + 2) * 32];
     __shared__ CellInfo ci;
     __shared__ UpdateShared<D, K> us;
     __shared__ double w_new[D + 2], w0s[D + 2];
     const int c = cell_list[blockIdx.x];
-    if (threadIdx.x == 0) ci = g.cells[c];
+    copy_words(g.cells + c, &ci, (int)(sizeof(CellInfo) / sizeof(int)));
     __syncthreads();
-    load_slots(g, ci, sh_slots);
-    __syncthreads();
-    const int ns = ci.slot_end - ci.slot_begin;
-    wall_density<D, K>(g, ci, sh_slots, ns, dt, rho_w, red);
+    const int n = ci.n, np = ci.np;
+    const int ns = (MODE == MODE_UPDATE) ? 0 : ci.slot_end - ci.slot_begin;
+    if (MODE != MODE_UPDATE) {
+        copy_words(g.slots + ci.slot_begin, sh_slots, ns * (int)(sizeof(Slot) / sizeof(int)));
+        __syncthreads();
+        if (threadIdx.x == 0) {  // slots are sorted by direction at flatten time
+            int nh = 0, nr = 0, d = 0;
+            for (int q = 0; q < ns; ++q) {
+                const Slot& sl = sh_slots[q];
+                while (d < sl.dir) hot_end[d++] = nh;
+                if (sl.kind == SLOT_INNER) {
+                    HotSlot<D>& h = hot[nh++];
+                    h.nf = g.df + sl.nbr_doff * K;
+                    h.nsl = g.sdl + sl.nbr_doff * (K * D);
+                    h.np = sl.nbr_np;
+                    h.flags = (sl.is_here ? 1 : 0) | (sl.rel_off < 0 ? 2 : 0);
+                    h.rot = sl.rot; h.area = sl.area;
+#pragma unroll
+                    for (int t = 0; t < D; ++t) {
+                        h.fmid[t] = sl.fmid[t]; h.own_mid[t] = sl.own_mid[t]; h.nbr_mid[t] = sl.nbr_mid[t];
+                    }
+                    if (sl.rel_off >= 0) rare[nr++] = q;
+                } else {
+                    rare[nr++] = q;
+                }
+            }
+            while (d < D) hot_end[d++] = nh;
+            hot_end[D] = nr;
+        }
+        __syncthreads();
+        wall_density<D, K>(g, ci, sh_slots, ns, dt, rho_w, red);
+    }
+    const int nrare = (MODE == MODE_UPDATE) ? 0 : hot_end[D];
     const CellPtr<D, K> own(g, ci);
     const double dtv = dt / ci.vol;
+    double* vflux = g.flux + ci.doff * K;
+    double* fout = (MODE == MODE_FUSED ? g.df_new : g.df) + ci.doff * K;
+    double* fs = STAGE_SMEM ? dyn : fout;
+    const int fstride = STAGE_SMEM ? n : np;
+
+    // ---- phase 1: face fluxes, convection, moments
     double acc[2 * (D + 2)];  // [0,D+2): macro flux, [D+2, 2D+4): moments of the convected f
 #pragma unroll
     for (int q = 0; q < 2 * (D + 2); ++q) acc[q] = 0.0;
-    for (int i = threadIdx.x; i < ci.n; i += blockDim.x) {
-        double fl[K], f[K], v[D];
+    for (int i = threadIdx.x; i < n; i += NT) {  // pass A
+        double v[D], f[K], fl[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) fl[k] = 0.0;
-        point_flux<D, K>(g, gas, ci, sh_slots, ns, rho_w, i, dt, fl, acc);
+        for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+        const double wt = own.wt[i];
 #pragma unroll
-        for (int t = 0; t < D; ++t) v[t] = own.v[t * own.np + i];
+        for (int k = 0; k < K; ++k) { f[k] = own.f[k * np + i]; fl[k] = 0.0; }
+        if (MODE != MODE_UPDATE) {
+            double s[K * D];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            f[k] = own.f[k * own.np + i] + dtv * fl[k];
-            dyn[k * ci.n + i] = f[k];
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int t = 0; t < D; ++t) s[k * D + t] = own.sl[(t * K + k) * np + i];
+            hot_flux<D, K>(hot, hot_end, i, dt, v, f, s, fl);
+            add_moments<D, K>(acc, wt, v, fl);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) { fl[k] = vflux[k * np + i]; vflux[k * np + i] = 0.0; }
         }
-        add_moments<D, K>(acc + (D + 2), own.wt[i], v, f);
+        if (MODE == MODE_FLUX) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) vflux[k * np + i] += fl[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                f[k] += dtv * fl[k];
+                fs[k * fstride + i] = f[k];
+            }
+            add_moments<D, K>(acc + (D + 2), wt, v, f);
+        }
+    }
+    if (MODE != MODE_UPDATE && nrare > 0) {  // pass B (block-uniform branch)
+        for (int qq = 0; qq < nrare; ++qq) {
+            const Slot& sl = sh_slots[rare[qq]];
+            const int kind = sl.kind;
+            for (int i = threadIdx.x; i < n; i += NT) {
+                double v[D], fl[K];
+#pragma unroll
+                for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+                const double wt = own.wt[i];
+#pragma unroll
+                for (int k = 0; k < K; ++k) fl[k] = 0.0;
+                const double vn = pick<D>(v, sl.dir);
+                const double x = sl.rot * vn;
+                const bool own_up = sl.is_here ? (x <= 0.) : (x > 0.);
+                if (kind > SLOT_NBR_SOLID || (kind == SLOT_NBR_SOLID && own_up)) {
+                    double f[K], s[K * D];  // raw (unlimited) slopes
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        f[k] = own.f[k * np + i];
+#pragma unroll
+                        for (int t = 0; t < D; ++t) s[k * D + t] = own.s[(t * K + k) * np + i];
+                    }
+                    if (kind > SLOT_NBR_SOLID) {
+                        domain_flux<D, K>(sl, ci, gas, v, f, s, rho_w[rare[qq]], own_up, dt, fl);
+                    } else {  // fluid side of a solid / SolidNeighbor face: unlimited, CAIDVM.jl:110
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            double s_dx = 0.0;
+#pragma unroll
+                            for (int t = 0; t < D; ++t)
+                                s_dx += face_dx(sl.fmid[t], __dmul_rn(v[t], dt), sl.own_mid[t]) * s[k * D + t];
+                            fl[k] += sl.area * ((f[k] + s_dx) * vn);
+                        }
+                    }
+                    add_moments<D, K>(acc, wt, v, fl);
+                } else if (own_up) {
+                    continue;  // own half of a pair-mapped fluid slot was gathered in pass A
+                } else if (sl.rel_off < 0) {  // solid side, identical grids: f_wall v_n, CAIDVM.jl:111
+                    const double* nf = g.df + sl.nbr_doff * K + i;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) fl[k] += sl.area * (nf[k * sl.nbr_np] * vn);
+                    add_moments<D, K>(acc, wt, v, fl);
+                } else {
+                    pair_flux<D, K>(g, sl, wt, own.lev[i], i, dt, fl, acc);
+                }
+                if (MODE == MODE_FLUX) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) vflux[k * np + i] += fl[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        fl[k] *= dtv;
+                        fs[k * fstride + i] += fl[k];
+                    }
+                    add_moments<D, K>(acc + (D + 2), wt, v, fl);
+                }
+            }
+        }
+    }
+    if (MODE == MODE_FLUX) {
+        if (gas.flux_type == 0) {
+            block_reduce<D + 2>(*reinterpret_cast<double(*)[D + 2]>(acc), red);
+            if (threadIdx.x == 0) {
+                acc[D + 1] *= 0.5;
+#pragma unroll
+                for (int q = 0; q < D + 2; ++q) g.mflux[(size_t)c * (D + 2) + q] += acc[q];
+            }
+        }
+        return;
     }
     block_reduce<2 * (D + 2)>(acc, red);
     if (threadIdx.x == 0) {
@@ -596,95 +576,332 @@ __global__ void __launch_bounds__(256) step_kernel(DevView g, GasPar gas, const 
         acc[2 * D + 3] *= 0.5;
 #pragma unroll
         for (int m = 0; m < D + 2; ++m) {
-            const double mf = g.mflux[(size_t)c * (D + 2) + m] + ((gas.flux_type == 0) ? acc[m] : 0.0);
+            double mf = g.mflux[(size_t)c * (D + 2) + m];
+            if (MODE == MODE_FUSED && gas.flux_type == 0) mf += acc[m];
             w_new[m] = g.w[(size_t)c * (D + 2) + m] + mf * dt / ci.vol;
             w0s[m] = acc[D + 2 + m];
         }
+        get_prim<D>(w_new, gas.gamma, us.prim_c);
+        get_prim<D>(w0s, gas.gamma, us.prim);
+        us.tau = gas.mu_ref * 2.0 * pow(us.prim_c[D + 1], 1 - gas.omega) / us.prim_c[0];  // Gas/Model.jl:14
+        us.coef_c = maxwell_coef<D>(us.prim_c);
+        us.coef = maxwell_coef<D>(us.prim);
+        us.cb_c = gas.K / (2.0 * us.prim_c[D + 1]);
+        us.cb = gas.K / (2.0 * us.prim[D + 1]);
     }
     __syncthreads();
-    double* fout = g.df_new + ci.doff * K;
-    relax_phases<D, K>(g, gas, ci, c, dyn, ci.n, fout, dt, w_new, w0s, red, &us, want_residual);
+
+    // ---- phase 2: conservation correction f += M[prim_c] - M[prim]; heat flux of the corrected f about prim_c
+    double prim_c[D + 2];
+#pragma unroll
+    for (int m = 0; m < D + 2; ++m) prim_c[m] = us.prim_c[m];
+    const double coef_c = us.coef_c, cb_c = us.cb_c;
+    double* fch = dyn + (size_t)K * n;  // staged h-component of M[prim_c] (STAGE_SMEM only)
+    {
+        double prim[D + 2];
+#pragma unroll
+        for (int m = 0; m < D + 2; ++m) prim[m] = us.prim[m];
+        const double coef = us.coef, cb = us.cb;
+        double q[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) q[d] = 0.0;
+        for (int i = threadIdx.x; i < n; i += NT) {
+            double v[D], Fc[K], F[K], f[K];
+#pragma unroll
+            for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+            maxwell_c<D, K>(v, prim_c, coef_c, cb_c, Fc);
+            maxwell_c<D, K>(v, prim, coef, cb, F);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                f[k] = fs[k * fstride + i] + (Fc[k] - F[k]);
+                fs[k * fstride + i] = f[k];
+            }
+            if (STAGE_SMEM) fch[i] = Fc[0];
+            // heat_flux (2D2F.jl:68-88, 3D1F.jl:41-72): q_d = 1/2 sum w c_d (c^2 h + b)
+            const double gq = own.wt[i] * (c2_of<D>(v, prim_c) * f[0] + ((K > 1) ? f[1] : 0.0));
+#pragma unroll
+            for (int d = 0; d < D; ++d) q[d] += (v[d] - prim_c[1 + d]) * gq;
+        }
+        block_reduce<D>(q, red);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) { us.qf[d] = 0.5 * q[d]; g.qf[(size_t)c * D + d] = 0.5 * q[d]; }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 3: f = f*tau/(tau+dt) + dt/(tau+dt)*(M_c + S[M_c])
+    {
+        const double tau = us.tau;
+        const double a = tau / (tau + dt), b = dt / (tau + dt);
+        double qf[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) qf[d] = us.qf[d];
+        for (int i = threadIdx.x; i < n; i += NT) {
+            double v[D], Fc[K], Fp[K];
+#pragma unroll
+            for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+            if (STAGE_SMEM) {
+                Fc[0] = fch[i];
+                if (K > 1) Fc[1] = Fc[0] * cb_c;
+            } else {
+                maxwell_c<D, K>(v, prim_c, coef_c, cb_c, Fc);
+            }
+            shakhov<D, K>(v, Fc, prim_c, qf, gas.Pr, gas.K, Fp);
+#pragma unroll
+            for (int k = 0; k < K; ++k) fout[k * np + i] = fs[k * fstride + i] * a + b * (Fc[k] + Fp[k]);
+        }
+    }
+    if (threadIdx.x == 0) {
+        double* prim_old = g.prim + (size_t)c * (D + 2);
+        if (want_residual) {  // residual_check!, Solver/Finalize.jl:5-11
+#pragma unroll
+            for (int m = 0; m < D + 2; ++m) {
+                const double dd = prim_c[m] - prim_old[m];
+                g.res_cell[(size_t)c * 2 * (D + 2) + m] = dd * dd;
+                g.res_cell[(size_t)c * 2 * (D + 2) + (D + 2) + m] = fabs(prim_c[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < D + 2; ++m) {
+            g.w[(size_t)c * (D + 2) + m] = w_new[m];
+            prim_old[m] = prim_c[m];
+            g.mflux[(size_t)c * (D + 2) + m] = 0.0;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// slopes: one block per (cell of the current level); all DIM directions in one pass.
-//   sL = (1/nL) sum_nbr diff(f, P[f_nbr (+ dm . sdf_nbr)]) / dsL   (diff_vs!, Slope.jl:29-64, :278-333)
-//   sdf = minmod(sL, sR) | sL | 0                                    (Slope.jl:90-116, 68-86, 471-472)
-__device__ __forceinline__ double sgn_(double x) { return (double)((x > 0.) - (x < 0.)); }
-__device__ __forceinline__ double minmod(double a, double b) {
-    return 0.5 * (sgn_(a) + sgn_(b)) * fmin(fabs(a), fabs(b));
+// iterate!(Euler), Theory/Iterate.jl:131-162: qf from the pre-convection f, single relaxation with prim(w^{n+1})
+template <int D, int K>
+__global__ void __launch_bounds__(256) euler_update_kernel(DevView g, GasPar gas, const int* __restrict__ cell_list,
+                                                           double dt, int want_residual) {
+    __shared__ double red[D * 32];
+    __shared__ CellInfo ci;
+    __shared__ UpdateShared<D, K> us;
+    __shared__ double w_new[D + 2];
+    const int c = cell_list[blockIdx.x];
+    if (threadIdx.x == 0) ci = g.cells[c];
+    __syncthreads();
+    const CellPtr<D, K> own(g, ci);
+    double* f = g.df + ci.doff * K;
+    double* vflux = g.flux + ci.doff * K;
+    const double dtv = dt / ci.vol;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int m = 0; m < D + 2; ++m)
+            w_new[m] = g.w[(size_t)c * (D + 2) + m] + g.mflux[(size_t)c * (D + 2) + m] * dt / ci.vol;
+        get_prim<D>(w_new, gas.gamma, us.prim_c);
+        us.tau = gas.mu_ref * 2.0 * pow(us.prim_c[D + 1], 1 - gas.omega) / us.prim_c[0];
+        us.coef_c = maxwell_coef<D>(us.prim_c);
+    }
+    __syncthreads();
+    double q[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) q[d] = 0.0;
+    for (int i = threadIdx.x; i < ci.n; i += blockDim.x) {
+        double v[D];
+#pragma unroll
+        for (int t = 0; t < D; ++t) v[t] = own.v[t * own.np + i];
+        const double wt = own.wt[i];
+        const double c2 = c2_of<D>(v, us.prim_c);
+        const double f0 = f[i];
+        const double f1 = (K > 1) ? f[ci.np + i] : 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const double cd = v[d] - us.prim_c[1 + d];
+            q[d] += wt * cd * c2 * f0 + ((K > 1) ? wt * cd * f1 : 0.0);
+        }
+    }
+    block_reduce<D>(q, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) { us.qf[d] = 0.5 * q[d]; g.qf[(size_t)c * D + d] = 0.5 * q[d]; }
+    }
+    __syncthreads();
+    const double tau = us.tau;
+    const double a = tau / (tau + dt), b = dt / (tau + dt);
+    for (int i = threadIdx.x; i < ci.n; i += blockDim.x) {
+        double v[D], F[K], Fp[K];
+#pragma unroll
+        for (int t = 0; t < D; ++t) v[t] = own.v[t * own.np + i];
+        maxwell<D, K>(v, us.prim_c, us.coef_c, gas.K, F);
+        shakhov<D, K>(v, F, us.prim_c, us.qf, gas.Pr, gas.K, Fp);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            f[k * ci.np + i] = (f[k * ci.np + i] + dtv * vflux[k * ci.np + i]) * a + b * (F[k] + Fp[k]);
+            vflux[k * ci.np + i] = 0.0;
+        }
+    }
+    if (threadIdx.x == 0) {
+        double* prim_old = g.prim + (size_t)c * (D + 2);
+        if (want_residual) {
+#pragma unroll
+            for (int m = 0; m < D + 2; ++m) {
+                const double dd = us.prim_c[m] - prim_old[m];
+                g.res_cell[(size_t)c * 2 * (D + 2) + m] = dd * dd;
+                g.res_cell[(size_t)c * 2 * (D + 2) + (D + 2) + m] = fabs(us.prim_c[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < D + 2; ++m) {
+            g.w[(size_t)c * (D + 2) + m] = w_new[m];
+            prim_old[m] = us.prim_c[m];
+            g.mflux[(size_t)c * (D + 2) + m] = 0.0;
+        }
+    }
 }
 
-template <int D, int K>
-__device__ __forceinline__ void side_diff(const DevView& g, const CellInfo& ci, const SlopeSide& sd, int i, int li,
-                                          const double* f, double* out) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) out[k] = 0.0;
-    for (int a = 0; a < sd.n; ++a) {
-        const CellInfo& cn = g.cells[sd.nbr[a]];
-        const CellPtr<D, K> nb(g, cn);
-        int j0 = i, cnt = 1;
-        if (sd.rel[a] >= 0) {
-            const int* st = g.pm_start + g.rel_off[sd.rel[a]];
-            j0 = st[i];
-            cnt = max(1, st[i + 1] - j0);
-        }
-        for (int j = j0; j < j0 + cnt; ++j) {
+// ------------------------------------------------------------------------------------------------
+// slopes: one block per cell of the current dependency wave; all DIM directions in one pass.
+//   sL = (1/nL) sum_nbr diff(f, P[f_nbr (+ dm . sdf_nbr)]) / dsL   (diff_vs!, Slope.jl:29-64, :278-333)
+//   sdf = minmod(sL, sR) | sL | 0                                    (Slope.jl:90-116, 68-86, 471-472)
+// minmod, Slope.jl:20-24: 0.5 (sign a + sign b) min(|a|,|b|)
+__device__ __forceinline__ double minmod(double a, double b) {
+    const double m = fmin(fabs(a), fabs(b));
+    const bool pos = (a > 0.) && (b > 0.), neg = (a < 0.) && (b < 0.);
+    return pos ? m : (neg ? -m : 0.0);
+}
+
+// accumulated difference to the neighbours of one side
+template <int D, int K, bool GENERIC>
+__device__ __forceinline__ void side_sum(const DevView& g, const SlopeNbr* nb, int cnt, int i, int li,
+                                         const double* f, double* acc) {
+    for (int a = 0; a < cnt; ++a) {
+        const SlopeNbr& e = nb[a];
+        const int np = e.np;
+        if (!GENERIC || e.rel_off < 0) {
+            const double* __restrict__ nf = g.df + e.doff * K + i;
+            const double* __restrict__ nsd = g.sdf + e.doff * (K * D) + i;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                double proj = nb.f[k * nb.np + j];
-                if (sd.proj[a]) {
+                double proj = nf[k * np];
+                if (e.proj) {
 #pragma unroll
-                    for (int t = 0; t < D; ++t) proj += sd.dm[a][t] * nb.s[(t * K + k) * nb.np + j];
+                    for (int t = 0; t < D; ++t) proj += e.dm[t] * nsd[(t * K + k) * np];
                 }
-                if (cnt > 1)
-                    out[k] += (f[k] - proj) / (double)(1 << (D * (nb.lev[j] - li))) / sd.ds;
-                else
-                    out[k] += (f[k] - proj) / sd.ds;
+                acc[k] += f[k] - proj;
+            }
+        } else {
+            // pair-mapped neighbour (mismatched velocity grids): mean over the covering finer points or
+            // injection from the coarser one (diff_vs!, Slope.jl:29-64)
+            const double* nf = g.df + e.doff * K;
+            const double* nsd = g.sdf + e.doff * K * D;
+            const int8_t* nlev = g.v_level + e.goff;
+            const int* st = g.pm_start + e.rel_off;
+            const int j0 = st[i];
+            const int cn = max(1, st[i + 1] - j0);
+            for (int j = j0; j < j0 + cn; ++j) {
+                const double scale = (cn > 1) ? 1.0 / (double)(1 << (D * (nlev[j] - li))) : 1.0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    double proj = nf[k * np + j];
+                    if (e.proj) {
+#pragma unroll
+                        for (int t = 0; t < D; ++t) proj += e.dm[t] * nsd[(t * K + k) * np + j];
+                    }
+                    acc[k] += (f[k] - proj) * scale;
+                }
             }
         }
     }
-#pragma unroll
-    for (int k = 0; k < K; ++k) out[k] /= (double)sd.n;
 }
 
-template <int D, int K>
-__global__ void __launch_bounds__(256) slope_kernel(DevView g, const SlopeTask* __restrict__ tasks) {
+// Besides the reference's sdf (raw slopes) the kernel leaves the LIMITED slopes r*sdf in g.sdl, with
+// r = min(|f - eps()| / (1/2 sum_t ds_t |sdf_t| + EPS), 1) of positivity_preserving_reconstruct
+// (CAIDVM.jl:134-139): r depends on the cell's own f, sdf and ds only, so evaluating it here once per
+// point replaces the 1 + 2*DIM evaluations (with their fp64 divisions) the flux gather would need.
+// Raw sdf is written only where something reads it (tk.flags bit0: coarse neighbours of projecting cells,
+// cells on domain / solid faces, halo mirrors) or when the host asked for it (raw_all: kamr_slope,
+// KAMR_OPT_KEEP_SDF).
+template <int D, int K, bool GENERIC, int NT>
+__global__ void __launch_bounds__(NT) slope_kernel(DevView g, const SlopeTask* __restrict__ tasks, int raw_all) {
     __shared__ SlopeTask tk;
     __shared__ CellInfo ci;
+    __shared__ SlopeNbr nb[MAX_SLOPE_NB];
+    copy_words(tasks + blockIdx.x, &tk, (int)(sizeof(SlopeTask) / sizeof(int)));
+    __syncthreads();
+    copy_words(g.cells + tk.cell, &ci, (int)(sizeof(CellInfo) / sizeof(int)));
+    int base[D];
     {
-        const int* src = reinterpret_cast<const int*>(tasks + blockIdx.x);
-        int* dst = reinterpret_cast<int*>(&tk);
-        for (int t = threadIdx.x; t < (int)(sizeof(SlopeTask) / sizeof(int)); t += blockDim.x) dst[t] = src[t];
+        int b = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int cnt = tk.d[d].nA + tk.d[d].nB;
+            copy_words(g.slope_nb + tk.d[d].nb_begin, nb + b, cnt * (int)(sizeof(SlopeNbr) / sizeof(int)));
+            base[d] = b;
+            b += cnt;
+        }
     }
     __syncthreads();
-    if (threadIdx.x == 0) ci = g.cells[tk.cell];
-    __syncthreads();
     const CellPtr<D, K> own(g, ci);
+    const int n = ci.n, np = ci.np;
+    const bool raw = raw_all || (tk.flags & 1);
     double* sdf = g.sdf + ci.doff * K * D;
-    for (int i = threadIdx.x; i < ci.n; i += blockDim.x) {
-        double f[K];
+    double* sdl = g.sdl + ci.doff * K * D;
+    for (int i = threadIdx.x; i < n; i += NT) {
+        double f[K], s[D][K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) f[k] = own.f[k * own.np + i];
-        const int li = own.lev[i];
+        for (int k = 0; k < K; ++k) f[k] = own.f[k * np + i];
+        const int li = GENERIC ? (int)own.lev[i] : 0;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             const SlopeDir& sd = tk.d[d];
-            if (sd.mode == SLOPE_KEEP) continue;
-            double sA[K], sB[K];
-            if (sd.mode == SLOPE_ZERO) {
+            const int mode = sd.mode;
+            if (mode == SLOPE_KEEP) {  // untouched by the reference's sweep: keep what is stored
 #pragma unroll
-                for (int k = 0; k < K; ++k) sA[k] = 0.0;
-            } else {
-                side_diff<D, K>(g, ci, sd.A, i, li, f, sA);
-                if (sd.mode == SLOPE_INNER) {
-                    side_diff<D, K>(g, ci, sd.B, i, li, f, sB);
+                for (int k = 0; k < K; ++k) s[d][k] = sdf[(d * K + k) * np + i];
+                continue;
+            }
+            double sB[K];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) sA[k] = minmod(sA[k], sB[k]);
+            for (int k = 0; k < K; ++k) { s[d][k] = 0.0; sB[k] = 0.0; }
+            if (mode != SLOPE_ZERO) {
+                side_sum<D, K, GENERIC>(g, nb + base[d], sd.nA, i, li, f, s[d]);
+#pragma unroll
+                for (int k = 0; k < K; ++k) s[d][k] *= sd.invA;
+                if (mode == SLOPE_INNER) {
+                    side_sum<D, K, GENERIC>(g, nb + base[d] + sd.nA, sd.nB, i, li, f, sB);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) s[d][k] = minmod(s[d][k], sB[k] * sd.invB);
                 }
             }
+            if (raw) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) sdf[(d * K + k) * ci.np + i] = sA[k];
+                for (int k = 0; k < K; ++k) sdf[(d * K + k) * np + i] = s[d][k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double s_abs = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) s_abs += ci.ds[d] * fabs(s[d][k]);
+            const double r = limiter(f[k], s_abs);
+#pragma unroll
+            for (int d = 0; d < D; ++d) sdl[(d * K + k) * np + i] = r * s[d][k];
+        }
+    }
+}
+
+// sdl = r * sdf for cells whose raw slopes came from outside the slope kernel (ghost cells after the halo
+// exchange, kamr_upload_aux)
+template <int D, int K>
+__global__ void __launch_bounds__(256) limit_kernel(DevView g, const int* __restrict__ cell_list) {
+    __shared__ CellInfo ci;
+    copy_words(g.cells + cell_list[blockIdx.x], &ci, (int)(sizeof(CellInfo) / sizeof(int)));
+    __syncthreads();
+    const CellPtr<D, K> own(g, ci);
+    const int n = ci.n, np = ci.np;
+    double* sdl = g.sdl + ci.doff * K * D;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double s[D], s_abs = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) { s[d] = own.s[(d * K + k) * np + i]; s_abs += ci.ds[d] * fabs(s[d]); }
+            const double r = limiter(own.f[k * np + i], s_abs);
+#pragma unroll
+            for (int d = 0; d < D; ++d) sdl[(d * K + k) * np + i] = r * s[d];
         }
     }
 }

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -50,13 +51,15 @@ struct DBuf {
 struct Bin {
     std::vector<int> cells;
     int* d_cells = nullptr;
-    size_t smem = 0;  // dynamic shared memory per block (0 => global staging)
+    size_t smem = 0;     // dynamic shared memory per block (0 => global staging)
+    bool generic = false;  // some slot of some cell needs a pair map (mismatched velocity grids)
 };
 
 enum KernelId { KID_SLOPE = 0, KID_MACRO_SLOPE, KID_FLUX, KID_UPDATE, KID_STEP, KID_RESIDUAL, KID_PACK, KID_UNPACK,
-                KID_COUNT };
-const char* const kKernelNames[KID_COUNT] = {"slope_kernel", "macro_slope_kernel", "flux_kernel", "update_kernel",
-                                             "step_kernel", "residual_reduce_kernel", "pack_kernel", "unpack_kernel"};
+                KID_LIMIT, KID_COUNT };
+const char* const kKernelNames[KID_COUNT] = {"slope_kernel", "macro_slope_kernel", "phase_kernel<FLUX>",
+                                             "phase_kernel<UPDATE>", "phase_kernel<FUSED>", "residual_reduce_kernel",
+                                             "pack_kernel", "unpack_kernel", "limit_kernel"};
 
 struct PeerPlan {
     int rank;
@@ -95,8 +98,16 @@ struct kamr_ctx {
     std::map<std::pair<int, int>, int> rel_id;
     std::vector<long long> rel_off;
     std::vector<int> pm_start;
-    std::vector<std::pair<int, std::vector<SlopeTask>>> level_tasks;
+    std::vector<std::pair<int, std::vector<SlopeTask>>> level_tasks;  // (wave, tasks), ascending
     std::vector<SlopeTask*> d_level_tasks;
+    std::vector<char> level_generic;  // the task list holds pair-mapped stencils
+    std::vector<SlopeNbr> slope_nb;
+    int max_smem_optin = 0;
+    bool keep_sdf = false;        // KAMR_OPT_KEEP_SDF: fused steps also write the raw slopes of every cell
+    bool raw_sdf_valid = false;   // g.sdf holds the reference's sdf for every local cell
+    std::vector<int> limit_cells; // local fluid + ghost fluid cells (limit_kernel after upload_aux)
+    int* d_limit_cells = nullptr;
+    std::map<int, std::pair<int*, int>> ghost_wave_cells;  // wave -> ghost fluid cells whose sdf arrives then
     std::vector<int> fluid_cells;
     int* d_fluid_cells = nullptr;
     std::vector<Bin> bins;
@@ -147,9 +158,10 @@ struct kamr_ctx {
         device_bytes = 0;
         cells.clear(); slots.clear(); host_off.clear(); grid_n.clear(); grid_np.clear(); grid_goff.clear();
         grid_hoff.clear(); h_level.clear(); rel_id.clear(); rel_off.clear(); pm_start.clear();
-        level_tasks.clear(); d_level_tasks.clear(); fluid_cells.clear(); bins.clear(); peers.clear();
+        level_tasks.clear(); d_level_tasks.clear(); level_generic.clear(); slope_nb.clear(); fluid_cells.clear(); bins.clear(); peers.clear();
         dv = DevView{};
-        d_res = nullptr; d_sendbuf = d_recvbuf = nullptr; d_fluid_cells = nullptr;
+        d_res = nullptr; d_sendbuf = d_recvbuf = nullptr; d_fluid_cells = nullptr; d_limit_cells = nullptr;
+        limit_cells.clear(); ghost_wave_cells.clear(); raw_sdf_valid = false;
     }
 };
 
@@ -253,24 +265,50 @@ bool has_offset(const kamr_ctx* c, int cell, NbList nb, int dir) {
     return false;
 }
 
-void fill_side(kamr_ctx* c, int cell, NbList nb, double ds, int dir, int project /*0 no,1 yes*/, SlopeSide& s) {
+long long rel_offset(kamr_ctx* c, int ga, int gb) {
+    const int id = build_rel(c, ga, gb);
+    return id < 0 ? -1 : c->rel_off[id];
+}
+
+// appends the neighbours of one side to c->slope_nb; returns the count
+int fill_side(kamr_ctx* c, int cell, NbList nb, int dir, int project /*0 no,1 yes*/) {
     if (nb.cnt > 4) throw Fail("more than 4 neighbours on one face");
-    s.n = nb.cnt;
-    s.ds = ds;
-    for (int a = 0; a < 4; ++a) { s.nbr[a] = 0; s.rel[a] = -1; s.proj[a] = 0; for (int t = 0; t < MAXD; ++t) s.dm[a][t] = 0.0; }
     for (int a = 0; a < nb.cnt; ++a) {
         const int nbr = nb.ids[a];
-        s.nbr[a] = nbr;
-        s.rel[a] = build_rel(c, c->cells[cell].grid, c->cells[nbr].grid);
+        const CellInfo& cn = c->cells[nbr];
+        SlopeNbr e;
+        memset(&e, 0, sizeof(e));
+        e.doff = cn.doff; e.goff = cn.goff; e.np = cn.np;
+        e.rel_off = rel_offset(c, c->cells[cell].grid, cn.grid);
         if (project) {
             bool any = false;
             for (int t = 0; t < c->D; ++t) {
-                s.dm[a][t] = (t == dir) ? 0.0 : (c->cells[cell].mid[t] - c->cells[nbr].mid[t]);
-                any = any || s.dm[a][t] != 0.0;
+                e.dm[t] = (t == dir) ? 0.0 : (c->cells[cell].mid[t] - cn.mid[t]);
+                any = any || e.dm[t] != 0.0;
             }
-            s.proj[a] = any ? 1 : 0;  // dm == 0 contributes exactly 0 in the reference as well
+            e.proj = any ? 1 : 0;  // dm == 0 contributes exactly 0 in the reference as well
         }
+        c->slope_nb.push_back(e);
     }
+    return nb.cnt;
+}
+
+void set_bound(kamr_ctx* c, int cell, NbList nb, double ds, int dir, int project, SlopeDir& out) {
+    out.mode = SLOPE_BOUND;
+    out.nb_begin = (int)c->slope_nb.size();
+    out.nA = fill_side(c, cell, nb, dir, project);
+    out.nB = 0;
+    out.invA = 1.0 / (ds * out.nA);
+    out.invB = 0.0;
+}
+void set_inner(kamr_ctx* c, int cell, NbList L, NbList R, double dsL, double dsR, int dir, int projL, int projR,
+               SlopeDir& out) {
+    out.mode = SLOPE_INNER;
+    out.nb_begin = (int)c->slope_nb.size();
+    out.nA = fill_side(c, cell, L, dir, projL);
+    out.nB = fill_side(c, cell, R, dir, projR);
+    out.invA = 1.0 / (dsL * out.nA);
+    out.invB = 1.0 / (dsR * out.nB);
 }
 
 // the 15 update_slope! methods (Flux/Slope.jl:458-771) resolved into a stencil descriptor
@@ -286,23 +324,19 @@ void baseline_dir(kamr_ctx* c, const kamr_mesh* m, int cell, int dir, SlopeDir& 
     if (sL == 1 && sR == 1) {
         const bool solidL = c->cells[L.ids[0]].bound_enc < 0, solidR = c->cells[R.ids[0]].bound_enc < 0;
         if (solidL && solidR) { out.mode = SLOPE_ZERO; return; }
-        if (solidL) { out.mode = SLOPE_BOUND; fill_side(c, cell, R, ci.mid[dir] - midd(R.ids[0]), dir, 0, out.A); return; }
-        if (solidR) { out.mode = SLOPE_BOUND; fill_side(c, cell, L, ci.mid[dir] - midd(L.ids[0]), dir, 0, out.A); return; }
-        out.mode = SLOPE_INNER;
-        fill_side(c, cell, L, ci.ds[dir], dir, 0, out.A);
-        fill_side(c, cell, R, -ci.ds[dir], dir, 0, out.B);
+        if (solidL) { set_bound(c, cell, R, ci.mid[dir] - midd(R.ids[0]), dir, 0, out); return; }
+        if (solidR) { set_bound(c, cell, L, ci.mid[dir] - midd(L.ids[0]), dir, 0, out); return; }
+        set_inner(c, cell, L, R, ci.ds[dir], -ci.ds[dir], dir, 0, 0, out);
         return;
     }
     if (sL == 0 && sR == 0) throw Fail("cell with domain boundaries on both sides of one direction (no such "
                                        "update_slope! method in the reference)");
-    if (sL == 0) { out.mode = SLOPE_BOUND; fill_side(c, cell, R, ci.mid[dir] - midd(R.ids[0]), dir, 0, out.A); return; }
-    if (sR == 0) { out.mode = SLOPE_BOUND; fill_side(c, cell, L, ci.mid[dir] - midd(L.ids[0]), dir, 0, out.A); return; }
+    if (sL == 0) { set_bound(c, cell, R, ci.mid[dir] - midd(R.ids[0]), dir, 0, out); return; }
+    if (sR == 0) { set_bound(c, cell, L, ci.mid[dir] - midd(L.ids[0]), dir, 0, out); return; }
     const double ds = ci.ds[dir];
     const double dsL = (sL == 1) ? ds : ((sL == -1 ? 1.5 : 0.75) * ds);
     const double dsR = (sR == 1) ? -ds : (-(sR == -1 ? 1.5 : 0.75) * ds);
-    out.mode = SLOPE_INNER;
-    fill_side(c, cell, L, dsL, dir, 0, out.A);
-    fill_side(c, cell, R, dsR, dir, 0, out.B);
+    set_inner(c, cell, L, R, dsL, dsR, dir, 0, 0, out);
 }
 
 // update_slope_transverse_level!, Flux/Slope.jl:849-945
@@ -319,19 +353,16 @@ void transverse_dir(kamr_ctx* c, const kamr_mesh* m, int cell, int dir, SlopeDir
     if (sL != 0 && sR != 0) {
         const double dsL = ci.mid[dir] - c->cells[L.ids[0]].mid[dir];
         const double dsR = ci.mid[dir] - c->cells[R.ids[0]].mid[dir];
-        if (solid(L)) { out.mode = SLOPE_BOUND; fill_side(c, cell, R, dsR, dir, 1, out.A); return; }
-        if (solid(R)) { out.mode = SLOPE_BOUND; fill_side(c, cell, L, dsL, dir, 1, out.A); return; }
-        out.mode = SLOPE_INNER;
-        fill_side(c, cell, L, dsL, dir, has_offset(c, cell, L, dir) ? 1 : 0, out.A);
-        fill_side(c, cell, R, dsR, dir, has_offset(c, cell, R, dir) ? 1 : 0, out.B);
+        if (solid(L)) { set_bound(c, cell, R, dsR, dir, 1, out); return; }
+        if (solid(R)) { set_bound(c, cell, L, dsL, dir, 1, out); return; }
+        set_inner(c, cell, L, R, dsL, dsR, dir, has_offset(c, cell, L, dir) ? 1 : 0,
+                  has_offset(c, cell, R, dir) ? 1 : 0, out);
     } else if (sR == 0 && sL == -1) {
         if (solid(L)) { out.mode = SLOPE_KEEP; return; }
-        out.mode = SLOPE_BOUND;
-        fill_side(c, cell, L, ci.mid[dir] - c->cells[L.ids[0]].mid[dir], dir, 1, out.A);
+        set_bound(c, cell, L, ci.mid[dir] - c->cells[L.ids[0]].mid[dir], dir, 1, out);
     } else {
         if (solid(R)) { out.mode = SLOPE_KEEP; return; }
-        out.mode = SLOPE_BOUND;
-        fill_side(c, cell, R, ci.mid[dir] - c->cells[R.ids[0]].mid[dir], dir, 1, out.A);
+        set_bound(c, cell, R, ci.mid[dir] - c->cells[R.ids[0]].mid[dir], dir, 1, out);
     }
 }
 
@@ -415,7 +446,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         if (dir < 0 || dir >= D) throw Fail("face_dir out of range");
         Slot s;
         memset(&s, 0, sizeof(s));
-        s.dir = dir; s.rot = rot; s.face = f; s.is_here = 1; s.rel = -1;
+        s.dir = dir; s.rot = rot; s.face = f; s.is_here = 1; s.rel_off = -1;
         const CellInfo& ch = c->cells[here];
         for (int t = 0; t < D; ++t) { s.fmid[t] = m->face_mid[(size_t)f * D + t]; s.own_mid[t] = ch.mid[t]; }
         double area = face_area_of(ch, D, dir);
@@ -441,76 +472,134 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         else area = area * rot;                                                     // Flux.jl:87-89
         const CellInfo& ct = c->cells[there];
         s.nbr = there;
+        s.nbr_doff = ct.doff; s.nbr_goff = ct.goff; s.nbr_np = ct.np;
         s.kind = (ct.bound_enc < 0) ? SLOT_NBR_SOLID : SLOT_INNER;
-        s.rel = build_rel(c, ch.grid, ct.grid);
+        s.rel_off = rel_offset(c, ch.grid, ct.grid);
         s.area = area;
-        for (int t = 0; t < D; ++t) s.nbr_mid[t] = m->face_there_mid[(size_t)f * D + t];
+        for (int t = 0; t < D; ++t) { s.nbr_mid[t] = m->face_there_mid[(size_t)f * D + t]; s.nds[t] = ct.ds[t]; }
         per_cell[here].push_back(s);
         if (there < c->n_local && ct.bound_enc >= 0) {  // update_macro_flux!/update_micro_flux! write-back side
             Slot r = s;
             r.is_here = 0; r.nbr = here; r.kind = SLOT_INNER;
-            r.rel = build_rel(c, ct.grid, ch.grid);
+            r.nbr_doff = ch.doff; r.nbr_goff = ch.goff; r.nbr_np = ch.np;
+            r.rel_off = rel_offset(c, ct.grid, ch.grid);
             r.area = -area;
-            for (int t = 0; t < D; ++t) { r.own_mid[t] = s.nbr_mid[t]; r.nbr_mid[t] = ch.mid[t]; }
+            for (int t = 0; t < D; ++t) { r.own_mid[t] = s.nbr_mid[t]; r.nbr_mid[t] = ch.mid[t]; r.nds[t] = ch.ds[t]; }
             per_cell[there].push_back(r);
         }
     }
     for (int i = 0; i < c->n_local; ++i) {
-        if ((int)per_cell[i].size() > MAX_SLOTS) throw Fail("too many faces on one cell");
+        if ((int)per_cell[i].size() > max_slots(D)) throw Fail("too many faces on one cell");
+        std::stable_sort(per_cell[i].begin(), per_cell[i].end(), [](const Slot& a, const Slot& b) { return a.dir < b.dir; });
         c->cells[i].slot_begin = (int)c->slots.size();
         c->slots.insert(c->slots.end(), per_cell[i].begin(), per_cell[i].end());
         c->cells[i].slot_end = (int)c->slots.size();
     }
-    // ---- slope tasks per level (slope!, Slope.jl:1047-1070)
+    // ---- slope tasks in dependency waves (slope!, Slope.jl:1047-1070).  The reference sweeps the levels
+    // coarse to fine because a fine cell next to a coarse one projects the coarse cell's FINISHED slopes
+    // (Slope.jl:165-175).  Only those cells depend on anything: a cell none of whose stencils projects
+    // reads df only and can run in wave 0 whatever its level; a projecting cell of level L runs in wave
+    // L - Lmin (its coarse neighbours are done by then).  With peers every wave is followed by its halo
+    // exchange (slope_exchange_level!, Parallel/Ghost.jl:896), so there the waves are the reference's
+    // levels for every cell: both sides of a partition boundary must agree on when a cell is final.
     {
-        std::map<int, std::vector<SlopeTask>> by_level;
+        std::map<std::pair<int, int>, std::vector<SlopeTask>> by_wave;  // (wave, pair-mapped?) -> tasks
+        const bool by_level = m->n_peer > 0;
+        std::vector<SlopeTask> tasks;
+        std::vector<char> gen, dep;
+        std::vector<std::vector<int>> deps;       // cells whose finished sdf this task projects
+        std::vector<char> need_raw(c->n_cell, 0);
+        std::vector<int> task_of(c->n_cell, -1);
+        std::map<long long, int> cell_of_doff;
+        for (int i = 0; i < c->n_cell; ++i) cell_of_doff[c->cells[i].doff] = i;
         for (int i = 0; i < c->n_local; ++i) {
             if (c->cells[i].bound_enc < 0) continue;
             const int L = c->cells[i].ps_level;
             SlopeTask t;
             memset(&t, 0, sizeof(t));
             t.cell = i;
+            bool g_ = false;
+            std::vector<int> dl;
             for (int d = 0; d < D; ++d) {
                 if (L <= m->ps_minlevel) baseline_dir(c, m, i, d, t.d[d]);
                 else transverse_dir(c, m, i, d, t.d[d]);
+                if (t.d[d].nA + t.d[d].nB > 2 * (1 << (D - 1))) throw Fail("slope stencil too large");
+                if (t.d[d].mode == SLOPE_KEEP) need_raw[i] = 1;
+                for (int a = 0; a < t.d[d].nA + t.d[d].nB; ++a) {
+                    const SlopeNbr& e = c->slope_nb[t.d[d].nb_begin + a];
+                    if (e.proj) {
+                        // A true dependency only if the target is coarser.  (Rounding in the averaged midpoints of a
+                        // finer neighbour list can also switch the projection on, with dm ~ 1 ulp; the reference
+                        // then reads the finer cells' slopes of the PREVIOUS sweep, as they are processed later —
+                        // reproduced here: they run in a later wave and keep their raw sdf.)
+                        const int tgt = cell_of_doff[e.doff];
+                        need_raw[tgt] = 1;
+                        if (c->cells[tgt].ps_level < L) dl.push_back(tgt);
+                    }
+                    g_ = g_ || e.rel_off >= 0;
+                }
             }
-            by_level[L].push_back(t);
+            for (int sidx = c->cells[i].slot_begin; sidx < c->cells[i].slot_end; ++sidx)
+                if (c->slots[sidx].kind != SLOT_INNER) need_raw[i] = 1;
+            task_of[i] = (int)tasks.size();
+            tasks.push_back(t); gen.push_back(g_); dep.push_back(!dl.empty()); deps.push_back(std::move(dl));
         }
-        for (auto& kv : by_level) {
-            // heaviest cells first: better tail behaviour of the block scheduler
-            std::stable_sort(kv.second.begin(), kv.second.end(), [&](const SlopeTask& a, const SlopeTask& b) {
-                return c->cells[a.cell].n > c->cells[b.cell].n;
-            });
+        for (int p = 0; p < m->n_peer; ++p)  // mirrors: their raw slopes travel (slope_exchange_level!)
+            for (int q = m->send_off[p]; q < m->send_off[p + 1]; ++q) need_raw[m->send_cells[q]] = 1;
+        // wave of a task: with peers the reference's level sweep (both sides of a partition boundary must agree
+        // on when a cell is final); on one rank the true dependency depth
+        std::vector<int> wave(tasks.size(), -1);
+        std::function<int(int)> depth = [&](int ti) -> int {
+            if (wave[ti] >= 0) return wave[ti];
+            if (wave[ti] == -2) throw Fail("cyclic slope dependency");
+            wave[ti] = -2;
+            int w = 0;
+            for (int tgt : deps[ti]) {
+                const int tj = (tgt < c->n_local) ? task_of[tgt] : -1;
+                if (tj >= 0) w = std::max(w, depth(tj) + 1);
+            }
+            return wave[ti] = w;
+        };
+        for (size_t ti = 0; ti < tasks.size(); ++ti) {
+            const int L = c->cells[tasks[ti].cell].ps_level;
+            const int w = by_level ? std::max(0, L - m->ps_minlevel) : depth((int)ti);
+            tasks[ti].flags = need_raw[tasks[ti].cell] ? 1 : 0;
+            by_wave[std::make_pair(w, gen[ti] ? 1 : 0)].push_back(tasks[ti]);
+        }
+        for (auto& kv : by_wave) {
             c->d_level_tasks.push_back(c->dupload(kv.second));
-            c->level_tasks.emplace_back(kv.first, std::move(kv.second));
+            c->level_generic.push_back((char)kv.first.second);
+            c->level_tasks.emplace_back(kv.first.first, std::move(kv.second));
         }
     }
-    // ---- fluid cell list and update bins
+    // ---- fluid cell list (Morton order: neighbours in space are neighbours in the launch, so the blocks
+    // resident at one time share their neighbour reads through L2) and the phase-kernel bins
     for (int i = 0; i < c->n_local; ++i)
         if (c->cells[i].bound_enc >= 0) c->fluid_cells.push_back(i);
-    std::stable_sort(c->fluid_cells.begin(), c->fluid_cells.end(),
-                     [&](int a, int b) { return c->cells[a].n > c->cells[b].n; });
     c->d_fluid_cells = c->dupload(c->fluid_cells);
+    c->limit_cells = c->fluid_cells;
+    for (int i = c->n_local; i < c->n_local + c->n_ghost; ++i)
+        if (c->cells[i].bound_enc >= 0) c->limit_cells.push_back(i);
+    c->d_limit_cells = c->dupload(c->limit_cells);
     {
-        const size_t caps[] = {16 << 10, 48 << 10, 96 << 10, 200 << 10};
-        std::vector<Bin> bins(5);
-        for (int q = 0; q < 4; ++q) bins[q].smem = caps[q];
-        bins[4].smem = 0;
+        // dynamic shared memory classes: K planes of convected f + 1 plane of M[prim_c]
+        const size_t caps[] = {8 << 10, 16 << 10, 24 << 10, 32 << 10, 48 << 10, 64 << 10, 96 << 10, 128 << 10,
+                               (size_t)c->max_smem_optin - (12 << 10)};
+        const int ncap = (int)(sizeof(caps) / sizeof(caps[0]));
+        std::vector<Bin> bins(ncap + 1);
         c->fused_cells = 0;
         for (int cell : c->fluid_cells) {
-            const size_t need = (size_t)c->cells[cell].n * K * sizeof(double);
+            const CellInfo& ci = c->cells[cell];
+            const size_t need = (size_t)ci.n * (K + 1) * sizeof(double);
             int q = 0;
-            while (q < 4 && need > caps[q]) ++q;
-            bins[q].cells.push_back(cell);
-            if (q < 4) c->fused_cells++;
+            while (q < ncap && need > caps[q]) ++q;
+            Bin& b = bins[q];
+            b.smem = (q < ncap) ? std::max(b.smem, need) : 0;
+            b.cells.push_back(cell);
+            if (q < ncap) c->fused_cells++;
         }
         for (auto& b : bins) {
             if (b.cells.empty()) continue;
-            if (b.smem) {  // request only what the largest cell of the bin needs
-                size_t mx = 0;
-                for (int cell : b.cells) mx = std::max(mx, (size_t)c->cells[cell].n * K * sizeof(double));
-                b.smem = mx;
-            }
             b.d_cells = c->dupload(b.cells);
             c->bins.push_back(b);
         }
@@ -520,10 +609,11 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     c->dv.cells = c->dupload(c->cells);
     c->dv.slots = c->dupload(c->slots);
     c->dv.pm_start = c->dupload(c->pm_start);
-    c->dv.rel_off = c->dupload(c->rel_off);
+    c->dv.slope_nb = c->dupload(c->slope_nb);
     c->dv.df = c->dalloc<double>(np * K);
     c->dv.df_new = c->dalloc<double>(np * K);
     c->dv.sdf = c->dalloc<double>(np * K * D);
+    c->dv.sdl = c->dalloc<double>(np * K * D);
     c->dv.flux = c->dalloc<double>(np * K);
     c->dv.w = c->dalloc<double>((size_t)c->n_cell * M);
     c->dv.prim = c->dalloc<double>((size_t)c->n_cell * M);
@@ -536,6 +626,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     CK(cudaMemsetAsync(c->dv.df, 0, np * K * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->dv.df_new, 0, np * K * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->dv.sdf, 0, np * K * D * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->dv.sdl, 0, np * K * D * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->dv.flux, 0, np * K * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->dv.w, 0, (size_t)c->n_cell * M * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->dv.prim, 0, (size_t)c->n_cell * M * sizeof(double), c->stream));
@@ -546,6 +637,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     // ---- halo plan (Parallel/Ghost.jl:133-145, 203-284)
     c->halo_bytes_step = 0;
     long long send_total = 0, recv_total = 0;
+    std::map<int, std::vector<int>> ghost_by_wave;
     for (int p = 0; p < m->n_peer; ++p) {
         PeerPlan pp;
         pp.rank = m->peer_rank[p];
@@ -557,8 +649,9 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             pp.df_send.push_back(CopySeg{ci.doff * K, pp.send_base + pos, (long long)ci.np * K});
             pos += (long long)ci.np * K;
             if (ci.bound_enc >= 0) {  // solid cells carry no slopes
-                auto& lv = pp.sdf[ci.ps_level];
-                long long& lp = lpos[ci.ps_level];
+                const int wv = std::max(0, ci.ps_level - m->ps_minlevel);
+                auto& lv = pp.sdf[wv];
+                long long& lp = lpos[wv];
                 lv.send.push_back(CopySeg{ci.doff * K * D, pp.send_base + lp, (long long)ci.np * K * D});
                 lp += (long long)ci.np * K * D;
                 lv.send_len = lp;
@@ -576,8 +669,10 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         for (int gidx = g0; gidx < g1; ++gidx) {
             const CellInfo& ci = c->cells[gidx];
             if (ci.bound_enc < 0) continue;
-            auto& lv = pp.sdf[ci.ps_level];
-            long long& rp = rpos[ci.ps_level];
+            const int wv = std::max(0, ci.ps_level - m->ps_minlevel);
+            ghost_by_wave[wv].push_back(gidx);
+            auto& lv = pp.sdf[wv];
+            long long& rp = rpos[wv];
             lv.recv.push_back(CopySeg{pp.recv_base + rp, ci.doff * K * D, (long long)ci.np * K * D});
             rp += (long long)ci.np * K * D;
             lv.recv_len = rp;
@@ -594,6 +689,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         recv_total += rpos_max;
         c->peers.push_back(std::move(pp));
     }
+    for (auto& kv : ghost_by_wave) c->ghost_wave_cells[kv.first] = std::make_pair(c->dupload(kv.second), (int)kv.second.size());
     if (m->n_peer > 0) {
         c->d_sendbuf = c->dalloc<double>((size_t)send_total);
         c->d_recvbuf = c->dalloc<double>((size_t)recv_total);
@@ -708,56 +804,99 @@ void exchange(kamr_ctx* c, int what /*0 df, 1 sdf*/, int level) {
 
 // ------------------------------------------------------------------------------------------------
 // launch sequences
+#ifndef KAMR_NT
+#define KAMR_NT 256
+#endif
+#ifndef KAMR_MINB
+#define KAMR_MINB 3
+#endif
+constexpr int NT = KAMR_NT;      // threads per CTA (one CTA per physical cell)
+constexpr int MINB = KAMR_MINB;  // CTAs per SM the phase kernel is register-budgeted for
+
 template <int D, int K>
-void run_slope(kamr_ctx* c, bool with_sw) {
-    for (size_t l = 0; l < c->level_tasks.size(); ++l) {
-        const int nt = (int)c->level_tasks[l].second.size();
-        if (nt) {
-            { Launch L_(c, KID_SLOPE);
-              slope_kernel<D, K><<<nt, 256, 0, c->stream>>>(c->dv, c->d_level_tasks[l]); }
-        }
-    }
-    CK(cudaGetLastError());
-    // per-level halo of the fresh slopes (slope_exchange_level!, Parallel/Ghost.jl:896).  With one rank
-    // the levels above simply run back to back; with peers each level is followed by its exchange.
-    if (with_sw && !c->fluid_cells.empty()) {
-        { Launch L_(c, KID_MACRO_SLOPE);
-          macro_slope_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->d_fluid_cells); }
-        CK(cudaGetLastError());
-    }
+void launch_slope_wave(kamr_ctx* c, size_t l, int raw_all) {
+    const int nt = (int)c->level_tasks[l].second.size();
+    if (!nt) return;
+    Launch L_(c, KID_SLOPE);
+    if (c->level_generic[l]) slope_kernel<D, K, true, NT><<<nt, NT, 0, c->stream>>>(c->dv, c->d_level_tasks[l], raw_all);
+    else slope_kernel<D, K, false, NT><<<nt, NT, 0, c->stream>>>(c->dv, c->d_level_tasks[l], raw_all);
 }
 
 template <int D, int K>
-void run_slope_mpi(kamr_ctx* c, bool with_sw) {
-    // levels present locally or in the halo, ascending
-    std::vector<int> levels;
-    for (auto& lt : c->level_tasks) levels.push_back(lt.first);
-    for (auto& pp : c->peers)
-        for (auto& kv : pp.sdf) levels.push_back(kv.first);
-    std::sort(levels.begin(), levels.end());
-    levels.erase(std::unique(levels.begin(), levels.end()), levels.end());
-    for (int L : levels) {
-        for (size_t l = 0; l < c->level_tasks.size(); ++l) {
-            if (c->level_tasks[l].first != L) continue;
-            const int nt = (int)c->level_tasks[l].second.size();
-            { Launch L_(c, KID_SLOPE);
-              slope_kernel<D, K><<<nt, 256, 0, c->stream>>>(c->dv, c->d_level_tasks[l]); }
-        }
-        exchange(c, 1, L);
-    }
-    CK(cudaGetLastError());
-    if (with_sw && !c->fluid_cells.empty()) {
-        { Launch L_(c, KID_MACRO_SLOPE);
-          macro_slope_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->d_fluid_cells); }
-        CK(cudaGetLastError());
-    }
+void run_limit(kamr_ctx* c, const int* d_cells, int n) {
+    if (!n) return;
+    Launch L_(c, KID_LIMIT);
+    limit_kernel<D, K><<<n, 256, 0, c->stream>>>(c->dv, d_cells);
 }
 
 template <int D, int K>
-void run_flux(kamr_ctx* c, double dt, const int* d_cells, int ncells) {
-    if (!ncells) return;
-    { Launch L_(c, KID_FLUX);
-      flux_kernel<D, K><<<ncells, 256, 0, c->stream>>>(c->dv, c->gas, d_cells, dt); }
+void run_macro_slope(kamr_ctx* c) {
+    if (c->fluid_cells.empty()) return;
+    Launch L_(c, KID_MACRO_SLOPE);
+    macro_slope_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->d_fluid_cells);
+}
+
+// slope!(p4est, ka).  raw_all: every cell's reference sdf is written (public kamr_slope, KAMR_OPT_KEEP_SDF);
+// otherwise only where a kernel reads it, and the limited slopes everywhere.
+template <int D, int K>
+void do_slope(kamr_ctx* c, bool with_sw, bool raw_all) {
+    raw_all = raw_all || c->keep_sdf;
+    if (c->peers.empty()) {
+        for (size_t l = 0; l < c->level_tasks.size(); ++l) launch_slope_wave<D, K>(c, l, raw_all);
+    } else {
+        // waves present locally or in the halo, ascending; each followed by its exchange
+        // (slope_exchange_level!, Parallel/Ghost.jl:896) and the limited slopes of the ghosts that arrived
+        std::vector<int> waves;
+        for (auto& lt : c->level_tasks) waves.push_back(lt.first);
+        for (auto& pp : c->peers)
+            for (auto& kv : pp.sdf) waves.push_back(kv.first);
+        std::sort(waves.begin(), waves.end());
+        waves.erase(std::unique(waves.begin(), waves.end()), waves.end());
+        for (int w : waves) {
+            for (size_t l = 0; l < c->level_tasks.size(); ++l)
+                if (c->level_tasks[l].first == w) launch_slope_wave<D, K>(c, l, raw_all);
+            exchange(c, 1, w);
+            auto it = c->ghost_wave_cells.find(w);
+            if (it != c->ghost_wave_cells.end()) run_limit<D, K>(c, it->second.first, it->second.second);
+        }
+    }
+    c->raw_sdf_valid = raw_all;
+    CK(cudaGetLastError());
+    if (with_sw) run_macro_slope<D, K>(c);
+    CK(cudaGetLastError());
+}
+
+template <class Kern>
+void prepare_kernel(Kern kern, int max_dyn) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+}
+
+template <int D, int K, int MODE, bool STAGE>
+void launch_phase_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want, int kid) {
+    auto kern = phase_kernel<D, K, MODE, STAGE, NT, MINB>;
+    static bool prepared = false;  // per instantiation; attributes are per device function
+    if (!prepared) {
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, kern));
+        prepare_kernel(kern, c->max_smem_optin - (int)fa.sharedSizeBytes);
+        prepared = true;
+    }
+    Launch L_(c, kid);
+    kern<<<(int)b.cells.size(), NT, smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
+}
+
+template <int D, int K, int MODE>
+void launch_phase(kamr_ctx* c, const Bin& b, double dt, int want) {
+    const int kid = MODE == MODE_FUSED ? KID_STEP : (MODE == MODE_FLUX ? KID_FLUX : KID_UPDATE);
+    const bool stage = (MODE != MODE_FLUX) && b.smem > 0;
+    if (stage) launch_phase_inst<D, K, MODE, true>(c, b, b.smem, dt, want, kid);
+    else launch_phase_inst<D, K, MODE, false>(c, b, 0, dt, want, kid);
+}
+
+template <int D, int K>
+void do_flux(kamr_ctx* c, double dt) {
+    for (auto& b : c->bins) launch_phase<D, K, MODE_FLUX>(c, b, dt, 0);
     CK(cudaGetLastError());
 }
 
@@ -767,44 +906,25 @@ void fetch_residual(kamr_ctx* c, int want, double* res_out) {
     const int M = D + 2;
     { Launch L_(c, KID_RESIDUAL);
       residual_reduce_kernel<<<1, 256, 0, c->stream>>>(c->dv.res_cell, c->d_fluid_cells, (int)c->fluid_cells.size(),
-                                                     2 * M, c->d_res); }
+                                                       2 * M, c->d_res); }
     CK(cudaMemcpyAsync(c->h_res, c->d_res, 2 * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (res_out) memcpy(res_out, c->h_res, 2 * M * sizeof(double));
 }
 
 template <int D, int K>
-void run_update(kamr_ctx* c, double dt, int want, const double* fin, double* fout, bool only_global) {
-    for (auto& b : c->bins) {
-        const int nb = (int)b.cells.size();
-        if (b.smem) {
-            if (only_global) continue;
-            CK(cudaFuncSetAttribute(update_kernel<D, K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem));
-            Launch L_(c, KID_UPDATE);
-            update_kernel<D, K, 1><<<nb, 256, b.smem, c->stream>>>(c->dv, c->gas, b.d_cells, fin, fout, dt, want);
-        } else {
-            Launch L_(c, KID_UPDATE);
-            update_kernel<D, K, 0><<<nb, 256, 0, c->stream>>>(c->dv, c->gas, b.d_cells, fin, fout, dt, want);
-        }
-    }
-    CK(cudaGetLastError());
-}
-
-template <int D, int K>
-void do_slope(kamr_ctx* c, bool with_sw) {
-    if (c->peers.empty()) run_slope<D, K>(c, with_sw);
-    else run_slope_mpi<D, K>(c, with_sw);
-}
-
-template <int D, int K>
-void do_flux(kamr_ctx* c, double dt) {
-    run_flux<D, K>(c, dt, c->d_fluid_cells, (int)c->fluid_cells.size());
-}
-
-template <int D, int K>
 void do_iterate(kamr_ctx* c, double dt, int want, double* res_out) {
     if (c->gas.marching == KAMR_MARCH_CIP) throw Fail("CIP_Marching is not implemented on the device yet");
-    run_update<D, K>(c, dt, want, c->dv.df, c->dv.df, false);
+    if (c->gas.marching == KAMR_MARCH_EULER) {
+        if (!c->fluid_cells.empty()) {
+            Launch L_(c, KID_UPDATE);
+            euler_update_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->gas, c->d_fluid_cells,
+                                                                                          dt, want);
+        }
+    } else {
+        for (auto& b : c->bins) launch_phase<D, K, MODE_UPDATE>(c, b, dt, want);
+    }
+    CK(cudaGetLastError());
     fetch_residual<D, K>(c, want, res_out);
     exchange(c, 0, 0);
 }
@@ -812,24 +932,16 @@ void do_iterate(kamr_ctx* c, double dt, int want, double* res_out) {
 template <int D, int K>
 void do_step(kamr_ctx* c, double dt, int want, double* res_out) {
     if (c->gas.marching != KAMR_MARCH_CAIDVM) {  // only CAIDVM_Marching has the fused kernel
-        do_slope<D, K>(c, false);
+        do_slope<D, K>(c, false, false);
         do_flux<D, K>(c, dt);
         do_iterate<D, K>(c, dt, want, res_out);
         return;
     }
-    do_slope<D, K>(c, false);
-    // cells too large for shared-memory staging: separate flux kernel, then out-of-place update
-    for (auto& b : c->bins)
-        if (!b.smem) run_flux<D, K>(c, dt, b.d_cells, (int)b.cells.size());
-    for (auto& b : c->bins) {
-        if (!b.smem) continue;
-        CK(cudaFuncSetAttribute(step_kernel<D, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem));
-        Launch L_(c, KID_STEP);
-        step_kernel<D, K><<<(int)b.cells.size(), 256, b.smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
-    }
+    do_slope<D, K>(c, false, false);
+    for (auto& b : c->bins) launch_phase<D, K, MODE_FUSED>(c, b, dt, want);
     CK(cudaGetLastError());
-    run_update<D, K>(c, dt, want, c->dv.df, c->dv.df_new, true);
-    // cells that are not updated (solid ghost cells) keep their values in the other buffer as well
+    // cells that are not updated (solid ghost cells, ghosts) are refreshed in the new buffer by the IB
+    // kernels / the halo exchange below
     std::swap(c->dv.df, c->dv.df_new);
     fetch_residual<D, K>(c, want, res_out);
     exchange(c, 0, 0);
@@ -879,6 +991,7 @@ int kamr_create(const kamr_config* cfg, kamr_ctx** out) {
         if (cfg->device < 0 || cfg->device >= ndev) throw Fail("device ordinal out of range");
         CK(cudaSetDevice(cfg->device));
         c = new kamr_ctx();
+        CK(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
         c->cfg = *cfg;
         c->D = cfg->dim; c->K = cfg->ndf; c->M = cfg->dim + 2;
         c->gas = GasPar{cfg->K, cfg->Pr, cfg->gamma, cfg->omega, cfg->mu_ref, cfg->flux_type, cfg->marching};
@@ -958,7 +1071,11 @@ int kamr_upload_aux(kamr_ctx* c, const double* sdf, const double* flux, const do
     return guarded(c, [&] {
         CK(cudaSetDevice(c->cfg.device));
         if (c->cells.empty()) throw Fail("upload_topology first");
-        if (sdf) copy_points(c, c->dv.sdf, nullptr, sdf, c->K * c->D, true);
+        if (sdf) {
+            copy_points(c, c->dv.sdf, nullptr, sdf, c->K * c->D, true);
+            DISPATCH(c, run_limit, c, c->d_limit_cells, (int)c->limit_cells.size());
+            c->raw_sdf_valid = true;
+        }
         if (flux) copy_points(c, c->dv.flux, nullptr, flux, c->K, true);
         if (mflux) CK(cudaMemcpyAsync(c->dv.mflux, mflux, (size_t)c->n_local * c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
@@ -972,7 +1089,12 @@ int kamr_download_state(kamr_ctx* c, uint32_t mask, double* df, double* sdf, dou
         if (c->cells.empty()) throw Fail("upload_topology first");
         const int M = c->M, D = c->D;
         if ((mask & KAMR_DL_DF) && df) copy_points(c, c->dv.df, df, nullptr, c->K, false);
-        if ((mask & KAMR_DL_SDF) && sdf) copy_points(c, c->dv.sdf, sdf, nullptr, c->K * D, false);
+        if ((mask & KAMR_DL_SDF) && sdf) {
+            if (!c->raw_sdf_valid)
+                throw Fail("raw sdf is not resident: the fused step keeps only the limited slopes; call kamr_slope "
+                           "or set KAMR_OPT_KEEP_SDF before the step whose slopes the host needs");
+            copy_points(c, c->dv.sdf, sdf, nullptr, c->K * D, false);
+        }
         if ((mask & KAMR_DL_FLUX) && flux) copy_points(c, c->dv.flux, flux, nullptr, c->K, false);
         const size_t nl = (size_t)c->n_local;
         if ((mask & KAMR_DL_W) && w) CK(cudaMemcpyAsync(w, c->dv.w, nl * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -985,7 +1107,7 @@ int kamr_download_state(kamr_ctx* c, uint32_t mask, double* df, double* sdf, dou
 }
 
 int kamr_slope(kamr_ctx* c) {
-    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_slope, c, true); });
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_slope, c, true, true); });
 }
 int kamr_flux(kamr_ctx* c, double dt) {
     return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_flux, c, dt); });
@@ -1015,6 +1137,13 @@ int kamr_get_stats(kamr_ctx* c, kamr_stats* out) {
         out->halo_bytes_per_step = c->halo_bytes_step;
         out->n_levels = (int)c->level_tasks.size();
         out->fused_cells = c->fused_cells;
+    });
+}
+
+int kamr_set_option(kamr_ctx* c, int32_t option, int32_t value) {
+    return guarded(c, [&] {
+        if (option == KAMR_OPT_KEEP_SDF) c->keep_sdf = value != 0;
+        else throw Fail("unknown option");
     });
 }
 

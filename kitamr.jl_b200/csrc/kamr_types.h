@@ -6,7 +6,11 @@ namespace kamr {
 
 constexpr int MAXD = 3;
 constexpr int MAXM = 5;
-constexpr int MAX_SLOTS = 32;   // 2*DIM sides x 2^(DIM-1) sub-faces, plus slack
+// face slots of one cell: 2*DIM sides x 2^(DIM-1) sub-faces
+template <int DIM> struct MaxSlots { static constexpr int value = 2 * DIM * (1 << (DIM - 1)); };
+inline int max_slots(int dim) { return 2 * dim * (1 << (dim - 1)); }
+constexpr int MAX_SLOTS = MaxSlots<MAXD>::value;
+constexpr int MAX_SLOPE_NB = 24;  // DIM dirs x 2 sides x 2^(DIM-1) neighbours
 constexpr int PAD = 4;          // planes padded to 4 doubles (32 B) so 128-bit loads stay aligned
 
 constexpr double EPS_KIT = 1e-12;                   // src/Abstract/Types.jl:3
@@ -33,41 +37,46 @@ enum SlotKind : int {
     SLOT_BC_INTERP = 5,   // CAIDVM.jl:71
 };
 
-// One (cell, face) incidence: what a cell gathers through one face.
+// One (cell, face) incidence: what a cell gathers through one face.  Everything the kernel needs
+// about the neighbour is resolved at flatten time so that the device never chases cell records.
 struct Slot {
-    int nbr;        // neighbour cell id, -1 for domain faces
-    int rel;        // pair-map id of (own grid -> nbr grid), -1 when the grids are identical
+    long long nbr_doff;  // neighbour's point offset (df/sdf blocks)
+    long long nbr_goff;  // neighbour's velocity-grid offset
+    long long rel_off;   // offset of the pair map (own grid -> nbr grid) in pm_start; -1: identical grids
+    int nbr;             // neighbour cell id, -1 for domain faces
+    int nbr_np;
     int dir;
-    int kind;       // SlotKind
-    int is_here;    // 1: this cell is the face's here side, 0: there side
-    int face;       // index in the host face list
-    double rot;     // face rot (+1/-1)
-    double area;    // signed: +rot*A for here, -rot*A for there (Flux.jl:84-136)
-    double fmid[MAXD];
+    int kind;            // SlotKind
+    int is_here;         // 1: this cell is the face's here side, 0: there side
+    int face;            // index in the host face list
+    double rot;          // face rot (+1/-1)
+    double area;         // signed: +rot*A for here, -rot*A for there (Flux.jl:84-136)
+    double fmid[MAXD];     // face midpoint
     double own_mid[MAXD];  // midpoint this cell carries in the face record (periodic aliases are shifted)
-    double nbr_mid[MAXD];
+    double nbr_mid[MAXD];  // neighbour midpoint of the face record
+    double nds[MAXD];    // neighbour ds
     double bc[MAXM];
 };
 
 // Slope stencil of one (cell, direction): Flux/Slope.jl:458-771, 849-945 resolved at flatten time.
-struct SlopeSide {
-    int n;             // neighbours on this side (1, or 2^(DIM-1) finer cells)
-    int nbr[4];
-    int rel[4];        // pair-map id per neighbour (-1 identity)
-    int proj[4];       // transverse projection active for this neighbour
-    int pad_;
-    double ds;         // divisor (signed)
-    double dm[4][MAXD];
+struct SlopeNbr {
+    long long doff;      // neighbour's point offset
+    long long goff;      // neighbour's velocity-grid offset
+    long long rel_off;   // pair map offset, -1 identity
+    int np;
+    int proj;            // transverse projection active for this neighbour
+    double dm[MAXD];     // own midpoint - neighbour midpoint (0 along the slope direction)
 };
 enum SlopeMode : int { SLOPE_ZERO = 0, SLOPE_BOUND = 1, SLOPE_INNER = 2, SLOPE_KEEP = 3 };
 struct SlopeDir {
-    int mode;          // SlopeMode; BOUND uses side A only
-    int pad_;
-    SlopeSide A, B;
+    int mode;            // SlopeMode; BOUND uses side A only
+    int nA, nB;          // neighbours on side A / B: entries [nb_begin, +nA) and [nb_begin+nA, +nB)
+    int nb_begin;        // into the SlopeNbr array
+    double invA, invB;   // 1 / (divisor * number of neighbours), signed
 };
 struct SlopeTask {
     int cell;
-    int pad_;
+    int flags;           // bit0: write raw sdf (somebody reads it)
     SlopeDir d[MAXD];
 };
 
@@ -81,14 +90,15 @@ struct CopySeg {
 struct DevView {
     const CellInfo* cells;
     const Slot* slots;
+    const SlopeNbr* slope_nb;
     const int8_t* v_level;
     const double* v_weight;
     const double* v_mid;
     const int* pm_start;        // concatenated pair maps
-    const long long* rel_off;   // [n_rel] offset of each map in pm_start
     double* df;                 // current distribution (read side of a fused step)
     double* df_new;             // write side of a fused step
-    double* sdf;
+    double* sdf;                // raw slopes (reference semantics)
+    double* sdl;                // limited slopes r*sdf (device-internal)
     double* flux;
     double* w;
     double* prim;

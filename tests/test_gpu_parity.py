@@ -25,6 +25,9 @@ def _cases():
                                                 seed=4),
         "amr3d_samegrid_l2": lambda: cases.amr_case(dim=3, trees=2, maxlevel=2, vtrees=6, vs_maxlevel=0,
                                                      ragged=False, seed=5),
+        # non-dyadic cell sizes (32/5/2^L) and O(10) coordinates: exercises the rounding-sensitive paths
+        # (face dx cancellation, transverse-offset detection on averaged midpoints)
+        "s2_small": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2),
         "euler2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=1, vtrees=8, vs_maxlevel=1, ragged=True, seed=6,
                                           marching=abi.MARCH_EULER),
     }
