@@ -1,0 +1,24 @@
+"""Cases and helpers shared by tests/golden/make_golden.py (fixture generator) and the tests that read
+the fixtures.  The fixtures freeze OUTPUTS OF THE ORACLE (oracle/kamr_oracle.c): the reference is pure Julia +
+libp4est + MPI and cannot run in this image, and its own tests hold no vectors, so these are a
+regression pin of the restatement, not reference outputs."""
+import hashlib
+
+import numpy as np
+
+from kitamr_jl_b200.synth import cases
+
+CASES = {
+    "S0": lambda: cases.smoke_s0(),
+    "amr2d_ragged": lambda: cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=8, vs_maxlevel=2, ragged=True),
+    "amr3d_ragged": lambda: cases.amr_case(dim=3, trees=3, maxlevel=1, vtrees=4, vs_maxlevel=1, ragged=True, seed=4),
+}
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def sample_idx(n, k=4096, seed=99):
+    rng = np.random.default_rng(seed)
+    return np.sort(rng.choice(n, size=min(k, n), replace=False))
