@@ -56,10 +56,11 @@ struct Bin {
 };
 
 enum KernelId { KID_SLOPE = 0, KID_MACRO_SLOPE, KID_FLUX, KID_UPDATE, KID_STEP, KID_RESIDUAL, KID_PACK, KID_UNPACK,
-                KID_LIMIT, KID_COUNT };
+                KID_LIMIT, KID_SOLID_CELL, KID_SOLID_NBR, KID_COUNT };
 const char* const kKernelNames[KID_COUNT] = {"slope_kernel", "macro_slope_kernel", "phase_kernel<FLUX>",
                                              "phase_kernel<UPDATE>", "phase_kernel<FUSED>", "residual_reduce_kernel",
-                                             "pack_kernel", "unpack_kernel", "limit_kernel"};
+                                             "pack_kernel", "unpack_kernel", "limit_kernel", "solid_cell_kernel",
+                                             "solid_neighbor_kernel"};
 
 struct PeerPlan {
     int rank;
@@ -75,6 +76,7 @@ struct PeerPlan {
         long long send_len = 0, recv_len = 0;
     };
     std::map<int, Lvl> sdf;
+    Lvl solid;                                // df of solid ghost cells, mid-flux (Boundary/Parallel.jl:138-259)
     long long send_base = 0, recv_base = 0;  // offsets of this peer's region in the staging buffers
 };
 
@@ -110,6 +112,12 @@ struct kamr_ctx {
     std::map<int, std::pair<int*, int>> ghost_wave_cells;  // wave -> ghost fluid cells whose sdf arrives then
     std::vector<int> fluid_cells;
     int* d_fluid_cells = nullptr;
+    // immersed boundary
+    std::vector<SolidTask> solid_tasks;
+    std::vector<SnTask> sn_tasks;
+    std::vector<IbNbr> ib_nb;
+    SolidTask* d_solid_tasks = nullptr;
+    SnTask* d_sn_tasks = nullptr;
     std::vector<Bin> bins;
     bool padded = false;
     long long npts_pad = 0, npts_host = 0;
@@ -162,6 +170,7 @@ struct kamr_ctx {
         dv = DevView{};
         d_res = nullptr; d_sendbuf = d_recvbuf = nullptr; d_fluid_cells = nullptr; d_limit_cells = nullptr;
         limit_cells.clear(); ghost_wave_cells.clear(); raw_sdf_valid = false;
+        solid_tasks.clear(); sn_tasks.clear(); ib_nb.clear(); d_solid_tasks = nullptr; d_sn_tasks = nullptr;
     }
 };
 
@@ -546,6 +555,12 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         }
         for (int p = 0; p < m->n_peer; ++p)  // mirrors: their raw slopes travel (slope_exchange_level!)
             for (int q = m->send_off[p]; q < m->send_off[p + 1]; ++q) need_raw[m->send_cells[q]] = 1;
+        if (m->ib) {  // the wall kernels extrapolate with the raw slopes of the fluid cells around the body
+            const kamr_ib* ib = m->ib;
+            for (int q = 0; q < ib->solid_nb_off[ib->n_solid]; ++q) need_raw[ib->solid_nb_ids[q]] = 1;
+            for (int q = 0; q < ib->sn_nb_off[ib->n_sn]; ++q) need_raw[ib->sn_nb_ids[q]] = 1;
+            for (int q = 0; q < ib->n_sn; ++q) need_raw[ib->sn_donor[q]] = 1;
+        }
         // wave of a task: with peers the reference's level sweep (both sides of a partition boundary must agree
         // on when a cell is final); on one rank the true dependency depth
         std::vector<int> wave(tasks.size(), -1);
@@ -604,6 +619,69 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             c->bins.push_back(b);
         }
     }
+    // ---- immersed boundary tables (kernel d)
+    std::vector<int> cvc_index;
+    std::vector<double> cvc_gw, cvc_sw;
+    if (m->ib) {
+        const kamr_ib* ib = m->ib;
+        if (ib->n_sn != m->n_solidnbr) throw Fail("kamr_ib.n_sn must equal kamr_mesh.n_solidnbr");
+        auto add_nb = [&](int tgt, int src) {
+            if (src < 0 || src >= c->n_cell) throw Fail("immersed-boundary neighbour id out of range");
+            const CellInfo& cs = c->cells[src];
+            IbNbr e;
+            memset(&e, 0, sizeof(e));
+            e.doff = cs.doff; e.goff = cs.goff; e.np = cs.np;
+            e.rel_off = rel_offset(c, c->cells[tgt].grid, cs.grid);
+            for (int t = 0; t < D; ++t) e.mid[t] = cs.mid[t];
+            c->ib_nb.push_back(e);
+        };
+        for (int q = 0; q < ib->n_solid; ++q) {
+            const int cell = ib->solid_cell[q];
+            if (cell < 0 || cell >= c->n_local || c->cells[cell].bound_enc >= 0)
+                throw Fail("solid_cell must be a local cell with bound_enc < 0");
+            SolidTask t;
+            memset(&t, 0, sizeof(t));
+            t.cell = cell; t.nb_begin = (int)c->ib_nb.size();
+            t.nb_count = ib->solid_nb_off[q + 1] - ib->solid_nb_off[q];
+            if (t.nb_count <= 0 || t.nb_count > 32) throw Fail("solid cell needs 1..32 fluid neighbours");
+            for (int a = ib->solid_nb_off[q]; a < ib->solid_nb_off[q + 1]; ++a) add_nb(cell, ib->solid_nb_ids[a]);
+            c->solid_tasks.push_back(t);
+        }
+        const int sn0 = c->n_local + c->n_ghost;
+        for (int q = 0; q < ib->n_sn; ++q) {
+            SnTask t;
+            memset(&t, 0, sizeof(t));
+            t.sn_cell = sn0 + q; t.donor = ib->sn_donor[q]; t.solid = ib->sn_solid[q];
+            if (t.donor < 0 || t.donor >= c->n_local) throw Fail("sn_donor must be a local cell");
+            if (t.solid < 0 || t.solid >= sn0) throw Fail("sn_solid out of range");
+            if (c->cells[t.sn_cell].grid != c->cells[t.donor].grid) throw Fail("a SolidNeighbor shares its donor's velocity grid");
+            t.dir = ib->sn_faceid[q] / 2;
+            t.nb_begin = (int)c->ib_nb.size();
+            t.nb_count = ib->sn_nb_off[q + 1] - ib->sn_nb_off[q] + 1;
+            if (t.nb_count > 8) throw Fail("too many fluid neighbours of a donor cell");
+            for (int a = ib->sn_nb_off[q]; a < ib->sn_nb_off[q + 1]; ++a) add_nb(t.donor, ib->sn_nb_ids[a]);
+            add_nb(t.donor, t.donor);  // fluid_cells[end] = ps_data, Immersed_boundary.jl:372
+            t.cvc_begin = ib->cvc_off[q]; t.cvc_count = ib->cvc_off[q + 1] - ib->cvc_off[q];
+            for (int a = t.cvc_begin + 1; a < t.cvc_begin + t.cvc_count; ++a)
+                if (ib->cvc_index[a] <= ib->cvc_index[a - 1]) throw Fail("cvc_index must ascend within a SolidNeighbor");
+            t.rel_ps = rel_offset(c, c->cells[t.donor].grid, c->cells[t.solid].grid);
+            for (int k = 0; k < D; ++k) { t.aux[k] = ib->sn_aux[(size_t)q * D + k]; t.normal[k] = ib->sn_normal[(size_t)q * D + k]; }
+            for (int k = 0; k < M; ++k) t.bc[k] = ib->sn_bc[(size_t)q * M + k];
+            c->sn_tasks.push_back(t);
+        }
+        const int ncvc = ib->n_sn ? ib->cvc_off[ib->n_sn] : 0;
+        cvc_index.assign(ib->cvc_index, ib->cvc_index + ncvc);
+        cvc_gw.assign(ib->cvc_gas_w, ib->cvc_gas_w + ncvc);
+        cvc_sw.assign(ib->cvc_solid_w, ib->cvc_solid_w + ncvc);
+    } else if (m->n_solidnbr) {
+        throw Fail("n_solidnbr > 0 needs the kamr_ib tables");
+    }
+    c->d_solid_tasks = c->dupload(c->solid_tasks);
+    c->d_sn_tasks = c->dupload(c->sn_tasks);
+    c->dv.ib_nb = c->dupload(c->ib_nb);
+    c->dv.cvc_index = c->dupload(cvc_index);
+    c->dv.cvc_gas_w = c->dupload(cvc_gw);
+    c->dv.cvc_solid_w = c->dupload(cvc_sw);
     // ---- device state
     const size_t np = (size_t)c->npts_pad;
     c->dv.cells = c->dupload(c->cells);
@@ -647,6 +725,10 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         for (int q = m->send_off[p]; q < m->send_off[p + 1]; ++q) {
             const CellInfo& ci = c->cells[m->send_cells[q]];
             pp.df_send.push_back(CopySeg{ci.doff * K, pp.send_base + pos, (long long)ci.np * K});
+            if (ci.bound_enc < 0) {  // solid ghost cells also travel mid-flux (solid_exchange_begin!)
+                pp.solid.send.push_back(CopySeg{ci.doff * K, pp.send_base + pp.solid.send_len, (long long)ci.np * K});
+                pp.solid.send_len += (long long)ci.np * K;
+            }
             pos += (long long)ci.np * K;
             if (ci.bound_enc >= 0) {  // solid cells carry no slopes
                 const int wv = std::max(0, ci.ps_level - m->ps_minlevel);
@@ -668,7 +750,12 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         long long rpos_max = 0;
         for (int gidx = g0; gidx < g1; ++gidx) {
             const CellInfo& ci = c->cells[gidx];
-            if (ci.bound_enc < 0) continue;
+            if (ci.bound_enc < 0) {
+                pp.solid.recv.push_back(CopySeg{pp.recv_base + pp.solid.recv_len, ci.doff * K, (long long)ci.np * K});
+                pp.solid.recv_len += (long long)ci.np * K;
+                rpos_max = std::max(rpos_max, pp.solid.recv_len);
+                continue;
+            }
             const int wv = std::max(0, ci.ps_level - m->ps_minlevel);
             ghost_by_wave[wv].push_back(gidx);
             auto& lv = pp.sdf[wv];
@@ -684,7 +771,9 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             c->halo_bytes_step += 8 * kv.second.send_len;
         }
         pp.d_df_send = c->dupload(pp.df_send);
-        c->halo_bytes_step += 8 * pp.df_send_len;
+        pp.solid.d_send = c->dupload(pp.solid.send);
+        pp.solid.d_recv = c->dupload(pp.solid.recv);
+        c->halo_bytes_step += 8 * (pp.df_send_len + pp.solid.send_len);
         send_total += std::max(pos, spos_max);
         recv_total += rpos_max;
         c->peers.push_back(std::move(pp));
@@ -750,12 +839,19 @@ void copy_points(kamr_ctx* c, double* dev, double* host_rw, const double* host_r
 
 // ------------------------------------------------------------------------------------------------
 // halo
-void exchange(kamr_ctx* c, int what /*0 df, 1 sdf*/, int level) {
+PeerPlan::Lvl* halo_level(PeerPlan& pp, int what, int level) {
+    if (what == 2) return (pp.solid.send.empty() && pp.solid.recv.empty()) ? nullptr : &pp.solid;
+    auto it = pp.sdf.find(level);
+    return it == pp.sdf.end() ? nullptr : &it->second;
+}
+
+// what: 0 df of all mirrors (data_exchange!), 1 sdf of one level (slope_exchange_level!), 2 df of solid ghost
+// cells (solid_exchange_begin!/finish!)
+void exchange(kamr_ctx* c, int what, int level) {
     if (c->peers.empty()) return;
     if (!c->comm) throw Fail("mesh has peers but kamr_comm_init was not called");
-    const int K = c->K, D = c->D;
-    (void)K; (void)D;
-    double* src = what == 0 ? c->dv.df : c->dv.sdf;
+    double* src = what == 1 ? c->dv.sdf : c->dv.df;
+    double* dst = src;
     bool any = false;
     for (auto& pp : c->peers) {
         if (what == 0) {
@@ -766,12 +862,12 @@ void exchange(kamr_ctx* c, int what /*0 df, 1 sdf*/, int level) {
             }
             any = true;
         } else {
-            auto it = pp.sdf.find(level);
-            if (it == pp.sdf.end()) continue;
-            if (!it->second.send.empty()) {
+            PeerPlan::Lvl* lv = halo_level(pp, what, level);
+            if (!lv) continue;
+            if (!lv->send.empty()) {
                 { Launch L_(c, KID_PACK);
-                  copy_segments_kernel<<<std::min<int>((int)it->second.send.size(), 2048), 256, 0, c->stream>>>(
-                    it->second.d_send, (int)it->second.send.size(), src, c->d_sendbuf); }
+                  copy_segments_kernel<<<std::min<int>((int)lv->send.size(), 2048), 256, 0, c->stream>>>(
+                    lv->d_send, (int)lv->send.size(), src, c->d_sendbuf); }
             }
             any = true;
         }
@@ -783,20 +879,20 @@ void exchange(kamr_ctx* c, int what /*0 df, 1 sdf*/, int level) {
             if (pp.df_send_len) NCK(nccl().Send(c->d_sendbuf + pp.send_base, (size_t)pp.df_send_len, ncclFloat64, pp.rank, c->comm, c->stream));
             if (pp.df_recv_len) NCK(nccl().Recv(c->dv.df + pp.df_recv_off, (size_t)pp.df_recv_len, ncclFloat64, pp.rank, c->comm, c->stream));
         } else {
-            auto it = pp.sdf.find(level);
-            if (it == pp.sdf.end()) continue;
-            if (it->second.send_len) NCK(nccl().Send(c->d_sendbuf + pp.send_base, (size_t)it->second.send_len, ncclFloat64, pp.rank, c->comm, c->stream));
-            if (it->second.recv_len) NCK(nccl().Recv(c->d_recvbuf + pp.recv_base, (size_t)it->second.recv_len, ncclFloat64, pp.rank, c->comm, c->stream));
+            PeerPlan::Lvl* lv = halo_level(pp, what, level);
+            if (!lv) continue;
+            if (lv->send_len) NCK(nccl().Send(c->d_sendbuf + pp.send_base, (size_t)lv->send_len, ncclFloat64, pp.rank, c->comm, c->stream));
+            if (lv->recv_len) NCK(nccl().Recv(c->d_recvbuf + pp.recv_base, (size_t)lv->recv_len, ncclFloat64, pp.rank, c->comm, c->stream));
         }
     }
     NCK(nccl().GroupEnd());
-    if (what == 1) {
+    if (what != 0) {
         for (auto& pp : c->peers) {
-            auto it = pp.sdf.find(level);
-            if (it == pp.sdf.end() || it->second.recv.empty()) continue;
+            PeerPlan::Lvl* lv = halo_level(pp, what, level);
+            if (!lv || lv->recv.empty()) continue;
             { Launch L_(c, KID_UNPACK);
-              copy_segments_kernel<<<std::min<int>((int)it->second.recv.size(), 2048), 256, 0, c->stream>>>(
-                it->second.d_recv, (int)it->second.recv.size(), c->d_recvbuf, c->dv.sdf); }
+              copy_segments_kernel<<<std::min<int>((int)lv->recv.size(), 2048), 256, 0, c->stream>>>(
+                lv->d_recv, (int)lv->recv.size(), c->d_recvbuf, dst); }
         }
     }
     CK(cudaGetLastError());
@@ -894,8 +990,25 @@ void launch_phase(kamr_ctx* c, const Bin& b, double dt, int want) {
     else launch_phase_inst<D, K, MODE, false>(c, b, 0, dt, want, kid);
 }
 
+// the wall half of flux!(p4est, ka) (Flux.jl:463-481): update_solid_cell!, the solid halo, update_solid_neighbor!.
+// df2: second buffer that receives the same values (the write side of a fused step), or null.
+template <int D, int K>
+void do_ib(kamr_ctx* c, double* df2) {
+    if (!c->solid_tasks.empty()) {
+        Launch L_(c, KID_SOLID_CELL);
+        solid_cell_kernel<D, K><<<(int)c->solid_tasks.size(), 256, 0, c->stream>>>(c->dv, c->gas, c->d_solid_tasks, df2);
+    }
+    exchange(c, 2, 0);
+    if (!c->sn_tasks.empty()) {
+        Launch L_(c, KID_SOLID_NBR);
+        solid_neighbor_kernel<D, K><<<(int)c->sn_tasks.size(), 256, 0, c->stream>>>(c->dv, c->gas, c->d_sn_tasks, df2);
+    }
+    CK(cudaGetLastError());
+}
+
 template <int D, int K>
 void do_flux(kamr_ctx* c, double dt) {
+    do_ib<D, K>(c, nullptr);
     for (auto& b : c->bins) launch_phase<D, K, MODE_FLUX>(c, b, dt, 0);
     CK(cudaGetLastError());
 }
@@ -938,6 +1051,7 @@ void do_step(kamr_ctx* c, double dt, int want, double* res_out) {
         return;
     }
     do_slope<D, K>(c, false, false);
+    do_ib<D, K>(c, c->dv.df_new);
     for (auto& b : c->bins) launch_phase<D, K, MODE_FUSED>(c, b, dt, want);
     CK(cudaGetLastError());
     // cells that are not updated (solid ghost cells, ghosts) are refreshed in the new buffer by the IB
@@ -1049,8 +1163,6 @@ int kamr_upload_topology(kamr_ctx* c, const kamr_mesh* m) {
     return guarded(c, [&] {
         if (!m) throw Fail("null mesh");
         CK(cudaSetDevice(c->cfg.device));
-        if (m->ib && (m->ib->n_sn > 0 || m->ib->n_solid > 0))
-            throw Fail("immersed-boundary tables are not consumed by the device path yet");
         build_topology(c, m);
     });
 }

@@ -80,6 +80,26 @@ struct SlopeTask {
     SlopeDir d[MAXD];
 };
 
+// Immersed boundary (kernel d): tables resolved at flatten time from kamr_ib.
+struct IbNbr {            // one fluid cell a solid cell / an image point extrapolates from
+    long long doff, goff; // its df/sdf block and velocity-grid statics
+    long long rel_off;    // pair map (target grid -> this cell's grid), -1 identical
+    int np, pad_;
+    double mid[MAXD];
+};
+struct SolidTask {        // update_solid_cell!, Boundary/Immersed_boundary.jl:122-141
+    int cell;
+    int nb_begin, nb_count;
+    int pad_;
+};
+struct SnTask {           // update_solid_neighbor!, Boundary/Immersed_boundary.jl:436-480
+    int sn_cell, donor, solid, dir;
+    int nb_begin, nb_count;        // donor's fluid neighbours followed by the donor itself
+    int cvc_begin, cvc_count;      // cut velocity cells (sorted by point index)
+    long long rel_ps;              // pair map donor grid -> solid cell's grid, -1 identical
+    double aux[MAXD], normal[MAXD], bc[MAXM];
+};
+
 // Segment copy descriptor (halo pack / unpack)
 struct CopySeg {
     long long src, dst;   // offsets in doubles
@@ -95,6 +115,10 @@ struct DevView {
     const double* v_weight;
     const double* v_mid;
     const int* pm_start;        // concatenated pair maps
+    const IbNbr* ib_nb;
+    const int* cvc_index;       // cut velocity cells of all SolidNeighbors
+    const double* cvc_gas_w;
+    const double* cvc_solid_w;
     double* df;                 // current distribution (read side of a fused step)
     double* df_new;             // write side of a fused step
     double* sdf;                // raw slopes (reference semantics)

@@ -141,18 +141,38 @@ def pack_grids(grids, dim):
 
 
 def build_rank_view(forest: Forest, grids, cell_grid_global, bc_type, bc_prim, ndf,
-                    owner=None, rank=0, bound_enc_global=None) -> HostMesh:
+                    owner=None, rank=0, bound_enc_global=None, cell_class=None, ib_shape=None) -> HostMesh:
     """Flatten one rank's partition of the forest (the re-flatten step of the host shim).
 
     Faces follow the decision tree of initialize_faces! (src/Solver/Initialize.jl:5-158); since
     p4est's callback order is unavailable the canonical order is: local cells ascending, faceid
     ascending, a local/local full face emitted from the lower-index side.
+
+    Immersed boundary (cell_class + ib_shape): INSIDE_SOLID cells are not listed (InsideSolidData placeholders,
+    Solver/Initialize.jl:358-376); SOLID_GHOST cells are listed with bound_enc = -1; a fluid cell with a solid ghost
+    face-neighbour becomes a donor (bound_enc = +1) and that neighbour slot / face `there` is replaced by a
+    SolidNeighbor pseudo-cell (Boundary/Immersed_boundary.jl:282-305) appended after the ghosts.
     """
+    from .synth import ib as ibm
     D = forest.dim
     N = forest.n
     owner = np.zeros(N, dtype=np.int32) if owner is None else owner
-    benc = np.zeros(N, dtype=np.int32) if bound_enc_global is None else bound_enc_global
-    local = np.nonzero(owner == rank)[0]
+    if cell_class is not None:
+        benc = np.where(cell_class == ibm.SOLID_GHOST, -1, 0).astype(np.int32)
+        dropped = cell_class == ibm.INSIDE_SOLID
+    else:
+        benc = np.zeros(N, dtype=np.int32) if bound_enc_global is None else np.asarray(bound_enc_global).copy()
+        dropped = np.zeros(N, dtype=bool)
+    if ib_shape is not None:   # donors: fluid cells with a solid ghost face neighbour (Immersed_boundary.jl:285-287)
+        for g in np.nonzero(benc < 0)[0]:
+            for f in range(2 * D):
+                state, nbs = forest.face_neighbors(int(g), f)
+                for j in nbs:
+                    if benc[j] >= 0 and not dropped[j]:
+                        if state != 1:
+                            raise RuntimeError("immersed boundary crosses a refinement-level jump")
+                        benc[j] = 1
+    local = np.nonzero((owner == rank) & ~dropped)[0]
     n_local = len(local)
     loc_of = {int(g): i for i, g in enumerate(local)}
     is_local = owner == rank
@@ -164,7 +184,7 @@ def build_rank_view(forest: Forest, grids, cell_grid_global, bc_type, bc_prim, n
     if multi:
         for g in local:
             for j in forest.adjacent(int(g)):
-                if not is_local[j]:
+                if not is_local[j] and not dropped[j]:
                     ghost_set.add(j)
                     mirror_of_peer.setdefault(int(owner[j]), set()).add(int(g))
     ghosts = sorted(ghost_set, key=lambda j: (int(owner[j]), j))
@@ -186,12 +206,16 @@ def build_rank_view(forest: Forest, grids, cell_grid_global, bc_type, bc_prim, n
     gmap = {g: i for i, g in enumerate(used)}
     cell_grid = np.array([gmap[int(x)] for x in cg_global[gids]], dtype=np.int32)
     grid_off, v_level, v_weight, v_mid = pack_grids([grids[g] for g in used], D)
+    benc_l = benc[gids].astype(np.int32)
 
     nb_state = np.zeros(n_local * 2 * D, dtype=np.int32)
     nb_off = np.zeros(n_local * 2 * D + 1, dtype=np.int32)
     nb_ids = []
     kinds, heres, theres, dirs, rots, fmids, tmids = [], [], [], [], [], [], []
     geo = forest.geometry
+    # SolidNeighbor records
+    sn = dict(donor=[], solid=[], faceid=[], aux=[], normal=[], bc=[], nb=[], ds=[], mid=[], grid=[], lvl=[])
+    n_lg = n_local + n_ghost
 
     def on_edge(x, d):
         return x == geo[2 * d] or x == geo[2 * d + 1]
@@ -200,14 +224,34 @@ def build_rank_view(forest: Forest, grids, cell_grid_global, bc_type, bc_prim, n
         g = int(g)
         for f in range(2 * D):
             state, nbs = forest.face_neighbors(g, f)
+            if any(dropped[j] for j in nbs):
+                if benc[g] >= 0:
+                    raise RuntimeError("fluid cell next to an inside-solid cell")
+                state, nbs = 0, []   # a solid ghost cell looking into the body: InsideSolidData, never read
             e = ci * 2 * D + f
             nb_state[e] = state
-            nb_ids += [loc_of[j] for j in nbs]
-            nb_off[e + 1] = len(nb_ids)
             d = f // 2
             rot = 1.0 if f % 2 == 0 else -1.0
             if benc[g] < 0:
-                continue  # solid cells never own a face record here (IB flattening adds theirs)
+                nb_ids += [loc_of[j] for j in nbs]
+                nb_off[e + 1] = len(nb_ids)
+                continue  # solid cells never own a face record: the fluid side emits it (Initialize.jl:67-71,92-105)
+            if state == 1 and benc[nbs[0]] < 0 and ib_shape is not None:
+                j = nbs[0]
+                sid = n_lg + len(sn["donor"])
+                aux, normal = ib_shape.calc_intersect(forest.mid[g], forest.mid[j])
+                sn["donor"].append(ci); sn["solid"].append(loc_of[j]); sn["faceid"].append(f)
+                sn["aux"].append(aux); sn["normal"].append(normal); sn["bc"].append(np.asarray(ib_shape.bc, float))
+                sn["ds"].append(forest.ds[j]); sn["mid"].append(forest.mid[j]); sn["grid"].append(cell_grid[ci])
+                sn["lvl"].append(int(forest.level[j]))
+                nb_ids.append(sid)
+                nb_off[e + 1] = len(nb_ids)
+                fm = forest.mid[g].copy(); fm[d] -= 0.5 * rot * forest.ds[g][d]
+                kinds.append(FACE_FULL); heres.append(ci); theres.append(sid); dirs.append(d); rots.append(rot)
+                fmids.append(fm); tmids.append(forest.mid[j].copy())
+                continue
+            nb_ids += [loc_of[j] for j in nbs]
+            nb_off[e + 1] = len(nb_ids)
             if state == 0:
                 fm = forest.mid[g].copy(); fm[d] -= 0.5 * rot * forest.ds[g][d]
                 kinds.append(FACE_DOMAIN); heres.append(ci); theres.append(f); dirs.append(d); rots.append(rot)
@@ -243,13 +287,51 @@ def build_rank_view(forest: Forest, grids, cell_grid_global, bc_type, bc_prim, n
                     kinds.append(FACE_HANGING); heres.append(ci); theres.append(loc_of[j]); dirs.append(d)
                     rots.append(rot); fmids.append(fm); tmids.append(tm)
 
-    fluid_local = benc[local] >= 0
-    minlevel = int(forest.level[benc >= 0].min()) if (benc >= 0).any() else 0
+    n_sn = len(sn["donor"])
+    host_ib = None
+    if ib_shape is not None:
+        # fluid neighbours of solid ghost cells: first element of every face / corner list (Immersed_boundary.jl:207-213)
+        solid_cells, s_off, s_ids = [], [0], []
+        for ci, g in enumerate(local):
+            if benc[g] >= 0:
+                continue
+            fl = [j for j in forest.direction_neighbors(int(g)) if j is not None and not dropped[j] and benc[j] >= 0]
+            if not fl:
+                continue   # no fluid neighbour in reach (only possible on coarse test meshes): nothing reads this cell
+            solid_cells.append(ci)
+            s_ids += [loc_of[j] for j in fl]
+            s_off.append(len(s_ids))
+        # donor's fluid face neighbours (image_df, Immersed_boundary.jl:366-373); the donor itself goes last
+        n_off, n_ids = [0], []
+        c_off, c_idx, c_gw, c_sw = [0], [], [], []
+        for s in range(n_sn):
+            ci = sn["donor"][s]; g = int(local[ci])
+            for f in range(2 * D):
+                state, nbs = forest.face_neighbors(g, f)
+                if nbs and not dropped[nbs[0]] and benc[nbs[0]] >= 0:
+                    n_ids.append(loc_of[nbs[0]])
+            n_off.append(len(n_ids))
+            idx, gw, sw = ibm.cut_cells(sn["normal"][s], grids[int(cg_global[g])])
+            c_idx += list(idx); c_gw += list(gw); c_sw += list(sw)
+            c_off.append(len(c_idx))
+        i32a = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+        f64a = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+        host_ib = ibm.HostIB(i32a(solid_cells), i32a(s_off), i32a(s_ids), i32a(sn["donor"]), i32a(sn["solid"]),
+                             i32a(sn["faceid"]), f64a(sn["aux"]), f64a(sn["normal"]), f64a(sn["bc"]), i32a(n_off),
+                             i32a(n_ids), i32a(c_off), i32a(c_idx), f64a(c_gw), f64a(c_sw))
+        if n_sn:
+            ds = np.concatenate([ds, np.array(sn["ds"])]); mid = np.concatenate([mid, np.array(sn["mid"])])
+            lvl = np.concatenate([lvl, np.array(sn["lvl"], dtype=np.int32)])
+            cell_grid = np.concatenate([cell_grid, np.array(sn["grid"], dtype=np.int32)])
+            benc_l = np.concatenate([benc_l, np.full(n_sn, -1, dtype=np.int32)])
+
+    fluid_sel = (benc >= 0) & ~dropped
+    minlevel = int(forest.level[fluid_sel].min()) if fluid_sel.any() else 0
     i32 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.int32))
     f64 = lambda a, shape=None: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
     return HostMesh(
-        dim=D, ndf=ndf, n_local=n_local, n_ghost=n_ghost, n_solidnbr=0,
-        ds=f64(ds), mid=f64(mid), bound_enc=i32(benc[gids]), ps_level=i32(lvl), cell_grid=cell_grid,
+        dim=D, ndf=ndf, n_local=n_local, n_ghost=n_ghost, n_solidnbr=n_sn,
+        ds=f64(ds), mid=f64(mid), bound_enc=i32(benc_l), ps_level=i32(lvl), cell_grid=i32(cell_grid),
         grid_off=grid_off, v_level=v_level, v_weight=v_weight, v_mid=v_mid,
         nb_state=nb_state, nb_off=nb_off, nb_ids=i32(nb_ids),
         ps_maxlevel=int(forest.maxlevel), ps_minlevel=minlevel,
@@ -258,5 +340,5 @@ def build_rank_view(forest: Forest, grids, cell_grid_global, bc_type, bc_prim, n
         face_there_mid=f64(np.array(tmids).reshape(-1, D) if tmids else np.zeros((0, D))),
         bc_type=i32(bc_type), bc_prim=f64(bc_prim),
         peer_rank=i32(peers), send_off=i32(send_off), send_cells=i32(send_cells), recv_off=i32(recv_off),
-        global_ids=gids,
+        global_ids=gids, ib=host_ib,
     )

@@ -101,6 +101,8 @@ class Case:
     flux_type: int = abi.FLUX_CAIDVM
     noise: float = 0.01
     bound_enc: np.ndarray = None
+    cell_class: np.ndarray = None    # synth.ib.classify(...) when an immersed boundary is present
+    ib_shape: object = None
 
     # ------------------------------------------------------------------ config
     def config(self, device=0, rank=0, nranks=1, stream=None) -> abi.KamrConfig:
@@ -119,13 +121,18 @@ class Case:
 
     # ------------------------------------------------------------------ partition / flatten
     def owner(self, nranks):
-        n_of = np.array([g.n for g in self.grids])[self.cell_grid]
-        return partition(n_of.astype(np.float64), nranks)
+        """partition_weight (Parallel/Partition.jl:213-224): vs_num per cell, x2 for solid ghost cells; cells
+        inside the body carry no velocity grid."""
+        n_of = np.array([g.n for g in self.grids])[self.cell_grid].astype(np.float64)
+        if self.cell_class is not None:
+            n_of = np.where(self.cell_class == -2, 0.0, np.where(self.cell_class == -1, 2.0 * n_of, n_of))
+        return partition(n_of, nranks)
 
     def rank_mesh(self, rank=0, nranks=1) -> HostMesh:
         owner = self.owner(nranks) if nranks > 1 else None
         return build_rank_view(self.forest, self.grids, self.cell_grid, self.bc_type, self.bc_prim, self.ndf,
-                               owner=owner, rank=rank, bound_enc_global=self.bound_enc)
+                               owner=owner, rank=rank, bound_enc_global=self.bound_enc,
+                               cell_class=self.cell_class, ib_shape=self.ib_shape)
 
     # ------------------------------------------------------------------ state
     def cell_df(self, gid):
@@ -273,7 +280,8 @@ def uniform_case(dim=2, trees=64, maxlevel=0, vtrees=60, name=None, seed=3, refi
 
 
 # ---------------------------------------------------------------------- bench workloads
-def cylinder_s2(copies=1, ps_maxlevel=7, box_level=4, vs_maxlevel=3, vtrees=16, trees=25, noise=0.01) -> Case:
+def cylinder_s2(copies=1, ps_maxlevel=7, box_level=4, vs_maxlevel=3, vtrees=16, trees=25, noise=0.01,
+                ib=False) -> Case:
     """S2 cylinder2d (example/cylinder/cylinder.jl:5-47): 25x25 roots on [-16,16]^2, level `box_level`
     in max-norm(x)<5 (the converged dynamic-AMR region, cylinder_udf.jl:9-15), level `ps_maxlevel`
     within search_coeffi*ds_min = 4*ds_min of the r=1 circle; velocity grids 16x16 roots on
@@ -327,10 +335,16 @@ def cylinder_s2(copies=1, ps_maxlevel=7, box_level=4, vs_maxlevel=3, vtrees=16, 
     grids, cell_grid = _dedup_grids(per_cell)
     bt, bp = _bcs(2, [abi.BC_SUPERSONIC_INFLOW] + [abi.BC_UNIFORM_OUTFLOW] * 3,
                   [[1.0, Ma * math.sqrt(5 / 6), 0.0, 1.0], None, None, None])
-    return Case(f"S2-cylinder2d-x{copies}", 2, 2, forest, grids, cell_grid, bt, bp, gas, quad, (vtrees, vtrees),
-                vs_maxlevel, prim_fn, SEED_BASE + 2, noise=noise)
+    case = Case(f"S2-cylinder2d{'-ib' if ib else ''}-x{copies}", 2, 2, forest, grids, cell_grid, bt, bp, gas, quad,
+                (vtrees, vtrees), vs_maxlevel, prim_fn, SEED_BASE + 2, noise=noise)
+    if ib:   # IB = [Circle(Maxwellian,[0.,0.],1.,true,4.0,[1.,0.,0.,1.])], example/cylinder/cylinder.jl:41
+        from . import ib as ibm
+        case.ib_shape = ibm.Ball(centers, 1.0, np.array([1.0, 0.0, 0.0, 1.0]))
+        case.cell_class = ibm.classify(forest, case.ib_shape)
+    return case
 
 
 WORKLOADS = {
     "S2": cylinder_s2,
+    "S2ib": lambda copies=1: cylinder_s2(copies=copies, ib=True),
 }

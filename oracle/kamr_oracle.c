@@ -763,11 +763,260 @@ int orc_flux(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double d
     hv.idx = (int*)malloc(sizeof(int) * maxn); tv.idx = (int*)malloc(sizeof(int) * maxn);
     hv.micro = (double*)malloc(sizeof(double) * (size_t)maxn * o.K);
     tv.micro = (double*)malloc(sizeof(double) * (size_t)maxn * o.K);
-    for (int f = 0; f < m->n_face; ++f) {
-        if (m->face_kind[f] == KAMR_FACE_DOMAIN) flux_domain_face(&o, st, f, dt, &hv, &tv);
-        else flux_inner_face(&o, st, f, dt, &hv, &tv);
-    }
+    /* _flux_nonib_faces! first, _flux_ib_faces! (there is a SolidNeighbor) after the wall update, Flux.jl:466-485 */
+    const int sn0 = m->n_local + m->n_ghost;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int f = 0; f < m->n_face; ++f) {
+            int is_ib = m->face_kind[f] != KAMR_FACE_DOMAIN && m->face_there[f] >= sn0;
+            if (is_ib != pass) continue;
+            if (m->face_kind[f] == KAMR_FACE_DOMAIN) flux_domain_face(&o, st, f, dt, &hv, &tv);
+            else flux_inner_face(&o, st, f, dt, &hv, &tv);
+        }
     free(hv.idx); free(tv.idx); free(hv.micro); free(tv.micro);
+    octx_free(&o);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ immersed boundary */
+
+/* vs_extrapolate!, Boundary/Immersed_boundary.jl:98-121: adds weight[i]*(df + sdf.dx) of the source cell `src`
+ * (mean over covering finer points / injection from the coarser point) to dft, laid out on the grid of cell `tgt`. */
+static void vs_extrapolate(const octx* o, orc_state* st, int src, int tgt, const double* dx, const double* weight,
+                           double* dft) {
+    const int D = o->D, K = o->K;
+    const int ns = cell_n(o, src), nt = cell_n(o, tgt);
+    const int8_t* level = cell_level(o, src);
+    const int8_t* levelt = cell_level(o, tgt);
+    const double* df = cell_df(o, st, src);
+    const double* sdf = cell_sdf(o, st, src);
+    int j = 0;
+    double flag = 0.0;
+    for (int i = 0; i < nt; ++i) {
+        if (levelt[i] == level[j]) {
+            for (int k = 0; k < K; ++k) {
+                double ddf = 0.0;
+                for (int t = 0; t < D; ++t) ddf += sdf[(t * K + k) * ns + j] * dx[t];
+                dft[k * nt + i] += (df[k * ns + j] + ddf) * weight[i];
+            }
+            j += 1;
+        } else if (levelt[i] < level[j]) {
+            while (flag != 1.0) {
+                for (int k = 0; k < K; ++k) {
+                    double ddf = 0.0;
+                    for (int t = 0; t < D; ++t) ddf += sdf[(t * K + k) * ns + j] * dx[t];
+                    dft[k * nt + i] += (df[k * ns + j] + ddf) / pow2i(D * (level[j] - levelt[i])) * weight[i];
+                }
+                flag += 1 / pow2i(D * (level[j] - levelt[i]));
+                j += 1;
+            }
+            flag = 0.0;
+        } else {
+            for (int k = 0; k < K; ++k) {
+                double ddf = 0.0;
+                for (int t = 0; t < D; ++t) ddf += sdf[(t * K + k) * ns + j] * dx[t];
+                dft[k * nt + i] += (df[k * ns + j] + ddf) * weight[i];
+            }
+            flag += 1 / pow2i(D * (levelt[i] - level[j]));
+            if (flag == 1.0) { j += 1; flag = 0.0; }
+        }
+    }
+}
+
+/* the directional weighting shared by update_solid_cell! (:122-141) and image_df (:376-395):
+ * out (K planes on the grid of cell `tgt`) = sum_i w_i(v) * extrapolate(cell_i -> point x) with
+ * w_i = max(0, v.l_i/|v|)^2 normalised over i, l_i the unit vector from cell i's centre to x. */
+static void directional_extrapolate(const octx* o, orc_state* st, int tgt, const double* x, int ncell,
+                                    const int32_t* cells, double* out, double* weights /* n*ncell */, double* wi) {
+    const int D = o->D, K = o->K, n = cell_n(o, tgt);
+    const double* vm = cell_vmid(o, tgt);
+    memset(out, 0, sizeof(double) * (size_t)n * K);
+    for (int a = 0; a < ncell; ++a) {
+        double l[MAXD], nl = 0.0;
+        for (int t = 0; t < D; ++t) { l[t] = x[t] - o->m->mid[(size_t)cells[a] * D + t]; nl += l[t] * l[t]; }
+        nl = sqrt(nl);
+        for (int t = 0; t < D; ++t) l[t] /= nl;
+        for (int j = 0; j < n; ++j) {
+            double dot = 0.0, nu = 0.0;
+            for (int t = 0; t < D; ++t) { dot += vm[t * n + j] * l[t]; nu += vm[t * n + j] * vm[t * n + j]; }
+            double q = dot / sqrt(nu);
+            q = q > 0. ? q : 0.;
+            weights[(size_t)a * n + j] = q * q;
+        }
+    }
+    for (int a = 0; a < ncell; ++a) {
+        for (int j = 0; j < n; ++j) {
+            double ws = 0.0;
+            for (int b = 0; b < ncell; ++b) ws += weights[(size_t)b * n + j];
+            wi[j] = (ws == 0.) ? 1.0 / ncell : weights[(size_t)a * n + j] / ws;
+        }
+        double dx[MAXD];
+        for (int t = 0; t < D; ++t) dx[t] = x[t] - o->m->mid[(size_t)cells[a] * D + t];
+        vs_extrapolate(o, st, cells[a], tgt, dx, wi, out);
+    }
+}
+
+static int ib_maxn(const octx* o) {
+    int maxn = 1;
+    for (int c = 0; c < o->n_cell; ++c) if (cell_n(o, c) > maxn) maxn = cell_n(o, c);
+    return maxn;
+}
+
+/* update_solid_cell!(ka), Boundary/Immersed_boundary.jl:122-141,207-213 */
+int orc_ib_solid_cells(const kamr_config* cfg, const kamr_mesh* m, orc_state* st) {
+    if (!m->ib) return 0;
+    octx o;
+    if (octx_init(&o, cfg, m)) return 1;
+    const kamr_ib* ib = m->ib;
+    const int D = o.D, K = o.K, M = o.M;
+    int maxn = ib_maxn(&o), maxnb = 1;
+    for (int s = 0; s < ib->n_solid; ++s) {
+        int c = ib->solid_nb_off[s + 1] - ib->solid_nb_off[s];
+        if (c > maxnb) maxnb = c;
+    }
+    double* weights = (double*)malloc(sizeof(double) * (size_t)maxn * maxnb);
+    double* wi = (double*)malloc(sizeof(double) * (size_t)maxn);
+    for (int s = 0; s < ib->n_solid; ++s) {
+        int c = ib->solid_cell[s];
+        int nb = ib->solid_nb_off[s + 1] - ib->solid_nb_off[s];
+        directional_extrapolate(&o, st, c, m->mid + (size_t)c * D, nb, ib->solid_nb_ids + ib->solid_nb_off[s],
+                                cell_df(&o, st, c), weights, wi);
+        micro_to_macro_idx(D, K, cell_n(&o, c), NULL, cell_df(&o, st, c), cell_n(&o, c), cell_vmid(&o, c),
+                           cell_weight(&o, c), st->w + (size_t)c * M);
+        orc_get_prim(D, st->w + (size_t)c * M, cfg->gamma, st->prim + (size_t)c * M);
+    }
+    free(weights); free(wi);
+    octx_free(&o);
+    return 0;
+}
+
+/* update_solid_neighbor!(ka), Boundary/Immersed_boundary.jl:436-500 (image_df :366-395, boundary_slope! :396-435,
+ * cvc_* :332-365) */
+int orc_ib_solid_neighbors(const kamr_config* cfg, const kamr_mesh* m, orc_state* st) {
+    if (!m->ib) return 0;
+    octx o;
+    if (octx_init(&o, cfg, m)) return 1;
+    const kamr_ib* ib = m->ib;
+    const int D = o.D, K = o.K;
+    const int maxn = ib_maxn(&o);
+    const int sn0 = m->n_local + m->n_ghost;
+    int maxnb = 1;
+    for (int s = 0; s < ib->n_sn; ++s) {
+        int c = ib->sn_nb_off[s + 1] - ib->sn_nb_off[s] + 1;
+        if (c > maxnb) maxnb = c;
+    }
+    double* weights = (double*)malloc(sizeof(double) * (size_t)maxn * maxnb);
+    double* wi = (double*)malloc(sizeof(double) * (size_t)maxn);
+    double* ib_df = (double*)malloc(sizeof(double) * (size_t)maxn * K);
+    double* sL = (double*)malloc(sizeof(double) * (size_t)maxn * K);
+    double* Mx = (double*)malloc(sizeof(double) * (size_t)maxn * K);
+    double* vn = (double*)malloc(sizeof(double) * (size_t)maxn);
+    double* cw = (double*)malloc(sizeof(double) * (size_t)maxn);
+    double* gas_dfs = (double*)malloc(sizeof(double) * (size_t)maxn * K);
+    int32_t* cells = (int32_t*)malloc(sizeof(int32_t) * (size_t)maxnb);
+    for (int s = 0; s < ib->n_sn; ++s) {
+        const int P = ib->sn_donor[s], S = ib->sn_solid[s], SN = sn0 + s;
+        const int dir = ib->sn_faceid[s] / 2;
+        const int n = cell_n(&o, P), nS = cell_n(&o, S);
+        const double* vm = cell_vmid(&o, P);
+        const double* wt = cell_weight(&o, P);
+        const double* aux = ib->sn_aux + (size_t)s * D;
+        const double* nrm = ib->sn_normal + (size_t)s * D;
+        const double* pmid = m->mid + (size_t)P * D;
+        const double* smid = m->mid + (size_t)S * D;
+        const double* snmid = m->mid + (size_t)SN * D;
+        double ib_point[MAXD];
+        for (int t = 0; t < D; ++t) ib_point[t] = aux[t] + pmid[t] - smid[t];
+        for (int j = 0; j < n; ++j) {
+            double a = 0.0;
+            for (int t = 0; t < D; ++t) a += vm[t * n + j] * nrm[t];
+            vn[j] = a;
+        }
+        int nb = ib->sn_nb_off[s + 1] - ib->sn_nb_off[s];
+        for (int a = 0; a < nb; ++a) cells[a] = ib->sn_nb_ids[ib->sn_nb_off[s] + a];
+        cells[nb] = P; /* fluid_cells[end] = ps_data, :372 */
+        directional_extrapolate(&o, st, P, ib_point, nb + 1, cells, ib_df, weights, wi);
+        /* boundary_slope!, :396-435 */
+        const double dxf = ib_point[dir] - pmid[dir], dxs = pmid[dir] - snmid[dir];
+        {
+            const int8_t* level = cell_level(&o, P);
+            const int8_t* level_n = cell_level(&o, S);
+            const double* df = cell_df(&o, st, P);
+            const double* dfn = cell_df(&o, st, S);
+            memset(sL, 0, sizeof(double) * (size_t)n * K);
+            int index = 0;
+            double flag = 0.0;
+            for (int i = 0; i < n; ++i) {
+                if (level[i] == level_n[index]) {
+                    for (int j = 0; j < K; ++j) sL[j * n + i] = (df[j * n + i] - dfn[j * nS + index]) / dxs;
+                    index += 1;
+                } else if (level[i] < level_n[index]) {
+                    while (flag != 1.0) {
+                        for (int j = 0; j < K; ++j)
+                            sL[j * n + i] += (df[j * n + i] - dfn[j * nS + index]) /
+                                             pow2i(D * (level_n[index] - level[i])) / dxs;
+                        flag += 1 / pow2i(D * (level_n[index] - level[i]));
+                        index += 1;
+                    }
+                    flag = 0.0;
+                } else {
+                    for (int j = 0; j < K; ++j) sL[j * n + i] += (df[j * n + i] - dfn[j * nS + index]) / dxs;
+                    flag += 1 / pow2i(D * (level[i] - level_n[index]));
+                    if (flag == 1.0) { index += 1; flag = 0.0; }
+                }
+            }
+            for (int j = 0; j < K; ++j)
+                for (int i = 0; i < n; ++i)
+                    sL[j * n + i] = minmod(sL[j * n + i], (ib_df[j * n + i] - df[j * n + i]) / dxf);
+        }
+        const double dxL = aux[dir] - ib_point[dir];
+        double* aux_df = cell_df(&o, st, SN);
+        double* ssdf = cell_sdf(&o, st, SN) + (size_t)dir * K * n;
+        for (int j = 0; j < K; ++j)
+            for (int i = 0; i < n; ++i) {
+                double sv = sL[j * n + i];
+                sv = fmin(fabs((ib_df[j * n + i] - EPS_MACH) / (sv * dxL + EPS_MACH)), 1.0) * sv; /* :452-457 */
+                ssdf[j * n + i] = sv;
+                aux_df[j * n + i] = ib_df[j * n + i] + sv * dxL;
+            }
+        /* cut velocity cells: cvc.weight = weight with the cut cells zeroed */
+        const int c0 = ib->cvc_off[s], c1 = ib->cvc_off[s + 1];
+        memcpy(cw, wt, sizeof(double) * (size_t)n);
+        for (int q = c0; q < c1; ++q) {
+            cw[ib->cvc_index[q]] = 0.0;
+            for (int j = 0; j < K; ++j) gas_dfs[j * (c1 - c0) + (q - c0)] = aux_df[j * n + ib->cvc_index[q]];
+        }
+        double aux_prim[MAXM];
+        for (int q = 0; q < D + 2; ++q) aux_prim[q] = ib->sn_bc[(size_t)s * (D + 2) + q];
+        aux_prim[0] = 1.0;
+        orc_discrete_maxwell(D, K, n, vm, aux_prim, cfg->K, Mx);
+        double MuR = 0.0, SF = 0.0;
+        for (int i = 0; i < n; ++i) { /* cvc_Mu :347-358, cvc_density :338-346 */
+            double th = vn[i] >= 0 ? 1.0 : 0.0;
+            MuR += cw[i] * vn[i] * Mx[i] * th;
+            SF += cw[i] * vn[i] * aux_df[i] * (1.0 - th);
+        }
+        for (int q = c0; q < c1; ++q) {
+            int i = ib->cvc_index[q];
+            MuR += ib->cvc_solid_w[q] * vn[i] * Mx[i];
+            SF += ib->cvc_gas_w[q] * vn[i] * gas_dfs[q - c0];
+        }
+        const double rho_w = -SF / MuR;
+        for (int j = 0; j < K; ++j)
+            for (int i = 0; i < n; ++i) Mx[j * n + i] *= rho_w;
+        for (int i = 0; i < n; ++i)
+            if (vn[i] >= 0)
+                for (int j = 0; j < K; ++j) aux_df[j * n + i] = Mx[j * n + i];
+        for (int q = c0; q < c1; ++q) { /* cvc_correction!, :360-365 */
+            int i = ib->cvc_index[q];
+            double gw = ib->cvc_gas_w[q], sw = ib->cvc_solid_w[q];
+            for (int j = 0; j < K; ++j)
+                aux_df[j * n + i] = (gw * gas_dfs[j * (c1 - c0) + (q - c0)] + sw * Mx[j * n + i]) / (gw + sw);
+        }
+        double* snflux = cell_flux(&o, st, SN);
+        for (int j = 0; j < K; ++j)
+            for (int i = 0; i < n; ++i) snflux[j * n + i] = ssdf[j * n + i] * (snmid[dir] - aux[dir]); /* :474-475 */
+    }
+    free(weights); free(wi); free(ib_df); free(sL); free(Mx); free(vn); free(cw); free(gas_dfs); free(cells);
     octx_free(&o);
     return 0;
 }
@@ -868,6 +1117,10 @@ int orc_iterate(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, doubl
 int orc_step(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt, int want_residual,
              double* res_out) {
     int rc = orc_slope(cfg, m, st);
+    if (rc) return rc;
+    rc = orc_ib_solid_cells(cfg, m, st);      /* flux!(p4est,ka): update_solid_cell!, Flux.jl:463 */
+    if (rc) return rc;
+    rc = orc_ib_solid_neighbors(cfg, m, st);  /* update_solid_neighbor!, Flux.jl:481 */
     if (rc) return rc;
     rc = orc_flux(cfg, m, st, dt);
     if (rc) return rc;

@@ -28,6 +28,8 @@ int    orc_pair_map(int D, int n_a, const int8_t* lev_a, int n_b, const int8_t* 
 int orc_slope_level(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, int Lv, int transverse);
 int orc_macro_slope(const kamr_config* cfg, const kamr_mesh* m, orc_state* st);
 int orc_slope(const kamr_config* cfg, const kamr_mesh* m, orc_state* st);
+int orc_ib_solid_cells(const kamr_config* cfg, const kamr_mesh* m, orc_state* st);
+int orc_ib_solid_neighbors(const kamr_config* cfg, const kamr_mesh* m, orc_state* st);
 int orc_flux(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt);
 int orc_iterate(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt, int want_residual,
                 double* res_out);

@@ -63,6 +63,16 @@ def macro_slope(cfg, mesh, st):
     assert lib().orc_macro_slope(C.byref(cfg), C.byref(m), C.byref(s)) == 0
 
 
+def ib_solid_cells(cfg, mesh, st):
+    m = mesh.c_struct(); s = state_struct(st)
+    assert lib().orc_ib_solid_cells(C.byref(cfg), C.byref(m), C.byref(s)) == 0
+
+
+def ib_solid_neighbors(cfg, mesh, st):
+    m = mesh.c_struct(); s = state_struct(st)
+    assert lib().orc_ib_solid_neighbors(C.byref(cfg), C.byref(m), C.byref(s)) == 0
+
+
 def flux(cfg, mesh, st, dt):
     m = mesh.c_struct(); s = state_struct(st)
     rc = lib().orc_flux(C.byref(cfg), C.byref(m), C.byref(s), C.c_double(dt))

@@ -11,7 +11,7 @@ def _cells_block(mesh, arr, comps, cells):
     return np.concatenate([arr[off[c] * comps: off[c + 1] * comps] for c in cells]) if len(cells) else np.zeros(0)
 
 
-def exchange(mesh, arr, comps, level=None):
+def exchange(mesh, arr, comps, level=None, solid_only=False):
     """Exchange per-point blocks (`comps` planes per cell) of mirror cells -> ghost cells.  level: only cells of
     that physical level and not solid (slope_exchange_level!), None: all (data_exchange!)."""
     off = mesh.vs_off()
@@ -22,6 +22,9 @@ def exchange(mesh, arr, comps, level=None):
         if level is not None:
             send = [c for c in send if mesh.ps_level[c] == level and mesh.bound_enc[c] >= 0]
             ghosts = [c for c in ghosts if mesh.ps_level[c] == level and mesh.bound_enc[c] >= 0]
+        if solid_only:   # solid_exchange_begin!/finish!, Boundary/Parallel.jl:138-259
+            send = [c for c in send if mesh.bound_enc[c] < 0]
+            ghosts = [c for c in ghosts if mesh.bound_enc[c] < 0]
         sb = torch.from_numpy(_cells_block(mesh, arr, comps, send))
         rb = torch.zeros(int(sum(off[c + 1] - off[c] for c in ghosts)) * comps, dtype=torch.float64)
         if sb.numel():
@@ -66,6 +69,9 @@ def oracle_step_distributed(orc, cfg, mesh, st, dt, want_residual=False):
         orc.slope_level(cfg, mesh, st, L, 1)
         exchange(mesh, st.sdf, K * D, level=L)
     orc.macro_slope(cfg, mesh, st)
+    orc.ib_solid_cells(cfg, mesh, st)
+    exchange(mesh, st.df, K, solid_only=True)
+    orc.ib_solid_neighbors(cfg, mesh, st)
     orc.flux(cfg, mesh, st, dt)
     res = orc.iterate(cfg, mesh, st, dt, want_residual)
     exchange(mesh, st.df, K)

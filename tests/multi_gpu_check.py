@@ -29,6 +29,7 @@ def main():
         "periodic2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=6, vs_maxlevel=1, ragged=True,
                                              periodic=(True, True), seed=33),
         "s2_small": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2),
+        "s2_ib": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=5, box_level=2, vtrees=8, vs_maxlevel=2, ib=True),
     }
     for name, fn in names.items():
         case = fn()
@@ -53,8 +54,9 @@ def main():
         off_l, off_g = mesh.vs_off(), full.vs_off()
         K, M = mesh.ndf, case.dim + 2
         num = den = 0.0
+        index_of = {int(g): i for i, g in enumerate(full.global_ids[: full.n_local])}
         for i in range(mesh.n_local):
-            g = int(mesh.global_ids[i])
+            g = index_of[int(mesh.global_ids[i])]
             a = out.df[off_l[i] * K: off_l[i + 1] * K]; b = ref.df[off_g[g] * K: off_g[g + 1] * K]
             num += float(np.sum((a - b) ** 2)); den += float(np.sum(b ** 2))
         t = torch.tensor([num, den], dtype=torch.float64, device="cuda")

@@ -28,6 +28,9 @@ def _cases():
         # non-dyadic cell sizes (32/5/2^L) and O(10) coordinates: exercises the rounding-sensitive paths
         # (face dx cancellation, transverse-offset detection on averaged midpoints)
         "s2_small": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2),
+        # immersed boundary (kernel d): Circle r=1 with a Maxwellian wall, solid ghost cells, donors, cut velocity cells
+        "s2_ib_small": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True),
+        "s2_ib_fine": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=5, box_level=2, vtrees=8, vs_maxlevel=3, ib=True),
         "euler2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=1, vtrees=8, vs_maxlevel=1, ragged=True, seed=6,
                                           marching=abi.MARCH_EULER),
     }
@@ -61,10 +64,17 @@ def test_phases_match_oracle(setup):
     assert rel_l2(local_pts(mesh, out.sdf, K * D), local_pts(mesh, ref.sdf, K * D)) <= TOL
     nl = mesh.n_local
     assert rel_l2(out.sw[: nl * (D + 2) * D], ref.sw[: nl * (D + 2) * D]) <= 1e-11  # sums of signed slopes
-    # flux
+    # flux (with the wall half of flux!: update_solid_cell!, update_solid_neighbor!)
+    orc.ib_solid_cells(cfg, mesh, ref)
+    orc.ib_solid_neighbors(cfg, mesh, ref)
     orc.flux(cfg, mesh, ref, dt)
     ctx.flux(dt)
     out = ctx.download_state(st0.copy())
+    if mesh.n_solidnbr:   # solid ghost cells are local cells; SolidNeighbor blocks sit after the ghosts
+        off = mesh.vs_off()
+        a, b = off[mesh.n_local + mesh.n_ghost] * K, off[-1] * K
+        assert rel_l2(out.df[a:b], ref.df[a:b]) <= TOL
+        assert rel_l2(local_pts(mesh, out.df, K), local_pts(mesh, ref.df, K)) <= TOL
     assert rel_l2(local_pts(mesh, out.flux, K), local_pts(mesh, ref.flux, K)) <= TOL
     assert rel_l2(out.mflux[: nl * (D + 2)], ref.mflux[: nl * (D + 2)]) <= 1e-11
     # update
