@@ -18,6 +18,10 @@
 namespace kamr {
 
 #define KAMR_PI 3.14159265358979323846
+#ifndef KAMR_UNROLL
+#define KAMR_UNROLL 1
+#endif
+constexpr int UNROLL = KAMR_UNROLL;  // point-loop unrolling of the phase kernels: independent points in flight per thread
 
 // ------------------------------------------------------------------------------------------------
 // block-wide sum of NV doubles (warp shuffles + one shared-memory stage); result broadcast to all threads.
@@ -320,62 +324,90 @@ __device__ __forceinline__ void copy_words(const void* src_, void* dst_, int nwo
 }
 
 // ------------------------------------------------------------------------------------------------
-// The hot half of the face gather: fluid/fluid slots.  The own-upwind half needs the cell's own data only;
-// the neighbour-upwind half is taken here when the two velocity grids are identical (the neighbour's point
-// i IS this point).  Both use the LIMITED slopes r*sdf the slope kernel left in g.sdl, so the loop has no
-// division: micro = (f + dx . (r s)) v_n  (positivity_preserving_reconstruct, CAIDVM.jl:127-141).
-// Slots arrive sorted by direction, so v_n is a register, not a select.
-template <int D>
-struct HotSlot {
-    const double* nf;     // neighbour df block
-    const double* nsl;    // neighbour limited-slope block
-    int np, flags;        // flags bit0: this cell is the face's here side; bit1: neighbour half handled here
-    double rot, area;
-    double fmid[D], own_mid[D], nbr_mid[D];
-};
-
+// The hot half of the face gather: fluid/fluid faces (FaceRec, sorted by direction and side at flatten time).
+// For a point with v_d > 0 the neighbour across the LOW face of direction d is upwind and the cell itself is upwind
+// at the HIGH face; for v_d < 0 the other way round (v_d = 0 never occurs, Solver/Types.jl:335-353, and would
+// contribute 0).  So a point visits, per direction, the records of one side with its own data and the records of the
+// other side with the neighbour's — no per-face upwind test.  Both halves use the LIMITED slopes r*sdf the slope
+// kernel left in g.sdl, so there is no division: micro = (f + dx . (r s)) v_n
+// (positivity_preserving_reconstruct, CAIDVM.jl:127-141).
+// The neighbour values of the first record of every direction are loaded before any arithmetic so that the
+// L2 round trips of the D directions overlap; further records of a side (hanging sub-faces) are rare.
 template <int D, int K>
-__device__ __forceinline__ void hot_flux(const HotSlot<D>* hot, const int* hot_end, int i, double dt,
-                                         const double* v, const double* f, const double* s /*[K][D] limited*/,
-                                         double* fl) {
+__device__ __forceinline__ void hot_flux(const DevView& g, const FaceRec* hot, const unsigned char* sb, int i,
+                                         double dt, const double* v, const double* f,
+                                         const double* s /*[K][D] limited*/, double* fl) {
     double vdt[D];
+    double nfv[D][K], nsv[D][K * D];
+    int qn[D];
 #pragma unroll
-    for (int t = 0; t < D; ++t) vdt[t] = __dmul_rn(v[t], dt);
-    int q = 0;
+    for (int d = 0; d < D; ++d) {
+        vdt[d] = __dmul_rn(v[d], dt);
+        const int sn = v[d] > 0. ? 0 : 1;                    // side whose neighbour is upwind
+        const int q = sb[2 * d + sn];
+        qn[d] = (q < sb[2 * d + sn + 1] && (hot[q].flags & 2)) ? q : -1;
+        if (qn[d] >= 0) {
+            const FaceRec& h = hot[q];
+            const double* __restrict__ nf = g.df + h.nf_off + i;
+            const double* __restrict__ nsl = g.sdl + h.nsl_off + i;
+            const int np = h.np;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                nfv[d][k] = nf[k * np];
+#pragma unroll
+                for (int t = 0; t < D; ++t) nsv[d][k * D + t] = nsl[(t * K + k) * np];
+            }
+        }
+    }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const double vn = v[d];
-        const int qe = hot_end[d];
-        for (; q < qe; ++q) {
-            const HotSlot<D>& h = hot[q];
-            const double x = h.rot * vn;
-            const bool own_up = (h.flags & 1) ? (x <= 0.) : (x > 0.);
+        const int so = vn > 0. ? 1 : 0;                      // side where the cell itself is upwind
+        for (int q = sb[2 * d + so]; q < sb[2 * d + so + 1]; ++q) {
+            const FaceRec& h = hot[q];
             const double Avn = h.area * vn;
-            if (own_up) {
-                double dx[D];
+            double dx[D];
 #pragma unroll
-                for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.own_mid[t]);
+            for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.own_mid[t]);
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    double val = f[k];
+            for (int k = 0; k < K; ++k) {
+                double val = f[k];
 #pragma unroll
-                    for (int t = 0; t < D; ++t) val += dx[t] * s[k * D + t];
-                    fl[k] += val * Avn;
-                }
-            } else if (h.flags & 2) {
-                const double* __restrict__ nf = h.nf + i;
-                const double* __restrict__ nsl = h.nsl + i;
-                const int np = h.np;
-                double dx[D];
+                for (int t = 0; t < D; ++t) val += dx[t] * s[k * D + t];
+                fl[k] += val * Avn;
+            }
+        }
+        if (qn[d] >= 0) {
+            const FaceRec& h = hot[qn[d]];
+            const double Avn = h.area * vn;
+            double dx[D];
 #pragma unroll
-                for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.nbr_mid[t]);
+            for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.nbr_mid[t]);
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    double val = nf[k * np];
+            for (int k = 0; k < K; ++k) {
+                double val = nfv[d][k];
 #pragma unroll
-                    for (int t = 0; t < D; ++t) val += dx[t] * nsl[(t * K + k) * np];
-                    fl[k] += val * Avn;
-                }
+                for (int t = 0; t < D; ++t) val += dx[t] * nsv[d][k * D + t];
+                fl[k] += val * Avn;
+            }
+        }
+        const int sn = 1 - so;
+        for (int q = sb[2 * d + sn] + 1; q < sb[2 * d + sn + 1]; ++q) {   // further sub-faces of a hanging side
+            const FaceRec& h = hot[q];
+            if (!(h.flags & 2)) continue;
+            const double* __restrict__ nf = g.df + h.nf_off + i;
+            const double* __restrict__ nsl = g.sdl + h.nsl_off + i;
+            const int np = h.np;
+            const double Avn = h.area * vn;
+            double dx[D];
+#pragma unroll
+            for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.nbr_mid[t]);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double val = nf[k * np];
+#pragma unroll
+                for (int t = 0; t < D; ++t) val += dx[t] * nsl[(t * K + k) * np];
+                fl[k] += val * Avn;
             }
         }
     }
@@ -408,15 +440,125 @@ __device__ __forceinline__ void maxwell_c(const double* v, const double* prim, d
     if (K > 1) out[1] = h * cb;
 }
 
+// The update half shared by the phase kernels: given the block-partial sums acc = [macro flux | moments of the
+// convected f] and the convected f staged in fs, finish iterate!(CAIDVM_Marching) (Theory/Iterate.jl:108-126).
+template <int D, int K, int MODE, bool STAGE_SMEM, int NT>
+__device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas, const CellInfo& ci, int c, double dt,
+                                            int want_residual, double (&acc)[2 * (D + 2)], const CellPtr<D, K>& own,
+                                            double* fs, int fstride, double* fout, double* dyn, double* red,
+                                            UpdateShared<D, K>& us, double* w_new, double* w0s) {
+    const int n = ci.n, np = ci.np;
+    block_reduce<2 * (D + 2)>(acc, red);
+    if (threadIdx.x == 0) {
+        acc[D + 1] *= 0.5;
+        acc[2 * D + 3] *= 0.5;
+#pragma unroll
+        for (int m = 0; m < D + 2; ++m) {
+            double mf = g.mflux[(size_t)c * (D + 2) + m];
+            if (MODE == MODE_FUSED && gas.flux_type == 0) mf += acc[m];
+            w_new[m] = g.w[(size_t)c * (D + 2) + m] + mf * dt / ci.vol;
+            w0s[m] = acc[D + 2 + m];
+        }
+        get_prim<D>(w_new, gas.gamma, us.prim_c);
+        get_prim<D>(w0s, gas.gamma, us.prim);
+        us.tau = gas.mu_ref * 2.0 * pow(us.prim_c[D + 1], 1 - gas.omega) / us.prim_c[0];  // Gas/Model.jl:14
+        us.coef_c = maxwell_coef<D>(us.prim_c);
+        us.coef = maxwell_coef<D>(us.prim);
+        us.cb_c = gas.K / (2.0 * us.prim_c[D + 1]);
+        us.cb = gas.K / (2.0 * us.prim[D + 1]);
+    }
+    __syncthreads();
+
+    // ---- phase 2: conservation correction f += M[prim_c] - M[prim]; heat flux of the corrected f about prim_c
+    double prim_c[D + 2];
+#pragma unroll
+    for (int m = 0; m < D + 2; ++m) prim_c[m] = us.prim_c[m];
+    const double coef_c = us.coef_c, cb_c = us.cb_c;
+    double* fch = dyn + (size_t)K * n;  // staged h-component of M[prim_c] (STAGE_SMEM only)
+    {
+        double prim[D + 2];
+#pragma unroll
+        for (int m = 0; m < D + 2; ++m) prim[m] = us.prim[m];
+        const double coef = us.coef, cb = us.cb;
+        double q[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) q[d] = 0.0;
+#pragma unroll UNROLL
+        for (int i = threadIdx.x; i < n; i += NT) {
+            double v[D], Fc[K], F[K], f[K];
+#pragma unroll
+            for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+            maxwell_c<D, K>(v, prim_c, coef_c, cb_c, Fc);
+            maxwell_c<D, K>(v, prim, coef, cb, F);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                f[k] = fs[k * fstride + i] + (Fc[k] - F[k]);
+                fs[k * fstride + i] = f[k];
+            }
+            if (STAGE_SMEM) fch[i] = Fc[0];
+            // heat_flux (2D2F.jl:68-88, 3D1F.jl:41-72): q_d = 1/2 sum w c_d (c^2 h + b)
+            const double gq = own.wt[i] * (c2_of<D>(v, prim_c) * f[0] + ((K > 1) ? f[1] : 0.0));
+#pragma unroll
+            for (int d = 0; d < D; ++d) q[d] += (v[d] - prim_c[1 + d]) * gq;
+        }
+        block_reduce<D>(q, red);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) { us.qf[d] = 0.5 * q[d]; g.qf[(size_t)c * D + d] = 0.5 * q[d]; }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 3: f = f*tau/(tau+dt) + dt/(tau+dt)*(M_c + S[M_c])
+    {
+        const double tau = us.tau;
+        const double a = tau / (tau + dt), b = dt / (tau + dt);
+        double qf[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) qf[d] = us.qf[d];
+#pragma unroll UNROLL
+        for (int i = threadIdx.x; i < n; i += NT) {
+            double v[D], Fc[K], Fp[K];
+#pragma unroll
+            for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+            if (STAGE_SMEM) {
+                Fc[0] = fch[i];
+                if (K > 1) Fc[1] = Fc[0] * cb_c;
+            } else {
+                maxwell_c<D, K>(v, prim_c, coef_c, cb_c, Fc);
+            }
+            shakhov<D, K>(v, Fc, prim_c, qf, gas.Pr, gas.K, Fp);
+#pragma unroll
+            for (int k = 0; k < K; ++k) fout[k * np + i] = fs[k * fstride + i] * a + b * (Fc[k] + Fp[k]);
+        }
+    }
+    if (threadIdx.x == 0) {
+        double* prim_old = g.prim + (size_t)c * (D + 2);
+        if (want_residual) {  // residual_check!, Solver/Finalize.jl:5-11
+#pragma unroll
+            for (int m = 0; m < D + 2; ++m) {
+                const double dd = prim_c[m] - prim_old[m];
+                g.res_cell[(size_t)c * 2 * (D + 2) + m] = dd * dd;
+                g.res_cell[(size_t)c * 2 * (D + 2) + (D + 2) + m] = fabs(prim_c[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < D + 2; ++m) {
+            g.w[(size_t)c * (D + 2) + m] = w_new[m];
+            prim_old[m] = prim_c[m];
+            g.mflux[(size_t)c * (D + 2) + m] = 0.0;
+        }
+    }
+}
+
 template <int D, int K, int MODE, bool STAGE_SMEM, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
     phase_kernel(DevView g, GasPar gas, const int* __restrict__ cell_list, double dt, int want_residual) {
     extern __shared__ double dyn[];
     constexpr int NSLOT = (MODE == MODE_UPDATE) ? 1 : MaxSlots<D>::value;
     __shared__ Slot sh_slots[NSLOT];
-    __shared__ HotSlot<D> hot[NSLOT];
+    __shared__ FaceRec hot[NSLOT];
     __shared__ int rare[NSLOT];
-    __shared__ int hot_end[D + 1];  // [d]: end of direction d's hot slots; [D]: number of rare slots
     __shared__ double rho_w[NSLOT];
     __shared__ double red[2 * (D + 2) * 32];
     __shared__ CellInfo ci;
@@ -427,37 +569,16 @@ __global__ void __launch_bounds__(NT, MINB)
     __syncthreads();
     const int n = ci.n, np = ci.np;
     const int ns = (MODE == MODE_UPDATE) ? 0 : ci.slot_end - ci.slot_begin;
+    const int nrare = (MODE == MODE_UPDATE) ? 0 : ci.rare_count;
     if (MODE != MODE_UPDATE) {
-        copy_words(g.slots + ci.slot_begin, sh_slots, ns * (int)(sizeof(Slot) / sizeof(int)));
-        __syncthreads();
-        if (threadIdx.x == 0) {  // slots are sorted by direction at flatten time
-            int nh = 0, nr = 0, d = 0;
-            for (int q = 0; q < ns; ++q) {
-                const Slot& sl = sh_slots[q];
-                while (d < sl.dir) hot_end[d++] = nh;
-                if (sl.kind == SLOT_INNER) {
-                    HotSlot<D>& h = hot[nh++];
-                    h.nf = g.df + sl.nbr_doff * K;
-                    h.nsl = g.sdl + sl.nbr_doff * (K * D);
-                    h.np = sl.nbr_np;
-                    h.flags = (sl.is_here ? 1 : 0) | (sl.rel_off < 0 ? 2 : 0);
-                    h.rot = sl.rot; h.area = sl.area;
-#pragma unroll
-                    for (int t = 0; t < D; ++t) {
-                        h.fmid[t] = sl.fmid[t]; h.own_mid[t] = sl.own_mid[t]; h.nbr_mid[t] = sl.nbr_mid[t];
-                    }
-                    if (sl.rel_off >= 0) rare[nr++] = q;
-                } else {
-                    rare[nr++] = q;
-                }
-            }
-            while (d < D) hot_end[d++] = nh;
-            hot_end[D] = nr;
+        copy_words(g.hot + ci.hot_begin, hot, ci.side_begin[2 * D] * (int)(sizeof(FaceRec) / sizeof(int)));
+        if (nrare > 0) {  // block-uniform: only cells on the domain edge / next to another velocity grid / the body
+            copy_words(g.slots + ci.slot_begin, sh_slots, ns * (int)(sizeof(Slot) / sizeof(int)));
+            copy_words(g.rare + ci.rare_begin, rare, nrare);
         }
         __syncthreads();
-        wall_density<D, K>(g, ci, sh_slots, ns, dt, rho_w, red);
+        if (ci.flags & CELL_HAS_MAXWELL_WALL) wall_density<D, K>(g, ci, sh_slots, ns, dt, rho_w, red);
     }
-    const int nrare = (MODE == MODE_UPDATE) ? 0 : hot_end[D];
     const CellPtr<D, K> own(g, ci);
     const double dtv = dt / ci.vol;
     double* vflux = g.flux + ci.doff * K;
@@ -482,7 +603,7 @@ __global__ void __launch_bounds__(NT, MINB)
             for (int k = 0; k < K; ++k)
 #pragma unroll
                 for (int t = 0; t < D; ++t) s[k * D + t] = own.sl[(t * K + k) * np + i];
-            hot_flux<D, K>(hot, hot_end, i, dt, v, f, s, fl);
+            hot_flux<D, K>(g, hot, ci.side_begin, i, dt, v, f, s, fl);
             add_moments<D, K>(acc, wt, v, fl);
         } else {
 #pragma unroll
@@ -570,105 +691,112 @@ __global__ void __launch_bounds__(NT, MINB)
         }
         return;
     }
-    block_reduce<2 * (D + 2)>(acc, red);
-    if (threadIdx.x == 0) {
-        acc[D + 1] *= 0.5;
-        acc[2 * D + 3] *= 0.5;
-#pragma unroll
-        for (int m = 0; m < D + 2; ++m) {
-            double mf = g.mflux[(size_t)c * (D + 2) + m];
-            if (MODE == MODE_FUSED && gas.flux_type == 0) mf += acc[m];
-            w_new[m] = g.w[(size_t)c * (D + 2) + m] + mf * dt / ci.vol;
-            w0s[m] = acc[D + 2 + m];
-        }
-        get_prim<D>(w_new, gas.gamma, us.prim_c);
-        get_prim<D>(w0s, gas.gamma, us.prim);
-        us.tau = gas.mu_ref * 2.0 * pow(us.prim_c[D + 1], 1 - gas.omega) / us.prim_c[0];  // Gas/Model.jl:14
-        us.coef_c = maxwell_coef<D>(us.prim_c);
-        us.coef = maxwell_coef<D>(us.prim);
-        us.cb_c = gas.K / (2.0 * us.prim_c[D + 1]);
-        us.cb = gas.K / (2.0 * us.prim[D + 1]);
-    }
-    __syncthreads();
+    update_tail<D, K, MODE, STAGE_SMEM, NT>(g, gas, ci, c, dt, want_residual, acc, own, fs, fstride, fout, dyn, red, us,
+                                            w_new, w0s);
+}
 
-    // ---- phase 2: conservation correction f += M[prim_c] - M[prim]; heat flux of the corrected f about prim_c
-    double prim_c[D + 2];
+// ------------------------------------------------------------------------------------------------
+// phase_regular_kernel: the fused flux + update for REGULAR cells — every one of the 2*DIM sides is a single
+// fluid/fluid face to a neighbour on the same velocity grid (CELL_REGULAR, decided at flatten time; the bulk of
+// every mesh away from level jumps, domain edges, velocity-grid changes and the body).  Same arithmetic as
+// phase_kernel<FUSED> pass A, with the structure fixed at compile time: no slot loops, no rare pass; the record of a
+// side is picked by the sign of v_d and the 2*DIM neighbour values are requested before any arithmetic.
+template <int D, int K, bool STAGE_SMEM, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+    phase_regular_kernel(DevView g, GasPar gas, const int* __restrict__ cell_list, double dt, int want_residual) {
+    extern __shared__ double dyn[];
+    __shared__ FaceRec rec[2 * D];
+    __shared__ double red[2 * (D + 2) * 32];
+    __shared__ CellInfo ci;
+    __shared__ UpdateShared<D, K> us;
+    __shared__ double w_new[D + 2], w0s[D + 2];
+    const int c = cell_list[blockIdx.x];
+    copy_words(g.cells + c, &ci, (int)(sizeof(CellInfo) / sizeof(int)));
+    __syncthreads();
+    copy_words(g.hot + ci.hot_begin, rec, 2 * D * (int)(sizeof(FaceRec) / sizeof(int)));
+    __syncthreads();
+    const int n = ci.n, np = ci.np;
+    const CellPtr<D, K> own(g, ci);
+    const double dtv = dt / ci.vol;
+    double* fout = g.df_new + ci.doff * K;
+    double* fs = STAGE_SMEM ? dyn : fout;
+    const int fstride = STAGE_SMEM ? n : np;
+    const double* __restrict__ gdf = g.df;
+    const double* __restrict__ gsl = g.sdl;
+    double acc[2 * (D + 2)];
 #pragma unroll
-    for (int m = 0; m < D + 2; ++m) prim_c[m] = us.prim_c[m];
-    const double coef_c = us.coef_c, cb_c = us.cb_c;
-    double* fch = dyn + (size_t)K * n;  // staged h-component of M[prim_c] (STAGE_SMEM only)
-    {
-        double prim[D + 2];
+    for (int q = 0; q < 2 * (D + 2); ++q) acc[q] = 0.0;
+#pragma unroll UNROLL
+    for (int i = threadIdx.x; i < n; i += NT) {
+        double v[D], vdt[D], f[K], s[K * D], fl[K];
+        double nfv[D][K], nsv[D][K * D];
+        int rn[D];
 #pragma unroll
-        for (int m = 0; m < D + 2; ++m) prim[m] = us.prim[m];
-        const double coef = us.coef, cb = us.cb;
-        double q[D];
+        for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
 #pragma unroll
-        for (int d = 0; d < D; ++d) q[d] = 0.0;
-        for (int i = threadIdx.x; i < n; i += NT) {
-            double v[D], Fc[K], F[K], f[K];
-#pragma unroll
-            for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
-            maxwell_c<D, K>(v, prim_c, coef_c, cb_c, Fc);
-            maxwell_c<D, K>(v, prim, coef, cb, F);
+        for (int d = 0; d < D; ++d) {  // neighbour-upwind side: low face for v_d > 0, high face otherwise
+            rn[d] = 2 * d + (v[d] > 0. ? 0 : 1);
+            const double* __restrict__ nf = gdf + rec[rn[d]].nf_off + i;
+            const double* __restrict__ nsl = gsl + rec[rn[d]].nsl_off + i;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                f[k] = fs[k * fstride + i] + (Fc[k] - F[k]);
-                fs[k * fstride + i] = f[k];
-            }
-            if (STAGE_SMEM) fch[i] = Fc[0];
-            // heat_flux (2D2F.jl:68-88, 3D1F.jl:41-72): q_d = 1/2 sum w c_d (c^2 h + b)
-            const double gq = own.wt[i] * (c2_of<D>(v, prim_c) * f[0] + ((K > 1) ? f[1] : 0.0));
+                nfv[d][k] = nf[k * np];
 #pragma unroll
-            for (int d = 0; d < D; ++d) q[d] += (v[d] - prim_c[1 + d]) * gq;
-        }
-        block_reduce<D>(q, red);
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) { us.qf[d] = 0.5 * q[d]; g.qf[(size_t)c * D + d] = 0.5 * q[d]; }
-        }
-        __syncthreads();
-    }
-
-    // ---- phase 3: f = f*tau/(tau+dt) + dt/(tau+dt)*(M_c + S[M_c])
-    {
-        const double tau = us.tau;
-        const double a = tau / (tau + dt), b = dt / (tau + dt);
-        double qf[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) qf[d] = us.qf[d];
-        for (int i = threadIdx.x; i < n; i += NT) {
-            double v[D], Fc[K], Fp[K];
-#pragma unroll
-            for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
-            if (STAGE_SMEM) {
-                Fc[0] = fch[i];
-                if (K > 1) Fc[1] = Fc[0] * cb_c;
-            } else {
-                maxwell_c<D, K>(v, prim_c, coef_c, cb_c, Fc);
-            }
-            shakhov<D, K>(v, Fc, prim_c, qf, gas.Pr, gas.K, Fp);
-#pragma unroll
-            for (int k = 0; k < K; ++k) fout[k * np + i] = fs[k * fstride + i] * a + b * (Fc[k] + Fp[k]);
-        }
-    }
-    if (threadIdx.x == 0) {
-        double* prim_old = g.prim + (size_t)c * (D + 2);
-        if (want_residual) {  // residual_check!, Solver/Finalize.jl:5-11
-#pragma unroll
-            for (int m = 0; m < D + 2; ++m) {
-                const double dd = prim_c[m] - prim_old[m];
-                g.res_cell[(size_t)c * 2 * (D + 2) + m] = dd * dd;
-                g.res_cell[(size_t)c * 2 * (D + 2) + (D + 2) + m] = fabs(prim_c[m]);
+                for (int t = 0; t < D; ++t) nsv[d][k * D + t] = nsl[(t * K + k) * np];
             }
         }
+        const double wt = own.wt[i];
 #pragma unroll
-        for (int m = 0; m < D + 2; ++m) {
-            g.w[(size_t)c * (D + 2) + m] = w_new[m];
-            prim_old[m] = prim_c[m];
-            g.mflux[(size_t)c * (D + 2) + m] = 0.0;
+        for (int k = 0; k < K; ++k) {
+            f[k] = own.f[k * np + i];
+            fl[k] = 0.0;
+#pragma unroll
+            for (int t = 0; t < D; ++t) s[k * D + t] = own.sl[(t * K + k) * np + i];
         }
+#pragma unroll
+        for (int t = 0; t < D; ++t) vdt[t] = __dmul_rn(v[t], dt);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const double vn = v[d];
+            {   // own-upwind face: the other side of this direction
+                const FaceRec& h = rec[rn[d] ^ 1];
+                const double Avn = h.area * vn;
+                double dx[D];
+#pragma unroll
+                for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.own_mid[t]);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    double val = f[k];
+#pragma unroll
+                    for (int t = 0; t < D; ++t) val += dx[t] * s[k * D + t];
+                    fl[k] += val * Avn;
+                }
+            }
+            {   // neighbour-upwind face
+                const FaceRec& h = rec[rn[d]];
+                const double Avn = h.area * vn;
+                double dx[D];
+#pragma unroll
+                for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.nbr_mid[t]);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    double val = nfv[d][k];
+#pragma unroll
+                    for (int t = 0; t < D; ++t) val += dx[t] * nsv[d][k * D + t];
+                    fl[k] += val * Avn;
+                }
+            }
+        }
+        add_moments<D, K>(acc, wt, v, fl);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            f[k] += dtv * fl[k];
+            fs[k * fstride + i] = f[k];
+        }
+        add_moments<D, K>(acc + (D + 2), wt, v, f);
     }
+    update_tail<D, K, MODE_FUSED, STAGE_SMEM, NT>(g, gas, ci, c, dt, want_residual, acc, own, fs, fstride, fout, dyn, red,
+                                                  us, w_new, w0s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -814,13 +942,27 @@ __device__ __forceinline__ void side_sum(const DevView& g, const SlopeNbr* nb, i
 // Raw sdf is written only where something reads it (tk.flags bit0: coarse neighbours of projecting cells,
 // cells on domain / solid faces, halo mirrors) or when the host asked for it (raw_all: kamr_slope,
 // KAMR_OPT_KEEP_SDF).
+//
+// Dependency sweep in ONE launch: tasks are ordered by wave; a task that projects the finished slopes of coarser
+// cells computed by this same launch waits on their per-cell epoch flags (thread t spins on dependency t), and
+// every task publishes its own flag when its stores are visible.  A waiting CTA only ever waits for CTAs with a
+// lower block index, which the hardware dispatches first, so the sweep cannot deadlock.
 template <int D, int K, bool GENERIC, int NT>
-__global__ void __launch_bounds__(NT) slope_kernel(DevView g, const SlopeTask* __restrict__ tasks, int raw_all) {
+__global__ void __launch_bounds__(NT) slope_kernel(DevView g, const SlopeTask* __restrict__ tasks, int raw_all,
+                                                   int epoch) {
     __shared__ SlopeTask tk;
     __shared__ CellInfo ci;
     __shared__ SlopeNbr nb[MAX_SLOPE_NB];
     copy_words(tasks + blockIdx.x, &tk, (int)(sizeof(SlopeTask) / sizeof(int)));
     __syncthreads();
+    if (tk.dep_count > 0) {
+        if ((int)threadIdx.x < tk.dep_count) {
+            const volatile int* flag = g.slope_done + g.slope_deps[tk.dep_begin + threadIdx.x];
+            while (*flag != epoch) __nanosleep(64);
+            __threadfence();
+        }
+        __syncthreads();
+    }
     copy_words(g.cells + tk.cell, &ci, (int)(sizeof(CellInfo) / sizeof(int)));
     int base[D];
     {
@@ -876,6 +1018,58 @@ __global__ void __launch_bounds__(NT) slope_kernel(DevView g, const SlopeTask* _
             double s_abs = 0.0;
 #pragma unroll
             for (int d = 0; d < D; ++d) s_abs += ci.ds[d] * fabs(s[d][k]);
+            const double r = limiter(f[k], s_abs);
+#pragma unroll
+            for (int d = 0; d < D; ++d) sdl[(d * K + k) * np + i] = r * s[d][k];
+        }
+    }
+    if (epoch) {  // publish: every thread's stores first, then the flag
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *((volatile int*)(g.slope_done + tk.cell)) = epoch;
+        }
+    }
+}
+
+// slopes of REGULAR stencils (SlopeReg): same arithmetic as slope_kernel's SLOPE_INNER branch with one neighbour per
+// side, all 2*DIM neighbour values requested up front.
+template <int D, int K, int NT>
+__global__ void __launch_bounds__(NT) slope_regular_kernel(DevView g, const SlopeReg* __restrict__ tasks, int raw_all) {
+    __shared__ SlopeReg tk;
+    copy_words(tasks + blockIdx.x, &tk, (int)(sizeof(SlopeReg) / sizeof(int)));
+    __syncthreads();
+    const int n = tk.n, np = tk.np;
+    const bool raw = raw_all || (tk.flags & 1);
+    const double* __restrict__ df = g.df;
+    const double* __restrict__ own = df + tk.doff * K;
+    double* sdf = g.sdf + tk.doff * K * D;
+    double* sdl = g.sdl + tk.doff * K * D;
+    for (int i = threadIdx.x; i < n; i += NT) {
+        double f[K], nf[2 * D][K], s[D][K];
+#pragma unroll
+        for (int q = 0; q < 2 * D; ++q) {
+            const double* __restrict__ p = df + tk.nb_doff[q] * K + i;
+#pragma unroll
+            for (int k = 0; k < K; ++k) nf[q][k] = p[k * np];
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) f[k] = own[k * np + i];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double a = (0.0 + (f[k] - nf[2 * d][k])) * tk.inv[2 * d];
+                const double b = (0.0 + (f[k] - nf[2 * d + 1][k])) * tk.inv[2 * d + 1];
+                s[d][k] = minmod(a, b);
+                if (raw) sdf[(d * K + k) * np + i] = s[d][k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double s_abs = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) s_abs += tk.ds[d] * fabs(s[d][k]);
             const double r = limiter(f[k], s_abs);
 #pragma unroll
             for (int d = 0; d < D; ++d) sdl[(d * K + k) * np + i] = r * s[d][k];

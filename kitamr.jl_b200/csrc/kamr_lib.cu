@@ -19,6 +19,11 @@
 
 using namespace kamr;
 
+#ifndef KAMR_NT
+#define KAMR_NT 256
+#endif
+constexpr int NT_SLOPE = KAMR_NT;
+
 namespace {
 
 std::string g_create_err;
@@ -52,15 +57,16 @@ struct Bin {
     std::vector<int> cells;
     int* d_cells = nullptr;
     size_t smem = 0;     // dynamic shared memory per block (0 => global staging)
-    bool generic = false;  // some slot of some cell needs a pair map (mismatched velocity grids)
+    bool regular = false;  // all cells are CELL_REGULAR: phase_regular_kernel
 };
 
 enum KernelId { KID_SLOPE = 0, KID_MACRO_SLOPE, KID_FLUX, KID_UPDATE, KID_STEP, KID_RESIDUAL, KID_PACK, KID_UNPACK,
-                KID_LIMIT, KID_SOLID_CELL, KID_SOLID_NBR, KID_COUNT };
+                KID_LIMIT, KID_SOLID_CELL, KID_SOLID_NBR, KID_STEP_REGULAR, KID_SLOPE_REGULAR, KID_COUNT };
 const char* const kKernelNames[KID_COUNT] = {"slope_kernel", "macro_slope_kernel", "phase_kernel<FLUX>",
                                              "phase_kernel<UPDATE>", "phase_kernel<FUSED>", "residual_reduce_kernel",
                                              "pack_kernel", "unpack_kernel", "limit_kernel", "solid_cell_kernel",
-                                             "solid_neighbor_kernel"};
+                                             "solid_neighbor_kernel", "phase_regular_kernel",
+                                             "slope_regular_kernel"};
 
 struct PeerPlan {
     int rank;
@@ -89,10 +95,14 @@ struct kamr_ctx {
     int D = 0, K = 0, M = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side_stream = nullptr;   // wall kernels of a fused step run here, beside the regular cells' phase kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // topology (host copies)
     int n_local = 0, n_ghost = 0, n_sn = 0, n_cell = 0, n_grid = 0;
     std::vector<CellInfo> cells;
     std::vector<Slot> slots;
+    std::vector<FaceRec> hot;
+    std::vector<int> rare;
     std::vector<long long> host_off;  // unpadded point offset per cell (host layout)
     std::vector<int> grid_n, grid_np;
     std::vector<long long> grid_goff, grid_hoff;
@@ -100,9 +110,20 @@ struct kamr_ctx {
     std::map<std::pair<int, int>, int> rel_id;
     std::vector<long long> rel_off;
     std::vector<int> pm_start;
-    std::vector<std::pair<int, std::vector<SlopeTask>>> level_tasks;  // (wave, tasks), ascending
-    std::vector<SlopeTask*> d_level_tasks;
-    std::vector<char> level_generic;  // the task list holds pair-mapped stencils
+    // slope stages, ascending.  One rank: a single stage (regular stencils in one launch, everything else in a second
+    // launch that sweeps the dependency waves with flags).  With peers: one stage per refinement level, each followed
+    // by its halo exchange.
+    struct SlopeStage {
+        int wave = 0;
+        std::vector<SlopeReg> reg;
+        std::vector<SlopeTask> gen;
+        SlopeReg* d_reg = nullptr;
+        SlopeTask* d_gen = nullptr;
+        bool flags = false;   // gen tasks carry dependency lists
+    };
+    std::vector<SlopeStage> slope_stages;
+    std::vector<int> slope_deps;
+    int slope_epoch = 0;
     std::vector<SlopeNbr> slope_nb;
     int max_smem_optin = 0;
     bool keep_sdf = false;        // KAMR_OPT_KEEP_SDF: fused steps also write the raw slopes of every cell
@@ -164,9 +185,9 @@ struct kamr_ctx {
         for (void* p : allocs) cudaFree(p);
         allocs.clear();
         device_bytes = 0;
-        cells.clear(); slots.clear(); host_off.clear(); grid_n.clear(); grid_np.clear(); grid_goff.clear();
+        cells.clear(); slots.clear(); hot.clear(); rare.clear(); host_off.clear(); grid_n.clear(); grid_np.clear(); grid_goff.clear();
         grid_hoff.clear(); h_level.clear(); rel_id.clear(); rel_off.clear(); pm_start.clear();
-        level_tasks.clear(); d_level_tasks.clear(); level_generic.clear(); slope_nb.clear(); fluid_cells.clear(); bins.clear(); peers.clear();
+        slope_stages.clear(); slope_deps.clear(); slope_nb.clear(); fluid_cells.clear(); bins.clear(); peers.clear();
         dv = DevView{};
         d_res = nullptr; d_sendbuf = d_recvbuf = nullptr; d_fluid_cells = nullptr; d_limit_cells = nullptr;
         limit_cells.clear(); ghost_wave_cells.clear(); raw_sdf_valid = false;
@@ -179,8 +200,9 @@ namespace {
 // Counts a kernel launch and, while profiling is on, brackets it with events on the stream.
 struct Launch {
     kamr_ctx* c;
+    cudaStream_t st;
     cudaEvent_t b = nullptr;
-    Launch(kamr_ctx* c_, int kid) : c(c_) {
+    Launch(kamr_ctx* c_, int kid, cudaStream_t st_ = nullptr) : c(c_), st(st_ ? st_ : c_->stream) {
         c->launches++;
         if (!c->profiling) return;
         auto get = [&]() {
@@ -191,10 +213,10 @@ struct Launch {
         };
         cudaEvent_t a = get();
         b = get();
-        CK(cudaEventRecord(a, c->stream));
+        CK(cudaEventRecord(a, st));
         c->prof_recs.push_back({kid, a, b});
     }
-    ~Launch() { if (b) cudaEventRecord(b, c->stream); }
+    ~Launch() { if (b) cudaEventRecord(b, st); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -497,12 +519,44 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             per_cell[there].push_back(r);
         }
     }
+    // side of the cell a slot's face sits on: here & rot=+1 -> low face; the there side sees the same face from across
+    auto side_of = [](const Slot& s) { return (s.is_here ? (s.rot > 0) : (s.rot < 0)) ? 0 : 1; };
     for (int i = 0; i < c->n_local; ++i) {
         if ((int)per_cell[i].size() > max_slots(D)) throw Fail("too many faces on one cell");
-        std::stable_sort(per_cell[i].begin(), per_cell[i].end(), [](const Slot& a, const Slot& b) { return a.dir < b.dir; });
-        c->cells[i].slot_begin = (int)c->slots.size();
+        std::stable_sort(per_cell[i].begin(), per_cell[i].end(), [&](const Slot& a, const Slot& b) {
+            return 2 * a.dir + side_of(a) < 2 * b.dir + side_of(b);
+        });
+        CellInfo& ci = c->cells[i];
+        ci.slot_begin = (int)c->slots.size();
         c->slots.insert(c->slots.end(), per_cell[i].begin(), per_cell[i].end());
-        c->cells[i].slot_end = (int)c->slots.size();
+        ci.slot_end = (int)c->slots.size();
+        ci.hot_begin = (int)c->hot.size();
+        ci.rare_begin = (int)c->rare.size();
+        int key = 0, nh = 0;
+        for (int q = 0; q < (int)per_cell[i].size(); ++q) {
+            const Slot& sl = per_cell[i][q];
+            if (sl.kind == SLOT_BC_MAXWELL) ci.flags |= CELL_HAS_MAXWELL_WALL;
+            if (sl.kind == SLOT_INNER) {
+                while (key <= 2 * sl.dir + side_of(sl)) ci.side_begin[key++] = (unsigned char)nh;
+                FaceRec h;
+                memset(&h, 0, sizeof(h));
+                h.nf_off = sl.nbr_doff * K; h.nsl_off = sl.nbr_doff * K * D; h.np = sl.nbr_np;
+                h.flags = sl.rel_off < 0 ? 2 : 0;
+                h.area = sl.area;
+                for (int t = 0; t < D; ++t) { h.fmid[t] = sl.fmid[t]; h.own_mid[t] = sl.own_mid[t]; h.nbr_mid[t] = sl.nbr_mid[t]; }
+                c->hot.push_back(h);
+                ++nh;
+            }
+            if (sl.kind != SLOT_INNER || sl.rel_off >= 0) c->rare.push_back(q);
+        }
+        while (key <= 2 * D) ci.side_begin[key++] = (unsigned char)nh;
+        ci.rare_count = (int)c->rare.size() - ci.rare_begin;
+        bool regular = ci.rare_count == 0 && nh == 2 * D && ci.bound_enc >= 0;
+        for (int k2 = 0; regular && k2 < 2 * D; ++k2) {
+            const FaceRec& h = c->hot[ci.hot_begin + k2];
+            regular = ci.side_begin[k2] == k2 && (h.flags & 2) && h.np == ci.np;
+        }
+        if (regular) ci.flags |= CELL_REGULAR;
     }
     // ---- slope tasks in dependency waves (slope!, Slope.jl:1047-1070).  The reference sweeps the levels
     // coarse to fine because a fine cell next to a coarse one projects the coarse cell's FINISHED slopes
@@ -575,17 +629,68 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             }
             return wave[ti] = w;
         };
+        auto is_regular = [&](const SlopeTask& t) {
+            const CellInfo& ci = c->cells[t.cell];
+            for (int d = 0; d < D; ++d) {
+                const SlopeDir& sd = t.d[d];
+                if (sd.mode != SLOPE_INNER || sd.nA != 1 || sd.nB != 1) return false;
+                for (int a = 0; a < 2; ++a) {
+                    const SlopeNbr& e = c->slope_nb[sd.nb_begin + a];
+                    if (e.rel_off >= 0 || e.proj || e.np != ci.np) return false;
+                }
+            }
+            return true;
+        };
+        auto make_reg = [&](const SlopeTask& t) {
+            const CellInfo& ci = c->cells[t.cell];
+            SlopeReg r;
+            memset(&r, 0, sizeof(r));
+            r.doff = ci.doff; r.n = ci.n; r.np = ci.np; r.flags = t.flags;
+            for (int d = 0; d < D; ++d) {
+                r.ds[d] = ci.ds[d];
+                r.nb_doff[2 * d] = c->slope_nb[t.d[d].nb_begin].doff;
+                r.nb_doff[2 * d + 1] = c->slope_nb[t.d[d].nb_begin + 1].doff;
+                r.inv[2 * d] = t.d[d].invA; r.inv[2 * d + 1] = t.d[d].invB;
+            }
+            return r;
+        };
+        std::map<int, kamr_ctx::SlopeStage> stages;
+        std::vector<int> order(tasks.size());
         for (size_t ti = 0; ti < tasks.size(); ++ti) {
+            order[ti] = (int)ti;
             const int L = c->cells[tasks[ti].cell].ps_level;
-            const int w = by_level ? std::max(0, L - m->ps_minlevel) : depth((int)ti);
+            wave[ti] = by_level ? std::max(0, L - m->ps_minlevel) : depth((int)ti);
             tasks[ti].flags = need_raw[tasks[ti].cell] ? 1 : 0;
-            by_wave[std::make_pair(w, gen[ti] ? 1 : 0)].push_back(tasks[ti]);
         }
-        for (auto& kv : by_wave) {
-            c->d_level_tasks.push_back(c->dupload(kv.second));
-            c->level_generic.push_back((char)kv.first.second);
-            c->level_tasks.emplace_back(kv.first.first, std::move(kv.second));
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return wave[a] < wave[b]; });
+        std::vector<char> in_gen(tasks.size(), 0);
+        for (int ti : order) in_gen[ti] = !((by_level || wave[ti] == 0) && is_regular(tasks[ti]));
+        for (int ti : order) {
+            kamr_ctx::SlopeStage& st = stages[by_level ? wave[ti] : 0];
+            st.wave = by_level ? wave[ti] : 0;
+            if (!in_gen[ti]) { st.reg.push_back(make_reg(tasks[ti])); continue; }
+            SlopeTask t = tasks[ti];
+            if (!by_level) {  // dependencies computed by the same launch -> flags
+                t.dep_begin = (int)c->slope_deps.size();
+                for (int tgt : deps[ti]) {
+                    const int tj = (tgt < c->n_local) ? task_of[tgt] : -1;
+                    if (tj >= 0 && in_gen[tj]) c->slope_deps.push_back(tgt);
+                }
+                t.dep_count = (int)c->slope_deps.size() - t.dep_begin;
+                if (t.dep_count > NT_SLOPE) throw Fail("too many slope dependencies");
+                st.flags = true;
+            }
+            st.gen.push_back(t);
         }
+        for (auto& kv : stages) {
+            kv.second.d_reg = c->dupload(kv.second.reg);
+            kv.second.d_gen = c->dupload(kv.second.gen);
+            c->slope_stages.push_back(std::move(kv.second));
+        }
+        c->dv.slope_deps = c->dupload(c->slope_deps);
+        c->dv.slope_done = c->dalloc<int>((size_t)c->n_cell);
+        CK(cudaMemsetAsync(c->dv.slope_done, 0, (size_t)c->n_cell * sizeof(int), c->stream));
+        c->slope_epoch = 0;
     }
     // ---- fluid cell list (Morton order: neighbours in space are neighbours in the launch, so the blocks
     // resident at one time share their neighbour reads through L2) and the phase-kernel bins
@@ -601,14 +706,16 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         const size_t caps[] = {8 << 10, 16 << 10, 24 << 10, 32 << 10, 48 << 10, 64 << 10, 96 << 10, 128 << 10,
                                (size_t)c->max_smem_optin - (12 << 10)};
         const int ncap = (int)(sizeof(caps) / sizeof(caps[0]));
-        std::vector<Bin> bins(ncap + 1);
+        std::vector<Bin> bins(2 * (ncap + 1));
         c->fused_cells = 0;
         for (int cell : c->fluid_cells) {
             const CellInfo& ci = c->cells[cell];
             const size_t need = (size_t)ci.n * (K + 1) * sizeof(double);
             int q = 0;
             while (q < ncap && need > caps[q]) ++q;
-            Bin& b = bins[q];
+            const bool regular = (ci.flags & CELL_REGULAR) != 0;
+            Bin& b = bins[2 * q + (regular ? 1 : 0)];
+            b.regular = regular;
             b.smem = (q < ncap) ? std::max(b.smem, need) : 0;
             b.cells.push_back(cell);
             if (q < ncap) c->fused_cells++;
@@ -686,6 +793,8 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     const size_t np = (size_t)c->npts_pad;
     c->dv.cells = c->dupload(c->cells);
     c->dv.slots = c->dupload(c->slots);
+    c->dv.hot = c->dupload(c->hot);
+    c->dv.rare = c->dupload(c->rare);
     c->dv.pm_start = c->dupload(c->pm_start);
     c->dv.slope_nb = c->dupload(c->slope_nb);
     c->dv.df = c->dalloc<double>(np * K);
@@ -903,19 +1012,28 @@ void exchange(kamr_ctx* c, int what, int level) {
 #ifndef KAMR_NT
 #define KAMR_NT 256
 #endif
-#ifndef KAMR_MINB
-#define KAMR_MINB 3
+#ifndef KAMR_PNT
+#define KAMR_PNT 128
 #endif
-constexpr int NT = KAMR_NT;      // threads per CTA (one CTA per physical cell)
+#ifndef KAMR_MINB
+#define KAMR_MINB 6
+#endif
+constexpr int NT = KAMR_NT;      // threads per CTA of the slope kernel (one CTA per physical cell)
+constexpr int PNT = KAMR_PNT;    // threads per CTA of the phase kernel: small CTAs keep many cells in flight per SM,
+                                 // so one cell's barriers and serial moments->prim step hide behind the others
 constexpr int MINB = KAMR_MINB;  // CTAs per SM the phase kernel is register-budgeted for
 
 template <int D, int K>
-void launch_slope_wave(kamr_ctx* c, size_t l, int raw_all) {
-    const int nt = (int)c->level_tasks[l].second.size();
-    if (!nt) return;
-    Launch L_(c, KID_SLOPE);
-    if (c->level_generic[l]) slope_kernel<D, K, true, NT><<<nt, NT, 0, c->stream>>>(c->dv, c->d_level_tasks[l], raw_all);
-    else slope_kernel<D, K, false, NT><<<nt, NT, 0, c->stream>>>(c->dv, c->d_level_tasks[l], raw_all);
+void launch_slope_stage(kamr_ctx* c, const kamr_ctx::SlopeStage& st, int raw_all) {
+    if (!st.reg.empty()) {
+        Launch L_(c, KID_SLOPE_REGULAR);
+        slope_regular_kernel<D, K, NT><<<(int)st.reg.size(), NT, 0, c->stream>>>(c->dv, st.d_reg, raw_all);
+    }
+    if (!st.gen.empty()) {
+        Launch L_(c, KID_SLOPE);
+        slope_kernel<D, K, true, NT><<<(int)st.gen.size(), NT, 0, c->stream>>>(c->dv, st.d_gen, raw_all,
+                                                                              st.flags ? c->slope_epoch : 0);
+    }
 }
 
 template <int D, int K>
@@ -937,20 +1055,21 @@ void run_macro_slope(kamr_ctx* c) {
 template <int D, int K>
 void do_slope(kamr_ctx* c, bool with_sw, bool raw_all) {
     raw_all = raw_all || c->keep_sdf;
+    c->slope_epoch = c->slope_epoch == 0x7fffffff ? 1 : c->slope_epoch + 1;
     if (c->peers.empty()) {
-        for (size_t l = 0; l < c->level_tasks.size(); ++l) launch_slope_wave<D, K>(c, l, raw_all);
+        for (auto& st : c->slope_stages) launch_slope_stage<D, K>(c, st, raw_all);
     } else {
         // waves present locally or in the halo, ascending; each followed by its exchange
         // (slope_exchange_level!, Parallel/Ghost.jl:896) and the limited slopes of the ghosts that arrived
         std::vector<int> waves;
-        for (auto& lt : c->level_tasks) waves.push_back(lt.first);
+        for (auto& st : c->slope_stages) waves.push_back(st.wave);
         for (auto& pp : c->peers)
             for (auto& kv : pp.sdf) waves.push_back(kv.first);
         std::sort(waves.begin(), waves.end());
         waves.erase(std::unique(waves.begin(), waves.end()), waves.end());
         for (int w : waves) {
-            for (size_t l = 0; l < c->level_tasks.size(); ++l)
-                if (c->level_tasks[l].first == w) launch_slope_wave<D, K>(c, l, raw_all);
+            for (auto& st : c->slope_stages)
+                if (st.wave == w) launch_slope_stage<D, K>(c, st, raw_all);
             exchange(c, 1, w);
             auto it = c->ghost_wave_cells.find(w);
             if (it != c->ghost_wave_cells.end()) run_limit<D, K>(c, it->second.first, it->second.second);
@@ -970,7 +1089,7 @@ void prepare_kernel(Kern kern, int max_dyn) {
 
 template <int D, int K, int MODE, bool STAGE>
 void launch_phase_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want, int kid) {
-    auto kern = phase_kernel<D, K, MODE, STAGE, NT, MINB>;
+    auto kern = phase_kernel<D, K, MODE, STAGE, PNT, MINB>;
     static bool prepared = false;  // per instantiation; attributes are per device function
     if (!prepared) {
         cudaFuncAttributes fa;
@@ -979,11 +1098,30 @@ void launch_phase_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int wa
         prepared = true;
     }
     Launch L_(c, kid);
-    kern<<<(int)b.cells.size(), NT, smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
+    kern<<<(int)b.cells.size(), PNT, smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
+}
+
+template <int D, int K, bool STAGE>
+void launch_regular_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want) {
+    auto kern = phase_regular_kernel<D, K, STAGE, PNT, MINB>;
+    static bool prepared = false;
+    if (!prepared) {
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, kern));
+        prepare_kernel(kern, c->max_smem_optin - (int)fa.sharedSizeBytes);
+        prepared = true;
+    }
+    Launch L_(c, KID_STEP_REGULAR);
+    kern<<<(int)b.cells.size(), PNT, smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
 }
 
 template <int D, int K, int MODE>
 void launch_phase(kamr_ctx* c, const Bin& b, double dt, int want) {
+    if (MODE == MODE_FUSED && b.regular) {
+        if (b.smem > 0) launch_regular_inst<D, K, true>(c, b, b.smem, dt, want);
+        else launch_regular_inst<D, K, false>(c, b, 0, dt, want);
+        return;
+    }
     const int kid = MODE == MODE_FUSED ? KID_STEP : (MODE == MODE_FLUX ? KID_FLUX : KID_UPDATE);
     const bool stage = (MODE != MODE_FLUX) && b.smem > 0;
     if (stage) launch_phase_inst<D, K, MODE, true>(c, b, b.smem, dt, want, kid);
@@ -993,15 +1131,16 @@ void launch_phase(kamr_ctx* c, const Bin& b, double dt, int want) {
 // the wall half of flux!(p4est, ka) (Flux.jl:463-481): update_solid_cell!, the solid halo, update_solid_neighbor!.
 // df2: second buffer that receives the same values (the write side of a fused step), or null.
 template <int D, int K>
-void do_ib(kamr_ctx* c, double* df2) {
+void do_ib(kamr_ctx* c, double* df2, cudaStream_t st = nullptr) {
+    if (!st) st = c->stream;
     if (!c->solid_tasks.empty()) {
-        Launch L_(c, KID_SOLID_CELL);
-        solid_cell_kernel<D, K><<<(int)c->solid_tasks.size(), 256, 0, c->stream>>>(c->dv, c->gas, c->d_solid_tasks, df2);
+        Launch L_(c, KID_SOLID_CELL, st);
+        solid_cell_kernel<D, K><<<(int)c->solid_tasks.size(), 256, 0, st>>>(c->dv, c->gas, c->d_solid_tasks, df2);
     }
-    exchange(c, 2, 0);
+    if (st == c->stream) exchange(c, 2, 0);   // (callers use the side stream only when no solid cell crosses ranks)
     if (!c->sn_tasks.empty()) {
-        Launch L_(c, KID_SOLID_NBR);
-        solid_neighbor_kernel<D, K><<<(int)c->sn_tasks.size(), 256, 0, c->stream>>>(c->dv, c->gas, c->d_sn_tasks, df2);
+        Launch L_(c, KID_SOLID_NBR, st);
+        solid_neighbor_kernel<D, K><<<(int)c->sn_tasks.size(), 256, 0, st>>>(c->dv, c->gas, c->d_sn_tasks, df2);
     }
     CK(cudaGetLastError());
 }
@@ -1051,8 +1190,23 @@ void do_step(kamr_ctx* c, double dt, int want, double* res_out) {
         return;
     }
     do_slope<D, K>(c, false, false);
-    do_ib<D, K>(c, c->dv.df_new);
-    for (auto& b : c->bins) launch_phase<D, K, MODE_FUSED>(c, b, dt, want);
+    // The wall kernels feed the donor cells only, and a donor is never a regular cell: they run on the side stream
+    // while the regular cells' phase kernel runs here (the overlap flux!(p4est, ka) has between the solid halo and the
+    // non-IB faces, Flux.jl:461-485).  With solid cells in the halo the exchange keeps them on the main stream.
+    bool solid_halo = false;
+    for (auto& pp : c->peers) solid_halo = solid_halo || !pp.solid.send.empty() || !pp.solid.recv.empty();
+    const bool side = !solid_halo && (!c->solid_tasks.empty() || !c->sn_tasks.empty());
+    if (side) {
+        CK(cudaEventRecord(c->ev_fork, c->stream));
+        CK(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+        do_ib<D, K>(c, c->dv.df_new, c->side_stream);
+        CK(cudaEventRecord(c->ev_join, c->side_stream));
+    } else {
+        do_ib<D, K>(c, c->dv.df_new);
+    }
+    for (auto& b : c->bins) if (b.regular) launch_phase<D, K, MODE_FUSED>(c, b, dt, want);
+    if (side) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    for (auto& b : c->bins) if (!b.regular) launch_phase<D, K, MODE_FUSED>(c, b, dt, want);
     CK(cudaGetLastError());
     // cells that are not updated (solid ghost cells, ghosts) are refreshed in the new buffer by the IB
     // kernels / the halo exchange below
@@ -1111,6 +1265,9 @@ int kamr_create(const kamr_config* cfg, kamr_ctx** out) {
         c->gas = GasPar{cfg->K, cfg->Pr, cfg->gamma, cfg->omega, cfg->mu_ref, cfg->flux_type, cfg->marching};
         if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
         else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+        CK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         CK(cudaMallocHost((void**)&c->h_res, 64 * sizeof(double)));
         c->stage_doubles = (size_t)8 << 20;  // 64 MiB pinned staging
         CK(cudaMallocHost((void**)&c->h_stage, c->stage_doubles * sizeof(double)));
@@ -1132,6 +1289,9 @@ int kamr_destroy(kamr_ctx* c) {
     if (c->comm) nccl().CommDestroy(c->comm);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -1247,7 +1407,7 @@ int kamr_get_stats(kamr_ctx* c, kamr_stats* out) {
         out->kernel_launches = c->launches;
         out->device_bytes = c->device_bytes;
         out->halo_bytes_per_step = c->halo_bytes_step;
-        out->n_levels = (int)c->level_tasks.size();
+        out->n_levels = (int)c->slope_stages.size();
         out->fused_cells = c->fused_cells;
     });
 }

@@ -24,8 +24,17 @@ struct CellInfo {
     int grid;
     int bound_enc;
     int slot_begin, slot_end;
-    int ps_level, pad_;
+    int ps_level;
+    int flags;                     // CELL_* bits
+    int hot_begin;                 // first FaceRec of the cell; records sorted by (direction, side)
+    int rare_begin, rare_count;    // cell-relative indices of the slots pass B visits
+    unsigned char side_begin[8];   // [2*d + side] .. [2*d + side + 1]: FaceRec range of that side; [2*DIM]: total
+    int pad_;
     double ds[MAXD], mid[MAXD], vol;
+};
+enum CellFlags : int {
+    CELL_HAS_MAXWELL_WALL = 1,
+    CELL_REGULAR = 2,  // each of the 2*DIM sides is one fluid/fluid face to a neighbour on the same velocity grid
 };
 
 enum SlotKind : int {
@@ -58,6 +67,18 @@ struct Slot {
     double bc[MAXM];
 };
 
+// A fluid/fluid face as the flux gather sees it from one cell (built at flatten time from Slot; pass A of the phase
+// kernel reads nothing else).  side 0: the face at the low end of the direction, side 1: the high end.  Through the
+// low face the cell is upwind for points with v_d < 0 and the neighbour for v_d > 0; the high face the other way round.
+struct FaceRec {
+    long long nf_off;    // neighbour df block offset (doubles)
+    long long nsl_off;   // neighbour limited-slope block offset (doubles)
+    int np;              // neighbour plane stride
+    int flags;           // bit1: neighbour half gathered in pass A (identical velocity grids)
+    double area;         // signed, as Slot::area
+    double fmid[MAXD], own_mid[MAXD], nbr_mid[MAXD];
+};
+
 // Slope stencil of one (cell, direction): Flux/Slope.jl:458-771, 849-945 resolved at flatten time.
 struct SlopeNbr {
     long long doff;      // neighbour's point offset
@@ -77,7 +98,19 @@ struct SlopeDir {
 struct SlopeTask {
     int cell;
     int flags;           // bit0: write raw sdf (somebody reads it)
+    int dep_begin, dep_count;  // cells (in DevView::slope_deps) whose finished slopes this task projects, when they
+                               // are computed by the same launch (single-launch dependency sweep)
     SlopeDir d[MAXD];
+};
+// A REGULAR slope stencil: in every direction one same-level fluid neighbour per side on the same velocity grid,
+// no transverse projection (the bulk of every mesh).  Everything the kernel needs in one record.
+struct SlopeReg {
+    long long doff;
+    int n, np;
+    int flags, pad_;     // bit0: write raw sdf
+    double ds[MAXD];
+    long long nb_doff[2 * MAXD];   // [2*d + side]
+    double inv[2 * MAXD];          // 1/dsL, 1/dsR (signed) as SlopeDir::invA/invB
 };
 
 // Immersed boundary (kernel d): tables resolved at flatten time from kamr_ib.
@@ -110,7 +143,11 @@ struct CopySeg {
 struct DevView {
     const CellInfo* cells;
     const Slot* slots;
+    const FaceRec* hot;
+    const int* rare;
     const SlopeNbr* slope_nb;
+    const int* slope_deps;
+    int* slope_done;            // per cell: epoch of the last finished slope task (dependency flags)
     const int8_t* v_level;
     const double* v_weight;
     const double* v_mid;
