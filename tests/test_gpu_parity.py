@@ -107,7 +107,11 @@ def test_fused_step_matches_oracle(setup):
             tol = TOL if it == 0 else 1e-11
             assert rel_l2(local_pts(mesh, out.df, K), local_pts(mesh, ref.df, K)) <= tol
             assert rel_l2(out.w[: nl * (D + 2)], ref.w[: nl * (D + 2)]) <= tol
-            assert rel_l2(out.prim[: nl * (D + 2)], ref.prim[: nl * (D + 2)]) <= tol
+            # prim of FLUID cells: a solid ghost cell's prim is get_prim of an extrapolated distribution (Immersed_boundary.jl
+            # :139-140), whose lambda = rho/(2(gamma-1)(E - rho U^2/2)) can be arbitrarily ill-conditioned; nothing on the path
+            # reads it (the reference blanks solid cells in its output, IO/Types.jl:47-68)
+            fluid = np.repeat(mesh.bound_enc[:nl] >= 0, D + 2)
+            assert rel_l2(out.prim[: nl * (D + 2)][fluid], ref.prim[: nl * (D + 2)][fluid]) <= tol
 
 
 def test_pair_maps_bit_exact(setup):

@@ -9,17 +9,16 @@ case = cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxle
 mesh = case.rank_mesh(); st0 = case.init_state(mesh); cfg = case.config(); dt = case.dt()
 ctx = api.Context(cfg); ctx.upload_topology(mesh); ctx.upload_state(st0, aux=True)
 ref = st0.copy()
-orc.slope(cfg, mesh, ref); ctx.slope()
-orc.ib_solid_cells(cfg, mesh, ref); orc.ib_solid_neighbors(cfg, mesh, ref); orc.flux(cfg, mesh, ref, dt)
-ctx.flux(dt)
-out = ctx.download_state(st0.copy())
-off = mesh.vs_off(); K = 2
-for c in range(mesh.n_cell):
-    a = out.df[off[c]*K:off[c+1]*K]; b = ref.df[off[c]*K:off[c+1]*K]
-    e = np.linalg.norm(a-b)/(np.linalg.norm(b)+1e-300)
-    if e > 1e-12:
-        s = list(mesh.ib.solid_cell).index(c) if c in mesh.ib.solid_cell else -1
-        nbs = mesh.ib.solid_nb_ids[mesh.ib.solid_nb_off[s]:mesh.ib.solid_nb_off[s+1]] if s >= 0 else []
-        print("cell", c, "benc", mesh.bound_enc[c], "err", e, "grid", mesh.cell_grid[c], "nb grids", [int(mesh.cell_grid[j]) for j in nbs],
-              "init-vs-ref", np.linalg.norm(st0.df[off[c]*K:off[c+1]*K]-b)/np.linalg.norm(b), "init-vs-out", np.linalg.norm(st0.df[off[c]*K:off[c+1]*K]-a)/np.linalg.norm(b))
-print("w err", np.abs(out.w-ref.w).max())
+off = mesh.vs_off(); K = 2; M = 4
+for it in range(10):
+    orc.step(cfg, mesh, ref, dt, False); ctx.step(dt, False)
+    out = ctx.download_state(st0.copy(), abi.DL_DF | abi.DL_W | abi.DL_PRIM)
+    errs = []
+    for c in range(mesh.n_local):
+        a = out.df[off[c]*K:off[c+1]*K]; b = ref.df[off[c]*K:off[c+1]*K]
+        errs.append(np.linalg.norm(a-b)/(np.linalg.norm(b)+1e-300))
+    errs = np.array(errs)
+    pe = np.abs(out.prim[:mesh.n_local*M]-ref.prim[:mesh.n_local*M]).reshape(-1, M).max(axis=1)
+    top = np.argsort(-errs)[:5]
+    print(f"step {it}: df rel L2 max {errs.max():.2e} median {np.median(errs):.2e}; prim abs max {pe.max():.2e}; worst cells",
+          [(int(c), int(mesh.bound_enc[c]), f"{errs[c]:.1e}") for c in top])
