@@ -1084,7 +1084,8 @@ void do_slope(kamr_ctx* c, bool with_sw, bool raw_all) {
 template <class Kern>
 void prepare_kernel(Kern kern, int max_dyn) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // no carve-out preference: the driver sizes shared memory for the resident CTAs and leaves the rest of the 256 KB to
+    // L1, which serves the velocity-grid statics every pass re-reads (forcing MaxShared cost 12 % of the step, r01_i)
 }
 
 template <int D, int K, int MODE, bool STAGE>
