@@ -1388,6 +1388,21 @@ __global__ void __launch_bounds__(256) copy_segments_kernel(const CopySeg* __res
     }
 }
 
+// host layout (planes of n points, cells back to back) <-> device layout (planes padded to np): one block per cell
+__global__ void __launch_bounds__(256) repack_kernel(const CellInfo* __restrict__ cells, const long long* __restrict__ host_off,
+                                                     int ncell, int comps, double* __restrict__ padded,
+                                                     double* __restrict__ packed, int to_padded) {
+    for (int c = blockIdx.x; c < ncell; c += gridDim.x) {
+        const long long doff = cells[c].doff * comps, hoff = host_off[c] * comps;
+        const int n = cells[c].n, np = cells[c].np;
+        for (int t = threadIdx.x; t < comps * n; t += blockDim.x) {
+            const int p = t / n, i = t - p * n;
+            if (to_padded) padded[doff + (long long)p * np + i] = packed[hoff + t];
+            else packed[hoff + t] = padded[doff + (long long)p * np + i];
+        }
+    }
+}
+
 __global__ void fill_kernel(double* p, long long n, double v) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
         p[t] = v;

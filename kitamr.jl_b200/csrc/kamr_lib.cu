@@ -148,8 +148,9 @@ struct kamr_ctx {
     DevView dv{};
     double* d_res = nullptr;
     double* h_res = nullptr;  // pinned
-    double* h_stage = nullptr;  // pinned staging for padded transfers
-    size_t stage_doubles = 0;
+    double* d_stage = nullptr;  // device staging for padded transfers (host layout, contiguous)
+    size_t d_stage_doubles = 0;
+    long long* d_host_off = nullptr;
     // halo
     ncclComm_t comm = nullptr;
     std::vector<PeerPlan> peers;
@@ -189,6 +190,7 @@ struct kamr_ctx {
         grid_hoff.clear(); h_level.clear(); rel_id.clear(); rel_off.clear(); pm_start.clear();
         slope_stages.clear(); slope_deps.clear(); slope_nb.clear(); fluid_cells.clear(); bins.clear(); peers.clear();
         dv = DevView{};
+        d_host_off = nullptr;
         d_res = nullptr; d_sendbuf = d_recvbuf = nullptr; d_fluid_cells = nullptr; d_limit_cells = nullptr;
         limit_cells.clear(); ghost_wave_cells.clear(); raw_sdf_valid = false;
         solid_tasks.clear(); sn_tasks.clear(); ib_nb.clear(); d_solid_tasks = nullptr; d_sn_tasks = nullptr;
@@ -905,45 +907,23 @@ void copy_points(kamr_ctx* c, double* dev, double* host_rw, const double* host_r
         CK(cudaStreamSynchronize(c->stream));
         return;
     }
-    // padded: go through the pinned staging buffer in chunks of whole cells
-    int i = 0;
-    while (i < c->n_cell) {
-        int j = i;
-        size_t dcount = 0;
-        while (j < c->n_cell && dcount + (size_t)c->cells[j].np * comps <= c->stage_doubles) {
-            dcount += (size_t)c->cells[j].np * comps;
-            ++j;
-        }
-        if (j == i) throw Fail("staging buffer smaller than one cell block");
-        double* dptr = dev + (size_t)c->cells[i].doff * comps;
-        if (to_device) {
-            size_t pos = 0;
-            for (int q = i; q < j; ++q) {
-                const CellInfo& ci = c->cells[q];
-                const double* src = host_ro + (size_t)c->host_off[q] * comps;
-                for (int p = 0; p < comps; ++p) {
-                    memcpy(c->h_stage + pos, src + (size_t)p * ci.n, sizeof(double) * ci.n);
-                    for (int t = ci.n; t < ci.np; ++t) c->h_stage[pos + t] = 0.0;
-                    pos += ci.np;
-                }
-            }
-            CK(cudaMemcpyAsync(dptr, c->h_stage, dcount * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-        } else {
-            CK(cudaMemcpyAsync(c->h_stage, dptr, dcount * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-            size_t pos = 0;
-            for (int q = i; q < j; ++q) {
-                const CellInfo& ci = c->cells[q];
-                double* dst = host_rw + (size_t)c->host_off[q] * comps;
-                for (int p = 0; p < comps; ++p) {
-                    memcpy(dst + (size_t)p * ci.n, c->h_stage + pos, sizeof(double) * ci.n);
-                    pos += ci.np;
-                }
-            }
-        }
-        i = j;
+    // padded: one contiguous transfer at full PCIe rate into / out of a device staging buffer, re-laid-out by a kernel
+    if (c->d_stage_doubles < total_h) {
+        if (c->d_stage) { CK(cudaStreamSynchronize(c->stream)); cudaFree(c->d_stage); }
+        CK(cudaMalloc((void**)&c->d_stage, total_h * sizeof(double)));
+        c->d_stage_doubles = total_h;
     }
+    if (!c->d_host_off) c->d_host_off = c->dupload(c->host_off);
+    const int grid = std::min(c->n_cell, 148 * 16);
+    if (to_device) {
+        CK(cudaMemcpyAsync(c->d_stage, host_ro, total_h * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        repack_kernel<<<grid, 256, 0, c->stream>>>(c->dv.cells, c->d_host_off, c->n_cell, comps, dev, c->d_stage, 1);
+    } else {
+        repack_kernel<<<grid, 256, 0, c->stream>>>(c->dv.cells, c->d_host_off, c->n_cell, comps, dev, c->d_stage, 0);
+        CK(cudaMemcpyAsync(host_rw, c->d_stage, total_h * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1270,8 +1250,6 @@ int kamr_create(const kamr_config* cfg, kamr_ctx** out) {
         CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         CK(cudaMallocHost((void**)&c->h_res, 64 * sizeof(double)));
-        c->stage_doubles = (size_t)8 << 20;  // 64 MiB pinned staging
-        CK(cudaMallocHost((void**)&c->h_stage, c->stage_doubles * sizeof(double)));
         *out = c;
         return 0;
     } catch (const std::exception& e) {
@@ -1289,7 +1267,7 @@ int kamr_destroy(kamr_ctx* c) {
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->comm) nccl().CommDestroy(c->comm);
     if (c->h_res) cudaFreeHost(c->h_res);
-    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->d_stage) cudaFree(c->d_stage);
     if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
