@@ -1068,9 +1068,15 @@ void prepare_kernel(Kern kern, int max_dyn) {
     // L1, which serves the velocity-grid statics every pass re-reads (forcing MaxShared cost 12 % of the step, r01_i)
 }
 
-template <int D, int K, int MODE, bool STAGE>
+// cells whose staged block needs more than 32 KB of shared memory (n > ~1300 points in 2D2F, ~2000 in 3D1F) take
+// 1024-thread CTAs: one or two of them fill an SM, and a cell's points still spread over 32 warps
+constexpr int PNT_BIG = 1024;
+constexpr int MINB_BIG = 1;
+constexpr size_t BIG_SMEM = 32 << 10;
+
+template <int D, int K, int MODE, bool STAGE, int PT, int MB>
 void launch_phase_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want, int kid) {
-    auto kern = phase_kernel<D, K, MODE, STAGE, PNT, MINB>;
+    auto kern = phase_kernel<D, K, MODE, STAGE, PT, MB>;
     static bool prepared = false;  // per instantiation; attributes are per device function
     if (!prepared) {
         cudaFuncAttributes fa;
@@ -1079,12 +1085,12 @@ void launch_phase_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int wa
         prepared = true;
     }
     Launch L_(c, kid);
-    kern<<<(int)b.cells.size(), PNT, smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
+    kern<<<(int)b.cells.size(), PT, smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
 }
 
-template <int D, int K, bool STAGE>
+template <int D, int K, bool STAGE, int PT, int MB>
 void launch_regular_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want) {
-    auto kern = phase_regular_kernel<D, K, STAGE, PNT, MINB>;
+    auto kern = phase_regular_kernel<D, K, STAGE, PT, MB>;
     static bool prepared = false;
     if (!prepared) {
         cudaFuncAttributes fa;
@@ -1093,20 +1099,27 @@ void launch_regular_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int 
         prepared = true;
     }
     Launch L_(c, KID_STEP_REGULAR);
-    kern<<<(int)b.cells.size(), PNT, smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
+    kern<<<(int)b.cells.size(), PT, smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
 }
 
 template <int D, int K, int MODE>
 void launch_phase(kamr_ctx* c, const Bin& b, double dt, int want) {
+    const bool big = b.smem == 0 || b.smem > BIG_SMEM;
     if (MODE == MODE_FUSED && b.regular) {
-        if (b.smem > 0) launch_regular_inst<D, K, true>(c, b, b.smem, dt, want);
-        else launch_regular_inst<D, K, false>(c, b, 0, dt, want);
+        if (b.smem == 0) launch_regular_inst<D, K, false, PNT_BIG, MINB_BIG>(c, b, 0, dt, want);
+        else if (big) launch_regular_inst<D, K, true, PNT_BIG, MINB_BIG>(c, b, b.smem, dt, want);
+        else launch_regular_inst<D, K, true, PNT, MINB>(c, b, b.smem, dt, want);
         return;
     }
     const int kid = MODE == MODE_FUSED ? KID_STEP : (MODE == MODE_FLUX ? KID_FLUX : KID_UPDATE);
     const bool stage = (MODE != MODE_FLUX) && b.smem > 0;
-    if (stage) launch_phase_inst<D, K, MODE, true>(c, b, b.smem, dt, want, kid);
-    else launch_phase_inst<D, K, MODE, false>(c, b, 0, dt, want, kid);
+    if (stage) {
+        if (big) launch_phase_inst<D, K, MODE, true, PNT_BIG, MINB_BIG>(c, b, b.smem, dt, want, kid);
+        else launch_phase_inst<D, K, MODE, true, PNT, MINB>(c, b, b.smem, dt, want, kid);
+    } else {
+        if (big || MODE == MODE_FLUX) launch_phase_inst<D, K, MODE, false, PNT_BIG, MINB_BIG>(c, b, 0, dt, want, kid);
+        else launch_phase_inst<D, K, MODE, false, PNT, MINB>(c, b, 0, dt, want, kid);
+    }
 }
 
 // the wall half of flux!(p4est, ka) (Flux.jl:463-481): update_solid_cell!, the solid halo, update_solid_neighbor!.

@@ -344,7 +344,74 @@ def cylinder_s2(copies=1, ps_maxlevel=7, box_level=4, vs_maxlevel=3, vtrees=16, 
     return case
 
 
+def sphere_s4(copies=1, ps_maxlevel=4, trees=16, vtrees=16, vs_maxlevel=2, noise=0.01, ib=True,
+              shell=1.5) -> Case:
+    """S4 sphere3d (example/sphere/sphere.jl:5-47, sphere_udf.jl): trees^3 roots on [-4,4]^3, static refinement
+    to level L-2 in max-norm(x) < 1.2 and L-1 in < 0.8 outside the body (shock_wave_region), level L within
+    search_coeffi*ds_min = 1.5*ds_min of the r = 0.5 sphere; velocity grids vtrees^3 roots on [-7.28,7.28]^3 refined to
+    level <= 2 by maxwellian_refine_flag of the buffer IC (the stored static_vs_refine_flag is never called in the
+    reference); NDF = 1, K = 0, Ma 3.834 inflow at xmin, UniformOutflow elsewhere, isothermal
+    Maxwellian sphere.  `copies` places that many spheres side by side in x (weak scaling)."""
+    W = 8.0
+    geo = (-4.0, -4.0 + W * copies, -4.0, 4.0, -4.0, 4.0)
+    centers = np.array([[W * k, 0.0, 0.0] for k in range(copies)])
+    L = ps_maxlevel
+    ds_min = W / trees / 2 ** L
+    Ma = 3.834
+    Tw = 1.0 + (5 / 3 - 1) * 0.5 * Ma ** 2
+
+    def rel(mid):
+        d = mid[:, None, :] - centers[None, :, :]
+        k = np.argmin(np.abs(d[:, :, 0]), axis=1)
+        return d[np.arange(len(mid)), k]
+
+    def refine_fn(l, mid, ds):
+        x = rel(mid)
+        r = np.sqrt(np.sum(x ** 2, axis=1))
+        mx = np.max(np.abs(x), axis=1)
+        out = np.zeros(len(mid), dtype=bool)
+        out |= (mx < 1.2) & (r > 0.5) & (l < L - 2)
+        out |= (mx < 0.8) & (r > 0.5) & (l < L - 1)
+        half_diag = 0.5 * np.sqrt(np.sum(ds ** 2))
+        out |= np.abs(r - 0.5) < shell * ds_min + half_diag
+        return out
+
+    forest = Forest.build(3, geo, (trees * copies, trees, trees), L, refine_fn)
+    quad = (-7.28, 7.28) * 3
+    gas = Gas(K=0.0, Kn=0.03, omega=0.75, omega_r=0.75, mu_ref=5.0 * math.sqrt(math.pi) / 16.0 * 0.03)
+
+    def prim_fn(x):
+        d = np.asarray(x)[None, :] - centers
+        xr = d[np.argmin(np.abs(d[:, 0]))]
+        r = float(np.sqrt(np.sum(xr ** 2)))
+        if r > 1.0:
+            return np.array([1.0, Ma * math.sqrt(5 / 6), 0.0, 0.0, 1.0])
+        rr = max(r, 0.5)
+        return np.array([1.0, (rr - 0.5) / 0.5 * Ma * math.sqrt(5 / 6), 0.0, 0.0, 1.0 / (Tw - (rr - 0.5) * (Tw - 1.0))])
+
+    cache = {}
+    per_cell = []
+    for c in range(forest.n):
+        p = prim_fn(forest.mid[c])
+        key = (round(float(p[1]), 0), round(float(p[4]), 1))
+        if key not in cache:
+            cache[key] = vg.maxwellian_grid(quad, (vtrees,) * 3, vs_maxlevel,
+                                            np.array([1.0, key[0], 0.0, 0.0, max(key[1], 0.1)]), 1, gas.K)
+        per_cell.append(cache[key])
+    grids, cell_grid = _dedup_grids(per_cell)
+    bt, bp = _bcs(3, [abi.BC_SUPERSONIC_INFLOW] + [abi.BC_UNIFORM_OUTFLOW] * 5,
+                  [[1.0, Ma * math.sqrt(5 / 6), 0.0, 0.0, 1.0]] + [None] * 5)
+    case = Case(f"S4-sphere3d-x{copies}", 3, 1, forest, grids, cell_grid, bt, bp, gas, quad, (vtrees,) * 3,
+                vs_maxlevel, prim_fn, SEED_BASE + 4, noise=noise)
+    if ib:
+        from . import ib as ibm
+        case.ib_shape = ibm.Ball(centers, 0.5, np.array([1.0, 0.0, 0.0, 0.0, 1.0 / Tw]))
+        case.cell_class = ibm.classify(forest, case.ib_shape)
+    return case
+
+
 WORKLOADS = {
     "S2": cylinder_s2,
     "S2ib": lambda copies=1: cylinder_s2(copies=copies, ib=True),
+    "S4": sphere_s4,
 }

@@ -88,18 +88,19 @@ def classify(forest, shape) -> np.ndarray:
 
 # ------------------------------------------------------------------------------------------------ cut cells
 def _below_fraction(nv, alpha):
-    """volume fraction of the unit cube {x in [0,1]^D : nv.x < alpha}, all nv > 0 (inclusion-exclusion)."""
-    D = len(nv)
-    tot = 0.0
+    """volume fraction of the unit cube {x in [0,1]^D : nv.x < alpha}, all nv > 0 (inclusion-exclusion).
+    nv [m, D], alpha [m] -> [m]"""
+    nv = np.atleast_2d(nv); alpha = np.atleast_1d(alpha)
+    D = nv.shape[1]
+    tot = np.zeros(len(alpha))
     for k in range(D + 1):
         for sub in itertools.combinations(range(D), k):
-            a = alpha - sum(nv[i] for i in sub)
-            if a > 0:
-                tot += (-1) ** k * a ** D
+            a = alpha - (nv[:, list(sub)].sum(axis=1) if sub else 0.0)
+            tot += (-1) ** k * np.where(a > 0, a, 0.0) ** D
     fact = 1.0
     for i in range(1, D + 1):
         fact *= i
-    return min(max(tot / (fact * np.prod(nv)), 0.0), 1.0)
+    return np.clip(tot / (fact * np.prod(nv, axis=1)), 0.0, 1.0)
 
 
 def cut_cells(normal, grid):
@@ -109,25 +110,24 @@ def cut_cells(normal, grid):
     n = np.asarray(normal, dtype=np.float64)
     D = grid.dim
     small = np.abs(n) < 1e-6
+    z = np.zeros(0)
     if (D == 2 and small.any()) or (D == 3 and small.sum() > 1):
-        z = np.zeros(0)
         return np.zeros(0, np.int32), z, z
-    idx, gw, sw = [], [], []
-    ddu = grid.root_ds[None, :] / (2.0 ** grid.level.astype(np.float64))[:, None]
-    cand = np.nonzero(np.abs(grid.mid @ n) <= 0.5 * np.linalg.norm(ddu, axis=1))[0]
+    ddu_all = grid.root_ds[None, :] / (2.0 ** grid.level.astype(np.float64))[:, None]
+    cand = np.nonzero(np.abs(grid.mid @ n) <= 0.5 * np.linalg.norm(ddu_all, axis=1))[0]
+    if len(cand) == 0:
+        return np.zeros(0, np.int32), z, z
     act = [d for d in range(D) if not small[d]]
-    for i in cand:
-        lo = grid.mid[i] - 0.5 * ddu[i]
-        # map to the unit cube with positive normal components: x_d = (v_d - lo_d)/ddu_d, flipped where n_d < 0
-        nv = np.array([abs(n[d]) * ddu[i][d] for d in act])
-        corner = np.array([lo[d] if n[d] > 0 else lo[d] + ddu[i][d] for d in act])
-        alpha = -float(np.dot(n[act], corner))          # v.n < 0  <=>  nv.x < alpha
-        frac = _below_fraction(nv, alpha)
-        if frac <= 0.0 or frac >= 1.0:
-            continue                                    # the plane only touches the cell
-        vol = float(np.prod(ddu[i]))
-        idx.append(i); gw.append(frac * vol); sw.append((1.0 - frac) * vol)
-    return np.array(idx, dtype=np.int32), np.array(gw), np.array(sw)
+    ddu = ddu_all[cand]
+    lo = grid.mid[cand] - 0.5 * ddu
+    # map to the unit cube with positive normal components: x_d = (v_d - corner_d)/(+-ddu_d)
+    nv = np.abs(n[act])[None, :] * ddu[:, act]
+    corner = np.where(n[act][None, :] > 0, lo[:, act], lo[:, act] + ddu[:, act])
+    alpha = -(corner @ n[act])                      # v.n < 0  <=>  nv.x < alpha
+    frac = _below_fraction(nv, alpha)
+    keep = (frac > 0.0) & (frac < 1.0)              # drop cells the plane only touches
+    vol = np.prod(ddu, axis=1)
+    return cand[keep].astype(np.int32), (frac * vol)[keep], ((1.0 - frac) * vol)[keep]
 
 
 # ------------------------------------------------------------------------------------------------ host tables

@@ -29,6 +29,7 @@ def main():
         "periodic2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=6, vs_maxlevel=1, ragged=True,
                                              periodic=(True, True), seed=33),
         "s2_small": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2),
+        "s4_ib": lambda: cases.sphere_s4(trees=4, ps_maxlevel=2, vtrees=4, vs_maxlevel=1),
         "s2_ib": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=5, box_level=2, vtrees=8, vs_maxlevel=2, ib=True),
     }
     for name, fn in names.items():

@@ -31,6 +31,9 @@ def _cases():
         # immersed boundary (kernel d): Circle r=1 with a Maxwellian wall, solid ghost cells, donors, cut velocity cells
         "s2_ib_small": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True),
         "s2_ib_fine": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=5, box_level=2, vtrees=8, vs_maxlevel=3, ib=True),
+        # 3-D sphere with immersed boundary (3D1F): 26-direction solid-cell stencils, 3-D cut velocity cells
+        "s4_ib_small": lambda: cases.sphere_s4(trees=4, ps_maxlevel=2, vtrees=4, vs_maxlevel=1),
+        "s4_ib_l3": lambda: cases.sphere_s4(trees=4, ps_maxlevel=3, vtrees=6, vs_maxlevel=1),
         "euler2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=1, vtrees=8, vs_maxlevel=1, ragged=True, seed=6,
                                           marching=abi.MARCH_EULER),
     }
