@@ -25,7 +25,7 @@ constexpr int UNROLL = KAMR_UNROLL;  // point-loop unrolling of the phase kernel
 
 // ------------------------------------------------------------------------------------------------
 // block-wide sum of NV doubles (warp shuffles + one shared-memory stage); result broadcast to all threads.
-// `red` must hold NV*32 doubles.  Deterministic for a fixed block size.
+// `red` must hold NV*(nwarp+1) doubles.  Deterministic for a fixed block size.
 template <int NV>
 __device__ __forceinline__ void block_reduce(double (&v)[NV], double* red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
@@ -40,18 +40,16 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double* red) {
         for (int k = 0; k < NV; ++k) red[warp * NV + k] = v[k];
     }
     __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double x = (lane < nwarp) ? red[lane * NV + k] : 0.0;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-            if (lane == 0) red[k] = x;
-        }
+    // second stage: thread k adds the nwarp partials of value k in warp order (4 adds for a 128-thread CTA) and
+    // leaves the total behind the partials
+    if ((int)threadIdx.x < NV) {
+        double x = red[threadIdx.x];
+        for (int w = 1; w < nwarp; ++w) x += red[w * NV + threadIdx.x];
+        red[nwarp * NV + threadIdx.x] = x;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < NV; ++k) v[k] = red[k];
+    for (int k = 0; k < NV; ++k) v[k] = red[nwarp * NV + k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -79,7 +77,7 @@ __device__ __forceinline__ double c2_of(const double* v, const double* prim) {
     return c2;
 }
 // exp(x) for x <= 0 (every exponent on this path is -lambda*c^2): Cody-Waite reduction x = n ln2 + r,
-// |r| <= ln2/2, degree-13 Taylor polynomial (truncation 4e-18), exponent-field scaling.  <= 1 ulp like
+// |r| <= ln2/2, degree-13 Taylor polynomial (truncation 4e-18), exponent-field scaling.  ~1 ulp like
 // libdevice exp, without its overflow / NaN / large-argument paths.  Results below 2^-1022 go through a
 // two-step scaling so they denormalise gradually.
 __device__ __forceinline__ double exp_nonpos(double x) {
@@ -89,20 +87,19 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     t -= MAGIC;
     double r = fma(t, -6.93147180369123816490e-01, x);
     r = fma(t, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;            // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    // Estrin evaluation: the same 14 coefficients as a depth-4 tree instead of a 13-deep Horner chain (the chain's
+    // fixed latency was a visible stall with ~6 warps per scheduler)
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = 1.0 + r;
+    const double a1 = fma(1.6666666666666666e-01, r, 0.5);                        // 1/2! + r/3!
+    const double a2 = fma(8.333333333333333e-03, r, 4.1666666666666664e-02);      // 1/4! + r/5!
+    const double a3 = fma(1.984126984126984e-04, r, 1.388888888888889e-03);       // 1/6! + r/7!
+    const double a4 = fma(2.7557319223985893e-06, r, 2.48015873015873e-05);       // 1/8! + r/9!
+    const double a5 = fma(2.505210838544172e-08, r, 2.755731922398589e-07);       // 1/10! + r/11!
+    const double a6 = fma(1.6059043836821613e-10, r, 2.08767569878681e-09);       // 1/12! + r/13!
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+    const double c0 = fma(b1, r4, b0), c1 = fma(a6, r4, b2);
+    const double p = fma(c1, r8, c0);
     if (n >= -1021) return p * __hiloint2double((n + 1023) << 20, 0);
     if (n < -1100) return 0.0;
     const int h = n / 2;
@@ -150,6 +147,15 @@ __device__ __forceinline__ double pick(const double* a, int d) {
     if (D == 2) return d == 0 ? a[0] : a[1];
     return d == 0 ? a[0] : (d == 1 ? a[1] : a[2]);
 }
+
+// Loads of the state arrays (df, limited slopes).  Measured (gpurun_out/sweep4, S2): routing them around L1 with
+// ld.global.cg leaves the regular kernel unchanged and slows the general one by 20 % (its second pass re-reads the
+// cell's own planes from L1), so the default is a plain load; -DKAMR_USE_CG keeps the experiment reproducible.
+#ifndef KAMR_USE_CG
+__device__ __forceinline__ double ldg_stream(const double* p) { return *p; }
+#else
+__device__ __forceinline__ double ldg_stream(const double* p) { return __ldcg(p); }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // per-cell accessors
@@ -303,7 +309,7 @@ __device__ __forceinline__ void wall_density(const DevView& g, const CellInfo& c
                     s_dx += face_dx(sl.fmid[t], __dmul_rn(v[t], dt), ci.mid[t]) * own.s[(t * K + 0) * own.np + i];
                 acc[0] += wt * vn * (own.f[i] + s_dx);
             } else {
-                acc[1] += wt * vn * exp(-sl.bc[D + 1] * c2_of<D>(v, sl.bc));
+                acc[1] += wt * vn * exp_nonpos(-sl.bc[D + 1] * c2_of<D>(v, sl.bc));
             }
         }
         block_reduce<2>(acc, red);
@@ -335,7 +341,7 @@ __device__ __forceinline__ void copy_words(const void* src_, void* dst_, int nwo
 // L2 round trips of the D directions overlap; further records of a side (hanging sub-faces) are rare.
 template <int D, int K>
 __device__ __forceinline__ void hot_flux(const DevView& g, const FaceRec* hot, const unsigned char* sb, int i,
-                                         double dt, const double* v, const double* f,
+                                         unsigned sg, double dt, const double* v, const double* f,
                                          const double* s /*[K][D] limited*/, double* fl) {
     double vdt[D];
     double nfv[D][K], nsv[D][K * D];
@@ -343,7 +349,7 @@ __device__ __forceinline__ void hot_flux(const DevView& g, const FaceRec* hot, c
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         vdt[d] = __dmul_rn(v[d], dt);
-        const int sn = v[d] > 0. ? 0 : 1;                    // side whose neighbour is upwind
+        const int sn = ((sg >> d) & 1u) ? 0 : 1;             // side whose neighbour is upwind (v_d > 0: the low face)
         const int q = sb[2 * d + sn];
         qn[d] = (q < sb[2 * d + sn + 1] && (hot[q].flags & 2)) ? q : -1;
         if (qn[d] >= 0) {
@@ -353,16 +359,16 @@ __device__ __forceinline__ void hot_flux(const DevView& g, const FaceRec* hot, c
             const int np = h.np;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                nfv[d][k] = nf[k * np];
+                nfv[d][k] = ldg_stream(nf + k * np);
 #pragma unroll
-                for (int t = 0; t < D; ++t) nsv[d][k * D + t] = nsl[(t * K + k) * np];
+                for (int t = 0; t < D; ++t) nsv[d][k * D + t] = ldg_stream(nsl + (t * K + k) * np);
             }
         }
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const double vn = v[d];
-        const int so = vn > 0. ? 1 : 0;                      // side where the cell itself is upwind
+        const int so = ((sg >> d) & 1u) ? 1 : 0;             // side where the cell itself is upwind
         for (int q = sb[2 * d + so]; q < sb[2 * d + so + 1]; ++q) {
             const FaceRec& h = hot[q];
             const double Avn = h.area * vn;
@@ -404,10 +410,62 @@ __device__ __forceinline__ void hot_flux(const DevView& g, const FaceRec* hot, c
             for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.nbr_mid[t]);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                double val = nf[k * np];
+                double val = ldg_stream(nf + k * np);
 #pragma unroll
-                for (int t = 0; t < D; ++t) val += dx[t] * nsl[(t * K + k) * np];
+                for (int t = 0; t < D; ++t) val += dx[t] * ldg_stream(nsl + (t * K + k) * np);
                 fl[k] += val * Avn;
+            }
+        }
+    }
+}
+
+// The neighbour-upwind half of fluid/fluid faces whose neighbour lives on a DIFFERENT velocity grid (pair-mapped
+// records, FaceRec::flags bit1 clear), gathered in the same pass as the identical-grid faces: update_micro_flux!,
+// Flux.jl:151-344 in gather form.  Point i of the own grid is covered by / covers points st[i] .. st[i+1]-1 of the
+// neighbour's grid (one entry when the neighbour is equal or coarser there):
+//   fl[k]  += area * micro (mean over the covering finer points / injection from the coarser point)
+//   mac[m] += area * w_j psi(v_j) micro_j      (the neighbour's share of fw, CAIDVM.jl:119)
+template <int D, int K>
+__device__ __forceinline__ void mapped_flux(const DevView& g, const FaceRec* hot, const unsigned char* sb, int i,
+                                            unsigned sg, double dt, double wt, const int8_t* __restrict__ own_lev,
+                                            double* fl, double* mac) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const int sn = ((sg >> d) & 1u) ? 0 : 1;
+        for (int q = sb[2 * d + sn]; q < sb[2 * d + sn + 1]; ++q) {
+            const FaceRec& h = hot[q];
+            if (h.flags & 2) continue;   // block-uniform
+            const double* __restrict__ nf = g.df + h.nf_off;
+            const double* __restrict__ nsl = g.sdl + h.nsl_off;
+            const double* __restrict__ nv = g.v_mid + h.ngoff * D;
+            const int np = h.np;
+            const int* __restrict__ st = g.pm_start + h.rel_off;
+            const int j0 = st[i];
+            const int cnt = max(1, st[i + 1] - j0);
+            const double A = h.area;
+            const int li = (cnt > 1) ? (int)own_lev[i] : 0;
+            for (int j = j0; j < j0 + cnt; ++j) {
+                double vj[D], dx[D], m[K];
+#pragma unroll
+                for (int t = 0; t < D; ++t) {
+                    vj[t] = nv[t * np + j];
+                    dx[t] = face_dx(h.fmid[t], __dmul_rn(vj[t], dt), h.nbr_mid[t]);
+                }
+                const double vnj = vj[d];
+                double scale = 1.0, wq = wt;
+                if (cnt > 1) {
+                    scale = 1.0 / (double)(1 << (D * ((int)g.v_level[h.ngoff + j] - li)));
+                    wq = g.v_weight[h.ngoff + j];
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    double s_dx = 0.0;
+#pragma unroll
+                    for (int t = 0; t < D; ++t) s_dx += dx[t] * ldg_stream(nsl + (t * K + k) * np + j);
+                    m[k] = (ldg_stream(nf + k * np + j) + s_dx) * vnj;
+                    fl[k] += (A * m[k]) * scale;
+                }
+                add_moments<D, K>(mac, A * wq, vj, m);
             }
         }
     }
@@ -442,29 +500,42 @@ __device__ __forceinline__ void maxwell_c(const double* v, const double* prim, d
 
 // The update half shared by the phase kernels: given the block-partial sums acc = [macro flux | moments of the
 // convected f] and the convected f staged in fs, finish iterate!(CAIDVM_Marching) (Theory/Iterate.jl:108-126).
+// The point loops of phases 2 and 3 request the velocity-grid statics of TAIL_B2 / TAIL_B3 points before touching any of them, so
+// a thread waits for one L1/L2 round trip per batch instead of one per point.
+#ifndef KAMR_TAIL_B2
+#define KAMR_TAIL_B2 1
+#endif
+#ifndef KAMR_TAIL_B3
+#define KAMR_TAIL_B3 4
+#endif
+constexpr int TAIL_B2 = KAMR_TAIL_B2, TAIL_B3 = KAMR_TAIL_B3;
 template <int D, int K, int MODE, bool STAGE_SMEM, int NT>
-__device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas, const CellInfo& ci, int c, double dt,
-                                            int want_residual, double (&acc)[2 * (D + 2)], const CellPtr<D, K>& own,
-                                            double* fs, int fstride, double* fout, double* dyn, double* red,
+__device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas, int n, int np, double vol, int c,
+                                            double dt, int want_residual, double (&acc)[2 * (D + 2)],
+                                            const double* __restrict__ gv, const double* __restrict__ gwt,
+                                            double* fs, int fstride, double* __restrict__ fout, double* dyn, double* red,
                                             UpdateShared<D, K>& us, double* w_new, double* w0s) {
-    const int n = ci.n, np = ci.np;
     block_reduce<2 * (D + 2)>(acc, red);
+    // moments -> prim_c, prim, tau and the Maxwellian constants: two independent serial chains of fp64 divisions (and a
+    // pow); lane 0 of warp 0 takes the conserved state, lane 0 of warp 1 the convected one
     if (threadIdx.x == 0) {
         acc[D + 1] *= 0.5;
-        acc[2 * D + 3] *= 0.5;
 #pragma unroll
         for (int m = 0; m < D + 2; ++m) {
             double mf = g.mflux[(size_t)c * (D + 2) + m];
             if (MODE == MODE_FUSED && gas.flux_type == 0) mf += acc[m];
-            w_new[m] = g.w[(size_t)c * (D + 2) + m] + mf * dt / ci.vol;
-            w0s[m] = acc[D + 2 + m];
+            w_new[m] = g.w[(size_t)c * (D + 2) + m] + mf * dt / vol;
         }
         get_prim<D>(w_new, gas.gamma, us.prim_c);
-        get_prim<D>(w0s, gas.gamma, us.prim);
         us.tau = gas.mu_ref * 2.0 * pow(us.prim_c[D + 1], 1 - gas.omega) / us.prim_c[0];  // Gas/Model.jl:14
         us.coef_c = maxwell_coef<D>(us.prim_c);
-        us.coef = maxwell_coef<D>(us.prim);
         us.cb_c = gas.K / (2.0 * us.prim_c[D + 1]);
+    } else if (threadIdx.x == 32 % NT) {
+        acc[2 * D + 3] *= 0.5;
+#pragma unroll
+        for (int m = 0; m < D + 2; ++m) w0s[m] = acc[D + 2 + m];
+        get_prim<D>(w0s, gas.gamma, us.prim);
+        us.coef = maxwell_coef<D>(us.prim);
         us.cb = gas.K / (2.0 * us.prim[D + 1]);
     }
     __syncthreads();
@@ -483,23 +554,36 @@ __device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas,
         double q[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) q[d] = 0.0;
-#pragma unroll UNROLL
-        for (int i = threadIdx.x; i < n; i += NT) {
-            double v[D], Fc[K], F[K], f[K];
+        for (int i0 = threadIdx.x; i0 < n; i0 += TAIL_B2 * NT) {
+            double vb[TAIL_B2][D], wb[TAIL_B2];
 #pragma unroll
-            for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
-            maxwell_c<D, K>(v, prim_c, coef_c, cb_c, Fc);
-            maxwell_c<D, K>(v, prim, coef, cb, F);
+            for (int u = 0; u < TAIL_B2; ++u) {
+                const int i = i0 + u * NT;
+                if (i < n) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                f[k] = fs[k * fstride + i] + (Fc[k] - F[k]);
-                fs[k * fstride + i] = f[k];
+                    for (int t = 0; t < D; ++t) vb[u][t] = gv[t * np + i];
+                    wb[u] = gwt[i];
+                }
             }
-            if (STAGE_SMEM) fch[i] = Fc[0];
-            // heat_flux (2D2F.jl:68-88, 3D1F.jl:41-72): q_d = 1/2 sum w c_d (c^2 h + b)
-            const double gq = own.wt[i] * (c2_of<D>(v, prim_c) * f[0] + ((K > 1) ? f[1] : 0.0));
 #pragma unroll
-            for (int d = 0; d < D; ++d) q[d] += (v[d] - prim_c[1 + d]) * gq;
+            for (int u = 0; u < TAIL_B2; ++u) {
+                const int i = i0 + u * NT;
+                if (i < n) {
+                    double Fc[K], F[K], f[K];
+                    maxwell_c<D, K>(vb[u], prim_c, coef_c, cb_c, Fc);
+                    maxwell_c<D, K>(vb[u], prim, coef, cb, F);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        f[k] = fs[k * fstride + i] + (Fc[k] - F[k]);
+                        fs[k * fstride + i] = f[k];
+                    }
+                    if (STAGE_SMEM) fch[i] = Fc[0];
+                    // heat_flux (2D2F.jl:68-88, 3D1F.jl:41-72): q_d = 1/2 sum w c_d (c^2 h + b)
+                    const double gq = wb[u] * (c2_of<D>(vb[u], prim_c) * f[0] + ((K > 1) ? f[1] : 0.0));
+#pragma unroll
+                    for (int d = 0; d < D; ++d) q[d] += (vb[u][d] - prim_c[1 + d]) * gq;
+                }
+            }
         }
         block_reduce<D>(q, red);
         if (threadIdx.x == 0) {
@@ -516,20 +600,32 @@ __device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas,
         double qf[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) qf[d] = us.qf[d];
-#pragma unroll UNROLL
-        for (int i = threadIdx.x; i < n; i += NT) {
-            double v[D], Fc[K], Fp[K];
+        for (int i0 = threadIdx.x; i0 < n; i0 += TAIL_B3 * NT) {
+            double vb[TAIL_B3][D];
 #pragma unroll
-            for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
-            if (STAGE_SMEM) {
-                Fc[0] = fch[i];
-                if (K > 1) Fc[1] = Fc[0] * cb_c;
-            } else {
-                maxwell_c<D, K>(v, prim_c, coef_c, cb_c, Fc);
+            for (int u = 0; u < TAIL_B3; ++u) {
+                const int i = i0 + u * NT;
+                if (i < n) {
+#pragma unroll
+                    for (int t = 0; t < D; ++t) vb[u][t] = gv[t * np + i];
+                }
             }
-            shakhov<D, K>(v, Fc, prim_c, qf, gas.Pr, gas.K, Fp);
 #pragma unroll
-            for (int k = 0; k < K; ++k) fout[k * np + i] = fs[k * fstride + i] * a + b * (Fc[k] + Fp[k]);
+            for (int u = 0; u < TAIL_B3; ++u) {
+                const int i = i0 + u * NT;
+                if (i < n) {
+                    double Fc[K], Fp[K];
+                    if (STAGE_SMEM) {
+                        Fc[0] = fch[i];
+                        if (K > 1) Fc[1] = Fc[0] * cb_c;
+                    } else {
+                        maxwell_c<D, K>(vb[u], prim_c, coef_c, cb_c, Fc);
+                    }
+                    shakhov<D, K>(vb[u], Fc, prim_c, qf, gas.Pr, gas.K, Fp);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) fout[k * np + i] = fs[k * fstride + i] * a + b * (Fc[k] + Fp[k]);
+                }
+            }
         }
     }
     if (threadIdx.x == 0) {
@@ -560,7 +656,7 @@ __global__ void __launch_bounds__(NT, MINB)
     __shared__ FaceRec hot[NSLOT];
     __shared__ int rare[NSLOT];
     __shared__ double rho_w[NSLOT];
-    __shared__ double red[2 * (D + 2) * 32];
+    __shared__ double red[2 * (D + 2) * 33];
     __shared__ CellInfo ci;
     __shared__ UpdateShared<D, K> us;
     __shared__ double w_new[D + 2], w0s[D + 2];
@@ -590,21 +686,25 @@ __global__ void __launch_bounds__(NT, MINB)
     double acc[2 * (D + 2)];  // [0,D+2): macro flux, [D+2, 2D+4): moments of the convected f
 #pragma unroll
     for (int q = 0; q < 2 * (D + 2); ++q) acc[q] = 0.0;
+    const unsigned char* __restrict__ sgn = g.v_sign + ci.goff;
+    const bool has_mapped = (ci.flags & CELL_HAS_MAPPED) != 0;
     for (int i = threadIdx.x; i < n; i += NT) {  // pass A
         double v[D], f[K], fl[K];
+        const unsigned sg = (MODE != MODE_UPDATE) ? sgn[i] : 0u;
 #pragma unroll
         for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
         const double wt = own.wt[i];
 #pragma unroll
-        for (int k = 0; k < K; ++k) { f[k] = own.f[k * np + i]; fl[k] = 0.0; }
+        for (int k = 0; k < K; ++k) { f[k] = ldg_stream(own.f + k * np + i); fl[k] = 0.0; }
         if (MODE != MODE_UPDATE) {
             double s[K * D];
 #pragma unroll
             for (int k = 0; k < K; ++k)
 #pragma unroll
-                for (int t = 0; t < D; ++t) s[k * D + t] = own.sl[(t * K + k) * np + i];
-            hot_flux<D, K>(g, hot, ci.side_begin, i, dt, v, f, s, fl);
+                for (int t = 0; t < D; ++t) s[k * D + t] = ldg_stream(own.sl + (t * K + k) * np + i);
+            hot_flux<D, K>(g, hot, ci.side_begin, i, sg, dt, v, f, s, fl);
             add_moments<D, K>(acc, wt, v, fl);
+            if (has_mapped) mapped_flux<D, K>(g, hot, ci.side_begin, i, sg, dt, wt, own.lev, fl, acc);
         } else {
 #pragma unroll
             for (int k = 0; k < K; ++k) { fl[k] = vflux[k * np + i]; vflux[k * np + i] = 0.0; }
@@ -691,98 +791,101 @@ __global__ void __launch_bounds__(NT, MINB)
         }
         return;
     }
-    update_tail<D, K, MODE, STAGE_SMEM, NT>(g, gas, ci, c, dt, want_residual, acc, own, fs, fstride, fout, dyn, red, us,
-                                            w_new, w0s);
+    update_tail<D, K, MODE, STAGE_SMEM, NT>(g, gas, n, np, ci.vol, c, dt, want_residual, acc, own.v, own.wt, fs, fstride,
+                                            fout, dyn, red, us, w_new, w0s);
 }
 
 // ------------------------------------------------------------------------------------------------
 // phase_regular_kernel: the fused flux + update for REGULAR cells — every one of the 2*DIM sides is a single
-// fluid/fluid face to a neighbour on the same velocity grid (CELL_REGULAR, decided at flatten time; the bulk of
-// every mesh away from level jumps, domain edges, velocity-grid changes and the body).  Same arithmetic as
-// phase_kernel<FUSED> pass A, with the structure fixed at compile time: no slot loops, no rare pass; the record of a
-// side is picked by the sign of v_d and the 2*DIM neighbour values are requested before any arithmetic.
+// fluid/fluid face to a same-size neighbour on the same velocity grid, and the face / neighbour midpoints equal the
+// cell's own in the transverse coordinates bit for bit (checked at flatten time; the bulk of every mesh away from level
+// jumps, domain edges, velocity-grid changes and the body).  Same arithmetic as phase_kernel<FUSED> pass A with the
+// structure fixed at compile time: one RegCell record per CTA, no slot loops, no rare pass.  The side whose neighbour
+// is upwind comes from the point's sign byte (L1-resident, one per distinct velocity grid), so all global loads of a
+// point are requested together; the transverse dx = (x_t - v_t dt) - x_t is formed once per point instead of once per
+// face.
 template <int D, int K, bool STAGE_SMEM, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
-    phase_regular_kernel(DevView g, GasPar gas, const int* __restrict__ cell_list, double dt, int want_residual) {
+    phase_regular_kernel(DevView g, GasPar gas, const RegCell* __restrict__ recs, double dt, int want_residual) {
     extern __shared__ double dyn[];
-    __shared__ FaceRec rec[2 * D];
-    __shared__ double red[2 * (D + 2) * 32];
-    __shared__ CellInfo ci;
+    __shared__ RegCell rc;
+    __shared__ double red[2 * (D + 2) * 33];
     __shared__ UpdateShared<D, K> us;
     __shared__ double w_new[D + 2], w0s[D + 2];
-    const int c = cell_list[blockIdx.x];
-    copy_words(g.cells + c, &ci, (int)(sizeof(CellInfo) / sizeof(int)));
+    copy_words(recs + blockIdx.x, &rc, (int)(sizeof(RegCell) / sizeof(int)));
     __syncthreads();
-    copy_words(g.hot + ci.hot_begin, rec, 2 * D * (int)(sizeof(FaceRec) / sizeof(int)));
-    __syncthreads();
-    const int n = ci.n, np = ci.np;
-    const CellPtr<D, K> own(g, ci);
-    const double dtv = dt / ci.vol;
-    double* fout = g.df_new + ci.doff * K;
+    const int n = rc.n, np = rc.np, c = rc.cell;
+    const double dtv = dt / rc.vol;
+    double* __restrict__ fout = g.df_new + rc.doff * K;
     double* fs = STAGE_SMEM ? dyn : fout;
     const int fstride = STAGE_SMEM ? n : np;
     const double* __restrict__ gdf = g.df;
     const double* __restrict__ gsl = g.sdl;
+    const double* __restrict__ gv = g.v_mid + rc.goff * D;
+    const double* __restrict__ gwt = g.v_weight + rc.goff;
+    const unsigned char* __restrict__ sgn = g.v_sign + rc.goff;
+    const double* __restrict__ of = gdf + rc.doff * K;
+    const double* __restrict__ os = gsl + rc.doff * K * D;
     double acc[2 * (D + 2)];
 #pragma unroll
     for (int q = 0; q < 2 * (D + 2); ++q) acc[q] = 0.0;
 #pragma unroll UNROLL
     for (int i = threadIdx.x; i < n; i += NT) {
-        double v[D], vdt[D], f[K], s[K * D], fl[K];
+        double v[D], vdt[D], tdx[D], f[K], s[K * D], fl[K];
         double nfv[D][K], nsv[D][K * D];
-        int rn[D];
-#pragma unroll
-        for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+        const unsigned sg = sgn[i];
 #pragma unroll
         for (int d = 0; d < D; ++d) {  // neighbour-upwind side: low face for v_d > 0, high face otherwise
-            rn[d] = 2 * d + (v[d] > 0. ? 0 : 1);
-            const double* __restrict__ nf = gdf + rec[rn[d]].nf_off + i;
-            const double* __restrict__ nsl = gsl + rec[rn[d]].nsl_off + i;
+            const long long nd = rc.side[2 * d + (((sg >> d) & 1u) ? 0 : 1)].ndoff;
+            const double* __restrict__ nf = gdf + nd * K + i;
+            const double* __restrict__ nsl = gsl + nd * (K * D) + i;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                nfv[d][k] = nf[k * np];
+                nfv[d][k] = ldg_stream(nf + k * np);
 #pragma unroll
-                for (int t = 0; t < D; ++t) nsv[d][k * D + t] = nsl[(t * K + k) * np];
+                for (int t = 0; t < D; ++t) nsv[d][k * D + t] = ldg_stream(nsl + (t * K + k) * np);
             }
         }
-        const double wt = own.wt[i];
+#pragma unroll
+        for (int t = 0; t < D; ++t) v[t] = gv[t * np + i];
+        const double wt = gwt[i];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            f[k] = own.f[k * np + i];
+            f[k] = ldg_stream(of + k * np + i);
             fl[k] = 0.0;
 #pragma unroll
-            for (int t = 0; t < D; ++t) s[k * D + t] = own.sl[(t * K + k) * np + i];
+            for (int t = 0; t < D; ++t) s[k * D + t] = ldg_stream(os + (t * K + k) * np + i);
         }
 #pragma unroll
-        for (int t = 0; t < D; ++t) vdt[t] = __dmul_rn(v[t], dt);
+        for (int t = 0; t < D; ++t) {
+            vdt[t] = __dmul_rn(v[t], dt);
+            tdx[t] = face_dx(rc.mid[t], vdt[t], rc.mid[t]);
+        }
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             const double vn = v[d];
+            const int sn = ((sg >> d) & 1u) ? 0 : 1;
             {   // own-upwind face: the other side of this direction
-                const FaceRec& h = rec[rn[d] ^ 1];
+                const RegSide& h = rc.side[2 * d + (sn ^ 1)];
                 const double Avn = h.area * vn;
-                double dx[D];
-#pragma unroll
-                for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.own_mid[t]);
+                const double dxd = face_dx(h.fmid, vdt[d], rc.mid[d]);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     double val = f[k];
 #pragma unroll
-                    for (int t = 0; t < D; ++t) val += dx[t] * s[k * D + t];
+                    for (int t = 0; t < D; ++t) val += (t == d ? dxd : tdx[t]) * s[k * D + t];
                     fl[k] += val * Avn;
                 }
             }
             {   // neighbour-upwind face
-                const FaceRec& h = rec[rn[d]];
+                const RegSide& h = rc.side[2 * d + sn];
                 const double Avn = h.area * vn;
-                double dx[D];
-#pragma unroll
-                for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.nbr_mid[t]);
+                const double dxd = face_dx(h.fmid, vdt[d], h.nmid);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     double val = nfv[d][k];
 #pragma unroll
-                    for (int t = 0; t < D; ++t) val += dx[t] * nsv[d][k * D + t];
+                    for (int t = 0; t < D; ++t) val += (t == d ? dxd : tdx[t]) * nsv[d][k * D + t];
                     fl[k] += val * Avn;
                 }
             }
@@ -795,8 +898,8 @@ __global__ void __launch_bounds__(NT, MINB)
         }
         add_moments<D, K>(acc + (D + 2), wt, v, f);
     }
-    update_tail<D, K, MODE_FUSED, STAGE_SMEM, NT>(g, gas, ci, c, dt, want_residual, acc, own, fs, fstride, fout, dyn, red,
-                                                  us, w_new, w0s);
+    update_tail<D, K, MODE_FUSED, STAGE_SMEM, NT>(g, gas, n, np, rc.vol, c, dt, want_residual, acc, gv, gwt, fs, fstride,
+                                                  fout, dyn, red, us, w_new, w0s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -948,7 +1051,7 @@ __device__ __forceinline__ void side_sum(const DevView& g, const SlopeNbr* nb, i
 // every task publishes its own flag when its stores are visible.  A waiting CTA only ever waits for CTAs with a
 // lower block index, which the hardware dispatches first, so the sweep cannot deadlock.
 template <int D, int K, bool GENERIC, int NT>
-__global__ void __launch_bounds__(NT) slope_kernel(DevView g, const SlopeTask* __restrict__ tasks, int raw_all,
+__global__ void __launch_bounds__(NT, 1024 / NT) slope_kernel(DevView g, const SlopeTask* __restrict__ tasks, int raw_all,
                                                    int epoch) {
     __shared__ SlopeTask tk;
     __shared__ CellInfo ci;
@@ -981,6 +1084,78 @@ __global__ void __launch_bounds__(NT) slope_kernel(DevView g, const SlopeTask* _
     const bool raw = raw_all || (tk.flags & 1);
     double* sdf = g.sdf + ci.doff * K * D;
     double* sdl = g.sdl + ci.doff * K * D;
+    // Block-uniform fast path: every direction is an inner stencil with ONE neighbour per side and no transverse
+    // projection (same-level neighbours; their velocity grids may differ).  Indices into the neighbours' grids are
+    // resolved for all 2*DIM sides first (identity or pair map), then all neighbour values are requested together.
+    bool simple = true;
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+        simple = simple && tk.d[d].mode == SLOPE_INNER && tk.d[d].nA == 1 && tk.d[d].nB == 1 && !nb[base[d]].proj &&
+                 !nb[base[d] + 1].proj;
+    if (simple) {
+        const double* __restrict__ df = g.df;
+        for (int i = threadIdx.x; i < n; i += NT) {
+            double f[K], s[D][K];
+            int j0[2 * D], cn[2 * D];
+#pragma unroll
+            for (int q = 0; q < 2 * D; ++q) {
+                const SlopeNbr& e = nb[base[q >> 1] + (q & 1)];
+                j0[q] = i; cn[q] = 1;
+                if (GENERIC && e.rel_off >= 0) {
+                    const int* __restrict__ st = g.pm_start + e.rel_off;
+                    j0[q] = st[i];
+                    cn[q] = max(1, st[i + 1] - j0[q]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) f[k] = own.f[k * np + i];
+            double nfv[2 * D][K];
+#pragma unroll
+            for (int q = 0; q < 2 * D; ++q) {
+                const SlopeNbr& e = nb[base[q >> 1] + (q & 1)];
+                const double* __restrict__ p = df + e.doff * K + j0[q];
+#pragma unroll
+                for (int k = 0; k < K; ++k) nfv[q][k] = p[k * e.np];
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                double sAB[2][K];
+#pragma unroll
+                for (int sd2 = 0; sd2 < 2; ++sd2) {
+                    const int q = 2 * d + sd2;
+                    if (cn[q] == 1) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) sAB[sd2][k] = 0.0 + (f[k] - nfv[q][k]);
+                    } else {  // covered by several finer points of the neighbour's grid: mean, diff_vs! Slope.jl:29-64
+                        const SlopeNbr& e = nb[base[d] + sd2];
+                        const int8_t* __restrict__ nlev = g.v_level + e.goff;
+                        const int li = own.lev[i];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) sAB[sd2][k] = 0.0;
+                        for (int j = j0[q]; j < j0[q] + cn[q]; ++j) {
+                            const double scale = 1.0 / (double)(1 << (D * (nlev[j] - li)));
+#pragma unroll
+                            for (int k = 0; k < K; ++k) sAB[sd2][k] += (f[k] - df[e.doff * K + k * e.np + j]) * scale;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    s[d][k] = minmod(sAB[0][k] * tk.d[d].invA, sAB[1][k] * tk.d[d].invB);
+                    if (raw) sdf[(d * K + k) * np + i] = s[d][k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double s_abs = 0.0;
+#pragma unroll
+                for (int d = 0; d < D; ++d) s_abs += ci.ds[d] * fabs(s[d][k]);
+                const double r = limiter(f[k], s_abs);
+#pragma unroll
+                for (int d = 0; d < D; ++d) sdl[(d * K + k) * np + i] = r * s[d][k];
+            }
+        }
+    } else
     for (int i = threadIdx.x; i < n; i += NT) {
         double f[K], s[D][K];
 #pragma unroll
@@ -1147,36 +1322,53 @@ __global__ void __launch_bounds__(256) macro_slope_kernel(DevView g, const int* 
 // `max(0., dot(u,l)/norm(u))^2` with `l /= norm(l)`: where v is perpendicular to l the weight is pure rounding noise
 // (~1e-34) yet the reference normalises by the sum and only tests it against exactly 0, so the result at such points
 // is decided by the last bit; matching the oracle there needs the same bits, not the same formula.
+// Per-neighbour geometry of one extrapolation target x: l = x - x_a and l/|l|.  Point-independent, so each CTA
+// evaluates it once (same operations, same bits as evaluating it per point).
 template <int D>
-__device__ __forceinline__ double dir_weight(const double* x, const double* mid, const double* v, double nu_sqrt) {
-    double l[D], nl = 0.0, dot = 0.0;
+struct IbGeom { double l[D], lh[D]; };
+template <int D>
+__device__ __forceinline__ void ib_geometry(const IbNbr* nb, int cnt, const double* x, IbGeom<D>* geo) {
+    if ((int)threadIdx.x < cnt) {
+        const int a = threadIdx.x;
+        double l[D], nl = 0.0;
 #pragma unroll
-    for (int t = 0; t < D; ++t) { l[t] = __dsub_rn(x[t], mid[t]); nl = __dadd_rn(nl, __dmul_rn(l[t], l[t])); }
-    nl = __dsqrt_rn(nl);
+        for (int t = 0; t < D; ++t) { l[t] = __dsub_rn(x[t], nb[a].mid[t]); nl = __dadd_rn(nl, __dmul_rn(l[t], l[t])); }
+        nl = __dsqrt_rn(nl);
 #pragma unroll
-    for (int t = 0; t < D; ++t) dot = __dadd_rn(dot, __dmul_rn(v[t], __ddiv_rn(l[t], nl)));
+        for (int t = 0; t < D; ++t) { geo[a].l[t] = l[t]; geo[a].lh[t] = __ddiv_rn(l[t], nl); }
+    }
+}
+template <int D>
+__device__ __forceinline__ double dir_weight(const IbGeom<D>& ge, const double* v, double nu_sqrt) {
+    double dot = 0.0;
+#pragma unroll
+    for (int t = 0; t < D; ++t) dot = __dadd_rn(dot, __dmul_rn(v[t], ge.lh[t]));
     double q = __ddiv_rn(dot, nu_sqrt);
     q = q > 0. ? q : 0.;
     return __dmul_rn(q, q);
 }
 
+constexpr int IB_WREG = 4;  // direction weights of the first IB_WREG neighbours stay in registers between the passes
+
 template <int D, int K>
-__device__ __forceinline__ void directional_extrapolate(const DevView& g, const IbNbr* nb, int cnt, const double* x,
-                                                        const double* v, int li, int i, double* out) {
+__device__ __forceinline__ void directional_extrapolate(const DevView& g, const IbNbr* nb, const IbGeom<D>* geo,
+                                                        int cnt, const double* v, int li, int i, double* out) {
     double nu = 0.0;
 #pragma unroll
     for (int t = 0; t < D; ++t) nu = __dadd_rn(nu, __dmul_rn(v[t], v[t]));
     nu = __dsqrt_rn(nu);
-    double ws = 0.0;
-    for (int a = 0; a < cnt; ++a) ws = __dadd_rn(ws, dir_weight<D>(x, nb[a].mid, v, nu));
+    double ws = 0.0, wreg[IB_WREG];
+#pragma unroll
+    for (int a = 0; a < IB_WREG; ++a) {
+        wreg[a] = 0.0;
+        if (a < cnt) { wreg[a] = dir_weight<D>(geo[a], v, nu); ws = __dadd_rn(ws, wreg[a]); }
+    }
+    for (int a = IB_WREG; a < cnt; ++a) ws = __dadd_rn(ws, dir_weight<D>(geo[a], v, nu));
 #pragma unroll
     for (int k = 0; k < K; ++k) out[k] = 0.0;
-    for (int a = 0; a < cnt; ++a) {
+    auto gather = [&](int a, double wa) {
         const IbNbr& e = nb[a];
-        double dx[D];
-#pragma unroll
-        for (int t = 0; t < D; ++t) dx[t] = __dsub_rn(x[t], e.mid[t]);
-        const double wi = (ws == 0.) ? 1.0 / cnt : __ddiv_rn(dir_weight<D>(x, e.mid, v, nu), ws);
+        const double wi = (ws == 0.) ? 1.0 / cnt : __ddiv_rn(wa, ws);
         const double* sf = g.df + e.doff * K;
         const double* ss = g.sdf + e.doff * K * D;
         const int np = e.np;
@@ -1192,13 +1384,17 @@ __device__ __forceinline__ void directional_extrapolate(const DevView& g, const 
             for (int k = 0; k < K; ++k) {
                 double ddf = 0.0;
 #pragma unroll
-                for (int t = 0; t < D; ++t) ddf += ss[(t * K + k) * np + j] * dx[t];
+                for (int t = 0; t < D; ++t) ddf += ss[(t * K + k) * np + j] * geo[a].l[t];
                 double val = sf[k * np + j] + ddf;
                 if (cn > 1) val = val / (double)(1 << (D * (slev[j] - li)));
                 out[k] += val * wi;
             }
         }
-    }
+    };
+#pragma unroll
+    for (int a = 0; a < IB_WREG; ++a)
+        if (a < cnt) gather(a, wreg[a]);
+    for (int a = IB_WREG; a < cnt; ++a) gather(a, dir_weight<D>(geo[a], v, nu));
 }
 
 // update_solid_cell!: one CTA per solid ghost cell; also w = <psi f>, prim (Immersed_boundary.jl:139-140)
@@ -1209,10 +1405,13 @@ __global__ void __launch_bounds__(256) solid_cell_kernel(DevView g, GasPar gas, 
     __shared__ CellInfo ci;
     __shared__ SolidTask tk;
     __shared__ IbNbr nb[32];
+    __shared__ IbGeom<D> geo[32];
     copy_words(tasks + blockIdx.x, &tk, (int)(sizeof(SolidTask) / sizeof(int)));
     __syncthreads();
     copy_words(g.cells + tk.cell, &ci, (int)(sizeof(CellInfo) / sizeof(int)));
     copy_words(g.ib_nb + tk.nb_begin, nb, tk.nb_count * (int)(sizeof(IbNbr) / sizeof(int)));
+    __syncthreads();
+    ib_geometry<D>(nb, tk.nb_count, ci.mid, geo);
     __syncthreads();
     const CellPtr<D, K> own(g, ci);
     const int n = ci.n, np = ci.np;
@@ -1224,7 +1423,7 @@ __global__ void __launch_bounds__(256) solid_cell_kernel(DevView g, GasPar gas, 
         double v[D], f[K];
 #pragma unroll
         for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
-        directional_extrapolate<D, K>(g, nb, tk.nb_count, ci.mid, v, own.lev[i], i, f);
+        directional_extrapolate<D, K>(g, nb, geo, tk.nb_count, v, own.lev[i], i, f);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             out[k * np + i] = f[k];
@@ -1265,6 +1464,7 @@ __global__ void __launch_bounds__(256) solid_neighbor_kernel(DevView g, GasPar g
     __shared__ CellInfo cp, cs, cn_;
     __shared__ SnTask tk;
     __shared__ IbNbr nb[8];
+    __shared__ IbGeom<D> geo[8];
     __shared__ double rho_w_s;
     copy_words(tasks + blockIdx.x, &tk, (int)(sizeof(SnTask) / sizeof(int)));
     __syncthreads();
@@ -1278,6 +1478,8 @@ __global__ void __launch_bounds__(256) solid_neighbor_kernel(DevView g, GasPar g
     double ibp[D];
 #pragma unroll
     for (int t = 0; t < D; ++t) ibp[t] = tk.aux[t] + cp.mid[t] - cs.mid[t];
+    ib_geometry<D>(nb, tk.nb_count, ibp, geo);
+    __syncthreads();
     const double dxf = pick<D>(ibp, dir) - pick<D>(cp.mid, dir);
     const double dxs = pick<D>(cp.mid, dir) - pick<D>(cn_.mid, dir);
     const double dxL = pick<D>(tk.aux, dir) - pick<D>(ibp, dir);
@@ -1299,7 +1501,7 @@ __global__ void __launch_bounds__(256) solid_neighbor_kernel(DevView g, GasPar g
 #pragma unroll
         for (int t = 0; t < D; ++t) { v[t] = own.v[t * np + i]; vn = __dadd_rn(vn, __dmul_rn(v[t], tk.normal[t])); }
         const int li = own.lev[i];
-        directional_extrapolate<D, K>(g, nb, tk.nb_count, ibp, v, li, i, ibf);
+        directional_extrapolate<D, K>(g, nb, geo, tk.nb_count, v, li, i, ibf);
         int j0 = i, cc = 1;
         if (tk.rel_ps >= 0) {
             const int* st = g.pm_start + tk.rel_ps;
@@ -1324,7 +1526,7 @@ __global__ void __launch_bounds__(256) solid_neighbor_kernel(DevView g, GasPar g
             snf[k * np + i] = a;
             if (k == 0) aux0 = a;
         }
-        const double M0 = coef * exp(-bc[D + 1] * c2_of<D>(v, bc));
+        const double M0 = coef * exp_nonpos(-bc[D + 1] * c2_of<D>(v, bc));
         const int q = cvc_find(g.cvc_index, tk.cvc_begin, tk.cvc_count, i);
         if (q >= 0) {  // cut velocity cell: gas part feeds SF, solid part MuR (cvc_density :338, cvc_Mu :347)
             acc[0] += g.cvc_gas_w[q] * vn * aux0;
@@ -1346,8 +1548,9 @@ __global__ void __launch_bounds__(256) solid_neighbor_kernel(DevView g, GasPar g
         for (int t = 0; t < D; ++t) { v[t] = own.v[t * np + i]; vn = __dadd_rn(vn, __dmul_rn(v[t], tk.normal[t])); }
         const int q = cvc_find(g.cvc_index, tk.cvc_begin, tk.cvc_count, i);
         double Mw[K];
-        Mw[0] = (coef * exp(-bc[D + 1] * c2_of<D>(v, bc))) * rho_w;
-        if (K > 1) Mw[1] = ((coef * exp(-bc[D + 1] * c2_of<D>(v, bc))) * cb) * rho_w;
+        const double M1 = coef * exp_nonpos(-bc[D + 1] * c2_of<D>(v, bc));
+        Mw[0] = M1 * rho_w;
+        if (K > 1) Mw[1] = (M1 * cb) * rho_w;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             double a = snf[k * np + i];
@@ -1364,17 +1567,16 @@ __global__ void __launch_bounds__(256) solid_neighbor_kernel(DevView g, GasPar g
 }
 
 // ------------------------------------------------------------------------------------------------
-// residual sums over cells (residual_check! accumulators), single block, deterministic
-__global__ void __launch_bounds__(256) residual_reduce_kernel(const double* __restrict__ res_cell,
-                                                              const int* __restrict__ cell_list, int ncell, int nv,
-                                                              double* out) {
-    __shared__ double red[32];
-    for (int q = 0; q < nv; ++q) {
-        double a[1] = {0.0};
-        for (int t = threadIdx.x; t < ncell; t += blockDim.x) a[0] += res_cell[(size_t)cell_list[t] * nv + q];
-        block_reduce<1>(a, red);
-        if (threadIdx.x == 0) out[q] = a[0];
-    }
+// residual sums over cells (residual_check! accumulators): one block per accumulator, deterministic
+__global__ void __launch_bounds__(1024) residual_reduce_kernel(const double* __restrict__ res_cell,
+                                                               const int* __restrict__ cell_list, int ncell, int nv,
+                                                               double* out) {
+    __shared__ double red[33];
+    const int q = blockIdx.x;
+    double a[1] = {0.0};
+    for (int t = threadIdx.x; t < ncell; t += blockDim.x) a[0] += res_cell[(size_t)cell_list[t] * nv + q];
+    block_reduce<1>(a, red);
+    if (threadIdx.x == 0) out[q] = a[0];
 }
 
 // halo pack / unpack: copy variable-length segments (one block per segment, grid-stride over segments)

@@ -58,6 +58,7 @@ struct Bin {
     int* d_cells = nullptr;
     size_t smem = 0;     // dynamic shared memory per block (0 => global staging)
     bool regular = false;  // all cells are CELL_REGULAR: phase_regular_kernel
+    RegCell* d_recs = nullptr;  // regular bins: one record per cell, in launch order
 };
 
 enum KernelId { KID_SLOPE = 0, KID_MACRO_SLOPE, KID_FLUX, KID_UPDATE, KID_STEP, KID_RESIDUAL, KID_PACK, KID_UNPACK,
@@ -425,6 +426,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     c->h_level.assign(m->v_level, m->v_level + gpts_h);
     {
         std::vector<int8_t> lv(gpts_d, 0);
+        std::vector<unsigned char> sg(gpts_d, 0);
         std::vector<double> wt(gpts_d, 0.0), vm((size_t)gpts_d * D, 0.0);
         for (int g = 0; g < m->n_grid; ++g) {
             const int n = c->grid_n[g], np = c->grid_np[g];
@@ -439,6 +441,16 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
                 for (int d = 0; d < D; ++d) vm[go * D + (size_t)d * np + i] = vm[go * D + (size_t)d * np + n - 1];
             }
         }
+        // bit d of v_sign: v_d > 0, i.e. the neighbour across the LOW face of direction d is upwind.  One byte per
+        // point and per distinct grid, so the phase kernels find their upwind records from L1 instead of waiting for v
+        for (int g = 0; g < m->n_grid; ++g) {
+            const int np = c->grid_np[g];
+            const long long go = c->grid_goff[g];
+            for (int i = 0; i < np; ++i)
+                for (int d = 0; d < D; ++d)
+                    if (vm[go * D + (size_t)d * np + i] > 0.) sg[go + i] |= (unsigned char)(1u << d);
+        }
+        c->dv.v_sign = c->dupload(sg);
         c->dv.v_level = c->dupload(lv);
         c->dv.v_weight = c->dupload(wt);
         c->dv.v_mid = c->dupload(vm);
@@ -544,12 +556,14 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
                 memset(&h, 0, sizeof(h));
                 h.nf_off = sl.nbr_doff * K; h.nsl_off = sl.nbr_doff * K * D; h.np = sl.nbr_np;
                 h.flags = sl.rel_off < 0 ? 2 : 0;
+                h.rel_off = sl.rel_off; h.ngoff = sl.nbr_goff;
+                if (sl.rel_off >= 0) ci.flags |= CELL_HAS_MAPPED;
                 h.area = sl.area;
                 for (int t = 0; t < D; ++t) { h.fmid[t] = sl.fmid[t]; h.own_mid[t] = sl.own_mid[t]; h.nbr_mid[t] = sl.nbr_mid[t]; }
                 c->hot.push_back(h);
                 ++nh;
             }
-            if (sl.kind != SLOT_INNER || sl.rel_off >= 0) c->rare.push_back(q);
+            if (sl.kind != SLOT_INNER) c->rare.push_back(q);   // pair-mapped fluid faces are gathered in pass A
         }
         while (key <= 2 * D) ci.side_begin[key++] = (unsigned char)nh;
         ci.rare_count = (int)c->rare.size() - ci.rare_begin;
@@ -557,6 +571,11 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         for (int k2 = 0; regular && k2 < 2 * D; ++k2) {
             const FaceRec& h = c->hot[ci.hot_begin + k2];
             regular = ci.side_begin[k2] == k2 && (h.flags & 2) && h.np == ci.np;
+            // RegCell carries the normal coordinate of a side only: everything else must equal the cell's midpoint
+            for (int t = 0; regular && t < D; ++t) {
+                regular = h.own_mid[t] == ci.mid[t];
+                if (t != k2 / 2) regular = regular && h.fmid[t] == ci.mid[t] && h.nbr_mid[t] == ci.mid[t];
+            }
         }
         if (regular) ci.flags |= CELL_REGULAR;
     }
@@ -725,6 +744,25 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         for (auto& b : bins) {
             if (b.cells.empty()) continue;
             b.d_cells = c->dupload(b.cells);
+            if (b.regular) {
+                std::vector<RegCell> recs(b.cells.size());
+                for (size_t q = 0; q < b.cells.size(); ++q) {
+                    const CellInfo& ci = c->cells[b.cells[q]];
+                    RegCell& r = recs[q];
+                    memset(&r, 0, sizeof(r));
+                    r.doff = ci.doff; r.goff = ci.goff; r.n = ci.n; r.np = ci.np; r.cell = b.cells[q]; r.vol = ci.vol;
+                    for (int t = 0; t < D; ++t) r.mid[t] = ci.mid[t];
+                    for (int k2 = 0; k2 < 2 * D; ++k2) {
+                        const FaceRec& h = c->hot[ci.hot_begin + k2];
+                        r.side[k2].ndoff = h.nf_off / K;
+                        r.side[k2].area = h.area;
+                        r.side[k2].fmid = h.fmid[k2 / 2];
+                        r.side[k2].nmid = h.nbr_mid[k2 / 2];
+                    }
+                }
+                b.d_recs = c->dupload(recs);
+                CK(cudaStreamSynchronize(c->stream));  // recs is a local
+            }
             c->bins.push_back(b);
         }
     }
@@ -1001,6 +1039,10 @@ void exchange(kamr_ctx* c, int what, int level) {
 constexpr int NT = KAMR_NT;      // threads per CTA of the slope kernel (one CTA per physical cell)
 constexpr int PNT = KAMR_PNT;    // threads per CTA of the phase kernel: small CTAs keep many cells in flight per SM,
                                  // so one cell's barriers and serial moments->prim step hide behind the others
+#ifndef KAMR_MINB_GEN
+#define KAMR_MINB_GEN KAMR_MINB
+#endif
+constexpr int MINB_GEN = KAMR_MINB_GEN;  // same for the general phase kernel (more live state: slot loops, pair-mapped gather)
 constexpr int MINB = KAMR_MINB;  // CTAs per SM the phase kernel is register-budgeted for
 
 template <int D, int K>
@@ -1099,7 +1141,7 @@ void launch_regular_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int 
         prepared = true;
     }
     Launch L_(c, KID_STEP_REGULAR);
-    kern<<<(int)b.cells.size(), PT, smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
+    kern<<<(int)b.cells.size(), PT, smem, c->stream>>>(c->dv, c->gas, b.d_recs, dt, want);
 }
 
 template <int D, int K, int MODE>
@@ -1115,10 +1157,10 @@ void launch_phase(kamr_ctx* c, const Bin& b, double dt, int want) {
     const bool stage = (MODE != MODE_FLUX) && b.smem > 0;
     if (stage) {
         if (big) launch_phase_inst<D, K, MODE, true, PNT_BIG, MINB_BIG>(c, b, b.smem, dt, want, kid);
-        else launch_phase_inst<D, K, MODE, true, PNT, MINB>(c, b, b.smem, dt, want, kid);
+        else launch_phase_inst<D, K, MODE, true, PNT, MINB_GEN>(c, b, b.smem, dt, want, kid);
     } else {
         if (big || MODE == MODE_FLUX) launch_phase_inst<D, K, MODE, false, PNT_BIG, MINB_BIG>(c, b, 0, dt, want, kid);
-        else launch_phase_inst<D, K, MODE, false, PNT, MINB>(c, b, 0, dt, want, kid);
+        else launch_phase_inst<D, K, MODE, false, PNT, MINB_GEN>(c, b, 0, dt, want, kid);
     }
 }
 
@@ -1151,7 +1193,7 @@ void fetch_residual(kamr_ctx* c, int want, double* res_out) {
     if (!want) return;
     const int M = D + 2;
     { Launch L_(c, KID_RESIDUAL);
-      residual_reduce_kernel<<<1, 256, 0, c->stream>>>(c->dv.res_cell, c->d_fluid_cells, (int)c->fluid_cells.size(),
+      residual_reduce_kernel<<<2 * M, 1024, 0, c->stream>>>(c->dv.res_cell, c->d_fluid_cells, (int)c->fluid_cells.size(),
                                                        2 * M, c->d_res); }
     CK(cudaMemcpyAsync(c->h_res, c->d_res, 2 * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

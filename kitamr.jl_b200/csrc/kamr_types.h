@@ -34,6 +34,7 @@ struct CellInfo {
 };
 enum CellFlags : int {
     CELL_HAS_MAXWELL_WALL = 1,
+    CELL_HAS_MAPPED = 4,   // some fluid/fluid face leads to a neighbour on a different velocity grid
     CELL_REGULAR = 2,  // each of the 2*DIM sides is one fluid/fluid face to a neighbour on the same velocity grid
 };
 
@@ -74,9 +75,28 @@ struct FaceRec {
     long long nf_off;    // neighbour df block offset (doubles)
     long long nsl_off;   // neighbour limited-slope block offset (doubles)
     int np;              // neighbour plane stride
-    int flags;           // bit1: neighbour half gathered in pass A (identical velocity grids)
+    int flags;           // bit1: identical velocity grids (plain gather); clear: pair-mapped gather via rel_off
+    long long rel_off;   // pair map own grid -> neighbour grid in pm_start (flags bit1 clear)
+    long long ngoff;     // neighbour's velocity-grid statics offset
     double area;         // signed, as Slot::area
     double fmid[MAXD], own_mid[MAXD], nbr_mid[MAXD];
+};
+
+// A REGULAR cell as phase_regular_kernel sees it: one record per CTA.  Regular: every side is one fluid/fluid face to a
+// same-size neighbour on the same velocity grid, and in the coordinates transverse to a face the face midpoint and the
+// neighbour midpoint equal the cell's own bit for bit (build_topology checks), so only the normal coordinate of a
+// side is carried.
+struct RegSide {
+    long long ndoff;     // neighbour's padded point offset (df block at ndoff*NDF, slope block at ndoff*NDF*DIM)
+    double area;         // signed, as Slot::area
+    double fmid;         // face midpoint, normal coordinate
+    double nmid;         // neighbour midpoint, normal coordinate
+};
+struct RegCell {
+    long long doff, goff;
+    int n, np, cell, pad_;
+    double vol, mid[MAXD];
+    RegSide side[2 * MAXD];   // [2*d + side]
 };
 
 // Slope stencil of one (cell, direction): Flux/Slope.jl:458-771, 849-945 resolved at flatten time.
@@ -149,6 +169,7 @@ struct DevView {
     const int* slope_deps;
     int* slope_done;            // per cell: epoch of the last finished slope task (dependency flags)
     const int8_t* v_level;
+    const unsigned char* v_sign; // per point: bit d = (v_d > 0)
     const double* v_weight;
     const double* v_mid;
     const int* pm_start;        // concatenated pair maps
