@@ -984,6 +984,281 @@ __global__ void __launch_bounds__(256) euler_update_kernel(DevView g, GasPar gas
 }
 
 // ------------------------------------------------------------------------------------------------
+// iterate!(CIP_Marching), Theory/I-projection.jl:161-192: convection, heat flux, conserved I-projection of the
+// h-component onto the updated conserved moments (solve_I_projection :55-141: Newton on the dual with Armijo
+// backtracking; every Newton sum and every line-search objective is one block reduction), Shakhov relaxation.
+// One CTA per cell, in place on g.df from the stored g.flux.  Every thread carries lambda and takes the (identical)
+// scalar decisions from the broadcast reduction results, so the loop needs no extra broadcast.
+// positivity_preserving_ib! (Boundary/Positivity.jl) is not on the device: the host refuses CIP_Marching on meshes with
+// donor cells (kamr_upload_topology).
+template <int NV>
+__device__ __forceinline__ void block_min(double (&v)[NV], double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] = fmin(v[k], __shfl_down_sync(0xffffffffu, v[k], off));
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) red[warp * NV + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = red[k];
+        for (int w = 1; w < nwarp; ++w) x = fmin(x, red[w * NV + k]);
+        v[k] = x;
+    }
+    __syncthreads();
+}
+
+// Gaussian elimination with partial pivoting, M <= 5 (the oracle's orc_small_solve, same operation order)
+template <int M>
+__device__ __forceinline__ bool small_solve(double (&A)[M * M], double (&b)[M], double (&x)[M]) {
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+        int piv = c;
+        double best = fabs(A[c * M + c]);
+#pragma unroll
+        for (int r = c + 1; r < M; ++r)
+            if (fabs(A[r * M + c]) > best) { best = fabs(A[r * M + c]); piv = r; }
+        if (best == 0.0) return false;
+#pragma unroll
+        for (int r = c + 1; r < M; ++r) {
+            if (r == piv) {
+#pragma unroll
+                for (int q = 0; q < M; ++q) { const double t = A[c * M + q]; A[c * M + q] = A[r * M + q]; A[r * M + q] = t; }
+                const double t = b[c]; b[c] = b[r]; b[r] = t;
+            }
+        }
+#pragma unroll
+        for (int r = c + 1; r < M; ++r) {
+            const double l = A[r * M + c] / A[c * M + c];
+#pragma unroll
+            for (int q = c; q < M; ++q) A[r * M + q] -= l * A[c * M + q];
+            b[r] -= l * b[c];
+        }
+    }
+#pragma unroll
+    for (int r = M - 1; r >= 0; --r) {
+        double t = b[r];
+#pragma unroll
+        for (int q = r + 1; q < M; ++q) t -= A[r * M + q] * x[q];
+        x[r] = t / A[r * M + r];
+    }
+    return true;
+}
+
+template <int D>
+__device__ __forceinline__ void psi_of(const double* v, double* psi) {
+    double s2 = 0.0;
+    psi[0] = 1.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { psi[1 + d] = v[d]; s2 += v[d] * v[d]; }
+    psi[D + 1] = s2 / 2;
+}
+
+template <int D, int K>
+__global__ void __launch_bounds__(256) cip_update_kernel(DevView g, GasPar gas, const int* __restrict__ cell_list,
+                                                         double dt, int want_residual) {
+    constexpr int M = D + 2, NJ = M * (M + 1) / 2, NV = M + NJ;
+    __shared__ double red[NV * 9];
+    __shared__ CellInfo ci;
+    __shared__ UpdateShared<D, K> us;
+    __shared__ double w_new[M];
+    const int c = cell_list[blockIdx.x];
+    copy_words(g.cells + c, &ci, (int)(sizeof(CellInfo) / sizeof(int)));
+    __syncthreads();
+    const CellPtr<D, K> own(g, ci);
+    const int n = ci.n, np = ci.np;
+    double* f = g.df + ci.doff * K;
+    double* vflux = g.flux + ci.doff * K;
+    const double dtv = dt / ci.vol;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+            w_new[m] = g.w[(size_t)c * M + m] + g.mflux[(size_t)c * M + m] * dt / ci.vol;
+        get_prim<D>(w_new, gas.gamma, us.prim_c);
+        us.tau = gas.mu_ref * 2.0 * pow(us.prim_c[D + 1], 1 - gas.omega) / us.prim_c[0];
+        us.coef_c = maxwell_coef<D>(us.prim_c);
+        us.cb_c = gas.K / (2.0 * us.prim_c[D + 1]);
+    }
+    __syncthreads();
+    double prim_c[M], W[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) { prim_c[m] = us.prim_c[m]; W[m] = w_new[m]; }
+    // ---- convection (:177), heat flux of the convected f about prim_c (:179), internal energy of b (:145), minima
+    double qe[D + 1], mn[2] = {CUDART_INF, CUDART_INF};
+#pragma unroll
+    for (int d = 0; d < D + 1; ++d) qe[d] = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v[D], fk[K];
+#pragma unroll
+        for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+        const double wt = own.wt[i];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            fk[k] = f[k * np + i] + dtv * vflux[k * np + i];
+            f[k * np + i] = fk[k];
+            vflux[k * np + i] = 0.0;
+        }
+        const double c2 = c2_of<D>(v, prim_c);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const double cd = v[d] - prim_c[1 + d];
+            qe[d] += wt * cd * c2 * fk[0] + ((K > 1) ? wt * cd * fk[1] : 0.0);
+        }
+        if (K > 1) qe[D] += wt * fk[1];
+        mn[0] = fmin(mn[0], fk[0]);
+        if (fk[0] > 0.) mn[1] = fmin(mn[1], fk[0]);
+    }
+    block_reduce<D + 1>(qe, red);
+    block_min<2>(mn, red);
+    double qf[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) qf[d] = 0.5 * qe[d];
+    if (K > 1) W[M - 1] -= qe[D] / 2;
+    // ---- shave negative values (:73-83)
+    const double f_min = 1.1 * mn[0];
+    if (f_min < 0.) {
+        const double fp = mn[1], dd = fp - f_min;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const double x = f[i];
+            if (x < 0.) f[i] = (x - f_min) / dd * fp;
+        }
+    }
+    // ---- Newton iteration on the dual (:88-136); each thread revisits only the points it wrote, so no barrier is needed
+    // between the shave pass and the sums
+    double lam[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) lam[m] = 0.0;
+    {
+        double nW = 0.0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) nW += W[m] * W[m];
+        nW = sqrt(nW);
+        const double tol_eff = 1e-10 * fmax(1.0, nW);
+        double G_prev = CUDART_INF;
+        int stall = 0;
+        for (int it = 0; it < 10; ++it) {
+            double a[NV];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) a[q] = 0.0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                double v[D], psi[M];
+#pragma unroll
+                for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+                psi_of<D>(v, psi);
+                double lp = 0.0;
+#pragma unroll
+                for (int m = 0; m < M; ++m) lp += lam[m] * psi[m];
+                const double cc = own.wt[i] * f[i] * exp(lp);
+                int q = M;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const double cm = cc * psi[m];
+                    a[m] += cm;
+#pragma unroll
+                    for (int j = m; j < M; ++j) a[q++] += cm * psi[j];
+                }
+            }
+            block_reduce<NV>(a, red);
+            const double Phi_sum = a[0];
+            double G[M], Gn = 0.0;
+#pragma unroll
+            for (int m = 0; m < M; ++m) { G[m] = a[m] - W[m]; Gn += G[m] * G[m]; }
+            Gn = sqrt(Gn);
+            if (Gn < tol_eff) break;
+            if (Gn > 0.9 * G_prev) {
+                if (++stall >= 2) break;
+            } else {
+                stall = 0;
+            }
+            G_prev = Gn;
+            double A[M * M], b[M], dl[M];
+            {
+                int q = M;
+#pragma unroll
+                for (int m = 0; m < M; ++m)
+#pragma unroll
+                    for (int j = m; j < M; ++j) { A[m * M + j] = a[q]; A[j * M + m] = a[q]; ++q; }
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) b[m] = G[m];
+            if (!small_solve<M>(A, b, dl)) break;
+            double lW = 0.0, slope = 0.0;
+#pragma unroll
+            for (int m = 0; m < M; ++m) { dl[m] = -dl[m]; lW += lam[m] * W[m]; slope += G[m] * dl[m]; }
+            const double Phi0 = Phi_sum - lW;
+            double alpha = 1.0;
+            for (int ls = 0; ls < 10; ++ls) {
+                double lt[M], ltW = 0.0;
+#pragma unroll
+                for (int m = 0; m < M; ++m) { lt[m] = lam[m] + alpha * dl[m]; ltW += lt[m] * W[m]; }
+                double ph[1] = {0.0};
+                for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                    double v[D], psi[M];
+#pragma unroll
+                    for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+                    psi_of<D>(v, psi);
+                    double lp = 0.0;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) lp += lt[m] * psi[m];
+                    ph[0] += own.wt[i] * f[i] * exp(lp);
+                }
+                block_reduce<1>(ph, red);
+                if (ph[0] - ltW <= Phi0 + 1e-4 * alpha * slope) break;
+                alpha *= 0.5;
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) lam[m] += alpha * dl[m];
+        }
+    }
+    // ---- projection f_h *= exp(lambda.psi) (:147-149), relaxation towards M[prim_c] + S (:186-187)
+    const double tau = us.tau;
+    const double ra = tau / (tau + dt), rb = dt / (tau + dt);
+    const double coef_c = us.coef_c;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v[D], psi[M], F[K], Fp[K];
+#pragma unroll
+        for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+        psi_of<D>(v, psi);
+        double lp = 0.0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) lp += lam[m] * psi[m];
+        maxwell<D, K>(v, prim_c, coef_c, gas.K, F);
+        shakhov<D, K>(v, F, prim_c, qf, gas.Pr, gas.K, Fp);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double x = f[k * np + i];
+            if (k == 0) x *= exp(lp);
+            f[k * np + i] = x * ra + rb * (F[k] + Fp[k]);
+        }
+    }
+    if (threadIdx.x == 0) {
+        double* prim_old = g.prim + (size_t)c * M;
+#pragma unroll
+        for (int d = 0; d < D; ++d) g.qf[(size_t)c * D + d] = qf[d];
+        if (want_residual) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const double dd = prim_c[m] - prim_old[m];
+                g.res_cell[(size_t)c * 2 * M + m] = dd * dd;
+                g.res_cell[(size_t)c * 2 * M + M + m] = fabs(prim_c[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            g.w[(size_t)c * M + m] = w_new[m];
+            prim_old[m] = prim_c[m];
+            g.mflux[(size_t)c * M + m] = 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // slopes: one block per cell of the current dependency wave; all DIM directions in one pass.
 //   sL = (1/nL) sum_nbr diff(f, P[f_nbr (+ dm . sdf_nbr)]) / dsL   (diff_vs!, Slope.jl:29-64, :278-333)
 //   sdf = minmod(sL, sR) | sL | 0                                    (Slope.jl:90-116, 68-86, 471-472)

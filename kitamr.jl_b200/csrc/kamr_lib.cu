@@ -407,6 +407,9 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     c->n_cell = m->n_local + m->n_ghost + m->n_solidnbr;
     c->n_grid = m->n_grid;
     if (c->n_local <= 0) throw Fail("mesh has no local cells");
+    if (c->gas.marching == KAMR_MARCH_CIP)   // positivity_preserving_ib! (Boundary/Positivity.jl) is not on the device
+        for (int i = 0; i < m->n_local; ++i)
+            if (m->bound_enc[i] > 0) throw Fail("CIP_Marching with immersed-boundary donor cells is not supported");
     // ---- grids
     c->grid_n.resize(m->n_grid); c->grid_np.resize(m->n_grid);
     c->grid_goff.resize(m->n_grid + 1); c->grid_hoff.resize(m->n_grid + 1);
@@ -1159,7 +1162,8 @@ void launch_phase(kamr_ctx* c, const Bin& b, double dt, int want) {
         if (big) launch_phase_inst<D, K, MODE, true, PNT_BIG, MINB_BIG>(c, b, b.smem, dt, want, kid);
         else launch_phase_inst<D, K, MODE, true, PNT, MINB_GEN>(c, b, b.smem, dt, want, kid);
     } else {
-        if (big || MODE == MODE_FLUX) launch_phase_inst<D, K, MODE, false, PNT_BIG, MINB_BIG>(c, b, 0, dt, want, kid);
+        // (MODE_FLUX stages nothing: its CTA size follows the cell size only)
+        if (big) launch_phase_inst<D, K, MODE, false, PNT_BIG, MINB_BIG>(c, b, 0, dt, want, kid);
         else launch_phase_inst<D, K, MODE, false, PNT, MINB_GEN>(c, b, 0, dt, want, kid);
     }
 }
@@ -1202,8 +1206,13 @@ void fetch_residual(kamr_ctx* c, int want, double* res_out) {
 
 template <int D, int K>
 void do_iterate(kamr_ctx* c, double dt, int want, double* res_out) {
-    if (c->gas.marching == KAMR_MARCH_CIP) throw Fail("CIP_Marching is not implemented on the device yet");
-    if (c->gas.marching == KAMR_MARCH_EULER) {
+    if (c->gas.marching == KAMR_MARCH_CIP) {
+        if (!c->fluid_cells.empty()) {
+            Launch L_(c, KID_UPDATE);
+            cip_update_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->gas, c->d_fluid_cells,
+                                                                                        dt, want);
+        }
+    } else if (c->gas.marching == KAMR_MARCH_EULER) {
         if (!c->fluid_cells.empty()) {
             Launch L_(c, KID_UPDATE);
             euler_update_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->gas, c->d_fluid_cells,

@@ -410,8 +410,90 @@ def sphere_s4(copies=1, ps_maxlevel=4, trees=16, vtrees=16, vs_maxlevel=2, noise
     return case
 
 
+def riemann_s1(ps_level=4, band_level=5, trees=16, vtrees=8, vs_maxlevel=3, noise=0.01,
+               marching=abi.MARCH_CIP) -> Case:
+    """S1 riemann2d (example/Riemann_problem/rp_2D.jl:26-72, BASELINE.json configs[0]): 16x16 roots on [-.5,.5]^2,
+    uniform level `ps_level` with a diagonal band refined to `band_level` (hanging faces ~10 %); velocity grids 8x8
+    roots on [-5,5]^2 refined to level <= 3 by maxwellian_refine_flag of each cell's own quadrant state
+    (Riemann_2D_init :11-24), so grids differ across the state jumps; 4x UniformOutflow, K=1, Kn=1e-3, omega=0.81,
+    CIP_Marching (:37)."""
+    geo = (-0.5, 0.5, -0.5, 0.5)
+    ds_band = 1.0 / trees / 2 ** ps_level
+
+    def refine_fn(l, mid, ds):
+        if l < ps_level:
+            return np.ones(len(mid), dtype=bool)
+        return np.abs(mid[:, 0] + mid[:, 1]) < 1.5 * ds_band
+
+    forest = Forest.build(2, geo, (trees, trees), band_level, refine_fn)
+    quad = (-5.0, 5.0, -5.0, 5.0)
+    gas = Gas(K=1.0, Kn=1e-3, omega=0.81, omega_r=0.81)
+
+    def state(rho, u, v, p):
+        return np.array([rho, u, v, 0.5 * rho / p])
+
+    def prim_fn(x):
+        if x[0] >= 0.0 and x[1] >= 0.0:
+            return state(0.5313, 0.0, 0.0, 0.4)
+        if x[0] < 0.0 and x[1] >= 0.0:
+            return state(1.0, 0.7276, 0.0, 1.0)
+        if x[0] < 0.0 and x[1] < 0.0:
+            return state(0.8, 0.0, 0.0, 1.0)
+        return state(1.0, 0.0, 0.7276, 1.0)
+
+    cache = {}
+    per_cell = []
+    for c in range(forest.n):
+        key = tuple(prim_fn(forest.mid[c]))
+        if key not in cache:
+            cache[key] = vg.maxwellian_grid(quad, (vtrees, vtrees), vs_maxlevel, np.array(key), 2, gas.K)
+        per_cell.append(cache[key])
+    grids, cell_grid = _dedup_grids(per_cell)
+    bt, bp = _bcs(2, [abi.BC_UNIFORM_OUTFLOW] * 4, [None] * 4)
+    tag = {abi.MARCH_CIP: "cip", abi.MARCH_CAIDVM: "caidvm", abi.MARCH_EULER: "euler"}[marching]
+    return Case(f"S1-riemann2d-{tag}", 2, 2, forest, grids, cell_grid, bt, bp, gas, quad, (vtrees, vtrees),
+                vs_maxlevel, prim_fn, SEED_BASE + 1, noise=noise, marching=marching)
+
+
+def _naca0012(x):
+    """half thickness of a unit-chord NACA0012 at x in [0,1] (the reference's naca0012.csv is missing; analytic)"""
+    x = np.clip(x, 0.0, 1.0)
+    return 0.6 * (0.2969 * np.sqrt(x) - 0.1260 * x - 0.3516 * x ** 2 + 0.2843 * x ** 3 - 0.1015 * x ** 4)
+
+
+def airfoil_s3(ps_maxlevel=7, box_level=4, trees=(24, 32), vtrees=60, noise=0.01) -> Case:
+    """S3 airfoil2d (example/airfoil/airfoil.jl:5-46): 24x32 roots on [-3,7]x[-7,7], level `box_level` in the box
+    (-1,3)x(-1,1), level `ps_maxlevel` within 4.5 ds_min of a unit-chord NACA0012 (analytic; no immersed boundary in
+    this synthetic variant: the polygon IB needs the missing csv); ONE uniform 60x60 velocity grid on [-4,8]x[-6,6]
+    (n = 3600 for every cell: the identical-grid fast path only); Ma 2 inflow at xmin, 3x InterpolatedOutflow."""
+    geo = (-3.0, 7.0, -7.0, 7.0)
+    ds_min = min(10.0 / trees[0], 14.0 / trees[1]) / 2 ** ps_maxlevel
+    Ma = 2.0
+
+    def refine_fn(l, mid, ds):
+        x, y = mid[:, 0], mid[:, 1]
+        if l < box_level:
+            return (x > -1.0) & (x < 3.0) & (np.abs(y) < 1.0)
+        half_diag = 0.5 * np.sqrt(np.sum(ds ** 2))
+        dist = np.abs(np.abs(y) - _naca0012(x))
+        dist = np.where((x < 0.0) | (x > 1.0), np.sqrt(np.minimum(x ** 2, (x - 1.0) ** 2) + y ** 2), dist)
+        return dist < 4.5 * ds_min + half_diag
+
+    forest = Forest.build(2, geo, trees, ps_maxlevel, refine_fn)
+    quad = (-4.0, 8.0, -6.0, 6.0)
+    gas = Gas(K=1.0, Kn=0.05, omega=0.81, omega_r=0.81)
+    g = vg.root_grid(quad, (vtrees, vtrees))
+    inflow = [1.0, Ma * math.sqrt(5 / 6), 0.0, 1.0]
+    bt, bp = _bcs(2, [abi.BC_SUPERSONIC_INFLOW] + [abi.BC_INTERPOLATED_OUTFLOW] * 3, [inflow, None, None, None])
+    return Case("S3-airfoil2d", 2, 2, forest, [g], np.zeros(forest.n, np.int32), bt, bp, gas, quad, (vtrees, vtrees),
+                0, smooth_prim(2, geo, U0=inflow[1:3]), SEED_BASE + 3, noise=noise)
+
+
 WORKLOADS = {
     "S2": cylinder_s2,
     "S2ib": lambda copies=1: cylinder_s2(copies=copies, ib=True),
     "S4": sphere_s4,
+    "S1": lambda copies=1: riemann_s1(),
+    "S1caidvm": lambda copies=1: riemann_s1(marching=abi.MARCH_CAIDVM),
+    "S3": lambda copies=1: airfoil_s3(),
 }

@@ -1023,6 +1023,143 @@ int orc_ib_solid_neighbors(const kamr_config* cfg, const kamr_mesh* m, orc_state
 
 /* ------------------------------------------------------------------ update */
 
+/* ---- CIP_Marching: conserved I-projection, Theory/I-projection.jl ---------------------------------
+ * solve_I_projection (:55-141): Newton iteration on the dual G(lambda) = <psi f exp(lambda.psi)> - W = 0, lambda0 = 0,
+ * psi = (1, xi, |xi|^2/2) (build_psi_matrix :6-21), tolerance 1e-10*max(1,|W|), <= 10 iterations, stall exit
+ * (:113-120), Armijo backtracking on the dual objective (:125-134), negative-f shaving first (:73-83).
+ * The reference solves the (D+2)^2 Newton system with LAPACK's symmetric (Bunch-Kaufman) solver through
+ * `Symmetric(J,:U) \ G` (:124); LAPACK is not restated here: Gaussian elimination with partial pivoting on the
+ * symmetrised matrix.  The two differ by rounding error times cond(J) in each Newton direction, which the iteration
+ * itself removes (the converged lambda is the root of G, whatever solver produced the steps). */
+static void psi_of(int D, const double* vm, int n, int k, double* psi) {
+    double s2 = 0.0;
+    psi[0] = 1.0;
+    for (int d = 0; d < D; ++d) { double x = vm[d * n + k]; psi[1 + d] = x; s2 += x * x; }
+    psi[D + 1] = s2 / 2;
+}
+/* solves A x = b (A: M x M row-major, destroyed); returns 0 on success */
+int orc_small_solve(int M, double* A, double* b, double* x) {
+    for (int c = 0; c < M; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < M; ++r)
+            if (fabs(A[r * M + c]) > fabs(A[piv * M + c])) piv = r;
+        if (A[piv * M + c] == 0.0) return 1;
+        if (piv != c) {
+            for (int q = 0; q < M; ++q) { double t = A[c * M + q]; A[c * M + q] = A[piv * M + q]; A[piv * M + q] = t; }
+            double t = b[c]; b[c] = b[piv]; b[piv] = t;
+        }
+        for (int r = c + 1; r < M; ++r) {
+            double l = A[r * M + c] / A[c * M + c];
+            for (int q = c; q < M; ++q) A[r * M + q] -= l * A[c * M + q];
+            b[r] -= l * b[c];
+        }
+    }
+    for (int r = M - 1; r >= 0; --r) {
+        double t = b[r];
+        for (int q = r + 1; q < M; ++q) t -= A[r * M + q] * x[q];
+        x[r] = t / A[r * M + r];
+    }
+    return 0;
+}
+/* dual_objective :31-47 without the - lambda.W term */
+static double dual_sum(int D, int n, const double* vm, const double* f, const double* wt, const double* lam) {
+    const int M = D + 2;
+    double acc = 0.0, psi[MAXM];
+    for (int k = 0; k < n; ++k) {
+        psi_of(D, vm, n, k, psi);
+        double lp = 0.0;
+        for (int i = 0; i < M; ++i) lp += lam[i] * psi[i];
+        acc += wt[k] * f[k] * exp(lp);
+    }
+    return acc;
+}
+/* f is shaved in place (:73-83); lambda[D+2] out; returns the number of Newton systems solved */
+int orc_solve_I_projection(int D, int n, const double* vm, double* f, const double* W, const double* wt,
+                           double* lam) {
+    const int M = D + 2, maxiter = 10;
+    double G[MAXM], J[MAXM * MAXM], psi[MAXM];
+    for (int i = 0; i < M; ++i) lam[i] = 0.0;
+    double nW = 0.0;
+    for (int i = 0; i < M; ++i) nW += W[i] * W[i];
+    nW = sqrt(nW);
+    const double tol_eff = 1e-10 * (nW > 1.0 ? nW : 1.0);
+    double G_prev = INFINITY;
+    int stall = 0, solves = 0;
+    double fmin = f[0];
+    for (int k = 1; k < n; ++k) fmin = f[k] < fmin ? f[k] : fmin;
+    fmin *= 1.1;
+    if (fmin < 0) {
+        double fp = INFINITY;
+        for (int k = 0; k < n; ++k)
+            if (f[k] > 0 && f[k] < fp) fp = f[k];
+        const double d = fp - fmin;
+        for (int k = 0; k < n; ++k)
+            if (f[k] < 0) f[k] = (f[k] - fmin) / d * fp;
+    }
+    for (int it = 0; it < maxiter; ++it) {
+        for (int i = 0; i < M; ++i) G[i] = 0.0;
+        for (int i = 0; i < M * M; ++i) J[i] = 0.0;
+        for (int k = 0; k < n; ++k) {
+            psi_of(D, vm, n, k, psi);
+            double lp = 0.0;
+            for (int i = 0; i < M; ++i) lp += lam[i] * psi[i];
+            const double c = wt[k] * f[k] * exp(lp);
+            for (int i = 0; i < M; ++i) {
+                const double ci = c * psi[i];
+                G[i] += ci;
+                for (int j = i; j < M; ++j) J[i * M + j] += ci * psi[j];
+            }
+        }
+        const double Phi_sum = G[0]; /* = sum_k w f exp(lambda.psi): psi_1 = 1, same additions as dual_objective */
+        double Gn = 0.0;
+        for (int i = 0; i < M; ++i) { G[i] -= W[i]; Gn += G[i] * G[i]; }
+        Gn = sqrt(Gn);
+        if (Gn < tol_eff) return solves;
+        if (Gn > 0.9 * G_prev) {
+            if (++stall >= 2) return solves;
+        } else stall = 0;
+        G_prev = Gn;
+        double A[MAXM * MAXM], b[MAXM], dl[MAXM];
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < M; ++j) A[i * M + j] = (j >= i) ? J[i * M + j] : J[j * M + i];
+        for (int i = 0; i < M; ++i) b[i] = G[i];
+        if (orc_small_solve(M, A, b, dl)) return -1;
+        ++solves;
+        double lW = 0.0, slope = 0.0;
+        for (int i = 0; i < M; ++i) { dl[i] = -dl[i]; lW += lam[i] * W[i]; slope += G[i] * dl[i]; }
+        const double Phi0 = Phi_sum - lW;
+        double alpha = 1.0;
+        for (int ls = 0; ls < maxiter; ++ls) {
+            double lt[MAXM], ltW = 0.0;
+            for (int i = 0; i < M; ++i) { lt[i] = lam[i] + alpha * dl[i]; ltW += lt[i] * W[i]; }
+            if (dual_sum(D, n, vm, f, wt, lt) - ltW <= Phi0 + 1e-4 * alpha * slope) break;
+            alpha *= 0.5;
+        }
+        for (int i = 0; i < M; ++i) lam[i] += alpha * dl[i];
+    }
+    return solves;
+}
+/* conserved_I_porjection! :144-159 (2D2F: the h-component against w with the internal energy of b removed) */
+static int conserved_I_projection(int D, int K, int n, const double* vm, double* f, const double* wt,
+                                  const double* w) {
+    const int M = D + 2;
+    double W[MAXM], lam[MAXM], psi[MAXM];
+    for (int i = 0; i < M; ++i) W[i] = w[i];
+    if (K > 1) {
+        double e = 0.0;
+        for (int k = 0; k < n; ++k) e += wt[k] * f[n + k];
+        W[M - 1] -= e / 2;
+    }
+    if (orc_solve_I_projection(D, n, vm, f, W, wt, lam) < 0) return 1;
+    for (int k = 0; k < n; ++k) {
+        psi_of(D, vm, n, k, psi);
+        double lp = 0.0;
+        for (int i = 0; i < M; ++i) lp += lam[i] * psi[i];
+        f[k] *= exp(lp);
+    }
+    return 0;
+}
+
 /* iterate!(CAIDVM_Marching) Theory/Iterate.jl:96-130 ; iterate!(Euler) :131-162 ;
  * residual_check! Solver/Finalize.jl:5-11 */
 int orc_iterate(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt, int want_residual,
@@ -1092,9 +1229,32 @@ int orc_iterate(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, doubl
                                    dt / (tau + dt) * F[k];
                 }
             }
-        } else {
-            octx_free(&o);
-            return 2; /* CIP_Marching: see orc_iterate_cip */
+        } else { /* iterate!(CIP_Marching), Theory/I-projection.jl:161-192 */
+            if (m->bound_enc[c] != 0) { /* positivity_preserving_ib! (Boundary/Positivity.jl) is not restated */
+                octx_free(&o);
+                return 2;
+            }
+            for (int q = 0; q < M; ++q) w[q] += mfl[q] * dt / area;
+            orc_get_prim(D, w, cfg->gamma, prim_c);
+            for (int k = 0; k < K; ++k)
+                for (int i = 0; i < n; ++i) f[k * n + i] += dt / area * vflux[k * n + i];
+            heat_flux(D, K, n, vm, f, prim_c, wt, qf);
+            for (int d = 0; d < D; ++d) st->qf[(size_t)c * D + d] = qf[d];
+            if (conserved_I_projection(D, K, n, vm, f, wt, w)) { octx_free(&o); return 3; }
+            double tau = orc_get_tau(D, prim_c, cfg->mu_ref, cfg->omega);
+            for (int i = 0; i < n; ++i) {
+                double v[MAXD], Fc[2], Fp[2];
+                for (int t = 0; t < D; ++t) v[t] = vm[t * n + i];
+                maxwell_point(D, K, v, prim_c, cfg->K, Fc);
+                shakhov_point(D, K, v, Fc, prim_c, qf, cfg->Pr, cfg->K, Fp);
+                for (int k = 0; k < K; ++k) {
+                    Fc[k] += Fp[k];
+                    double x = f[k * n + i];
+                    x *= tau / (tau + dt);
+                    x += dt / (tau + dt) * Fc[k];
+                    f[k * n + i] = x;
+                }
+            }
         }
         if (want_residual) {
             for (int q = 0; q < M; ++q) {

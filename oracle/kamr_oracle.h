@@ -25,6 +25,10 @@ void   orc_heat_flux(int D, int K, int n, const double* vmid, const double* df, 
                      const double* weight, double* q);
 int    orc_pair_map(int D, int n_a, const int8_t* lev_a, int n_b, const int8_t* lev_b, int32_t* start);
 
+int    orc_small_solve(int M, double* A, double* b, double* x);
+int    orc_solve_I_projection(int D, int n, const double* vm, double* f, const double* W, const double* wt,
+                              double* lam);
+
 int orc_slope_level(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, int Lv, int transverse);
 int orc_macro_slope(const kamr_config* cfg, const kamr_mesh* m, orc_state* st);
 int orc_slope(const kamr_config* cfg, const kamr_mesh* m, orc_state* st);

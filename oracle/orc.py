@@ -100,3 +100,16 @@ def pair_map(dim, lev_a, lev_b):
     rc = lib().orc_pair_map(dim, len(lev_a), lev_a.ctypes.data_as(C.POINTER(C.c_int8)), len(lev_b),
                             lev_b.ctypes.data_as(C.POINTER(C.c_int8)), start.ctypes.data_as(C.POINTER(C.c_int32)))
     return rc, start
+
+
+def solve_I_projection(dim, vmid, f, W, weight):
+    """solve_I_projection, Theory/I-projection.jl:55-141.  vmid [dim, n] planes; f is shaved in place.
+    Returns (lambda[dim+2], Newton systems solved)."""
+    n = len(weight)
+    lam = np.zeros(dim + 2)
+    vm = np.ascontiguousarray(vmid, dtype=np.float64)
+    lib().orc_solve_I_projection.restype = C.c_int
+    rc = lib().orc_solve_I_projection(dim, n, _p(vm), _p(f), _p(np.ascontiguousarray(W, dtype=np.float64)),
+                                      _p(weight), _p(lam))
+    assert rc >= 0, "singular Newton system"
+    return lam, rc

@@ -6,12 +6,15 @@ import hashlib
 
 import numpy as np
 
+from kitamr_jl_b200 import abi
 from kitamr_jl_b200.synth import cases
 
 CASES = {
     "S0": lambda: cases.smoke_s0(),
     "amr2d_ragged": lambda: cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=8, vs_maxlevel=2, ragged=True),
     "amr3d_ragged": lambda: cases.amr_case(dim=3, trees=3, maxlevel=1, vtrees=4, vs_maxlevel=1, ragged=True, seed=4),
+    "cip2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=1, vtrees=8, vs_maxlevel=1, ragged=True, seed=8,
+                                    marching=abi.MARCH_CIP),
 }
 
 

@@ -9,6 +9,17 @@ from util import local_pts, rel_l2
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-12
+# CIP_Marching: the I-projection is a Newton iteration that stops at |G| < 1e-10 max(1,|W|) (or on its stall exit,
+# Theory/I-projection.jl:108-120) and whose Armijo test compares objectives that differ by less than their rounding
+# error near convergence, so WHICH iterate it stops at depends on the summation order.  The reference's own result is
+# therefore defined to that tolerance only; f is compared at 1e-8, everything that does not pass through the
+# projection (w, prim, qf, residual) at the usual bound, and the projected f must hit the moments like the oracle's.
+TOL_CIP_DF = 1e-8
+
+
+def df_tol(case, tol=TOL):
+    from kitamr_jl_b200 import abi
+    return TOL_CIP_DF if case.marching == abi.MARCH_CIP else tol
 
 
 def _cases():
@@ -36,6 +47,15 @@ def _cases():
         "s4_ib_l3": lambda: cases.sphere_s4(trees=4, ps_maxlevel=3, vtrees=6, vs_maxlevel=1),
         "euler2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=1, vtrees=8, vs_maxlevel=1, ragged=True, seed=6,
                                           marching=abi.MARCH_EULER),
+        # CIP_Marching (Theory/I-projection.jl): Newton I-projection per cell, un-fused slope/flux/iterate path
+        "cip2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=1, vtrees=8, vs_maxlevel=1, ragged=True, seed=8,
+                                        marching=abi.MARCH_CIP),
+        "cip3d": lambda: cases.amr_case(dim=3, trees=2, maxlevel=1, vtrees=4, vs_maxlevel=1, ragged=True, seed=9,
+                                        marching=abi.MARCH_CIP),
+        # S1 (BASELINE configs[0], example/Riemann_problem): quadrant states, grids differ across the jumps, CIP
+        "s1_small": lambda: cases.riemann_s1(ps_level=1, band_level=2, trees=4, vtrees=8, vs_maxlevel=2),
+        # S3 (example/airfoil): one uniform velocity grid, InterpolatedOutflow on three sides
+        "s3_small": lambda: cases.airfoil_s3(ps_maxlevel=3, box_level=2, trees=(6, 8), vtrees=12),
     }
 
 
@@ -84,7 +104,7 @@ def test_phases_match_oracle(setup):
     r_ref = orc.iterate(cfg, mesh, ref, dt, True)
     r_out = ctx.iterate(dt, True)
     out = ctx.download_state(st0.copy())
-    assert rel_l2(local_pts(mesh, out.df, K), local_pts(mesh, ref.df, K)) <= TOL
+    assert rel_l2(local_pts(mesh, out.df, K), local_pts(mesh, ref.df, K)) <= df_tol(case)
     assert rel_l2(out.w[: nl * (D + 2)], ref.w[: nl * (D + 2)]) <= TOL
     assert rel_l2(out.prim[: nl * (D + 2)], ref.prim[: nl * (D + 2)]) <= TOL
     assert rel_l2(out.qf[: nl * D], ref.qf[: nl * D]) <= 1e-10  # heat flux is a difference of O(1) moments
@@ -108,7 +128,9 @@ def test_fused_step_matches_oracle(setup):
         if it in (0, 9):
             out = ctx.download_state(st0.copy(), abi.DL_DF | abi.DL_W | abi.DL_PRIM)
             tol = TOL if it == 0 else 1e-11
-            assert rel_l2(local_pts(mesh, out.df, K), local_pts(mesh, ref.df, K)) <= tol
+            assert rel_l2(local_pts(mesh, out.df, K), local_pts(mesh, ref.df, K)) <= df_tol(case, tol)
+            if case.marching == abi.MARCH_CIP:   # the state carries the projection's tolerance from step to step
+                tol = TOL if it == 0 else TOL_CIP_DF
             assert rel_l2(out.w[: nl * (D + 2)], ref.w[: nl * (D + 2)]) <= tol
             # prim of FLUID cells: a solid ghost cell's prim is get_prim of an extrapolated distribution (Immersed_boundary.jl
             # :139-140), whose lambda = rho/(2(gamma-1)(E - rho U^2/2)) can be arbitrarily ill-conditioned; nothing on the path
@@ -138,3 +160,32 @@ def test_pair_maps_bit_exact(setup):
             assert np.array_equal(pm, start)
             checked += 1
     assert checked == ctx.stats().n_relations
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_cip_device_projection_hits_the_moments(kamr_lib, dim):
+    """The device's I-projection judged by its defining property instead of by the oracle's iterate: with tau >> dt
+    the CIP step returns f_proj, whose discrete moments must equal w^{n+1} to what the Newton exits leave (as in
+    tests/test_oracle_cpu.py::test_cip_step_conserves_the_updated_moments for the oracle)."""
+    from kitamr_jl_b200 import abi, api
+    from kitamr_jl_b200.synth import cases
+    case = cases.amr_case(dim=dim, trees=3, maxlevel=1, vtrees=8 if dim == 2 else 6, vs_maxlevel=1, ragged=True,
+                          seed=21, marching=abi.MARCH_CIP)
+    case.gas.mu_ref = 1e12
+    mesh = case.rank_mesh()
+    st = case.init_state(mesh)
+    ctx = api.Context(case.config(device=0))
+    try:
+        ctx.upload_topology(mesh)
+        ctx.upload_state(st, aux=True)
+        ctx.step(case.dt(), False)
+        out = ctx.download_state(st.copy(), abi.DL_DF | abi.DL_W)
+    finally:
+        ctx.close()
+    K, M = mesh.ndf, dim + 2
+    off = mesh.vs_off()
+    for c in range(mesh.n_local):
+        g = case.grids[int(case.cell_grid[int(mesh.global_ids[c])])]
+        f = out.df[off[c] * K: off[c + 1] * K].reshape(K, g.n)
+        m = cases.moments(g.mid, g.weight, f.T)
+        assert np.allclose(m, out.w[c * M:(c + 1) * M], rtol=0, atol=1e-8)

@@ -447,11 +447,130 @@ def test_residual_definition():
     assert np.allclose(res[M:], np.abs(pc).sum(axis=0), rtol=1e-12)
 
 
+# ------------------------------------------------------------------------------------------------ CIP_Marching
+def _np_I_projection(psi, wt, f, W):
+    """solve_I_projection (Theory/I-projection.jl:55-141) written independently in NumPy, Newton systems solved by
+    LAPACK (numpy.linalg.solve) as the reference's `Symmetric(J,:U) \\ G` does."""
+    f = f.copy()
+    M = len(W)
+    lam = np.zeros(M)
+    fm = 1.1 * f.min()
+    if fm < 0:
+        fp = f[f > 0].min()
+        d = fp - fm
+        neg = f < 0
+        f[neg] = (f[neg] - fm) / d * fp
+    tol = 1e-10 * max(1.0, np.linalg.norm(W))
+    G_prev, stall = np.inf, 0
+    for _ in range(10):
+        c = wt * f * np.exp(lam @ psi)
+        G = (psi * c).sum(axis=1) - W
+        J = (psi * c) @ psi.T
+        Gn = np.linalg.norm(G)
+        if Gn < tol:
+            break
+        if Gn > 0.9 * G_prev:
+            stall += 1
+            if stall >= 2:
+                break
+        else:
+            stall = 0
+        G_prev = Gn
+        dl = -np.linalg.solve(J, G)
+        phi = lambda l: (wt * f * np.exp(l @ psi)).sum() - l @ W  # noqa: E731
+        p0, sl, a = phi(lam), G @ dl, 1.0
+        for _ in range(10):
+            if phi(lam + a * dl) <= p0 + 1e-4 * a * sl:
+                break
+            a *= 0.5
+        lam = lam + a * dl
+    return lam, f
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_I_projection_matches_numpy_twin_and_hits_the_moments(D):
+    """the oracle's Newton I-projection against the NumPy/LAPACK twin, and its defining property
+    <psi f exp(lambda.psi)> = W (to the reference's tolerance 1e-10 max(1,|W|)); negative-f shaving included."""
+    K = 2 if D == 2 else 1
+    Kin = 1.0 if D == 2 else 0.0
+    rng = np.random.default_rng(5 + D)
+    prim = np.array([1.0, 0.8, -0.3, 1.2]) if D == 2 else np.array([1.0, 0.5, 0.1, -0.2, 0.9])
+    g = vg.maxwellian_grid((-6.0, 6.0) * D, (8,) * D, 2, prim, K, Kin)
+    df = vg.discrete_maxwell(g.mid, prim, K, Kin)
+    f = np.ascontiguousarray(df[:, 0] * (1 + 0.05 * rng.uniform(-1, 1, g.n)))
+    f[::37] *= -0.01
+    vm = np.ascontiguousarray(g.mid.T)
+    wt = np.ascontiguousarray(g.weight)
+    psi = np.vstack([np.ones(g.n), vm, 0.5 * (vm ** 2).sum(axis=0)])
+    W = (psi * wt * np.abs(f)).sum(axis=1) * np.array([1.02, 0.97, 1.01, 1.03, 0.99][: D + 2])
+    lam_t, f_t = _np_I_projection(psi, wt, f, W)
+    f_o = f.copy()
+    lam_o, solves = orc.solve_I_projection(D, vm, f_o, W, wt)
+    assert 1 <= solves <= 10
+    assert np.array_equal(f_o, f_t)                       # shaving: same arithmetic, bit for bit
+    assert (f_o >= 0).all() and (f < 0).any()
+    assert np.allclose(lam_o, lam_t, rtol=0, atol=1e-12)
+    G = (psi * wt * f_o * np.exp(lam_o @ psi)).sum(axis=1) - W
+    assert np.linalg.norm(G) < 1e-10 * max(1.0, np.linalg.norm(W))
+
+
+def test_I_projection_identity_when_moments_already_match():
+    """lambda0 = 0 is returned untouched when <psi f> = W already (first residual below tolerance, :108-110)"""
+    g = vg.root_grid((-5.0, 5.0) * 2, (12, 12))
+    df = vg.discrete_maxwell(g.mid, np.array([1.0, 0.2, 0.1, 1.0]), 2, 1.0)
+    f = np.ascontiguousarray(df[:, 0])
+    vm = np.ascontiguousarray(g.mid.T)
+    psi = np.vstack([np.ones(g.n), vm, 0.5 * (vm ** 2).sum(axis=0)])
+    W = (psi * g.weight * f).sum(axis=1)
+    lam, solves = orc.solve_I_projection(2, vm, f, W, np.ascontiguousarray(g.weight))
+    assert solves == 0 and np.all(lam == 0.0)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_cip_step_conserves_the_updated_moments(dim):
+    """iterate!(CIP_Marching), Theory/I-projection.jl:161-192: after the projection <psi f> = w^{n+1}; the relaxation
+    towards M[prim_c] + Shakhov then changes the discrete moments only by the quadrature error of the discrete
+    Maxwellian, which tau >> dt switches off: f_new = f_proj and its moments are w to what the Newton exits leave
+    (1e-10 max(1,|W|) on convergence; the stall exit :113-120 can stop a few 1e-9 short)."""
+    case = cases.amr_case(dim=dim, trees=3, maxlevel=1, vtrees=8 if dim == 2 else 6, vs_maxlevel=1, ragged=True,
+                          seed=21, marching=abi.MARCH_CIP)
+    case.gas.mu_ref = 1e12
+    mesh = case.rank_mesh()
+    st = case.init_state(mesh)
+    cfg = case.config()
+    orc.step(cfg, mesh, st, case.dt(), False)
+    D, K, M = dim, mesh.ndf, dim + 2
+    off = mesh.vs_off()
+    for c in range(mesh.n_local):
+        g = case.grids[int(case.cell_grid[int(mesh.global_ids[c])])]
+        f = st.df[off[c] * K: off[c + 1] * K].reshape(K, g.n)
+        m = cases.moments(g.mid, g.weight, f.T)
+        assert np.allclose(m, st.w[c * M:(c + 1) * M], rtol=0, atol=1e-8)   # Newton exits: tolerance, stall or 10 iterations
+
+
+def test_cip_and_caidvm_agree_to_first_order():
+    """Same convection, same relaxation target: the two marchings differ only in how the convected f is pulled onto
+    w^{n+1} (multiplicative exp(lambda.psi) vs additive M[prim_c]-M[prim]); for a smooth state one step of each stays
+    within O(correction^2) of the other."""
+    a = cases.amr_case(dim=2, trees=3, maxlevel=1, vtrees=10, vs_maxlevel=1, ragged=False, seed=22)
+    b = cases.amr_case(dim=2, trees=3, maxlevel=1, vtrees=10, vs_maxlevel=1, ragged=False, seed=22,
+                       marching=abi.MARCH_CIP)
+    out = []
+    for case in (a, b):
+        mesh = case.rank_mesh()
+        st = case.init_state(mesh)
+        orc.step(case.config(), mesh, st, case.dt(), False)
+        out.append((mesh, st))
+    (mesh, sa), (_, sb) = out
+    assert np.array_equal(sa.w, sb.w)                                     # the macroscopic update is shared
+    assert rel_l2(local_pts(mesh, sb.df, 2), local_pts(mesh, sa.df, 2)) < 2e-3
+
+
 # ------------------------------------------------------------------------------------------------ golden fixtures
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["S0", "amr2d_ragged", "amr3d_ragged"])
+@pytest.mark.parametrize("name", ["S0", "amr2d_ragged", "amr3d_ragged", "cip2d"])
 def test_oracle_reproduces_golden(name):
     import make_golden_cases as mg
     path = os.path.join(GOLD, f"{name}.npz")
