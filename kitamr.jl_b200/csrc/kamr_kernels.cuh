@@ -12,6 +12,7 @@
 // (planes of `np` doubles), so every global access of a warp is a run of 32 consecutive doubles.
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 #include <math_constants.h>
 #include "kamr_types.h"
 
@@ -146,6 +147,17 @@ template <int D>
 __device__ __forceinline__ double pick(const double* a, int d) {
     if (D == 2) return d == 0 ? a[0] : a[1];
     return d == 0 ? a[0] : (d == 1 ? a[1] : a[2]);
+}
+
+// DRAM -> L2 prefetch of a contiguous block (cp.async.bulk.prefetch.L2, one instruction, no destination): a CTA
+// requests the state block of the cell that the CTA launched PF_DIST blocks later will work on, so that cell's first
+// touch of its own planes is an L2 hit instead of a DRAM round trip.  p 16-byte aligned, bytes a multiple of 16.
+#ifndef KAMR_PF_DIST
+#define KAMR_PF_DIST 512
+#endif
+constexpr int PF_DIST = KAMR_PF_DIST;   // measured best on S1/S2 (gpurun_out/sweep6: 128 .. 2048 and "own cell at start")
+__device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // Loads of the state arrays (df, limited slopes).  Measured (gpurun_out/sweep4, S2): routing them around L1 with
@@ -791,6 +803,13 @@ __global__ void __launch_bounds__(NT, MINB)
         }
         return;
     }
+    if (PF_DIST > 0 && MODE == MODE_FUSED && threadIdx.x == NT - 1 && blockIdx.x + PF_DIST < gridDim.x) {
+        const CellInfo* __restrict__ nx = g.cells + cell_list[blockIdx.x + PF_DIST];
+        const long long nd = nx->doff;
+        const unsigned nb = (unsigned)nx->np * 8u;
+        l2_prefetch(g.df + nd * K, nb * K);
+        l2_prefetch(g.sdl + nd * (K * D), nb * (K * D));
+    }
     update_tail<D, K, MODE, STAGE_SMEM, NT>(g, gas, n, np, ci.vol, c, dt, want_residual, acc, own.v, own.wt, fs, fstride,
                                             fout, dyn, red, us, w_new, w0s);
 }
@@ -804,7 +823,7 @@ __global__ void __launch_bounds__(NT, MINB)
 // is upwind comes from the point's sign byte (L1-resident, one per distinct velocity grid), so all global loads of a
 // point are requested together; the transverse dx = (x_t - v_t dt) - x_t is formed once per point instead of once per
 // face.
-template <int D, int K, bool STAGE_SMEM, int NT, int MINB>
+template <int D, int K, bool STAGE_SMEM, int NT, int MINB, bool MAPPED>
 __global__ void __launch_bounds__(NT, MINB)
     phase_regular_kernel(DevView g, GasPar gas, const RegCell* __restrict__ recs, double dt, int want_residual) {
     extern __shared__ double dyn[];
@@ -815,6 +834,12 @@ __global__ void __launch_bounds__(NT, MINB)
     copy_words(recs + blockIdx.x, &rc, (int)(sizeof(RegCell) / sizeof(int)));
     __syncthreads();
     const int n = rc.n, np = rc.np, c = rc.cell;
+#ifdef KAMR_PF_SELF
+    if (threadIdx.x == NT - 1) {
+        l2_prefetch(g.df + rc.doff * K, (unsigned)np * 8u * K);
+        l2_prefetch(g.sdl + rc.doff * (K * D), (unsigned)np * 8u * (K * D));
+    }
+#endif
     const double dtv = dt / rc.vol;
     double* __restrict__ fout = g.df_new + rc.doff * K;
     double* fs = STAGE_SMEM ? dyn : fout;
@@ -833,10 +858,14 @@ __global__ void __launch_bounds__(NT, MINB)
     for (int i = threadIdx.x; i < n; i += NT) {
         double v[D], vdt[D], tdx[D], f[K], s[K * D], fl[K];
         double nfv[D][K], nsv[D][K * D];
+        bool mapped[D];
         const unsigned sg = sgn[i];
 #pragma unroll
         for (int d = 0; d < D; ++d) {  // neighbour-upwind side: low face for v_d > 0, high face otherwise
-            const long long nd = rc.side[2 * d + (((sg >> d) & 1u) ? 0 : 1)].ndoff;
+            const RegSide& hs = rc.side[2 * d + (((sg >> d) & 1u) ? 0 : 1)];
+            mapped[d] = MAPPED && hs.rel_off >= 0;
+            if (mapped[d]) continue;   // pair-mapped neighbour: gathered below
+            const long long nd = hs.ndoff;
             const double* __restrict__ nf = gdf + nd * K + i;
             const double* __restrict__ nsl = gsl + nd * (K * D) + i;
 #pragma unroll
@@ -877,7 +906,7 @@ __global__ void __launch_bounds__(NT, MINB)
                     fl[k] += val * Avn;
                 }
             }
-            {   // neighbour-upwind face
+            if (!mapped[d]) {   // neighbour-upwind face
                 const RegSide& h = rc.side[2 * d + sn];
                 const double Avn = h.area * vn;
                 const double dxd = face_dx(h.fmid, vdt[d], h.nmid);
@@ -891,12 +920,59 @@ __global__ void __launch_bounds__(NT, MINB)
             }
         }
         add_moments<D, K>(acc, wt, v, fl);
+        if (MAPPED) {
+            // neighbour-upwind halves across faces to another velocity grid (update_micro_flux!, Flux.jl:151-344 in
+            // gather form, as mapped_flux): point i is covered by / covers points st[i] .. st[i+1]-1 over there
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                if (!mapped[d]) continue;
+                const RegSide& h = rc.side[2 * d + (((sg >> d) & 1u) ? 0 : 1)];
+                const double* __restrict__ nf = gdf + h.ndoff * K;
+                const double* __restrict__ nsl = gsl + h.ndoff * (K * D);
+                const double* __restrict__ nv = g.v_mid + h.ngoff * D;
+                const int nnp = h.np;
+                const int* __restrict__ st = g.pm_start + h.rel_off;
+                const int j0 = st[i];
+                const int cnt = max(1, st[i + 1] - j0);
+                const double A = h.area;
+                const int li = (cnt > 1) ? (int)g.v_level[rc.goff + i] : 0;
+                for (int j = j0; j < j0 + cnt; ++j) {
+                    double vj[D], dx[D], m[K];
+#pragma unroll
+                    for (int t = 0; t < D; ++t) {
+                        vj[t] = nv[t * nnp + j];
+                        dx[t] = face_dx(t == d ? h.fmid : rc.mid[t], __dmul_rn(vj[t], dt), t == d ? h.nmid : rc.mid[t]);
+                    }
+                    double scale = 1.0, wq = wt;
+                    if (cnt > 1) {
+                        scale = 1.0 / (double)(1 << (D * ((int)g.v_level[h.ngoff + j] - li)));
+                        wq = g.v_weight[h.ngoff + j];
+                    }
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        double s_dx = 0.0;
+#pragma unroll
+                        for (int t = 0; t < D; ++t) s_dx += dx[t] * nsl[(t * K + k) * nnp + j];
+                        m[k] = (nf[k * nnp + j] + s_dx) * vj[d];
+                        fl[k] += (A * m[k]) * scale;
+                    }
+                    add_moments<D, K>(acc, A * wq, vj, m);
+                }
+            }
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             f[k] += dtv * fl[k];
             fs[k * fstride + i] = f[k];
         }
         add_moments<D, K>(acc + (D + 2), wt, v, f);
+    }
+    if (PF_DIST > 0 && threadIdx.x == NT - 1 && blockIdx.x + PF_DIST < gridDim.x) {
+        const RegCell* __restrict__ nx = recs + blockIdx.x + PF_DIST;
+        const long long nd = nx->doff;
+        const unsigned nb = (unsigned)nx->np * 8u;
+        l2_prefetch(gdf + nd * K, nb * K);
+        l2_prefetch(gsl + nd * (K * D), nb * (K * D));
     }
     update_tail<D, K, MODE_FUSED, STAGE_SMEM, NT>(g, gas, n, np, rc.vol, c, dt, want_residual, acc, gv, gwt, fs, fstride,
                                                   fout, dyn, red, us, w_new, w0s);
@@ -1483,35 +1559,73 @@ __global__ void __launch_bounds__(NT, 1024 / NT) slope_kernel(DevView g, const S
 }
 
 // slopes of REGULAR stencils (SlopeReg): same arithmetic as slope_kernel's SLOPE_INNER branch with one neighbour per
-// side, all 2*DIM neighbour values requested up front.
-template <int D, int K, int NT>
-__global__ void __launch_bounds__(NT) slope_regular_kernel(DevView g, const SlopeReg* __restrict__ tasks, int raw_all) {
-    __shared__ SlopeReg tk;
-    copy_words(tasks + blockIdx.x, &tk, (int)(sizeof(SlopeReg) / sizeof(int)));
+// side, all 2*DIM neighbour values requested up front.  MAPPED (SlopeRegMap): neighbours may live on other velocity
+// grids; their point indices come from the pair maps (mean over covering finer points, diff_vs! Slope.jl:29-64).
+template <int D, int K, int NT, bool MAPPED>
+__global__ void __launch_bounds__(NT) slope_regular_kernel(DevView g, const void* __restrict__ tasks_, int raw_all) {
+    using Task = typename std::conditional<MAPPED, SlopeRegMap, SlopeReg>::type;
+    const Task* __restrict__ tasks = reinterpret_cast<const Task*>(tasks_);
+    __shared__ Task tkm;
+    copy_words(tasks + blockIdx.x, &tkm, (int)(sizeof(Task) / sizeof(int)));
     __syncthreads();
+    const SlopeReg& tk = *reinterpret_cast<const SlopeReg*>(&tkm);
+    const SlopeRegMap& tm = *reinterpret_cast<const SlopeRegMap*>(&tkm);   // only read when MAPPED
     const int n = tk.n, np = tk.np;
     const bool raw = raw_all || (tk.flags & 1);
     const double* __restrict__ df = g.df;
+    if (PF_DIST > 0 && threadIdx.x == NT - 1 && blockIdx.x + PF_DIST < gridDim.x) {
+        const SlopeReg* __restrict__ nx = reinterpret_cast<const SlopeReg*>(tasks + blockIdx.x + PF_DIST);
+        l2_prefetch(df + nx->doff * K, (unsigned)nx->np * 8u * K);
+    }
     const double* __restrict__ own = df + tk.doff * K;
     double* sdf = g.sdf + tk.doff * K * D;
     double* sdl = g.sdl + tk.doff * K * D;
     for (int i = threadIdx.x; i < n; i += NT) {
         double f[K], nf[2 * D][K], s[D][K];
+        int j0[2 * D], cn[2 * D];
 #pragma unroll
         for (int q = 0; q < 2 * D; ++q) {
-            const double* __restrict__ p = df + tk.nb_doff[q] * K + i;
+            j0[q] = i; cn[q] = 1;
+            if (MAPPED && tm.nb_rel[q] >= 0) {
+                const int* __restrict__ st = g.pm_start + tm.nb_rel[q];
+                j0[q] = st[i];
+                cn[q] = max(1, st[i + 1] - j0[q]);
+            }
+        }
 #pragma unroll
-            for (int k = 0; k < K; ++k) nf[q][k] = p[k * np];
+        for (int q = 0; q < 2 * D; ++q) {
+            const double* __restrict__ p = df + tk.nb_doff[q] * K + j0[q];
+            const int nnp = MAPPED ? tm.nb_np[q] : np;
+#pragma unroll
+            for (int k = 0; k < K; ++k) nf[q][k] = p[k * nnp];
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) f[k] = own[k * np + i];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
+            double ab[2][K];
+#pragma unroll
+            for (int sd2 = 0; sd2 < 2; ++sd2) {
+                const int q = 2 * d + sd2;
+                if (!MAPPED || cn[q] == 1) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) ab[sd2][k] = 0.0 + (f[k] - nf[q][k]);
+                } else {
+                    const int8_t* __restrict__ nlev = g.v_level + tm.nb_goff[q];
+                    const int li = g.v_level[tm.goff + i];
+                    const int nnp = tm.nb_np[q];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) ab[sd2][k] = 0.0;
+                    for (int j = j0[q]; j < j0[q] + cn[q]; ++j) {
+                        const double scale = 1.0 / (double)(1 << (D * (nlev[j] - li)));
+#pragma unroll
+                        for (int k = 0; k < K; ++k) ab[sd2][k] += (f[k] - df[tk.nb_doff[q] * K + k * nnp + j]) * scale;
+                    }
+                }
+            }
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double a = (0.0 + (f[k] - nf[2 * d][k])) * tk.inv[2 * d];
-                const double b = (0.0 + (f[k] - nf[2 * d + 1][k])) * tk.inv[2 * d + 1];
-                s[d][k] = minmod(a, b);
+                s[d][k] = minmod(ab[0][k] * tk.inv[2 * d], ab[1][k] * tk.inv[2 * d + 1]);
                 if (raw) sdf[(d * K + k) * np + i] = s[d][k];
             }
         }

@@ -57,17 +57,20 @@ struct Bin {
     std::vector<int> cells;
     int* d_cells = nullptr;
     size_t smem = 0;     // dynamic shared memory per block (0 => global staging)
-    bool regular = false;  // all cells are CELL_REGULAR: phase_regular_kernel
+    bool regular = false;  // all cells are CELL_REGULAR / CELL_REGULAR_MAPPED: phase_regular_kernel
+    bool mapped = false;   // ... CELL_REGULAR_MAPPED: the MAPPED instantiation
     RegCell* d_recs = nullptr;  // regular bins: one record per cell, in launch order
 };
 
 enum KernelId { KID_SLOPE = 0, KID_MACRO_SLOPE, KID_FLUX, KID_UPDATE, KID_STEP, KID_RESIDUAL, KID_PACK, KID_UNPACK,
-                KID_LIMIT, KID_SOLID_CELL, KID_SOLID_NBR, KID_STEP_REGULAR, KID_SLOPE_REGULAR, KID_COUNT };
+                KID_LIMIT, KID_SOLID_CELL, KID_SOLID_NBR, KID_STEP_REGULAR, KID_SLOPE_REGULAR, KID_STEP_REGMAP,
+                KID_SLOPE_REGMAP, KID_COUNT };
 const char* const kKernelNames[KID_COUNT] = {"slope_kernel", "macro_slope_kernel", "phase_kernel<FLUX>",
                                              "phase_kernel<UPDATE>", "phase_kernel<FUSED>", "residual_reduce_kernel",
                                              "pack_kernel", "unpack_kernel", "limit_kernel", "solid_cell_kernel",
                                              "solid_neighbor_kernel", "phase_regular_kernel",
-                                             "slope_regular_kernel"};
+                                             "slope_regular_kernel", "phase_regular_kernel<MAPPED>",
+                                             "slope_regular_kernel<MAPPED>"};
 
 struct PeerPlan {
     int rank;
@@ -117,8 +120,10 @@ struct kamr_ctx {
     struct SlopeStage {
         int wave = 0;
         std::vector<SlopeReg> reg;
+        std::vector<SlopeRegMap> regm;   // regular stencils with neighbours on other velocity grids
         std::vector<SlopeTask> gen;
         SlopeReg* d_reg = nullptr;
+        SlopeRegMap* d_regm = nullptr;
         SlopeTask* d_gen = nullptr;
         bool flags = false;   // gen tasks carry dependency lists
     };
@@ -571,16 +576,19 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         while (key <= 2 * D) ci.side_begin[key++] = (unsigned char)nh;
         ci.rare_count = (int)c->rare.size() - ci.rare_begin;
         bool regular = ci.rare_count == 0 && nh == 2 * D && ci.bound_enc >= 0;
+        bool any_mapped = false;
         for (int k2 = 0; regular && k2 < 2 * D; ++k2) {
             const FaceRec& h = c->hot[ci.hot_begin + k2];
-            regular = ci.side_begin[k2] == k2 && (h.flags & 2) && h.np == ci.np;
+            regular = ci.side_begin[k2] == k2;
+            any_mapped = any_mapped || !(h.flags & 2);
+            if ((h.flags & 2) && h.np != ci.np) regular = false;
             // RegCell carries the normal coordinate of a side only: everything else must equal the cell's midpoint
             for (int t = 0; regular && t < D; ++t) {
                 regular = h.own_mid[t] == ci.mid[t];
                 if (t != k2 / 2) regular = regular && h.fmid[t] == ci.mid[t] && h.nbr_mid[t] == ci.mid[t];
             }
         }
-        if (regular) ci.flags |= CELL_REGULAR;
+        if (regular) ci.flags |= any_mapped ? CELL_REGULAR_MAPPED : CELL_REGULAR;
     }
     // ---- slope tasks in dependency waves (slope!, Slope.jl:1047-1070).  The reference sweeps the levels
     // coarse to fine because a fine cell next to a coarse one projects the coarse cell's FINISHED slopes
@@ -665,6 +673,15 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             }
             return true;
         };
+        auto is_regmapped = [&](const SlopeTask& t) {   // regular stencil, neighbours possibly on other grids
+            for (int d = 0; d < D; ++d) {
+                const SlopeDir& sd = t.d[d];
+                if (sd.mode != SLOPE_INNER || sd.nA != 1 || sd.nB != 1) return false;
+                for (int a = 0; a < 2; ++a)
+                    if (c->slope_nb[sd.nb_begin + a].proj) return false;
+            }
+            return true;
+        };
         auto make_reg = [&](const SlopeTask& t) {
             const CellInfo& ci = c->cells[t.cell];
             SlopeReg r;
@@ -688,11 +705,25 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         }
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return wave[a] < wave[b]; });
         std::vector<char> in_gen(tasks.size(), 0);
-        for (int ti : order) in_gen[ti] = !((by_level || wave[ti] == 0) && is_regular(tasks[ti]));
+        for (int ti : order)
+            in_gen[ti] = !((by_level || wave[ti] == 0) && (is_regular(tasks[ti]) || is_regmapped(tasks[ti])));
         for (int ti : order) {
             kamr_ctx::SlopeStage& st = stages[by_level ? wave[ti] : 0];
             st.wave = by_level ? wave[ti] : 0;
-            if (!in_gen[ti]) { st.reg.push_back(make_reg(tasks[ti])); continue; }
+            if (!in_gen[ti]) {
+                if (is_regular(tasks[ti])) { st.reg.push_back(make_reg(tasks[ti])); continue; }
+                SlopeRegMap rm;
+                memset(&rm, 0, sizeof(rm));
+                rm.r = make_reg(tasks[ti]);
+                rm.goff = c->cells[tasks[ti].cell].goff;
+                for (int d = 0; d < D; ++d)
+                    for (int a = 0; a < 2; ++a) {
+                        const SlopeNbr& e = c->slope_nb[tasks[ti].d[d].nb_begin + a];
+                        rm.nb_rel[2 * d + a] = e.rel_off; rm.nb_goff[2 * d + a] = e.goff; rm.nb_np[2 * d + a] = e.np;
+                    }
+                st.regm.push_back(rm);
+                continue;
+            }
             SlopeTask t = tasks[ti];
             if (!by_level) {  // dependencies computed by the same launch -> flags
                 t.dep_begin = (int)c->slope_deps.size();
@@ -708,6 +739,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         }
         for (auto& kv : stages) {
             kv.second.d_reg = c->dupload(kv.second.reg);
+            kv.second.d_regm = c->dupload(kv.second.regm);
             kv.second.d_gen = c->dupload(kv.second.gen);
             c->slope_stages.push_back(std::move(kv.second));
         }
@@ -730,16 +762,17 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         const size_t caps[] = {8 << 10, 16 << 10, 24 << 10, 32 << 10, 48 << 10, 64 << 10, 96 << 10, 128 << 10,
                                (size_t)c->max_smem_optin - (12 << 10)};
         const int ncap = (int)(sizeof(caps) / sizeof(caps[0]));
-        std::vector<Bin> bins(2 * (ncap + 1));
+        std::vector<Bin> bins(3 * (ncap + 1));
         c->fused_cells = 0;
         for (int cell : c->fluid_cells) {
             const CellInfo& ci = c->cells[cell];
             const size_t need = (size_t)ci.n * (K + 1) * sizeof(double);
             int q = 0;
             while (q < ncap && need > caps[q]) ++q;
-            const bool regular = (ci.flags & CELL_REGULAR) != 0;
-            Bin& b = bins[2 * q + (regular ? 1 : 0)];
-            b.regular = regular;
+            const bool mapped = (ci.flags & CELL_REGULAR_MAPPED) != 0;
+            const bool regular = mapped || (ci.flags & CELL_REGULAR) != 0;
+            Bin& b = bins[3 * q + (mapped ? 2 : (regular ? 1 : 0))];
+            b.regular = regular; b.mapped = mapped;
             b.smem = (q < ncap) ? std::max(b.smem, need) : 0;
             b.cells.push_back(cell);
             if (q < ncap) c->fused_cells++;
@@ -761,6 +794,9 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
                         r.side[k2].area = h.area;
                         r.side[k2].fmid = h.fmid[k2 / 2];
                         r.side[k2].nmid = h.nbr_mid[k2 / 2];
+                        r.side[k2].rel_off = (h.flags & 2) ? -1 : h.rel_off;
+                        r.side[k2].ngoff = h.ngoff;
+                        r.side[k2].np = h.np;
                     }
                 }
                 b.d_recs = c->dupload(recs);
@@ -1052,7 +1088,11 @@ template <int D, int K>
 void launch_slope_stage(kamr_ctx* c, const kamr_ctx::SlopeStage& st, int raw_all) {
     if (!st.reg.empty()) {
         Launch L_(c, KID_SLOPE_REGULAR);
-        slope_regular_kernel<D, K, NT><<<(int)st.reg.size(), NT, 0, c->stream>>>(c->dv, st.d_reg, raw_all);
+        slope_regular_kernel<D, K, NT, false><<<(int)st.reg.size(), NT, 0, c->stream>>>(c->dv, st.d_reg, raw_all);
+    }
+    if (!st.regm.empty()) {
+        Launch L_(c, KID_SLOPE_REGMAP);
+        slope_regular_kernel<D, K, NT, true><<<(int)st.regm.size(), NT, 0, c->stream>>>(c->dv, st.d_regm, raw_all);
     }
     if (!st.gen.empty()) {
         Launch L_(c, KID_SLOPE);
@@ -1133,9 +1173,9 @@ void launch_phase_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int wa
     kern<<<(int)b.cells.size(), PT, smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
 }
 
-template <int D, int K, bool STAGE, int PT, int MB>
-void launch_regular_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want) {
-    auto kern = phase_regular_kernel<D, K, STAGE, PT, MB>;
+template <int D, int K, bool STAGE, int PT, int MB, bool MAPPED>
+void launch_regular_inst2(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want) {
+    auto kern = phase_regular_kernel<D, K, STAGE, PT, MB, MAPPED>;
     static bool prepared = false;
     if (!prepared) {
         cudaFuncAttributes fa;
@@ -1143,8 +1183,13 @@ void launch_regular_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int 
         prepare_kernel(kern, c->max_smem_optin - (int)fa.sharedSizeBytes);
         prepared = true;
     }
-    Launch L_(c, KID_STEP_REGULAR);
+    Launch L_(c, MAPPED ? KID_STEP_REGMAP : KID_STEP_REGULAR);
     kern<<<(int)b.cells.size(), PT, smem, c->stream>>>(c->dv, c->gas, b.d_recs, dt, want);
+}
+template <int D, int K, bool STAGE, int PT, int MB>
+void launch_regular_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want) {
+    if (b.mapped) launch_regular_inst2<D, K, STAGE, PT, MB, true>(c, b, smem, dt, want);
+    else launch_regular_inst2<D, K, STAGE, PT, MB, false>(c, b, smem, dt, want);
 }
 
 template <int D, int K, int MODE>
@@ -1310,7 +1355,12 @@ int kamr_create(const kamr_config* cfg, kamr_ctx** out) {
         c->gas = GasPar{cfg->K, cfg->Pr, cfg->gamma, cfg->omega, cfg->mu_ref, cfg->flux_type, cfg->marching};
         if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
         else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-        CK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+        {   // the wall kernels are short, narrow (a few hundred CTAs) and feed the last phase kernel of the step: with
+            // the highest priority their CTAs are placed first and the regular cells' phase kernel fills the rest
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi));
+        }
         CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         CK(cudaMallocHost((void**)&c->h_res, 64 * sizeof(double)));

@@ -35,6 +35,7 @@ struct CellInfo {
 enum CellFlags : int {
     CELL_HAS_MAXWELL_WALL = 1,
     CELL_HAS_MAPPED = 4,   // some fluid/fluid face leads to a neighbour on a different velocity grid
+    CELL_REGULAR_MAPPED = 8,  // regular topology and geometry, but some neighbour is on a different velocity grid
     CELL_REGULAR = 2,  // each of the 2*DIM sides is one fluid/fluid face to a neighbour on the same velocity grid
 };
 
@@ -91,6 +92,9 @@ struct RegSide {
     double area;         // signed, as Slot::area
     double fmid;         // face midpoint, normal coordinate
     double nmid;         // neighbour midpoint, normal coordinate
+    long long rel_off;   // pair map own grid -> neighbour grid in pm_start; -1: identical grids (always, in plain bins)
+    long long ngoff;     // neighbour's velocity-grid statics offset
+    int np, pad_;        // neighbour's plane stride
 };
 struct RegCell {
     long long doff, goff;
@@ -131,6 +135,14 @@ struct SlopeReg {
     double ds[MAXD];
     long long nb_doff[2 * MAXD];   // [2*d + side]
     double inv[2 * MAXD];          // 1/dsL, 1/dsR (signed) as SlopeDir::invA/invB
+};
+// The same stencil with neighbours on other velocity grids (pair-mapped gather): slope_regular_kernel<MAPPED>
+struct SlopeRegMap {
+    SlopeReg r;
+    long long goff;                // own velocity-grid statics (levels)
+    long long nb_rel[2 * MAXD];    // pair map own grid -> neighbour grid, -1 identical
+    long long nb_goff[2 * MAXD];
+    int nb_np[2 * MAXD];
 };
 
 // Immersed boundary (kernel d): tables resolved at flatten time from kamr_ib.
