@@ -86,6 +86,8 @@ struct PeerPlan {
         long long send_len = 0, recv_len = 0;
     };
     std::map<int, Lvl> sdf;
+    Lvl sdf_final;                            // all levels this pair does not exchange early, in one message
+    unsigned long long early = 0;             // waves whose slopes this pair exchanges right after the wave
     Lvl solid;                                // df of solid ghost cells, mid-flux (Boundary/Parallel.jl:138-259)
     long long send_base = 0, recv_base = 0;  // offsets of this peer's region in the staging buffers
 };
@@ -137,6 +139,10 @@ struct kamr_ctx {
     std::vector<int> limit_cells; // local fluid + ghost fluid cells (limit_kernel after upload_aux)
     int* d_limit_cells = nullptr;
     std::map<int, std::pair<int*, int>> ghost_wave_cells;  // wave -> ghost fluid cells whose sdf arrives then
+    std::vector<unsigned long long> peer_early;   // per peer: waves with an early slope exchange (see build_topology)
+    unsigned long long early_mask = 0;            // union over the peers
+    int* d_ghost_fluid = nullptr;                 // all fluid ghost cells (limited after the final slope exchange)
+    int n_ghost_fluid = 0;
     std::vector<int> fluid_cells;
     int* d_fluid_cells = nullptr;
     // immersed boundary
@@ -199,6 +205,7 @@ struct kamr_ctx {
         d_host_off = nullptr;
         d_res = nullptr; d_sendbuf = d_recvbuf = nullptr; d_fluid_cells = nullptr; d_limit_cells = nullptr;
         limit_cells.clear(); ghost_wave_cells.clear(); raw_sdf_valid = false;
+        peer_early.clear(); early_mask = 0; d_ghost_fluid = nullptr; n_ghost_fluid = 0;
         solid_tasks.clear(); sn_tasks.clear(); ib_nb.clear(); d_solid_tasks = nullptr; d_sn_tasks = nullptr;
     }
 };
@@ -704,12 +711,56 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             tasks[ti].flags = need_raw[tasks[ti].cell] ? 1 : 0;
         }
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return wave[a] < wave[b]; });
+        // ---- with peers: which waves need their slope halo RIGHT AFTER the wave?  Only those whose mirror slopes a
+        // peer projects in a later wave (a fine cell next to a coarser ghost cell, Slope.jl:165-175).  Every other
+        // mirror's slopes are needed by the flux gather only and travel in one message after the last wave.  Each rank
+        // knows which ghost slopes it projects; one 8-byte handshake per pair makes the schedule symmetric.
+        c->peer_early.assign(m->n_peer, 0);
+        c->early_mask = 0;
+        if (by_level) {
+            std::vector<unsigned long long> need(m->n_peer, 0), got(m->n_peer, ~0ull);
+            for (size_t ti = 0; ti < tasks.size(); ++ti)
+                for (int tgt : deps[ti]) {
+                    if (tgt < c->n_local) continue;
+                    const int gi = tgt - c->n_local;
+                    for (int p = 0; p < m->n_peer; ++p)
+                        if (gi >= m->recv_off[p] && gi < m->recv_off[p + 1])
+                            need[p] |= 1ull << std::min(63, std::max(0, c->cells[tgt].ps_level - m->ps_minlevel));
+                }
+            if (c->comm) {
+                unsigned long long* d_hs = c->dalloc<unsigned long long>(2 * (size_t)m->n_peer);
+                CK(cudaMemcpyAsync(d_hs, need.data(), sizeof(unsigned long long) * m->n_peer, cudaMemcpyHostToDevice,
+                                   c->stream));
+                NCK(nccl().GroupStart());
+                for (int p = 0; p < m->n_peer; ++p) {
+                    NCK(nccl().Send(d_hs + p, 1, ncclFloat64, m->peer_rank[p], c->comm, c->stream));
+                    NCK(nccl().Recv(d_hs + m->n_peer + p, 1, ncclFloat64, m->peer_rank[p], c->comm, c->stream));
+                }
+                NCK(nccl().GroupEnd());
+                CK(cudaMemcpyAsync(got.data(), d_hs + m->n_peer, sizeof(unsigned long long) * m->n_peer,
+                                   cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+            }   // without a communicator yet: every wave early, as slope_exchange_level! does
+            for (int p = 0; p < m->n_peer; ++p) {
+                c->peer_early[p] = c->comm ? (need[p] | got[p]) : ~0ull;
+                c->early_mask |= c->peer_early[p];
+            }
+        }
+        // launches: the waves between two early exchanges form one stage (dependencies inside a stage go through the
+        // per-cell epoch flags); on one rank, or when no pair needs an early exchange, that is a single stage
+        auto stage_of = [&](int w) {
+            int sidx = 0;
+            for (int e = 0; e < w && e < 64; ++e)
+                if (c->early_mask >> e & 1ull) ++sidx;
+            return sidx;
+        };
         std::vector<char> in_gen(tasks.size(), 0);
         for (int ti : order)
             in_gen[ti] = !((by_level || wave[ti] == 0) && (is_regular(tasks[ti]) || is_regmapped(tasks[ti])));
         for (int ti : order) {
-            kamr_ctx::SlopeStage& st = stages[by_level ? wave[ti] : 0];
-            st.wave = by_level ? wave[ti] : 0;
+            const int sidx = by_level ? stage_of(wave[ti]) : 0;
+            kamr_ctx::SlopeStage& st = stages[sidx];
+            st.wave = sidx;
             if (!in_gen[ti]) {
                 if (is_regular(tasks[ti])) { st.reg.push_back(make_reg(tasks[ti])); continue; }
                 SlopeRegMap rm;
@@ -725,7 +776,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
                 continue;
             }
             SlopeTask t = tasks[ti];
-            if (!by_level) {  // dependencies computed by the same launch -> flags
+            {   // dependencies computed by the same or an earlier launch of this sweep -> epoch flags
                 t.dep_begin = (int)c->slope_deps.size();
                 for (int tgt : deps[ti]) {
                     const int tj = (tgt < c->n_local) ? task_of[tgt] : -1;
@@ -953,11 +1004,28 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             lv.recv_len = rp;
             rpos_max = std::max(rpos_max, rp);
         }
+        pp.early = (size_t)p < c->peer_early.size() ? c->peer_early[p] : ~0ull;
         for (auto& kv : pp.sdf) {
             kv.second.d_send = c->dupload(kv.second.send);
             kv.second.d_recv = c->dupload(kv.second.recv);
             c->halo_bytes_step += 8 * kv.second.send_len;
+            if (pp.early >> std::min(63, kv.first) & 1ull) continue;
+            // not exchanged early: appended (ascending level, mirror / ghost order inside a level) to the final message
+            for (CopySeg sg : kv.second.send) {
+                sg.dst = pp.send_base + pp.sdf_final.send_len;
+                pp.sdf_final.send.push_back(sg);
+                pp.sdf_final.send_len += sg.len;
+            }
+            for (CopySeg sg : kv.second.recv) {
+                sg.src = pp.recv_base + pp.sdf_final.recv_len;
+                pp.sdf_final.recv.push_back(sg);
+                pp.sdf_final.recv_len += sg.len;
+            }
         }
+        pp.sdf_final.d_send = c->dupload(pp.sdf_final.send);
+        pp.sdf_final.d_recv = c->dupload(pp.sdf_final.recv);
+        spos_max = std::max(spos_max, pp.sdf_final.send_len);
+        rpos_max = std::max(rpos_max, pp.sdf_final.recv_len);
         pp.d_df_send = c->dupload(pp.df_send);
         pp.solid.d_send = c->dupload(pp.solid.send);
         pp.solid.d_recv = c->dupload(pp.solid.recv);
@@ -967,6 +1035,12 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         c->peers.push_back(std::move(pp));
     }
     for (auto& kv : ghost_by_wave) c->ghost_wave_cells[kv.first] = std::make_pair(c->dupload(kv.second), (int)kv.second.size());
+    {
+        std::vector<int> gf;
+        for (auto& kv : ghost_by_wave) gf.insert(gf.end(), kv.second.begin(), kv.second.end());
+        c->d_ghost_fluid = c->dupload(gf);
+        c->n_ghost_fluid = (int)gf.size();
+    }
     if (m->n_peer > 0) {
         c->d_sendbuf = c->dalloc<double>((size_t)send_total);
         c->d_recvbuf = c->dalloc<double>((size_t)recv_total);
@@ -1007,16 +1081,19 @@ void copy_points(kamr_ctx* c, double* dev, double* host_rw, const double* host_r
 // halo
 PeerPlan::Lvl* halo_level(PeerPlan& pp, int what, int level) {
     if (what == 2) return (pp.solid.send.empty() && pp.solid.recv.empty()) ? nullptr : &pp.solid;
+    if (what == 3) return (pp.sdf_final.send.empty() && pp.sdf_final.recv.empty()) ? nullptr : &pp.sdf_final;
+    if (!(pp.early >> std::min(63, level) & 1ull)) return nullptr;   // this pair sends that level in the final message
     auto it = pp.sdf.find(level);
     return it == pp.sdf.end() ? nullptr : &it->second;
 }
 
-// what: 0 df of all mirrors (data_exchange!), 1 sdf of one level (slope_exchange_level!), 2 df of solid ghost
-// cells (solid_exchange_begin!/finish!)
+// what: 0 df of all mirrors (data_exchange!), 1 sdf of one level for the pairs that need it early
+// (slope_exchange_level!), 2 df of solid ghost cells (solid_exchange_begin!/finish!), 3 sdf of every level not sent
+// early, one message per pair
 void exchange(kamr_ctx* c, int what, int level) {
     if (c->peers.empty()) return;
     if (!c->comm) throw Fail("mesh has peers but kamr_comm_init was not called");
-    double* src = what == 1 ? c->dv.sdf : c->dv.df;
+    double* src = (what == 1 || what == 3) ? c->dv.sdf : c->dv.df;
     double* dst = src;
     bool any = false;
     for (auto& pp : c->peers) {
@@ -1124,21 +1201,21 @@ void do_slope(kamr_ctx* c, bool with_sw, bool raw_all) {
     if (c->peers.empty()) {
         for (auto& st : c->slope_stages) launch_slope_stage<D, K>(c, st, raw_all);
     } else {
-        // waves present locally or in the halo, ascending; each followed by its exchange
-        // (slope_exchange_level!, Parallel/Ghost.jl:896) and the limited slopes of the ghosts that arrived
-        std::vector<int> waves;
-        for (auto& st : c->slope_stages) waves.push_back(st.wave);
-        for (auto& pp : c->peers)
-            for (auto& kv : pp.sdf) waves.push_back(kv.first);
-        std::sort(waves.begin(), waves.end());
-        waves.erase(std::unique(waves.begin(), waves.end()), waves.end());
-        for (int w : waves) {
+        // stage s = the waves up to and including the s-th early wave; it is followed by that wave's exchange between
+        // the pairs that project each other's slopes of that level (slope_exchange_level!, Parallel/Ghost.jl:896).
+        // Everything else travels in one message per pair after the last stage, then the ghosts' limited slopes.
+        std::vector<int> early;
+        for (int e = 0; e < 64; ++e)
+            if (c->early_mask >> e & 1ull) early.push_back(e);
+        size_t nst = early.size() + 1;
+        for (auto& st : c->slope_stages) nst = std::max(nst, (size_t)st.wave + 1);
+        for (size_t sidx = 0; sidx < nst; ++sidx) {
             for (auto& st : c->slope_stages)
-                if (st.wave == w) launch_slope_stage<D, K>(c, st, raw_all);
-            exchange(c, 1, w);
-            auto it = c->ghost_wave_cells.find(w);
-            if (it != c->ghost_wave_cells.end()) run_limit<D, K>(c, it->second.first, it->second.second);
+                if ((size_t)st.wave == sidx) launch_slope_stage<D, K>(c, st, raw_all);
+            if (sidx < early.size()) exchange(c, 1, early[sidx]);
         }
+        exchange(c, 3, 0);
+        run_limit<D, K>(c, c->d_ghost_fluid, c->n_ghost_fluid);
     }
     c->raw_sdf_valid = raw_all;
     CK(cudaGetLastError());

@@ -31,6 +31,10 @@ def main():
         "s2_small": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2),
         "s4_ib": lambda: cases.sphere_s4(trees=4, ps_maxlevel=2, vtrees=4, vs_maxlevel=1),
         "s2_ib": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=5, box_level=2, vtrees=8, vs_maxlevel=2, ib=True),
+        # CIP_Marching: un-fused path with the per-level slope halo; f is defined to the Newton tolerance only
+        # (tests/test_gpu_parity.py, TOL_CIP_DF)
+        "cip2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=8, vs_maxlevel=1, ragged=True, seed=34,
+                                        marching=abi.MARCH_CIP),
     }
     for name, fn in names.items():
         case = fn()
@@ -63,7 +67,7 @@ def main():
         t = torch.tensor([num, den], dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
         err = float(torch.sqrt(t[0] / t[1]))
-        worst = max(worst, err)
+        worst = max(worst, err / (1e4 if case.marching == abi.MARCH_CIP else 1.0))
         if rank == 0:
             print(f"{name}: world={world} halo_bytes/step(rank0)={ctx.stats().halo_bytes_per_step} "
                   f"rel L2(df) vs single-rank oracle after {steps} steps = {err:.3e}", flush=True)
