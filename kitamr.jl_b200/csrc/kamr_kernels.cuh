@@ -859,12 +859,18 @@ __global__ void __launch_bounds__(NT, MINB)
         double v[D], vdt[D], tdx[D], f[K], s[K * D], fl[K];
         double nfv[D][K], nsv[D][K * D];
         bool mapped[D];
+        int mj0[D], mj1[D];
         const unsigned sg = sgn[i];
 #pragma unroll
         for (int d = 0; d < D; ++d) {  // neighbour-upwind side: low face for v_d > 0, high face otherwise
             const RegSide& hs = rc.side[2 * d + (((sg >> d) & 1u) ? 0 : 1)];
             mapped[d] = MAPPED && hs.rel_off >= 0;
-            if (mapped[d]) continue;   // pair-mapped neighbour: gathered below
+            if (mapped[d]) {   // pair-mapped neighbour: gathered below; its index range is requested now, with the rest
+                const int* __restrict__ st = g.pm_start + hs.rel_off;
+                mj0[d] = st[i];
+                mj1[d] = st[i + 1];
+                continue;
+            }
             const long long nd = hs.ndoff;
             const double* __restrict__ nf = gdf + nd * K + i;
             const double* __restrict__ nsl = gsl + nd * (K * D) + i;
@@ -931,9 +937,8 @@ __global__ void __launch_bounds__(NT, MINB)
                 const double* __restrict__ nsl = gsl + h.ndoff * (K * D);
                 const double* __restrict__ nv = g.v_mid + h.ngoff * D;
                 const int nnp = h.np;
-                const int* __restrict__ st = g.pm_start + h.rel_off;
-                const int j0 = st[i];
-                const int cnt = max(1, st[i + 1] - j0);
+                const int j0 = mj0[d];
+                const int cnt = max(1, mj1[d] - j0);
                 const double A = h.area;
                 const int li = (cnt > 1) ? (int)g.v_level[rc.goff + i] : 0;
                 for (int j = j0; j < j0 + cnt; ++j) {
