@@ -59,6 +59,9 @@ def n_cores():
         return os.cpu_count() or 1
 
 
+MARCH_NAMES = {0: "CAIDVM_Marching", 1: "CIP_Marching", 2: "Euler"}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle, one process per core on a Morton split of the same workload
 def _cpu_worker(case, rank, nparts, steps, warmup, barrier, q):
@@ -143,14 +146,16 @@ def run_reference(args):
     cores = n_cores()
     over, rate1 = calibrate_oversplit(case, cores, args.steps + args.warmup, 120.0)
     val, nph, secs = cpu_arm(case, args.steps, args.warmup, cores, over)
-    n_of = np.array([gr.n for gr in case.grids])[case.cell_grid]
-    sample = f"{nph} of {int(n_of.sum())} phase cells ({cores} of {cores * over} Morton chunks), {args.steps} steps"
+    # the whole job's phase cells = what the GPU arm reports: velocity points of the FLUID cells of every rank
+    nph_total = sum(case.rank_mesh(r, world).n_phase_local() for r in range(world)) if world > 1 \
+        else case.rank_mesh().n_phase_local()
+    sample = f"{nph} of {int(nph_total)} phase cells ({cores} of {cores * over} Morton chunks), {args.steps} steps"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": case.name, "phase_cells": int(n_of.sum()), "dim": case.dim, "ndf": case.ndf,
-                   "marching": "CAIDVM_Marching", "flux": "CAIDVM"},
+        "config": {"workload": case.name, "phase_cells": int(nph_total), "dim": case.dim, "ndf": case.ndf,
+                   "marching": MARCH_NAMES[case.marching], "flux": "CAIDVM"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "note": "oracle restatement of the Julia step (reference needs julia+libp4est+MPI, absent); "
                                  "one process per core, no halo exchange timed"},
@@ -402,7 +407,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": case.name, "phase_cells": int(nph_total), "cells_rank0": mesh.n_local,
-                       "dim": D, "ndf": K, "marching": "CAIDVM_Marching", "flux": "CAIDVM",
+                       "dim": D, "ndf": K, "marching": MARCH_NAMES[case.marching], "flux": "CAIDVM",
                        "l2_policy": "inputs larger than L2: %.2f GB of df/sdf/flux state per GPU vs 126 MB L2"
                                     % (s.device_bytes / 1e9),
                        "halo_bytes_per_step_rank0": int(s.halo_bytes_per_step)},
