@@ -22,6 +22,15 @@ namespace kamr {
 #ifndef KAMR_UNROLL
 #define KAMR_UNROLL 1
 #endif
+// big cells (n > ~1300 points in 2D2F, ~2000 in 3D1F) take PNT_BIG-thread CTAs, MINB_BIG of them per SM
+#ifndef KAMR_PNT_BIG
+#define KAMR_PNT_BIG 512
+#endif
+#ifndef KAMR_MINB_BIG
+#define KAMR_MINB_BIG 2
+#endif
+constexpr int PNT_BIG = KAMR_PNT_BIG;
+constexpr int MINB_BIG = KAMR_MINB_BIG;
 constexpr int UNROLL = KAMR_UNROLL;  // point-loop unrolling of the phase kernels: independent points in flight per thread
 
 // ------------------------------------------------------------------------------------------------
@@ -557,7 +566,10 @@ __device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas,
 #pragma unroll
     for (int m = 0; m < D + 2; ++m) prim_c[m] = us.prim_c[m];
     const double coef_c = us.coef_c, cb_c = us.cb_c;
-    double* fch = dyn + (size_t)K * n;  // staged h-component of M[prim_c] (STAGE_SMEM only)
+    // h-component of M[prim_c]: staged beside f by the small-CTA instantiations; the big-CTA ones (cells of thousands
+    // of points) recompute it in phase 3 instead, which halves (3D1F) their shared memory and lets two cells share an SM
+    constexpr bool STAGE_FC = STAGE_SMEM && NT != PNT_BIG;
+    double* fch = dyn + (size_t)K * n;
     {
         double prim[D + 2];
 #pragma unroll
@@ -589,7 +601,7 @@ __device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas,
                         f[k] = fs[k * fstride + i] + (Fc[k] - F[k]);
                         fs[k * fstride + i] = f[k];
                     }
-                    if (STAGE_SMEM) fch[i] = Fc[0];
+                    if (STAGE_FC) fch[i] = Fc[0];
                     // heat_flux (2D2F.jl:68-88, 3D1F.jl:41-72): q_d = 1/2 sum w c_d (c^2 h + b)
                     const double gq = wb[u] * (c2_of<D>(vb[u], prim_c) * f[0] + ((K > 1) ? f[1] : 0.0));
 #pragma unroll
@@ -627,7 +639,7 @@ __device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas,
                 const int i = i0 + u * NT;
                 if (i < n) {
                     double Fc[K], Fp[K];
-                    if (STAGE_SMEM) {
+                    if (STAGE_FC) {
                         Fc[0] = fch[i];
                         if (K > 1) Fc[1] = Fc[0] * cb_c;
                     } else {
@@ -1732,16 +1744,21 @@ __device__ __forceinline__ void ib_geometry(const IbNbr* nb, int cnt, const doub
         for (int t = 0; t < D; ++t) { geo[a].l[t] = l[t]; geo[a].lh[t] = __ddiv_rn(l[t], nl); }
     }
 }
+// v.l/|v| as a product with 1/|v| (one division per point instead of one per neighbour): the sign and the exact zeros
+// of v.l, which decide the weights where v is perpendicular to l, are unchanged; magnitudes move by <= 1 ulp.
 template <int D>
-__device__ __forceinline__ double dir_weight(const IbGeom<D>& ge, const double* v, double nu_sqrt) {
+__device__ __forceinline__ double dir_weight(const IbGeom<D>& ge, const double* v, double inv_nu) {
     double dot = 0.0;
 #pragma unroll
     for (int t = 0; t < D; ++t) dot = __dadd_rn(dot, __dmul_rn(v[t], ge.lh[t]));
-    double q = __ddiv_rn(dot, nu_sqrt);
+    double q = __dmul_rn(dot, inv_nu);
     q = q > 0. ? q : 0.;
     return __dmul_rn(q, q);
 }
 
+#ifndef KAMR_IB_MINB
+#define KAMR_IB_MINB 4   // 64 registers: some spill, twice the warps; measured best on S2 and S4 (gpurun_out/sweep11)
+#endif
 constexpr int IB_WREG = 4;  // direction weights of the first IB_WREG neighbours stay in registers between the passes
 
 template <int D, int K>
@@ -1750,7 +1767,7 @@ __device__ __forceinline__ void directional_extrapolate(const DevView& g, const 
     double nu = 0.0;
 #pragma unroll
     for (int t = 0; t < D; ++t) nu = __dadd_rn(nu, __dmul_rn(v[t], v[t]));
-    nu = __dsqrt_rn(nu);
+    nu = __ddiv_rn(1.0, __dsqrt_rn(nu));
     double ws = 0.0, wreg[IB_WREG];
 #pragma unroll
     for (int a = 0; a < IB_WREG; ++a) {
@@ -1760,9 +1777,11 @@ __device__ __forceinline__ void directional_extrapolate(const DevView& g, const 
     for (int a = IB_WREG; a < cnt; ++a) ws = __dadd_rn(ws, dir_weight<D>(geo[a], v, nu));
 #pragma unroll
     for (int k = 0; k < K; ++k) out[k] = 0.0;
+    const double inv_ws = (ws == 0.) ? 0.0 : __ddiv_rn(1.0, ws);
+    const double w_eq = 1.0 / cnt;
     auto gather = [&](int a, double wa) {
         const IbNbr& e = nb[a];
-        const double wi = (ws == 0.) ? 1.0 / cnt : __ddiv_rn(wa, ws);
+        const double wi = (ws == 0.) ? w_eq : __dmul_rn(wa, inv_ws);
         const double* sf = g.df + e.doff * K;
         const double* ss = g.sdf + e.doff * K * D;
         const int np = e.np;
@@ -1793,7 +1812,7 @@ __device__ __forceinline__ void directional_extrapolate(const DevView& g, const 
 
 // update_solid_cell!: one CTA per solid ghost cell; also w = <psi f>, prim (Immersed_boundary.jl:139-140)
 template <int D, int K>
-__global__ void __launch_bounds__(256) solid_cell_kernel(DevView g, GasPar gas, const SolidTask* __restrict__ tasks,
+__global__ void __launch_bounds__(256, KAMR_IB_MINB) solid_cell_kernel(DevView g, GasPar gas, const SolidTask* __restrict__ tasks,
                                                          double* __restrict__ df2) {
     __shared__ double red[(D + 2) * 32];
     __shared__ CellInfo ci;
@@ -1852,7 +1871,7 @@ __device__ __forceinline__ int cvc_find(const int* __restrict__ idx, int b, int 
 // extrapolation to the wall point, partial sums of the wall mass balance; pass 2: wall Maxwellian on the outgoing
 // half, cut-cell blending.  Writes SolidNeighbor.vs_data.df / .sdf[:,:,dir] / .flux.
 template <int D, int K>
-__global__ void __launch_bounds__(256) solid_neighbor_kernel(DevView g, GasPar gas, const SnTask* __restrict__ tasks,
+__global__ void __launch_bounds__(256, KAMR_IB_MINB) solid_neighbor_kernel(DevView g, GasPar gas, const SnTask* __restrict__ tasks,
                                                              double* __restrict__ df2) {
     __shared__ double red[2 * 32];
     __shared__ CellInfo cp, cs, cn_;
@@ -1878,6 +1897,7 @@ __global__ void __launch_bounds__(256) solid_neighbor_kernel(DevView g, GasPar g
     const double dxs = pick<D>(cp.mid, dir) - pick<D>(cn_.mid, dir);
     const double dxL = pick<D>(tk.aux, dir) - pick<D>(ibp, dir);
     const double dfl = pick<D>(cn_.mid, dir) - pick<D>(tk.aux, dir);
+    const double inv_dxs = 1.0 / dxs, inv_dxf = 1.0 / dxf;   // block-uniform: products instead of per-point divisions
     const double* sdfS = g.df + cs.doff * K;   // solid cell's df
     const int8_t* slev = g.v_level + cs.goff;
     double* snf = g.df + cn_.doff * K;
@@ -1910,9 +1930,9 @@ __global__ void __launch_bounds__(256) solid_neighbor_kernel(DevView g, GasPar g
             for (int j = j0; j < j0 + cc; ++j) {
                 double d = f[k] - sdfS[k * cs.np + j];
                 if (cc > 1) d = d / (double)(1 << (D * (slev[j] - li)));
-                sL += d / dxs;
+                sL += d * inv_dxs;
             }
-            double sv = minmod(sL, (ibf[k] - f[k]) / dxf);
+            double sv = minmod(sL, (ibf[k] - f[k]) * inv_dxf);
             sv = fmin(fabs((ibf[k] - EPS_MACH) / (sv * dxL + EPS_MACH)), 1.0) * sv;  // :452-457
             const double a = ibf[k] + sv * dxL;
             sns[k * np + i] = sv;

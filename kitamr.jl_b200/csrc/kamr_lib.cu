@@ -53,10 +53,13 @@ struct DBuf {
     size_t n = 0;
 };
 
+constexpr size_t BIG_SMEM = 32 << 10;   // a cell whose staged block (f + M[prim_c]) exceeds this is "big"
+
 struct Bin {
     std::vector<int> cells;
     int* d_cells = nullptr;
     size_t smem = 0;     // dynamic shared memory per block (0 => global staging)
+    bool big = false;      // cells of thousands of points: large CTAs, M[prim_c] not staged
     bool regular = false;  // all cells are CELL_REGULAR / CELL_REGULAR_MAPPED: phase_regular_kernel
     bool mapped = false;   // ... CELL_REGULAR_MAPPED: the MAPPED instantiation
     RegCell* d_recs = nullptr;  // regular bins: one record per cell, in launch order
@@ -809,21 +812,24 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         if (c->cells[i].bound_enc >= 0) c->limit_cells.push_back(i);
     c->d_limit_cells = c->dupload(c->limit_cells);
     {
-        // dynamic shared memory classes: K planes of convected f + 1 plane of M[prim_c]
-        const size_t caps[] = {8 << 10, 16 << 10, 24 << 10, 32 << 10, 48 << 10, 64 << 10, 96 << 10, 128 << 10,
-                               (size_t)c->max_smem_optin - (12 << 10)};
+        // dynamic shared memory classes.  Small cells (<= BIG_SMEM with M[prim_c] staged): K planes of convected f + 1
+        // plane of M[prim_c], 128-thread CTAs.  Big cells: K planes only, PNT_BIG-thread CTAs, MINB_BIG per SM.
+        const size_t big_max = (size_t)(227 << 10) / MINB_BIG - (8 << 10);
+        const size_t caps[] = {8 << 10, 16 << 10, 24 << 10, 32 << 10, 48 << 10, 64 << 10, 80 << 10, 96 << 10,
+                               std::min(big_max, (size_t)c->max_smem_optin - (12 << 10))};
         const int ncap = (int)(sizeof(caps) / sizeof(caps[0]));
-        std::vector<Bin> bins(3 * (ncap + 1));
+        std::vector<Bin> bins(6 * (ncap + 1));
         c->fused_cells = 0;
         for (int cell : c->fluid_cells) {
             const CellInfo& ci = c->cells[cell];
-            const size_t need = (size_t)ci.n * (K + 1) * sizeof(double);
+            const bool big = (size_t)ci.n * (K + 1) * sizeof(double) > BIG_SMEM;
+            const size_t need = (size_t)ci.n * (big ? K : K + 1) * sizeof(double);
             int q = 0;
             while (q < ncap && need > caps[q]) ++q;
             const bool mapped = (ci.flags & CELL_REGULAR_MAPPED) != 0;
             const bool regular = mapped || (ci.flags & CELL_REGULAR) != 0;
-            Bin& b = bins[3 * q + (mapped ? 2 : (regular ? 1 : 0))];
-            b.regular = regular; b.mapped = mapped;
+            Bin& b = bins[6 * q + 3 * (big ? 1 : 0) + (mapped ? 2 : (regular ? 1 : 0))];
+            b.regular = regular; b.mapped = mapped; b.big = big;
             b.smem = (q < ncap) ? std::max(b.smem, need) : 0;
             b.cells.push_back(cell);
             if (q < ncap) c->fused_cells++;
@@ -1153,7 +1159,8 @@ void exchange(kamr_ctx* c, int what, int level) {
 #define KAMR_MINB 6
 #endif
 constexpr int NT = KAMR_NT;      // threads per CTA of the slope kernel (one CTA per physical cell)
-constexpr int PNT = KAMR_PNT;    // threads per CTA of the phase kernel: small CTAs keep many cells in flight per SM,
+constexpr int PNT = KAMR_PNT;
+static_assert(KAMR_PNT != KAMR_PNT_BIG, "small- and big-cell CTA sizes must differ (STAGE_FC is keyed on the CTA size)");    // threads per CTA of the phase kernel: small CTAs keep many cells in flight per SM,
                                  // so one cell's barriers and serial moments->prim step hide behind the others
 #ifndef KAMR_MINB_GEN
 #define KAMR_MINB_GEN KAMR_MINB
@@ -1232,9 +1239,7 @@ void prepare_kernel(Kern kern, int max_dyn) {
 
 // cells whose staged block needs more than 32 KB of shared memory (n > ~1300 points in 2D2F, ~2000 in 3D1F) take
 // 1024-thread CTAs: one or two of them fill an SM, and a cell's points still spread over 32 warps
-constexpr int PNT_BIG = 1024;
-constexpr int MINB_BIG = 1;
-constexpr size_t BIG_SMEM = 32 << 10;
+
 
 template <int D, int K, int MODE, bool STAGE, int PT, int MB>
 void launch_phase_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want, int kid) {
@@ -1271,7 +1276,7 @@ void launch_regular_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int 
 
 template <int D, int K, int MODE>
 void launch_phase(kamr_ctx* c, const Bin& b, double dt, int want) {
-    const bool big = b.smem == 0 || b.smem > BIG_SMEM;
+    const bool big = b.big;
     if (MODE == MODE_FUSED && b.regular) {
         if (b.smem == 0) launch_regular_inst<D, K, false, PNT_BIG, MINB_BIG>(c, b, 0, dt, want);
         else if (big) launch_regular_inst<D, K, true, PNT_BIG, MINB_BIG>(c, b, b.smem, dt, want);

@@ -47,6 +47,14 @@ def _cases():
         "s4_ib_l3": lambda: cases.sphere_s4(trees=4, ps_maxlevel=3, vtrees=6, vs_maxlevel=1),
         "euler2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=1, vtrees=8, vs_maxlevel=1, ragged=True, seed=6,
                                           marching=abi.MARCH_EULER),
+        # big velocity grids: 512-thread CTAs with M[prim_c] recomputed instead of staged (n*(NDF+1)*8 > 32 KB) and,
+        # above ~100 KB of staged f, the output array as staging area
+        "big2d": lambda: cases.amr_case(dim=2, trees=3, maxlevel=1, vtrees=48, vs_maxlevel=2, ragged=True, seed=11),
+        "big2d_global": lambda: cases.amr_case(dim=2, trees=3, maxlevel=1, vtrees=72, vs_maxlevel=2, ragged=True,
+                                               seed=13),
+        "big3d": lambda: cases.amr_case(dim=3, trees=2, maxlevel=1, vtrees=14, vs_maxlevel=1, ragged=True, seed=12),
+        "big3d_global": lambda: cases.amr_case(dim=3, trees=2, maxlevel=1, vtrees=24, vs_maxlevel=1, ragged=True,
+                                               seed=14),
         # CIP_Marching (Theory/I-projection.jl): Newton I-projection per cell, un-fused slope/flux/iterate path
         "cip2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=1, vtrees=8, vs_maxlevel=1, ragged=True, seed=8,
                                         marching=abi.MARCH_CIP),
