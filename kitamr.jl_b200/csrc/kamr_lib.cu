@@ -116,6 +116,7 @@ struct kamr_ctx {
     std::vector<int> grid_n, grid_np;
     std::vector<long long> grid_goff, grid_hoff;
     std::vector<int8_t> h_level;      // host copy of v_level (host layout) for pair maps
+    const double* h_vmid = nullptr;   // the host's v_mid, valid during kamr_upload_topology only
     std::map<std::pair<int, int>, int> rel_id;
     std::vector<long long> rel_off;
     std::vector<int> pm_start;
@@ -282,6 +283,21 @@ int build_rel(kamr_ctx* c, int ga, int gb) {
     }
     if (j != nb || acc != 0) throw Fail("velocity grid walk did not consume the neighbour grid");
     start[na] = nb;
+    // Upwinding splits a face's points by the sign of v_d ON EACH SIDE'S OWN GRID (make_mask, Flux/Flux.jl); the gather
+    // decides by the receiving point's sign alone, which is the same thing as long as a point and the points it is
+    // matched with lie on the same side of v_d = 0, i.e. as long as v = 0 is a root-grid corner.  The reference
+    // enforces exactly that in check_vs_setting (Solver/Types.jl:335-353); enforce it here too.
+    if (c->h_vmid) {
+        const double* va = c->h_vmid + c->grid_hoff[ga] * D;
+        const double* vb = c->h_vmid + c->grid_hoff[gb] * D;
+        for (int i = 0; i < na; ++i)
+            for (int jj = start[i]; jj < std::max(start[i] + 1, start[i + 1]); ++jj)
+                for (int d = 0; d < D; ++d)
+                    if ((va[(size_t)d * na + i] > 0.) != (vb[(size_t)d * nb + jj] > 0.))
+                        throw Fail("velocity grids " + std::to_string(ga) + "/" + std::to_string(gb) +
+                                   ": matched points lie on different sides of v = 0; the origin must be a root-grid "
+                                   "corner of the velocity space (check_vs_setting, Solver/Types.jl:335)");
+    }
     const int id = (int)c->rel_off.size();
     c->rel_off.push_back(off);
     c->rel_id[key] = id;
@@ -442,6 +458,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     c->padded = padded;
     const long long gpts_h = c->grid_hoff[m->n_grid], gpts_d = c->grid_goff[m->n_grid];
     c->h_level.assign(m->v_level, m->v_level + gpts_h);
+    c->h_vmid = m->v_mid;
     {
         std::vector<int8_t> lv(gpts_d, 0);
         std::vector<unsigned char> sg(gpts_d, 0);
@@ -1498,6 +1515,7 @@ int kamr_upload_topology(kamr_ctx* c, const kamr_mesh* m) {
     return guarded(c, [&] {
         if (!m) throw Fail("null mesh");
         CK(cudaSetDevice(c->cfg.device));
+        struct Clear { kamr_ctx* c; ~Clear() { c->h_vmid = nullptr; } } clear_{c};   // the host array is the caller's
         build_topology(c, m);
     });
 }

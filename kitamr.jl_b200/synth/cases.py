@@ -410,6 +410,63 @@ def sphere_s4(copies=1, ps_maxlevel=4, trees=16, vtrees=16, vs_maxlevel=2, noise
     return case
 
 
+def x38like_s5(ps_maxlevel=4, trees=16, vtrees=10, vs_maxlevel=3, noise=0.01, radius=0.5, shell=0.3) -> Case:
+    """S5 x38-like3d (example/X38/X38_julia.jl:12-58): trees^3 roots on [-4,5]x[-4,4]^2, level L-2 in max-norm(x) < 2,
+    L-1 in < 1.2, level L within `shell` of the body surface; velocity grids vtrees^3 roots on the X38 quadrature box
+    [-14.2,21.3]x[-17.75,17.75]^2 refined to level <= 3 by maxwellian_refine_flag of the buffer IC (1 000 points in the
+    free stream, tens of thousands in the shock layer); NDF = 1, K = 0, Kn = 0.275, Ma 8 inflow at xmin,
+    UniformOutflow elsewhere, cold Maxwellian wall (lambda_w = 56/300 as in the reference's IB record).
+    The reference's body is a triangulated STL (`X38_normalized.stl`, missing from the repository); the surrogate body
+    here is a sphere of radius `radius` at the origin — same cell classes (solid ghost cells, donors, cut velocity
+    cells), different shape."""
+    geo = (-4.0, 5.0, -4.0, 4.0, -4.0, 4.0)
+    centers = np.array([[0.0, 0.0, 0.0]])
+    L = ps_maxlevel
+    Ma = 8.0
+    lam_w = 56.0 / 300.0
+
+    def refine_fn(l, mid, ds):
+        r = np.sqrt(np.sum(mid ** 2, axis=1))
+        mx = np.max(np.abs(mid), axis=1)
+        out = np.zeros(len(mid), dtype=bool)
+        out |= (mx < 2.0) & (r > radius) & (l < L - 2)
+        out |= (mx < 1.2) & (r > radius) & (l < L - 1)
+        half_diag = 0.5 * np.sqrt(np.sum(ds ** 2))
+        out |= np.abs(r - radius) < shell + half_diag
+        return out
+
+    forest = Forest.build(3, geo, (trees,) * 3, L, refine_fn)
+    quad = (-14.2, 21.3, -17.75, 17.75, -17.75, 17.75)
+    gas = Gas(K=0.0, Kn=0.275, omega=0.81, omega_r=0.81)
+
+    def prim_fn(x):
+        r = float(np.sqrt(np.sum(np.asarray(x) ** 2)))
+        if r > 2.0 * radius:
+            return np.array([1.0, Ma * math.sqrt(5 / 6), 0.0, 0.0, 1.0])
+        rr = max(r, radius)
+        t = (rr - radius) / radius
+        return np.array([1.0, t * Ma * math.sqrt(5 / 6), 0.0, 0.0, lam_w + t * (1.0 - lam_w)])
+
+    cache = {}
+    per_cell = []
+    for c in range(forest.n):
+        p = prim_fn(forest.mid[c])
+        key = (round(float(p[1]), 0), round(float(p[4]), 1))
+        if key not in cache:
+            cache[key] = vg.maxwellian_grid(quad, (vtrees,) * 3, vs_maxlevel,
+                                            np.array([1.0, key[0], 0.0, 0.0, max(key[1], 0.1)]), 1, gas.K)
+        per_cell.append(cache[key])
+    grids, cell_grid = _dedup_grids(per_cell)
+    bt, bp = _bcs(3, [abi.BC_SUPERSONIC_INFLOW] + [abi.BC_UNIFORM_OUTFLOW] * 5,
+                  [[1.0, Ma * math.sqrt(5 / 6), 0.0, 0.0, 1.0]] + [None] * 5)
+    case = Case("S5-x38like3d", 3, 1, forest, grids, cell_grid, bt, bp, gas, quad, (vtrees,) * 3, vs_maxlevel,
+                prim_fn, SEED_BASE + 5, noise=noise)
+    from . import ib as ibm
+    case.ib_shape = ibm.Ball(centers, radius, np.array([1.0, 0.0, 0.0, 0.0, lam_w]))
+    case.cell_class = ibm.classify(forest, case.ib_shape)
+    return case
+
+
 def riemann_s1(ps_level=4, band_level=5, trees=16, vtrees=8, vs_maxlevel=3, noise=0.01,
                marching=abi.MARCH_CIP) -> Case:
     """S1 riemann2d (example/Riemann_problem/rp_2D.jl:26-72, BASELINE.json configs[0]): 16x16 roots on [-.5,.5]^2,
@@ -496,4 +553,5 @@ WORKLOADS = {
     "S1": lambda copies=1: riemann_s1(),
     "S1caidvm": lambda copies=1: riemann_s1(marching=abi.MARCH_CAIDVM),
     "S3": lambda copies=1: airfoil_s3(),
+    "S5": lambda copies=1: x38like_s5(),
 }

@@ -45,6 +45,10 @@ def _cases():
         # 3-D sphere with immersed boundary (3D1F): 26-direction solid-cell stencils, 3-D cut velocity cells
         "s4_ib_small": lambda: cases.sphere_s4(trees=4, ps_maxlevel=2, vtrees=4, vs_maxlevel=1),
         "s4_ib_l3": lambda: cases.sphere_s4(trees=4, ps_maxlevel=3, vtrees=6, vs_maxlevel=1),
+        # S5 x38-like (example/X38): 3-D, wide velocity box, cold wall, sphere surrogate for the missing STL body
+        # (10 roots per direction: the smallest count that puts v = 0 on a root-grid corner of the X38 box, as
+        # check_vs_setting requires, Solver/Types.jl:335)
+        "s5_small": lambda: cases.x38like_s5(ps_maxlevel=2, trees=4, vtrees=10, vs_maxlevel=1),
         "euler2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=1, vtrees=8, vs_maxlevel=1, ragged=True, seed=6,
                                           marching=abi.MARCH_EULER),
         # big velocity grids: 512-thread CTAs with M[prim_c] recomputed instead of staged (n*(NDF+1)*8 > 32 KB) and,
@@ -197,3 +201,19 @@ def test_cip_device_projection_hits_the_moments(kamr_lib, dim):
         f = out.df[off[c] * K: off[c + 1] * K].reshape(K, g.n)
         m = cases.moments(g.mid, g.weight, f.T)
         assert np.allclose(m, out.w[c * M:(c + 1) * M], rtol=0, atol=1e-8)
+
+
+def test_origin_off_a_root_corner_is_refused(kamr_lib):
+    """the reference refuses a velocity space whose origin is not a root-grid corner (check_vs_setting,
+    Solver/Types.jl:335-353) because upwinding by the sign of v_d is ambiguous there; libkamr refuses it where it
+    matters, when two such grids meet at a face"""
+    from kitamr_jl_b200 import api
+    from kitamr_jl_b200.synth import cases
+    case = cases.x38like_s5(ps_maxlevel=2, trees=4, vtrees=4, vs_maxlevel=1)   # 4 roots on [-14.2, 21.3]
+    mesh = case.rank_mesh()
+    ctx = api.Context(case.config(device=0))
+    try:
+        with pytest.raises(Exception, match="root-grid"):
+            ctx.upload_topology(mesh)
+    finally:
+        ctx.close()
