@@ -49,7 +49,10 @@ def log(*a):
 def make_case(args, world):
     from kitamr_jl_b200.synth import cases
     fn = cases.WORKLOADS[args.workload]
-    return fn(copies=world)
+    case = fn(copies=world)
+    if getattr(args, "impl", "ours") == "ours":
+        case.partition_mode = getattr(args, "partition", "cost")
+    return case
 
 
 def n_cores():
@@ -335,6 +338,12 @@ def run_ours(args):
 
     # ---- roofline of the step's kernels (rank 0's shard)
     kern_ms = sum(v[1] for v in prof.values())
+    rank_kern_ms = [kern_ms / args.steps]
+    if world > 1:   # per-rank kernel time: how well the partition balances the device cost
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = kern_ms / args.steps
+        dist.all_reduce(t)
+        rank_kern_ms = [float(x) for x in t.tolist()]
     b_alg = B_ALG[(D, K)]
     peaks = {}
     try:
@@ -413,7 +422,11 @@ def run_ours(args):
                        "dim": D, "ndf": K, "marching": MARCH_NAMES[case.marching], "flux": "CAIDVM",
                        "l2_policy": "inputs larger than L2: %.2f GB of df/sdf/flux state per GPU vs 126 MB L2"
                                     % (s.device_bytes / 1e9),
-                       "halo_bytes_per_step_rank0": int(s.halo_bytes_per_step)},
+                       "halo_bytes_per_step_rank0": int(s.halo_bytes_per_step),
+                       "partition": ("cost-weighted Morton split (device cost model as the partition!(p4est, weight) "
+                                     "hook)" if case.partition_mode == "cost" else
+                                     "reference partition_weight (vs_num, x2 solid cells)") if world > 1 else "none",
+                       "kernels_ms_per_step_by_rank": rank_kern_ms},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_win / args.steps,
                     "d2h_bytes_per_step": d2h_win / args.steps,
@@ -446,6 +459,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="S2ib")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--partition", default="cost", choices=["cost", "reference"],
+                    help="weights of the Morton split at N>1: the device cost model handed to the reference's "
+                         "partition!(p4est, weight) hook, or the reference's own partition_weight")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -143,6 +143,8 @@ struct kamr_ctx {
     std::vector<int> limit_cells; // local fluid + ghost fluid cells (limit_kernel after upload_aux)
     int* d_limit_cells = nullptr;
     std::map<int, std::pair<int*, int>> ghost_wave_cells;  // wave -> ghost fluid cells whose sdf arrives then
+    struct MergedSegs { CopySeg *d_send = nullptr, *d_recv = nullptr; int n_send = 0, n_recv = 0; };
+    std::map<std::pair<int, int>, MergedSegs> merged_segs;   // (what, level) -> pack / unpack lists of ALL peers
     std::vector<unsigned long long> peer_early;   // per peer: waves with an early slope exchange (see build_topology)
     unsigned long long early_mask = 0;            // union over the peers
     int* d_ghost_fluid = nullptr;                 // all fluid ghost cells (limited after the final slope exchange)
@@ -209,7 +211,7 @@ struct kamr_ctx {
         d_host_off = nullptr;
         d_res = nullptr; d_sendbuf = d_recvbuf = nullptr; d_fluid_cells = nullptr; d_limit_cells = nullptr;
         limit_cells.clear(); ghost_wave_cells.clear(); raw_sdf_valid = false;
-        peer_early.clear(); early_mask = 0; d_ghost_fluid = nullptr; n_ghost_fluid = 0;
+        peer_early.clear(); early_mask = 0; d_ghost_fluid = nullptr; n_ghost_fluid = 0; merged_segs.clear();
         solid_tasks.clear(); sn_tasks.clear(); ib_nb.clear(); d_solid_tasks = nullptr; d_sn_tasks = nullptr;
     }
 };
@@ -1118,27 +1120,34 @@ void exchange(kamr_ctx* c, int what, int level) {
     if (!c->comm) throw Fail("mesh has peers but kamr_comm_init was not called");
     double* src = (what == 1 || what == 3) ? c->dv.sdf : c->dv.df;
     double* dst = src;
-    bool any = false;
-    for (auto& pp : c->peers) {
-        if (what == 0) {
-            if (!pp.df_send.empty()) {
-                { Launch L_(c, KID_PACK);
-                  copy_segments_kernel<<<std::min<int>((int)pp.df_send.size(), 2048), 256, 0, c->stream>>>(
-                    pp.d_df_send, (int)pp.df_send.size(), src, c->d_sendbuf); }
+    // one pack and one unpack launch per exchange: the segment lists of all peers taking part, concatenated once
+    auto key = std::make_pair(what, what == 1 ? level : 0);
+    auto it = c->merged_segs.find(key);
+    if (it == c->merged_segs.end()) {
+        std::vector<CopySeg> snd, rcv;
+        for (auto& pp : c->peers) {
+            if (what == 0) {
+                snd.insert(snd.end(), pp.df_send.begin(), pp.df_send.end());
+            } else if (PeerPlan::Lvl* lv = halo_level(pp, what, level)) {
+                snd.insert(snd.end(), lv->send.begin(), lv->send.end());
+                rcv.insert(rcv.end(), lv->recv.begin(), lv->recv.end());
             }
-            any = true;
-        } else {
-            PeerPlan::Lvl* lv = halo_level(pp, what, level);
-            if (!lv) continue;
-            if (!lv->send.empty()) {
-                { Launch L_(c, KID_PACK);
-                  copy_segments_kernel<<<std::min<int>((int)lv->send.size(), 2048), 256, 0, c->stream>>>(
-                    lv->d_send, (int)lv->send.size(), src, c->d_sendbuf); }
-            }
-            any = true;
         }
+        kamr_ctx::MergedSegs ms;
+        ms.n_send = (int)snd.size(); ms.n_recv = (int)rcv.size();
+        ms.d_send = c->dupload(snd); ms.d_recv = c->dupload(rcv);
+        CK(cudaStreamSynchronize(c->stream));   // snd / rcv are locals
+        it = c->merged_segs.emplace(key, ms).first;
     }
+    const kamr_ctx::MergedSegs& ms = it->second;
+    bool any = false;
+    for (auto& pp : c->peers) any = any || what == 0 || halo_level(pp, what, level) != nullptr;
     if (!any) return;
+    if (ms.n_send) {
+        Launch L_(c, KID_PACK);
+        copy_segments_kernel<<<std::min<int>(ms.n_send, 2048), 256, 0, c->stream>>>(ms.d_send, ms.n_send, src,
+                                                                                    c->d_sendbuf);
+    }
     NCK(nccl().GroupStart());
     for (auto& pp : c->peers) {
         if (what == 0) {
@@ -1152,14 +1161,10 @@ void exchange(kamr_ctx* c, int what, int level) {
         }
     }
     NCK(nccl().GroupEnd());
-    if (what != 0) {
-        for (auto& pp : c->peers) {
-            PeerPlan::Lvl* lv = halo_level(pp, what, level);
-            if (!lv || lv->recv.empty()) continue;
-            { Launch L_(c, KID_UNPACK);
-              copy_segments_kernel<<<std::min<int>((int)lv->recv.size(), 2048), 256, 0, c->stream>>>(
-                lv->d_recv, (int)lv->recv.size(), c->d_recvbuf, dst); }
-        }
+    if (ms.n_recv) {
+        Launch L_(c, KID_UNPACK);
+        copy_segments_kernel<<<std::min<int>(ms.n_recv, 2048), 256, 0, c->stream>>>(ms.d_recv, ms.n_recv, c->d_recvbuf,
+                                                                                    dst);
     }
     CK(cudaGetLastError());
 }

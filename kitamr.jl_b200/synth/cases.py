@@ -120,13 +120,50 @@ class Case:
         return self.cfl * min(a / b for a, b in zip(ds, U))
 
     # ------------------------------------------------------------------ partition / flatten
+    partition_mode: str = "reference"   # "reference": partition_weight of the reference; "cost": device cost model
+
     def owner(self, nranks):
-        """partition_weight (Parallel/Partition.jl:213-224): vs_num per cell, x2 for solid ghost cells; cells
-        inside the body carry no velocity grid."""
+        """Weighted split of the Morton curve.  "reference": partition_weight (Parallel/Partition.jl:213-224): vs_num per
+        cell, x2 for solid ghost cells; cells inside the body carry no velocity grid.  "cost": the weight function a
+        GPU-aware shim hands to the reference's `partition!(p4est, weight)` hook (Partition.jl:228) instead: vs_num
+        times the measured relative cost of the kernel class the cell falls into (regular 1, neighbour on
+        another velocity grid 2.1, general 3, solid ghost cell 4, +5.5 per solid face of a donor)."""
         n_of = np.array([g.n for g in self.grids])[self.cell_grid].astype(np.float64)
         if self.cell_class is not None:
             n_of = np.where(self.cell_class == -2, 0.0, np.where(self.cell_class == -1, 2.0 * n_of, n_of))
+        if self.partition_mode == "cost":
+            n_of = n_of * self.cost_factors()
         return partition(n_of, nranks)
+
+    def cost_factors(self):
+        """relative device cost per velocity point of every forest cell (1 = regular cell), from the face list of the
+        whole forest: which kernel class the cell will take (kamr_lib.cu build_topology)"""
+        if getattr(self, "_cost", None) is not None:
+            return self._cost
+        full = build_rank_view(self.forest, self.grids, self.cell_grid, self.bc_type, self.bc_prim, self.ndf,
+                               owner=None, rank=0, bound_enc_global=self.bound_enc, cell_class=self.cell_class,
+                               ib_shape=self.ib_shape)
+        nl = full.n_local
+        kind, here, there = full.face_kind, full.face_here, full.face_there
+        grid, be = full.cell_grid, full.bound_enc
+        general = np.zeros(nl, bool); mapped = np.zeros(nl, bool); nsolid = np.zeros(nl)
+        dom = kind == 0
+        general[here[dom]] = True
+        h, t, k = here[~dom], there[~dom], kind[~dom]
+        for a, b in ((h, t), (t, h)):
+            m = a < nl
+            aa, bb, kk = a[m], b[m], k[m]
+            sol = (bb >= nl) | (be[np.minimum(bb, len(be) - 1)] < 0)
+            np.logical_or.at(general, aa, sol | (kk != 1))
+            np.add.at(nsolid, aa, sol.astype(np.float64))
+            bb_ok = np.minimum(bb, len(grid) - 1)
+            np.logical_or.at(mapped, aa, (~sol) & (grid[aa] != grid[bb_ok]))
+        f_local = np.where(general, 3.0, np.where(mapped, 2.1, 1.0)) + 5.5 * nsolid
+        f_local = np.where(be[:nl] < 0, 2.0, f_local)        # solid ghost cells: 2 x vs_num above, x2 here = 4
+        cost = np.ones(self.forest.n)
+        cost[full.global_ids[:nl]] = f_local
+        self._cost = cost
+        return cost
 
     def rank_mesh(self, rank=0, nranks=1) -> HostMesh:
         owner = self.owner(nranks) if nranks > 1 else None
