@@ -22,7 +22,10 @@ using namespace kamr;
 #ifndef KAMR_NT
 #define KAMR_NT 256
 #endif
-constexpr int NT_SLOPE = KAMR_NT;
+#ifndef KAMR_NT_GEN
+#define KAMR_NT_GEN KAMR_NT
+#endif
+constexpr int NT_SLOPE = KAMR_NT_GEN;   // threads per CTA of the general slope kernel
 
 namespace {
 
@@ -1202,7 +1205,7 @@ void launch_slope_stage(kamr_ctx* c, const kamr_ctx::SlopeStage& st, int raw_all
     }
     if (!st.gen.empty()) {
         Launch L_(c, KID_SLOPE);
-        slope_kernel<D, K, true, NT><<<(int)st.gen.size(), NT, 0, c->stream>>>(c->dv, st.d_gen, raw_all,
+        slope_kernel<D, K, true, NT_SLOPE><<<(int)st.gen.size(), NT_SLOPE, 0, c->stream>>>(c->dv, st.d_gen, raw_all,
                                                                               st.flags ? c->slope_epoch : 0);
     }
 }
