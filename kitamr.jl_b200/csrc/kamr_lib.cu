@@ -771,19 +771,35 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
                 c->early_mask |= c->peer_early[p];
             }
         }
-        // launches: the waves between two early exchanges form one stage (dependencies inside a stage go through the
-        // per-cell epoch flags); on one rank, or when no pair needs an early exchange, that is a single stage
-        auto stage_of = [&](int w) {
-            int sidx = 0;
+        // launches: stage k runs before the k-th early exchange.  A task belongs to the first stage in which everything it
+        // projects is final: stage 0 unless it (transitively) projects the slopes of a ghost cell, which arrive with the
+        // early exchange of the ghost's wave.  So nearly every task of every wave sits in stage 0 (dependencies among
+        // local tasks go through the per-cell epoch flags) and the later stages hold the few cells behind a ghost; a
+        // mirror of early wave e only ever projects coarser cells, whose exchanges come before e's, so it is final in time.
+        auto exch_index = [&](int w) {   // position of wave w among the early waves
+            int k = 0;
             for (int e = 0; e < w && e < 64; ++e)
-                if (c->early_mask >> e & 1ull) ++sidx;
-            return sidx;
+                if (c->early_mask >> e & 1ull) ++k;
+            return k;
+        };
+        std::vector<int> gstage(tasks.size(), -1);
+        std::function<int(int)> stage_of_task = [&](int ti) -> int {
+            if (gstage[ti] >= 0) return gstage[ti];
+            int sg = 0;
+            for (int tgt : deps[ti]) {
+                if (tgt >= c->n_local) {
+                    sg = std::max(sg, 1 + exch_index(std::min(63, std::max(0, c->cells[tgt].ps_level - m->ps_minlevel))));
+                } else if (task_of[tgt] >= 0) {
+                    sg = std::max(sg, stage_of_task(task_of[tgt]));
+                }
+            }
+            return gstage[ti] = sg;
         };
         std::vector<char> in_gen(tasks.size(), 0);
         for (int ti : order)
             in_gen[ti] = !((by_level || wave[ti] == 0) && (is_regular(tasks[ti]) || is_regmapped(tasks[ti])));
         for (int ti : order) {
-            const int sidx = by_level ? stage_of(wave[ti]) : 0;
+            const int sidx = by_level ? stage_of_task(ti) : 0;
             kamr_ctx::SlopeStage& st = stages[sidx];
             st.wave = sidx;
             if (!in_gen[ti]) {
