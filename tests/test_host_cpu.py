@@ -130,3 +130,23 @@ def test_dt_follows_reference_formula():
     ds = 1.0 / 16
     U = 5.0 - (10.0 / 16) / 2
     assert case.dt() == pytest.approx(0.4 * ds / U, rel=1e-15)
+
+
+def test_cost_weighted_partition_balances_the_device_cost_model():
+    """bench.py --partition cost: the Morton split weighted by vs_num x the kernel-class cost factor (the weight function a
+    GPU-aware shim hands to partition!(p4est, weight)) is contiguous along the curve, keeps every
+    rank non-empty and balances the modelled cost better than the reference's vs_num weights."""
+    from kitamr_jl_b200.synth import cases
+    case = cases.cylinder_s2(copies=2, trees=6, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True)
+    n_of = np.array([g.n for g in case.grids])[case.cell_grid].astype(np.float64)
+    n_of = np.where(case.cell_class == -2, 0.0, np.where(case.cell_class == -1, 2.0 * n_of, n_of))
+    f = case.cost_factors()
+    assert f.shape == (case.forest.n,) and f.min() >= 1.0 and f.max() > 3.0      # donors: 3 + 5.5 per solid face
+    spread = {}
+    for mode in ("reference", "cost"):
+        case.partition_mode = mode
+        ow = case.owner(4)
+        assert np.all(np.diff(ow) >= 0) and set(ow.tolist()) == {0, 1, 2, 3}
+        cost = np.array([(n_of * f)[ow == r].sum() for r in range(4)])
+        spread[mode] = cost.max() / cost.mean()
+    assert spread["cost"] < spread["reference"] and spread["cost"] < 1.15
