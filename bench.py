@@ -364,7 +364,8 @@ def run_ours(args):
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic,
-        "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback",
+        "peak_source": "of measured: MEASURED_PEAKS.json hbm_gbs (STREAM-style copy)" if "hbm_gbs" in peaks
+                       else "of fallback: 6650 GB/s, B200_PROFILING.md (MEASURED_PEAKS.json absent)",
         "kernel": "kamr_step = all kernels of one step, device time of the timed region; B_alg/update = %g B "
                   "(DESIGN.md §6)" % b_alg,
         "kernels_ms_sum_per_step": kern_ms / args.steps,

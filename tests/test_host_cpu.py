@@ -1,6 +1,7 @@
 """Host-side logic: synthetic forest (p4est stand-in), velocity-grid ordering, and the flattener's face /
 neighbour tables that cross the C-ABI (include/kamr.h).  Integer / index work is checked bit-exact."""
 import itertools
+import os
 
 import numpy as np
 import pytest
@@ -150,3 +151,26 @@ def test_cost_weighted_partition_balances_the_device_cost_model():
         cost = np.array([(n_of * f)[ow == r].sum() for r in range(4)])
         spread[mode] = cost.max() / cost.mean()
     assert spread["cost"] < spread["reference"] and spread["cost"] < 1.15
+
+
+def test_reference_arm_prints_the_bench_contract():
+    """`bench.py --impl reference` (the CPU restatement on the host cores; no GPU involved) prints ONE JSON line with
+    the contract's keys, the same workload / metric / unit as the GPU arm, and counts the fluid phase cells only."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup",
+                        "0", "--workload", "S2ib"], capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in j, k
+    assert j["impl"] == "reference" and j["unit"] == "cell-updates/s" and j["higher_is_better"] is True
+    assert j["config"]["workload"] == "S2-cylinder2d-ib-x1" and j["config"]["phase_cells"] == 16407496
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0
+    assert j["value"] > 0
