@@ -405,11 +405,11 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         try:
             cores = n_cores()
-            over, _ = calibrate_oversplit(case, cores, 3, 20.0)
-            v, nph_s, secs = cpu_arm(case, 2, 1, cores, over)
+            over, _ = calibrate_oversplit(case, cores, 11, 30.0)
+            v, nph_s, secs = cpu_arm(case, 10, 1, cores, over)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{nph_s} of {int(nph_total)} phase cells ({cores} of {cores * over} Morton chunks), "
-                             f"2 steps after 1 warm-up, {secs:.1f}s"}
+                             f"10 steps after 1 warm-up, {secs:.1f}s"}
         except Exception as e:  # pragma: no cover
             cpu = {"error": repr(e)}
 

@@ -54,7 +54,11 @@ extern "C" {
 
 /* flux scheme: Solver.flux (src/Solver/Types.jl:69) */
 enum { KAMR_FLUX_CAIDVM = 0, KAMR_FLUX_DVM = 1 };
-/* time marching: Solver.time_marching (src/Solver/Types.jl:71) */
+/* time marching: Solver.time_marching (src/Solver/Types.jl:71).
+ *   CAIDVM  iterate!(::Type{CAIDVM_Marching}), Theory/Iterate.jl:96   (kamr_step fuses flux! + iterate!)
+ *   CIP     iterate!(::Type{CIP_Marching}),    Theory/I-projection.jl:161 (Newton I-projection per cell; refused by
+ *           kamr_upload_topology on meshes with immersed-boundary donor cells: positivity_preserving_ib! is not built)
+ *   EULER   iterate!(::Type{Euler}),           Theory/Iterate.jl:131 */
 enum { KAMR_MARCH_CAIDVM = 0, KAMR_MARCH_CIP = 1, KAMR_MARCH_EULER = 2 };
 /* face kinds (src/Physical_space/Types.jl:157-219, src/Boundary/Types.jl:27-33).
  * Hanging / BackHanging faces are passed as one record per (here, there) pair,
