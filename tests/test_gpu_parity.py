@@ -217,3 +217,33 @@ def test_origin_off_a_root_corner_is_refused(kamr_lib):
             ctx.upload_topology(mesh)
     finally:
         ctx.close()
+
+
+GOLDEN = ["S0", "amr2d_ragged", "amr3d_ragged", "cip2d", "s2_ib_small", "s4_ib_small", "s1_small", "s3_small",
+          "s5_small"]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_device_matches_golden_fixture(kamr_lib, name):
+    """one kamr_step on the device against the committed fixture (tests/golden/<name>.npz: a 4096-point sample of f
+    plus all of w after one step of the oracle, frozen by tests/golden/make_golden.py) — no oracle run involved."""
+    import os
+    import make_golden_cases as mg
+    from kitamr_jl_b200 import abi, api
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{name}.npz"))
+    case = mg.CASES[name]()
+    mesh = case.rank_mesh()
+    st = case.init_state(mesh)
+    assert mg.digest(st.df) == str(gold["input_digest"]), "synthetic generator changed: regenerate the fixtures"
+    ctx = api.Context(case.config(device=0))
+    try:
+        ctx.upload_topology(mesh)
+        ctx.upload_state(st, aux=True)
+        ctx.step(float(gold["dt"]), True)
+        out = ctx.download_state(st.copy(), abi.DL_DF | abi.DL_W)
+    finally:
+        ctx.close()
+    sel = gold["sample_idx"]
+    assert rel_l2(out.df[sel], gold["df_sample"]) <= df_tol(case)
+    nw = len(gold["w"])
+    assert rel_l2(out.w[:nw], gold["w"]) <= TOL

@@ -570,7 +570,8 @@ def test_cip_and_caidvm_agree_to_first_order():
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["S0", "amr2d_ragged", "amr3d_ragged", "cip2d"])
+@pytest.mark.parametrize("name", ["S0", "amr2d_ragged", "amr3d_ragged", "cip2d", "s2_ib_small", "s4_ib_small",
+                                  "s1_small", "s3_small", "s5_small"])
 def test_oracle_reproduces_golden(name):
     import make_golden_cases as mg
     path = os.path.join(GOLD, f"{name}.npz")
