@@ -79,6 +79,45 @@ def shakhov(vm, F, prim, qf, Pr, K):
     return np.stack(out, axis=-2)
 
 
+def i_projection(psi, wt, f, W):
+    """solve_I_projection (Theory/I-projection.jl:55-141), vectorised; the Newton systems go through LAPACK
+    (numpy.linalg.solve) like the reference's `Symmetric(J,:U) \\ G`.  Returns (lambda, shaved f)."""
+    f = f.copy()
+    lam = np.zeros(len(W))
+    fm = 1.1 * f.min()
+    if fm < 0:
+        fp = f[f > 0].min()
+        d = fp - fm
+        neg = f < 0
+        f[neg] = (f[neg] - fm) / d * fp
+    tol = 1e-10 * max(1.0, np.linalg.norm(W))
+    G_prev, stall = np.inf, 0
+    for _ in range(10):
+        c = wt * f * np.exp(lam @ psi)
+        G = (psi * c).sum(axis=1) - W
+        J = (psi * c) @ psi.T
+        Gn = np.linalg.norm(G)
+        if Gn < tol:
+            break
+        if Gn > 0.9 * G_prev:
+            stall += 1
+            if stall >= 2:
+                break
+        else:
+            stall = 0
+        G_prev = Gn
+        dl = -np.linalg.solve(J, G)
+        phi0 = (wt * f * np.exp(lam @ psi)).sum() - lam @ W
+        slope, a = G @ dl, 1.0
+        for _ in range(10):
+            lt = lam + a * dl
+            if (wt * f * np.exp(lt @ psi)).sum() - lt @ W <= phi0 + 1e-4 * a * slope:
+                break
+            a *= 0.5
+        lam = lam + a * dl
+    return lam, f
+
+
 def heat_flux(vm, wt, f, prim):
     D = vm.shape[0]
     c = [vm[d] - prim[..., 1 + d, None] for d in range(D)]
@@ -237,6 +276,20 @@ class Twin:
             f = f + (Fc - maxwell(vm, prim, gas.K, K))
             qf = heat_flux(vm, wt, f, prim_c)
             Fc = Fc + shakhov(vm, Fc, prim_c, qf, gas.Pr, gas.K)
+            f = f * (tau / (tau + dt)) + dt / (tau + dt) * Fc
+        elif marching == abi.MARCH_CIP:   # Theory/I-projection.jl:161-192
+            f = f + dt / vol * flux
+            qf = heat_flux(vm, wt, f, prim_c)
+            Fc = maxwell(vm, prim_c, gas.K, K)
+            Fc = Fc + shakhov(vm, Fc, prim_c, qf, gas.Pr, gas.K)
+            psi = np.vstack([np.ones(self.n), vm, 0.5 * np.sum(vm ** 2, axis=0)])
+            f = f.copy()
+            for idx in np.ndindex(*f.shape[:-2]):           # conserved_I_porjection! cell by cell
+                W = w[idx].copy()
+                if K == 2:
+                    W[-1] -= 0.5 * np.sum(wt * f[idx][1])
+                lam, fh = i_projection(psi, wt, f[idx][0], W)
+                f[idx][0] = fh * np.exp(lam @ psi)
             f = f * (tau / (tau + dt)) + dt / (tau + dt) * Fc
         else:  # Euler
             qf = heat_flux(vm, wt, f, prim_c)

@@ -142,6 +142,8 @@ def _twin_cases():
         "inflow3d": lambda: cases.uniform_case(dim=3, trees=4, vtrees=6),
         "euler2d": lambda: _with(cases.uniform_case(dim=2, trees=5, vtrees=8), marching=abi.MARCH_EULER),
         "interp_outflow2d": lambda: _interp_case(),
+        "cip2d": lambda: _with(cases.uniform_case(dim=2, trees=5, vtrees=10), marching=abi.MARCH_CIP),
+        "cip3d": lambda: _with(cases.uniform_case(dim=3, trees=3, vtrees=6), marching=abi.MARCH_CIP),
     }
 
 
@@ -186,7 +188,8 @@ def test_oracle_matches_numpy_twin(name):
     assert rel_l2(o.flux.reshape(nc, K, n), ref["flux"].reshape(nc, K, n)) <= 1e-12
     assert rel_l2(o.mflux, ref["mflux"].ravel()) <= 1e-11
     orc.iterate(cfg, mesh, o, dt, False)
-    assert rel_l2(o.df.reshape(nc, K, n), ref["df"].reshape(nc, K, n)) <= 1e-13
+    # CIP_Marching: f carries the Newton iteration's own tolerance (which iterate it stops at depends on rounding)
+    assert rel_l2(o.df.reshape(nc, K, n), ref["df"].reshape(nc, K, n)) <= (1e-8 if case.marching == abi.MARCH_CIP else 1e-13)
     assert rel_l2(o.w, ref["w"].ravel()) <= 1e-13
     assert rel_l2(o.prim, ref["prim"].ravel()) <= 1e-13
     assert np.allclose(o.qf, ref["qf"].ravel(), rtol=1e-9, atol=1e-14)
