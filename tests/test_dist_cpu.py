@@ -26,6 +26,14 @@ def _case(name):
         return cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=6, vs_maxlevel=2, ragged=True, seed=21)
     if name == "ib2d":
         return cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True)
+    if name == "ib2d_cost":   # the cost-weighted Morton split of bench.py --partition cost
+        c = cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True)
+        c.partition_mode = "cost"
+        return c
+    if name == "cip2d":       # CIP_Marching: un-fused path, f defined to the Newton tolerance
+        from kitamr_jl_b200 import abi
+        return cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=8, vs_maxlevel=1, ragged=True, seed=24,
+                              marching=abi.MARCH_CIP)
     if name == "amr3d":
         return cases.amr_case(dim=3, trees=3, maxlevel=1, vtrees=4, vs_maxlevel=1, ragged=True, seed=22)
     return cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=6, vs_maxlevel=1, ragged=True, periodic=(True, True), seed=23)
@@ -56,7 +64,7 @@ def _worker(rank, world, port, name, steps, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["amr2d", "amr3d", "periodic2d", "ib2d"])
+@pytest.mark.parametrize("name", ["amr2d", "amr3d", "periodic2d", "ib2d", "ib2d_cost", "cip2d"])
 def test_two_rank_oracle_equals_single_rank(name):
     from oracle import orc
     steps = 2
@@ -89,7 +97,7 @@ def test_two_rank_oracle_equals_single_rank(name):
             g = index_of[int(g)]
             n = int(off[g + 1] - off[g]) * K
             a, b = df[pos: pos + n], st.df[off[g] * K: off[g] * K + n]
-            assert np.linalg.norm(a - b) <= 1e-14 * np.linalg.norm(b), (rank, g)
+            assert np.linalg.norm(a - b) <= (1e-8 if name == "cip2d" else 1e-14) * np.linalg.norm(b), (rank, g)
             assert np.allclose(w[i * M:(i + 1) * M], st.w[g * M:(g + 1) * M], rtol=1e-13, atol=1e-15)
             pos += n
             seen += 1
