@@ -1160,6 +1160,68 @@ static int conserved_I_projection(int D, int K, int n, const double* vm, double*
     return 0;
 }
 
+/* positivity_preserving_ib!, Boundary/Positivity.jl:1-43 (called by iterate!(CIP_Marching) on donor cells only, after
+ * the macroscopic update): the slope-extrapolated correction of every SolidNeighbor face
+ *   micro = (sn.flux + ndx . sn.sdf) v_n A   on the points the wall side is upwind for (rot v_dir > 0),
+ * is added to w and to vs_data.flux limited by theta = min(theta_rho, theta_e) so that density and internal energy of
+ * w stay positive.  `vol` = reduce(*, ds).  ORACLE ONLY: the device refuses CIP_Marching on meshes with donor cells. */
+static void positivity_preserving_ib(const octx* o, orc_state* st, int c, double vol, double dt, double* w,
+                                     double* vflux) {
+    const kamr_mesh* m = o->m;
+    const kamr_ib* ib = m->ib;
+    const int D = o->D, K = o->K, M = o->M;
+    if (!ib || m->bound_enc[c] == 0) return;
+    const int n = cell_n(o, c);
+    const double* vm = cell_vmid(o, c);
+    const double* wt = cell_weight(o, c);
+    const int sn0 = m->n_local + m->n_ghost;
+    double* micros = (double*)calloc((size_t)n * K, sizeof(double));   /* sum over the solid faces, theta applied later */
+    double* one = (double*)malloc(sizeof(double) * (size_t)n * K);
+    double we[MAXM] = {0, 0, 0, 0, 0};
+    for (int s = 0; s < ib->n_sn; ++s) {
+        if (ib->sn_donor[s] != c) continue;
+        const int SN = sn0 + s;
+        const int dir = ib->sn_faceid[s] / 2;
+        const double rot = (ib->sn_faceid[s] % 2 == 0) ? 1.0 : -1.0;     /* get_rot, Theory/Math.jl:2 */
+        const double* snflux = cell_flux(o, st, SN);
+        const double* snsdf = cell_sdf(o, st, SN);
+        const double* snmid = m->mid + (size_t)SN * D;
+        double fmid[MAXD], area = rot;
+        for (int t = 0; t < D; ++t) {
+            fmid[t] = m->mid[(size_t)c * D + t];
+            if (t != dir) area *= m->ds[(size_t)c * D + t];
+        }
+        fmid[dir] -= 0.5 * rot * m->ds[(size_t)c * D + dir];
+        memset(one, 0, sizeof(double) * (size_t)n * K);
+        for (int i = 0; i < n; ++i) {
+            if (!(rot * vm[dir * n + i] > 0.)) continue;
+            for (int j = 0; j < K; ++j) {
+                double dot = 0.0;
+                for (int t = 0; t < D; ++t)
+                    dot += (fmid[t] - vm[t * n + i] * dt - snmid[t]) * snsdf[(size_t)(t * K + j) * n + i];
+                one[j * n + i] = (snflux[j * n + i] + dot) * vm[dir * n + i] * area;
+            }
+        }
+        double wf[MAXM];
+        micro_to_macro_idx(D, K, n, NULL, one, n, vm, wt, wf);
+        for (int q = 0; q < M; ++q) we[q] += wf[q];
+        for (int i = 0; i < n * K; ++i) micros[i] += one[i];
+    }
+    for (int q = 0; q < M; ++q) we[q] *= dt / vol;
+    const double delta = 1e-3, eps = 2.220446049250313e-16;
+    const double th_rho = we[0] > 0 ? 1.0 : fmin(1.0, (1 - delta) * w[0] / (fabs(we[0]) + eps));
+    double rub2 = 0.0, rube = 0.0, rue2 = 0.0;
+    for (int d = 1; d <= D; ++d) { rub2 += w[d] * w[d]; rube += w[d] * we[d]; rue2 += we[d] * we[d]; }
+    const double eb = w[M - 1] - rub2 / (2 * w[0]);
+    const double ee = we[M - 1] - rube / w[0];
+    const double gam = rue2 / (2 * w[0]);
+    const double th_e = fmin(1.0, 2 * (1 - delta) * eb / (sqrt(ee * ee + 4 * gam * (1 - delta) * eb) - ee + eps));
+    const double th = fmin(th_rho, th_e);
+    for (int q = 0; q < M; ++q) w[q] += th * we[q];
+    for (int i = 0; i < n * K; ++i) vflux[i] += th * micros[i];
+    free(micros); free(one);
+}
+
 /* iterate!(CAIDVM_Marching) Theory/Iterate.jl:96-130 ; iterate!(Euler) :131-162 ;
  * residual_check! Solver/Finalize.jl:5-11 */
 int orc_iterate(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt, int want_residual,
@@ -1230,11 +1292,8 @@ int orc_iterate(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, doubl
                 }
             }
         } else { /* iterate!(CIP_Marching), Theory/I-projection.jl:161-192 */
-            if (m->bound_enc[c] != 0) { /* positivity_preserving_ib! (Boundary/Positivity.jl) is not restated */
-                octx_free(&o);
-                return 2;
-            }
             for (int q = 0; q < M; ++q) w[q] += mfl[q] * dt / area;
+            positivity_preserving_ib(&o, st, c, area, dt, w, vflux);   /* donor cells only */
             orc_get_prim(D, w, cfg->gamma, prim_c);
             for (int k = 0; k < K; ++k)
                 for (int i = 0; i < n; ++i) f[k * n + i] += dt / area * vflux[k * n + i];

@@ -569,6 +569,26 @@ def test_cip_and_caidvm_agree_to_first_order():
     assert rel_l2(local_pts(mesh, sb.df, 2), local_pts(mesh, sa.df, 2)) < 2e-3
 
 
+def test_cip_with_immersed_boundary_keeps_density_and_energy_positive():
+    """positivity_preserving_ib! (Boundary/Positivity.jl, restated in the ORACLE only — libkamr refuses CIP_Marching on a
+    mesh with donor cells): the slope-extrapolated wall correction enters w and vs_data.flux scaled by
+    theta = min(theta_rho, theta_e) <= 1, chosen so that rho and the internal energy of the updated w stay positive."""
+    case = cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True)
+    case.marching = abi.MARCH_CIP
+    mesh = case.rank_mesh()
+    st = case.init_state(mesh)
+    cfg = case.config()
+    M, nl = 4, mesh.n_local
+    donors = mesh.bound_enc[:nl] > 0
+    assert donors.any()
+    for _ in range(3):
+        orc.step(cfg, mesh, st, case.dt(), False)
+        assert np.isfinite(st.df).all() and np.isfinite(st.w).all()
+        w = st.w.reshape(-1, M)[:nl][mesh.bound_enc[:nl] >= 0]
+        assert w[:, 0].min() > 0
+        assert (w[:, 3] - 0.5 * (w[:, 1] ** 2 + w[:, 2] ** 2) / w[:, 0]).min() > 0
+
+
 # ------------------------------------------------------------------------------------------------ golden fixtures
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
