@@ -145,7 +145,6 @@ struct kamr_ctx {
     bool raw_sdf_valid = false;   // g.sdf holds the reference's sdf for every local cell
     std::vector<int> limit_cells; // local fluid + ghost fluid cells (limit_kernel after upload_aux)
     int* d_limit_cells = nullptr;
-    std::map<int, std::pair<int*, int>> ghost_wave_cells;  // wave -> ghost fluid cells whose sdf arrives then
     struct MergedSegs { CopySeg *d_send = nullptr, *d_recv = nullptr; int n_send = 0, n_recv = 0; };
     std::map<std::pair<int, int>, MergedSegs> merged_segs;   // (what, level) -> pack / unpack lists of ALL peers
     std::vector<unsigned long long> peer_early;   // per peer: waves with an early slope exchange (see build_topology)
@@ -213,7 +212,7 @@ struct kamr_ctx {
         dv = DevView{};
         d_host_off = nullptr;
         d_res = nullptr; d_sendbuf = d_recvbuf = nullptr; d_fluid_cells = nullptr; d_limit_cells = nullptr;
-        limit_cells.clear(); ghost_wave_cells.clear(); raw_sdf_valid = false;
+        limit_cells.clear(); raw_sdf_valid = false;
         peer_early.clear(); early_mask = 0; d_ghost_fluid = nullptr; n_ghost_fluid = 0; merged_segs.clear();
         solid_tasks.clear(); sn_tasks.clear(); ib_nb.clear(); d_solid_tasks = nullptr; d_sn_tasks = nullptr;
     }
@@ -1078,7 +1077,6 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         recv_total += rpos_max;
         c->peers.push_back(std::move(pp));
     }
-    for (auto& kv : ghost_by_wave) c->ghost_wave_cells[kv.first] = std::make_pair(c->dupload(kv.second), (int)kv.second.size());
     {
         std::vector<int> gf;
         for (auto& kv : ghost_by_wave) gf.insert(gf.end(), kv.second.begin(), kv.second.end());
