@@ -223,6 +223,10 @@ int  kamr_get_pair_map(kamr_ctx* ctx, int32_t ga, int32_t gb, int32_t* start, in
 /* cell-face slots of a local cell: writes up to cap records {face, sign}; returns count via *n */
 int  kamr_get_cell_slots(kamr_ctx* ctx, int32_t cell, int32_t* face, int32_t* sign, int32_t cap, int32_t* n);
 
+/* test hook: y[i] = the device's exp(x[i]) for x[i] <= 0 as the CAIDVM kernels evaluate it (every exponent on that path
+ * is -lambda c^2; Theory/Math.jl:96-143 calls Base.exp).  Lets the tests sweep it against libm in ulps. */
+int  kamr_debug_exp_nonpos(kamr_ctx* ctx, const double* x, double* y, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,10 +107,17 @@ class Context:
 
     def profile_read(self):
         """{kernel name: (launches, total_ms)} since the last read."""
-        buf = (abi.KamrKernelTime * 16)()
+        buf = (abi.KamrKernelTime * 32)()
         n = C.c_int32(0)
-        self._ck(self.lib.kamr_profile_read(self.h, buf, 16, C.byref(n)))
+        self._ck(self.lib.kamr_profile_read(self.h, buf, 32, C.byref(n)))
         return {buf[i].name.decode(): (int(buf[i].launches), float(buf[i].total_ms)) for i in range(n.value)}
+
+    def debug_exp_nonpos(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        self._ck(self.lib.kamr_debug_exp_nonpos(self.h, x.ctypes.data_as(abi.c_f64p), y.ctypes.data_as(abi.c_f64p),
+                                                x.size))
+        return y
 
     def pair_map(self, ga, gb):
         n = int(self.mesh.grid_off[ga + 1] - self.mesh.grid_off[ga])

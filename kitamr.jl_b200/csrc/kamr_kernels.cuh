@@ -31,7 +31,8 @@ namespace kamr {
 #endif
 constexpr int PNT_BIG = KAMR_PNT_BIG;
 constexpr int MINB_BIG = KAMR_MINB_BIG;
-constexpr int UNROLL = KAMR_UNROLL;  // point-loop unrolling of the phase kernels: independent points in flight per thread
+constexpr int UNROLL = KAMR_UNROLL;
+constexpr int KAMR_FLUX_DVM_ = 1;   // == KAMR_FLUX_DVM of include/kamr.h (this header does not include the C-ABI)  // point-loop unrolling of the phase kernels: independent points in flight per thread
 
 // ------------------------------------------------------------------------------------------------
 // block-wide sum of NV doubles (warp shuffles + one shared-memory stage); result broadcast to all threads.
@@ -216,9 +217,10 @@ __device__ __forceinline__ double limiter(double f, double s_abs) {
 //   mac[m] += area * w_j psi(v_j) micro_j      (the neighbour's share of fw, CAIDVM.jl:119)
 template <int D, int K>
 __device__ __forceinline__ void pair_flux(const DevView& g, const Slot& sl, double wt, int li, int i, double dt,
-                                          double* fl, double* mac) {
+                                          bool dvm, double* fl, double* mac) {
     const double* nf = g.df + sl.nbr_doff * K;
-    const double* nsl = g.sdl + sl.nbr_doff * K * D;
+    // fluid/fluid: limited slopes; solid side under the DVM flux: the SolidNeighbor's own raw slopes (DVM.jl:91)
+    const double* nsl = (sl.kind == SLOT_INNER ? g.sdl : g.sdf) + sl.nbr_doff * K * D;
     const double* nv = g.v_mid + sl.nbr_goff * D;
     const double* nwt = g.v_weight + sl.nbr_goff;
     const int8_t* nlev = g.v_level + sl.nbr_goff;
@@ -243,7 +245,7 @@ __device__ __forceinline__ void pair_flux(const DevView& g, const Slot& sl, doub
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const double fj = nf[k * np + j];
-            if (sl.kind == SLOT_INNER) {
+            if (sl.kind == SLOT_INNER || dvm) {
                 double s_dx = 0.0;
 #pragma unroll
                 for (int t = 0; t < D; ++t) s_dx += dx[t] * nsl[(t * K + k) * np + j];
@@ -784,11 +786,25 @@ __global__ void __launch_bounds__(NT, MINB)
                     continue;  // own half of a pair-mapped fluid slot was gathered in pass A
                 } else if (sl.rel_off < 0) {  // solid side, identical grids: f_wall v_n, CAIDVM.jl:111
                     const double* nf = g.df + sl.nbr_doff * K + i;
+                    if (gas.flux_type == KAMR_FLUX_DVM_) {  // DVM.jl:91: (there_df + ndx . there_sdf) v_n, unlimited
+                        const double* nsd = g.sdf + sl.nbr_doff * (K * D) + i;
+                        double ndx[D];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) fl[k] += sl.area * (nf[k * sl.nbr_np] * vn);
+                        for (int t = 0; t < D; ++t) ndx[t] = face_dx(sl.fmid[t], __dmul_rn(v[t], dt), sl.nbr_mid[t]);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            double s_dx = 0.0;
+#pragma unroll
+                            for (int t = 0; t < D; ++t) s_dx += ndx[t] * nsd[(t * K + k) * sl.nbr_np];
+                            fl[k] += sl.area * ((nf[k * sl.nbr_np] + s_dx) * vn);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) fl[k] += sl.area * (nf[k * sl.nbr_np] * vn);
+                    }
                     add_moments<D, K>(acc, wt, v, fl);
                 } else {
-                    pair_flux<D, K>(g, sl, wt, own.lev[i], i, dt, fl, acc);
+                    pair_flux<D, K>(g, sl, wt, own.lev[i], i, dt, gas.flux_type == KAMR_FLUX_DVM_, fl, acc);
                 }
                 if (MODE == MODE_FLUX) {
 #pragma unroll
@@ -1416,20 +1432,36 @@ __device__ __forceinline__ void side_sum(const DevView& g, const SlopeNbr* nb, i
 //
 // Dependency sweep in ONE launch: tasks are ordered by wave; a task that projects the finished slopes of coarser
 // cells computed by this same launch waits on their per-cell epoch flags (thread t spins on dependency t), and
-// every task publishes its own flag when its stores are visible.  A waiting CTA only ever waits for CTAs with a
-// lower block index, which the hardware dispatches first, so the sweep cannot deadlock.
+// every task publishes its own flag when its stores are visible.  CUDA guarantees neither a dispatch order nor
+// forward progress between CTAs, so a CTA does not take the task of its block index: it draws a ticket from a
+// device-wide counter once it is running.  A task only depends on tasks earlier in the list, whose tickets were
+// therefore drawn by CTAs that are already resident, so every wait is on a running (or finished) CTA and the sweep
+// cannot deadlock under MPS, time-slicing or a debugger.  The spin is bounded all the same: on expiry the kernel
+// raises g.err_flag (surfaced by the next kamr_sync / download / residual read as an error) instead of hanging.
+constexpr unsigned SLOPE_SPIN_LIMIT = 1u << 25;   // x 64 ns sleep: seconds
 template <int D, int K, bool GENERIC, int NT>
 __global__ void __launch_bounds__(NT, 1024 / NT) slope_kernel(DevView g, const SlopeTask* __restrict__ tasks, int raw_all,
-                                                   int epoch) {
+                                                   int epoch, unsigned* __restrict__ ticket, unsigned ticket_base) {
     __shared__ SlopeTask tk;
     __shared__ CellInfo ci;
     __shared__ SlopeNbr nb[MAX_SLOPE_NB];
-    copy_words(tasks + blockIdx.x, &tk, (int)(sizeof(SlopeTask) / sizeof(int)));
+    __shared__ int s_task;
+    int ti = blockIdx.x;
+    if (epoch) {
+        if (threadIdx.x == 0) s_task = (int)(atomicAdd(ticket, 1u) - ticket_base);
+        __syncthreads();
+        ti = s_task;
+    }
+    copy_words(tasks + ti, &tk, (int)(sizeof(SlopeTask) / sizeof(int)));
     __syncthreads();
     if (tk.dep_count > 0) {
         if ((int)threadIdx.x < tk.dep_count) {
             const volatile int* flag = g.slope_done + g.slope_deps[tk.dep_begin + threadIdx.x];
-            while (*flag != epoch) __nanosleep(64);
+            unsigned spins = 0;
+            while (*flag != epoch) {
+                __nanosleep(64);
+                if (++spins > SLOPE_SPIN_LIMIT) { atomicExch(g.err_flag, 1); break; }
+            }
             __threadfence();
         }
         __syncthreads();
@@ -2017,6 +2049,11 @@ __global__ void __launch_bounds__(256) repack_kernel(const CellInfo* __restrict_
             else packed[hoff + t] = padded[doff + (long long)p * np + i];
         }
     }
+}
+
+__global__ void exp_nonpos_kernel(const double* __restrict__ x, double* __restrict__ y, long long n) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        y[t] = exp_nonpos(x[t]);
 }
 
 __global__ void fill_kernel(double* p, long long n, double v) {

@@ -139,6 +139,8 @@ struct kamr_ctx {
     std::vector<SlopeStage> slope_stages;
     std::vector<int> slope_deps;
     int slope_epoch = 0;
+    unsigned* d_slope_ticket = nullptr;   // device-wide ticket counter of the slope dependency sweep
+    unsigned slope_ticket_base = 0;       // its value before the next launch
     std::vector<SlopeNbr> slope_nb;
     int max_smem_optin = 0;
     bool keep_sdf = false;        // KAMR_OPT_KEEP_SDF: fused steps also write the raw slopes of every cell
@@ -168,6 +170,7 @@ struct kamr_ctx {
     DevView dv{};
     double* d_res = nullptr;
     double* h_res = nullptr;  // pinned
+    int* h_err = nullptr;     // pinned copy of dv.err_flag
     double* d_stage = nullptr;  // device staging for padded transfers (host layout, contiguous)
     size_t d_stage_doubles = 0;
     long long* d_host_off = nullptr;
@@ -211,6 +214,7 @@ struct kamr_ctx {
         slope_stages.clear(); slope_deps.clear(); slope_nb.clear(); fluid_cells.clear(); bins.clear(); peers.clear();
         dv = DevView{};
         d_host_off = nullptr;
+        d_slope_ticket = nullptr;
         d_res = nullptr; d_sendbuf = d_recvbuf = nullptr; d_fluid_cells = nullptr; d_limit_cells = nullptr;
         limit_cells.clear(); raw_sdf_valid = false;
         peer_early.clear(); early_mask = 0; d_ghost_fluid = nullptr; n_ghost_fluid = 0; merged_segs.clear();
@@ -442,6 +446,35 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     c->n_cell = m->n_local + m->n_ghost + m->n_solidnbr;
     c->n_grid = m->n_grid;
     if (c->n_local <= 0) throw Fail("mesh has no local cells");
+    if (m->n_ghost < 0 || m->n_solidnbr < 0 || m->n_peer < 0 || m->n_face < 0 || m->n_grid <= 0)
+        throw Fail("negative count in kamr_mesh");
+    // halo and immersed-boundary index arrays index host tables below: range-check them before first use
+    if (m->n_peer > 0) {
+        // the early-level handshake below makes this call collective over the pair communicator: every rank must have
+        // called kamr_comm_init first, or the two sides would build different exchange schedules (or block)
+        if (c->cfg.nranks > 1 && !c->comm)
+            throw Fail("mesh has peers: call kamr_comm_init on every rank before kamr_upload_topology");
+        if (m->send_off[0] != 0 || m->recv_off[0] != 0) throw Fail("send_off / recv_off must start at 0");
+        for (int p = 0; p < m->n_peer; ++p) {
+            if (m->peer_rank[p] < 0 || m->peer_rank[p] >= std::max(1, c->cfg.nranks) || m->peer_rank[p] == c->cfg.rank)
+                throw Fail("peer_rank out of range");
+            if (m->send_off[p + 1] < m->send_off[p] || m->recv_off[p + 1] < m->recv_off[p])
+                throw Fail("send_off / recv_off must ascend");
+        }
+        if (m->recv_off[m->n_peer] > m->n_ghost) throw Fail("recv_off exceeds n_ghost");
+        for (int q = 0; q < m->send_off[m->n_peer]; ++q)
+            if (m->send_cells[q] < 0 || m->send_cells[q] >= m->n_local) throw Fail("send_cells must be local cell ids");
+    }
+    if (m->ib) {
+        const kamr_ib* ib = m->ib;
+        if (ib->n_solid < 0 || ib->n_sn < 0) throw Fail("negative count in kamr_ib");
+        for (int q = 0; q < (ib->n_solid ? ib->solid_nb_off[ib->n_solid] : 0); ++q)
+            if (ib->solid_nb_ids[q] < 0 || ib->solid_nb_ids[q] >= c->n_cell) throw Fail("solid_nb_ids out of range");
+        for (int q = 0; q < (ib->n_sn ? ib->sn_nb_off[ib->n_sn] : 0); ++q)
+            if (ib->sn_nb_ids[q] < 0 || ib->sn_nb_ids[q] >= c->n_cell) throw Fail("sn_nb_ids out of range");
+        for (int q = 0; q < ib->n_sn; ++q)
+            if (ib->sn_donor[q] < 0 || ib->sn_donor[q] >= m->n_local) throw Fail("sn_donor must be a local cell");
+    }
     if (c->gas.marching == KAMR_MARCH_CIP)   // positivity_preserving_ib! (Boundary/Positivity.jl) is not on the device
         for (int i = 0; i < m->n_local; ++i)
             if (m->bound_enc[i] > 0) throw Fail("CIP_Marching with immersed-boundary donor cells is not supported");
@@ -539,7 +572,11 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             s.nbr = -1;
             s.area = rot * area;
             switch (m->bc_type[there]) {
-                case KAMR_BC_MAXWELLIAN: s.kind = SLOT_BC_MAXWELL; break;
+                case KAMR_BC_MAXWELLIAN:
+                    // calc_domain_flux(DVM, Maxwellian) reads undefined variables in the reference (Flux/DVM.jl:3,12)
+                    if (c->gas.flux_type == KAMR_FLUX_DVM)
+                        throw Fail("DVM flux with a Maxwellian domain wall cannot run in the reference (Flux/DVM.jl:12)");
+                    s.kind = SLOT_BC_MAXWELL; break;
                 case KAMR_BC_SUPERSONIC_INFLOW: s.kind = SLOT_BC_INFLOW; break;
                 case KAMR_BC_UNIFORM_OUTFLOW: s.kind = SLOT_BC_UNIFORM; break;
                 case KAMR_BC_INTERPOLATED_OUTFLOW:
@@ -838,6 +875,11 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         c->dv.slope_done = c->dalloc<int>((size_t)c->n_cell);
         CK(cudaMemsetAsync(c->dv.slope_done, 0, (size_t)c->n_cell * sizeof(int), c->stream));
         c->slope_epoch = 0;
+        c->d_slope_ticket = c->dalloc<unsigned>(1);
+        c->dv.err_flag = c->dalloc<int>(1);
+        CK(cudaMemsetAsync(c->d_slope_ticket, 0, sizeof(unsigned), c->stream));
+        CK(cudaMemsetAsync(c->dv.err_flag, 0, sizeof(int), c->stream));
+        c->slope_ticket_base = 0;
     }
     // ---- fluid cell list (Morton order: neighbours in space are neighbours in the launch, so the blocks
     // resident at one time share their neighbour reads through L2) and the phase-kernel bins
@@ -1090,6 +1132,17 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     CK(cudaStreamSynchronize(c->stream));
 }
 
+// Synchronises the stream and turns a device-side give-up (DevView::err_flag) into a host error.
+void sync_and_check(kamr_ctx* c) {
+    if (c->dv.err_flag) CK(cudaMemcpyAsync(c->h_err, c->dv.err_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->dv.err_flag && *c->h_err) {
+        *c->h_err = 0;
+        CK(cudaMemsetAsync(c->dv.err_flag, 0, sizeof(int), c->stream));
+        throw Fail("slope dependency sweep timed out waiting for another CTA (the results of this step are invalid)");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host <-> device transfer of per-point arrays (host layout: unpadded planes; device: padded planes)
 void copy_points(kamr_ctx* c, double* dev, double* host_rw, const double* host_ro, int comps, bool to_device) {
@@ -1219,8 +1272,9 @@ void launch_slope_stage(kamr_ctx* c, const kamr_ctx::SlopeStage& st, int raw_all
     }
     if (!st.gen.empty()) {
         Launch L_(c, KID_SLOPE);
-        slope_kernel<D, K, true, NT_SLOPE><<<(int)st.gen.size(), NT_SLOPE, 0, c->stream>>>(c->dv, st.d_gen, raw_all,
-                                                                              st.flags ? c->slope_epoch : 0);
+        slope_kernel<D, K, true, NT_SLOPE><<<(int)st.gen.size(), NT_SLOPE, 0, c->stream>>>(
+            c->dv, st.d_gen, raw_all, st.flags ? c->slope_epoch : 0, c->d_slope_ticket, c->slope_ticket_base);
+        if (st.flags) c->slope_ticket_base += (unsigned)st.gen.size();   // tickets drawn by this launch (wraps with the counter)
     }
 }
 
@@ -1366,7 +1420,7 @@ void fetch_residual(kamr_ctx* c, int want, double* res_out) {
       residual_reduce_kernel<<<2 * M, 1024, 0, c->stream>>>(c->dv.res_cell, c->d_fluid_cells, (int)c->fluid_cells.size(),
                                                        2 * M, c->d_res); }
     CK(cudaMemcpyAsync(c->h_res, c->d_res, 2 * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    sync_and_check(c);
     if (res_out) memcpy(res_out, c->h_res, 2 * M * sizeof(double));
 }
 
@@ -1468,6 +1522,10 @@ int kamr_create(const kamr_config* cfg, kamr_ctx** out) {
         if (e != cudaSuccess || ndev == 0)
             throw Fail(std::string("no CUDA device available (libkamr has no CPU fallback): ") + cudaGetErrorString(e));
         if (cfg->device < 0 || cfg->device >= ndev) throw Fail("device ordinal out of range");
+        if (cfg->flux_type != KAMR_FLUX_CAIDVM && cfg->flux_type != KAMR_FLUX_DVM)
+            throw Fail("unsupported flux type (CAIDVM and DVM are built; UGKS is 2-D only and broken in the reference)");
+        if (cfg->marching != KAMR_MARCH_CAIDVM && cfg->marching != KAMR_MARCH_CIP && cfg->marching != KAMR_MARCH_EULER)
+            throw Fail("unsupported time marching (CAIDVM_Marching, CIP_Marching and Euler are built)");
         CK(cudaSetDevice(cfg->device));
         c = new kamr_ctx();
         CK(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
@@ -1485,6 +1543,8 @@ int kamr_create(const kamr_config* cfg, kamr_ctx** out) {
         CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         CK(cudaMallocHost((void**)&c->h_res, 64 * sizeof(double)));
+        CK(cudaMallocHost((void**)&c->h_err, sizeof(int)));
+        *c->h_err = 0;
         *out = c;
         return 0;
     } catch (const std::exception& e) {
@@ -1502,6 +1562,7 @@ int kamr_destroy(kamr_ctx* c) {
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->comm) nccl().CommDestroy(c->comm);
     if (c->h_res) cudaFreeHost(c->h_res);
+    if (c->h_err) cudaFreeHost(c->h_err);
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1589,7 +1650,7 @@ int kamr_download_state(kamr_ctx* c, uint32_t mask, double* df, double* sdf, dou
         if ((mask & KAMR_DL_QF) && qf) CK(cudaMemcpyAsync(qf, c->dv.qf, nl * D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if ((mask & KAMR_DL_SW) && sw) CK(cudaMemcpyAsync(sw, c->dv.sw, nl * M * D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if ((mask & KAMR_DL_MFLUX) && mflux) CK(cudaMemcpyAsync(mflux, c->dv.mflux, nl * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        sync_and_check(c);
     });
 }
 
@@ -1609,7 +1670,7 @@ int kamr_exchange_df(kamr_ctx* c) {
     return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); exchange(c, 0, 0); });
 }
 int kamr_sync(kamr_ctx* c) {
-    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); CK(cudaStreamSynchronize(c->stream)); });
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); sync_and_check(c); });
 }
 
 int kamr_get_stats(kamr_ctx* c, kamr_stats* out) {
@@ -1667,6 +1728,22 @@ int kamr_profile_read(kamr_ctx* c, kamr_kernel_time* out, int32_t cap, int32_t* 
             ++k;
         }
         *n = k;
+    });
+}
+
+int kamr_debug_exp_nonpos(kamr_ctx* c, const double* x, double* y, int64_t n) {
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->cfg.device));
+        if (n <= 0) return;
+        double *dx = nullptr, *dy = nullptr;
+        CK(cudaMalloc((void**)&dx, n * sizeof(double)));
+        CK(cudaMalloc((void**)&dy, n * sizeof(double)));
+        CK(cudaMemcpyAsync(dx, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        exp_nonpos_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, c->stream>>>(dx, dy, n);
+        CK(cudaMemcpyAsync(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        cudaFree(dx); cudaFree(dy);
+        CK(e);
     });
 }
 

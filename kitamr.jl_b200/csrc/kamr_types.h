@@ -180,6 +180,7 @@ struct DevView {
     const SlopeNbr* slope_nb;
     const int* slope_deps;
     int* slope_done;            // per cell: epoch of the last finished slope task (dependency flags)
+    int* err_flag;              // raised by a kernel that gave up waiting (slope dependency sweep); checked at sync points
     const int8_t* v_level;
     const unsigned char* v_sign; // per point: bit d = (v_d > 0)
     const double* v_weight;

@@ -651,7 +651,10 @@ static void flux_inner_face(const octx* o, orc_state* st, int f, double dt, face
     make_mask(o, there, dir, rot, 1, tv);
     int there_solid = m->bound_enc[there] < 0;
     reconstruct(o, st, here, m->mid + (size_t)here * D, fmid, dt, dir, hv, there_solid ? 1 : 0);
-    reconstruct(o, st, there, m->face_there_mid + (size_t)f * D, fmid, dt, dir, tv, there_solid ? 2 : 0);
+    /* there side of a solid / SolidNeighbor face: CAIDVM takes f_wall*v_n (CAIDVM.jl:111), DVM reconstructs with the
+     * SolidNeighbor's own slopes, (there_df + ndx.there_sdf)*v_n (DVM.jl:91) */
+    reconstruct(o, st, there, m->face_there_mid + (size_t)f * D, fmid, dt, dir, tv,
+                there_solid ? (o->cfg->flux_type == KAMR_FLUX_DVM ? 1 : 2) : 0);
     double area = face_area(o, here, dir);
     if (kind == KAMR_FACE_HANGING) area = area / pow2i(D - 1) * rot; /* Flux.jl:84-86 */
     else area = area * rot;                                          /* Flux.jl:87-89 */
@@ -756,6 +759,11 @@ static void flux_domain_face(const octx* o, orc_state* st, int f, double dt, fac
 /* flux!(p4est, ka), Flux/Flux.jl:458-488 — face loop (IB phases handled by orc_ib_*) */
 int orc_flux(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt) {
     octx o;
+    /* calc_domain_flux(DVM, Maxwellian) reads undefined variables (DVM.jl:3,12: here_weight): the combination cannot
+     * run in the reference, so it is an error here too */
+    if (cfg->flux_type == KAMR_FLUX_DVM)
+        for (int f = 0; f < m->n_face; ++f)
+            if (m->face_kind[f] == KAMR_FACE_DOMAIN && m->bc_type[m->face_there[f]] == KAMR_BC_MAXWELLIAN) return 3;
     if (octx_init(&o, cfg, m)) return 1;
     int maxn = 1;
     for (int c = 0; c < o.n_cell; ++c) if (cell_n(&o, c) > maxn) maxn = cell_n(&o, c);

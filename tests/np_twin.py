@@ -303,5 +303,7 @@ class Twin:
         f, w, _ = self.unflat(st)
         s = self.slopes(f)
         flux, mflux = self.flux(f, s, dt, gas)
+        if self.case.flux_type == abi.FLUX_DVM:   # calc_flux(DVM, ...) returns no macro flux (Flux/DVM.jl:79-99)
+            mflux = np.zeros_like(mflux)
         f2, w2, prim, qf = self.update(f, w, flux, mflux, dt, gas, self.case.marching)
         return dict(sdf=s, flux=flux, mflux=mflux, df=f2, w=w2, prim=prim, qf=qf)

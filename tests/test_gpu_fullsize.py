@@ -94,3 +94,27 @@ def test_uniform_maxwellian_is_a_fixed_point(kamr_lib):
     M, nl = 4, mesh.n_local
     assert rel_l2(out.w[: nl * M], st.w[: nl * M]) < 1e-13
     assert rel_l2(local_pts(mesh, out.df, 2), local_pts(mesh, st.df, 2)) < 1e-6
+
+
+@pytest.mark.parametrize("workload,steps", [("S2ib", 2), ("S4", 1)])
+def test_full_size_elementwise_vs_oracle(kamr_lib, workload, steps):
+    """The bench workloads at BASELINE.json's full size, element by element against the CPU oracle (single process;
+    S2ib: 1.64e7 phase cells, S4 sphere3d: 2.2e8): relative L2 <= 1e-12 per step on f, w and prim of the fluid cells."""
+    from kitamr_jl_b200.synth import cases
+    from oracle import orc
+    case = cases.WORKLOADS[workload]()
+    mesh = case.rank_mesh()
+    st = case.init_state(mesh)
+    out = _run(case, mesh, st, steps)
+    ref = st.copy()
+    cfg = case.config()
+    for _ in range(steps):
+        orc.step(cfg, mesh, ref, case.dt(), False)
+    K, M, nl = mesh.ndf, mesh.dim + 2, mesh.n_local
+    tol = 1e-12 * steps
+    e_df = rel_l2(local_pts(mesh, out.df, K), local_pts(mesh, ref.df, K))
+    e_w = rel_l2(out.w[: nl * M], ref.w[: nl * M])
+    fluid = np.repeat(mesh.bound_enc[:nl] >= 0, M)
+    e_p = rel_l2(out.prim[: nl * M][fluid], ref.prim[: nl * M][fluid])
+    print(f"{case.name}: {mesh.n_phase_local()} phase cells, {steps} step(s): rel L2 df {e_df:.2e} w {e_w:.2e} prim {e_p:.2e}")
+    assert e_df <= tol and e_w <= tol and e_p <= tol

@@ -68,7 +68,33 @@ def _cases():
         "s1_small": lambda: cases.riemann_s1(ps_level=1, band_level=2, trees=4, vtrees=8, vs_maxlevel=2),
         # S3 (example/airfoil): one uniform velocity grid, InterpolatedOutflow on three sides
         "s3_small": lambda: cases.airfoil_s3(ps_maxlevel=3, box_level=2, trees=(6, 8), vtrees=12),
+        # DVM flux (Flux/DVM.jl:79-99; Solver.flux = DVM): micro flux only, hanging faces + mismatched grids; the domain
+        # BCs exclude the Maxwellian wall, which cannot run in the reference under DVM (DVM.jl:12)
+        "dvm2d": lambda: _dvm(cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=8, vs_maxlevel=2, ragged=True, seed=41,
+                                             bcs=_nowall_bcs(2))),
+        "dvm3d_euler": lambda: _dvm(cases.amr_case(dim=3, trees=3, maxlevel=1, vtrees=4, vs_maxlevel=1, ragged=True,
+                                                   seed=42, bcs=_nowall_bcs(3), marching=abi.MARCH_EULER)),
+        # DVM on immersed-boundary faces: there side = (there_df + ndx.there_sdf) v_n with the SolidNeighbor's slopes (:91)
+        "dvm_ib2d": lambda: _dvm(cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True)),
+        "dvm_ib3d": lambda: _dvm(cases.sphere_s4(trees=4, ps_maxlevel=2, vtrees=4, vs_maxlevel=1)),
     }
+
+
+def _dvm(case):
+    from kitamr_jl_b200 import abi
+    case.flux_type = abi.FLUX_DVM
+    return case
+
+
+def _nowall_bcs(dim):
+    from kitamr_jl_b200 import abi
+    from kitamr_jl_b200.synth import cases
+    kinds = [abi.BC_SUPERSONIC_INFLOW, abi.BC_UNIFORM_OUTFLOW,
+             abi.BC_INTERPOLATED_OUTFLOW if dim == 2 else abi.BC_UNIFORM_OUTFLOW, abi.BC_UNIFORM_OUTFLOW] + \
+            ([abi.BC_UNIFORM_OUTFLOW, abi.BC_SUPERSONIC_INFLOW] if dim == 3 else [])
+    prims = [[1.0] + [0.3] + [0.0] * (dim - 1) + [1.0], None, None, None] + \
+            ([None, [1.0] + [0.1] * dim + [1.1]] if dim == 3 else [])
+    return cases._bcs(dim, kinds, prims)
 
 
 @pytest.fixture(scope="module", params=list(_cases().keys()))
@@ -203,6 +229,19 @@ def test_cip_device_projection_hits_the_moments(kamr_lib, dim):
         assert np.allclose(m, out.w[c * M:(c + 1) * M], rtol=0, atol=1e-8)
 
 
+def test_dvm_with_maxwellian_domain_wall_is_refused(kamr_lib):
+    """calc_domain_flux(DVM, Maxwellian) cannot run in the reference (Flux/DVM.jl:3,12: undefined here_weight)"""
+    from kitamr_jl_b200 import api
+    from kitamr_jl_b200.synth import cases
+    case = _dvm(cases.smoke_s0(trees=4, vtrees=4))
+    ctx = api.Context(case.config(device=0))
+    try:
+        with pytest.raises(Exception, match="DVM"):
+            ctx.upload_topology(case.rank_mesh())
+    finally:
+        ctx.close()
+
+
 def test_origin_off_a_root_corner_is_refused(kamr_lib):
     """the reference refuses a velocity space whose origin is not a root-grid corner (check_vs_setting,
     Solver/Types.jl:335-353) because upwinding by the sign of v_d is ambiguous there; libkamr refuses it where it
@@ -247,3 +286,70 @@ def test_device_matches_golden_fixture(kamr_lib, name):
     assert rel_l2(out.df[sel], gold["df_sample"]) <= df_tol(case)
     nw = len(gold["w"])
     assert rel_l2(out.w[:nw], gold["w"]) <= TOL
+
+
+def test_exp_nonpos_ulp_sweep(kamr_lib):
+    """The device's own exp for non-positive arguments (kamr_kernels.cuh exp_nonpos: Cody-Waite + degree-13 Estrin
+    polynomial) against libm over the whole argument range it can see: dense near 0, log-spaced down to the underflow
+    threshold, the gradual-underflow (denormal) branch and beyond.  Bound: 2 ulp on normal results, 1 denormal
+    quantum (2^-1074) on denormal ones."""
+    from kitamr_jl_b200 import api
+    from kitamr_jl_b200.synth import cases
+    rng = np.random.default_rng(7)
+    x = np.concatenate([
+        [0.0, -0.0, -1e-300, -1e-17, -np.log(2) / 2, -np.log(2), -708.0, -708.3964185322641, -709.0, -744.0, -745.13,
+         -745.2, -746.0, -1000.0, -1e6, -1e300],
+        -rng.uniform(0.0, 1.0, 200000),
+        -rng.uniform(0.0, 50.0, 400000),            # the range -lambda c^2 lives in for every bench workload
+        -np.exp(rng.uniform(np.log(1e-12), np.log(708.0), 300000)),
+        -rng.uniform(700.0, 750.0, 100000),         # 2^-1022 boundary and the denormal branch
+    ])
+    ctx = api.Context(cases.smoke_s0(trees=2, vtrees=2).config(device=0))
+    try:
+        y = ctx.debug_exp_nonpos(x)
+    finally:
+        ctx.close()
+    ref = np.exp(x)
+    tiny = np.finfo(np.float64).tiny
+    normal = ref >= tiny
+    ulp = np.spacing(ref[normal])
+    err = np.abs(y[normal] - ref[normal]) / ulp
+    assert err.max() <= 2.0, f"max error {err.max()} ulp at x = {x[normal][err.argmax()]}"
+    den = ~normal
+    assert np.abs(y[den] - ref[den]).max() <= 2.0 ** -1074 * 1.0 + 0.0
+    assert np.all(y >= 0.0) and np.all(y <= 1.0) and np.all(np.isfinite(y))
+    print(f"exp_nonpos: max {err.max():.3f} ulp, mean {err.mean():.4f} ulp over {normal.sum()} normal results")
+
+
+@pytest.mark.parametrize("name", ["S0", "amr2d_ragged"])
+def test_1000_steps(kamr_lib, name):
+    """north_star: relative L2 <= 1e-9 after 1000 steps (device kamr_step vs the oracle's slope!+flux!+iterate!,
+    Theory/Iterate.jl:96), compared at steps 1, 10, 100 and 1000."""
+    from kitamr_jl_b200 import abi, api
+    from oracle import orc
+    case = _cases()[name]()
+    mesh = case.rank_mesh()
+    st0 = case.init_state(mesh)
+    cfg = case.config(device=0)
+    dt = case.dt()
+    D, K = mesh.dim, mesh.ndf
+    nl = mesh.n_local
+    ref = st0.copy()
+    ctx = api.Context(cfg)
+    try:
+        ctx.upload_topology(mesh)
+        ctx.upload_state(st0, aux=True)
+        worst = {}
+        for it in range(1, 1001):
+            orc.step(cfg, mesh, ref, dt, False)
+            ctx.step(dt, False)
+            if it in (1, 10, 100, 1000):
+                out = ctx.download_state(st0.copy(), abi.DL_DF | abi.DL_W | abi.DL_PRIM)
+                e_df = rel_l2(local_pts(mesh, out.df, K), local_pts(mesh, ref.df, K))
+                e_w = rel_l2(out.w[: nl * (D + 2)], ref.w[: nl * (D + 2)])
+                worst[it] = (e_df, e_w)
+                assert np.all(np.isfinite(out.df))
+                assert e_df <= (1e-12 if it == 1 else 1e-9) and e_w <= (1e-12 if it == 1 else 1e-9), (it, e_df, e_w)
+        print(f"{name}: rel L2 (df, w) by step: {worst}")
+    finally:
+        ctx.close()

@@ -144,6 +144,11 @@ def _twin_cases():
         "interp_outflow2d": lambda: _interp_case(),
         "cip2d": lambda: _with(cases.uniform_case(dim=2, trees=5, vtrees=10), marching=abi.MARCH_CIP),
         "cip3d": lambda: _with(cases.uniform_case(dim=3, trees=3, vtrees=6), marching=abi.MARCH_CIP),
+        # DVM flux (Flux/DVM.jl:79-99): the same micro fluxes, no macro flux, so w stays put under every marching (the
+        # Euler MicroFlux branch, Theory/Iterate.jl:144, tests a Type against a Union of types and is never taken)
+        "dvm2d": lambda: _with(cases.uniform_case(dim=2, trees=6, vtrees=10), flux_type=abi.FLUX_DVM),
+        "dvm3d_euler": lambda: _with(cases.uniform_case(dim=3, trees=3, vtrees=6), flux_type=abi.FLUX_DVM,
+                                     marching=abi.MARCH_EULER),
     }
 
 
@@ -193,6 +198,43 @@ def test_oracle_matches_numpy_twin(name):
     assert rel_l2(o.w, ref["w"].ravel()) <= 1e-13
     assert rel_l2(o.prim, ref["prim"].ravel()) <= 1e-13
     assert np.allclose(o.qf, ref["qf"].ravel(), rtol=1e-9, atol=1e-14)
+
+
+def test_dvm_refuses_maxwellian_domain_wall():
+    """calc_domain_flux(DVM, Maxwellian) reads undefined variables in the reference (Flux/DVM.jl:3,12)"""
+    case = _with(cases.smoke_s0(trees=4, vtrees=4), flux_type=abi.FLUX_DVM)
+    mesh = case.rank_mesh()
+    st = case.init_state(mesh)
+    with pytest.raises(Exception):
+        orc.flux(case.config(), mesh, st, case.dt())
+
+
+def test_dvm_solid_face_uses_the_solid_neighbor_slopes():
+    """DVM.jl:91: the there side of a solid face is (there_df + ndx.there_sdf) v_n; CAIDVM.jl:111 takes there_df v_n.
+    The two fluxes differ exactly where a SolidNeighbor has a non-zero slope."""
+    case = cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True)
+    mesh = case.rank_mesh()
+    st = case.init_state(mesh)
+    out = {}
+    for ft in (abi.FLUX_CAIDVM, abi.FLUX_DVM):
+        case.flux_type = ft
+        cfg = case.config()
+        o = st.copy()
+        orc.slope(cfg, mesh, o)
+        orc.ib_solid_cells(cfg, mesh, o)
+        orc.ib_solid_neighbors(cfg, mesh, o)
+        orc.flux(cfg, mesh, o, case.dt())
+        out[ft] = o
+    K = mesh.ndf
+    off = mesh.vs_off()
+    donors = np.nonzero(mesh.bound_enc[: mesh.n_local] > 0)[0]
+    others = np.nonzero(mesh.bound_enc[: mesh.n_local] == 0)[0]
+    assert len(donors)
+    d = lambda c: np.abs(out[abi.FLUX_CAIDVM].flux[off[c] * K: off[c + 1] * K]
+                         - out[abi.FLUX_DVM].flux[off[c] * K: off[c + 1] * K]).max()
+    assert max(d(c) for c in donors) > 0.0
+    assert all(d(c) == 0.0 for c in others)
+    assert np.all(out[abi.FLUX_DVM].mflux == 0.0)
 
 
 # ------------------------------------------------------------------------------------------------ invariants
