@@ -1934,7 +1934,7 @@ __global__ void __launch_bounds__(256, KAMR_IB_MINB) solid_neighbor_kernel(DevVi
     const int8_t* slev = g.v_level + cs.goff;
     double* snf = g.df + cn_.doff * K;
     double* sns = g.sdf + cn_.doff * K * D + (size_t)dir * K * np;
-    double* snflux = g.flux + cn_.doff * K;
+    double* snflux = g.flux ? g.flux + cn_.doff * K : nullptr;   // read by positivity_preserving_ib! only (un-fused path)
     double bc[D + 2];
 #pragma unroll
     for (int q = 0; q < D + 2; ++q) bc[q] = tk.bc[q];
@@ -1968,7 +1968,7 @@ __global__ void __launch_bounds__(256, KAMR_IB_MINB) solid_neighbor_kernel(DevVi
             sv = fmin(fabs((ibf[k] - EPS_MACH) / (sv * dxL + EPS_MACH)), 1.0) * sv;  // :452-457
             const double a = ibf[k] + sv * dxL;
             sns[k * np + i] = sv;
-            snflux[k * np + i] = sv * dfl;                                          // :474-475
+            if (snflux) snflux[k * np + i] = sv * dfl;                              // :474-475
             snf[k * np + i] = a;
             if (k == 0) aux0 = a;
         }

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -117,6 +118,7 @@ struct kamr_ctx {
     std::vector<int> rare;
     std::vector<long long> host_off;  // unpadded point offset per cell (host layout)
     std::vector<int> grid_n, grid_np;
+    std::vector<int> grid_canon;      // first grid with identical contents: pair maps and "same grid" tests go by this id
     std::vector<long long> grid_goff, grid_hoff;
     std::vector<int8_t> h_level;      // host copy of v_level (host layout) for pair maps
     const double* h_vmid = nullptr;   // the host's v_mid, valid during kamr_upload_topology only
@@ -210,7 +212,7 @@ struct kamr_ctx {
         allocs.clear();
         device_bytes = 0;
         cells.clear(); slots.clear(); hot.clear(); rare.clear(); host_off.clear(); grid_n.clear(); grid_np.clear(); grid_goff.clear();
-        grid_hoff.clear(); h_level.clear(); rel_id.clear(); rel_off.clear(); pm_start.clear();
+        grid_hoff.clear(); grid_canon.clear(); h_level.clear(); rel_id.clear(); rel_off.clear(); pm_start.clear();
         slope_stages.clear(); slope_deps.clear(); slope_nb.clear(); fluid_cells.clear(); bins.clear(); peers.clear();
         dv = DevView{};
         d_host_off = nullptr;
@@ -251,7 +253,8 @@ struct Launch {
 // in the reference's merge-walk (Flux/Slope.jl:29-64).  Integer volume accounting instead of the
 // reference's floating-point `flag` accumulation; tests check it against the oracle's restatement.
 int build_rel(kamr_ctx* c, int ga, int gb) {
-    if (ga == gb) return -1;
+    ga = c->grid_canon[ga]; gb = c->grid_canon[gb];   // identical grids stored twice (per-cell grids of a host that
+    if (ga == gb) return -1;                          // does not deduplicate) are the same grid
     auto key = std::make_pair(ga, gb);
     auto it = c->rel_id.find(key);
     if (it != c->rel_id.end()) return it->second;
@@ -493,6 +496,29 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         c->grid_goff[g + 1] = c->grid_goff[g] + c->grid_np[g];
     }
     c->padded = padded;
+    {   // canonical ids: grids with the same levels and midpoints are one grid for every index map (the host may hand
+        // every cell its own copy, as VsData objects are per cell in the reference)
+        c->grid_canon.resize(m->n_grid);
+        std::map<std::pair<int, unsigned long long>, std::vector<int>> buckets;
+        for (int g = 0; g < m->n_grid; ++g) {
+            const int n = c->grid_n[g];
+            const int8_t* lv = m->v_level + c->grid_hoff[g];
+            const double* vm = m->v_mid + c->grid_hoff[g] * D;
+            unsigned long long h = 1469598103934665603ull;
+            for (int i = 0; i < n; ++i) h = (h ^ (unsigned char)lv[i]) * 1099511628211ull;
+            unsigned long long b0, b1;
+            memcpy(&b0, vm, 8); memcpy(&b1, vm + (size_t)D * n - 1, 8);
+            h = (h ^ b0) * 1099511628211ull; h = (h ^ b1) * 1099511628211ull;
+            auto& bk = buckets[std::make_pair(n, h)];
+            int canon = g;
+            for (int g2 : bk) {
+                if (memcmp(lv, m->v_level + c->grid_hoff[g2], n) == 0 &&
+                    memcmp(vm, m->v_mid + c->grid_hoff[g2] * D, sizeof(double) * D * n) == 0) { canon = g2; break; }
+            }
+            if (canon == g) bk.push_back(g);
+            c->grid_canon[g] = canon;
+        }
+    }
     const long long gpts_h = c->grid_hoff[m->n_grid], gpts_d = c->grid_goff[m->n_grid];
     c->h_level.assign(m->v_level, m->v_level + gpts_h);
     c->h_vmid = m->v_mid;
@@ -976,7 +1002,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             t.sn_cell = sn0 + q; t.donor = ib->sn_donor[q]; t.solid = ib->sn_solid[q];
             if (t.donor < 0 || t.donor >= c->n_local) throw Fail("sn_donor must be a local cell");
             if (t.solid < 0 || t.solid >= sn0) throw Fail("sn_solid out of range");
-            if (c->cells[t.sn_cell].grid != c->cells[t.donor].grid) throw Fail("a SolidNeighbor shares its donor's velocity grid");
+            if (c->grid_canon[c->cells[t.sn_cell].grid] != c->grid_canon[c->cells[t.donor].grid]) throw Fail("a SolidNeighbor shares its donor's velocity grid");
             t.dir = ib->sn_faceid[q] / 2;
             t.nb_begin = (int)c->ib_nb.size();
             t.nb_count = ib->sn_nb_off[q + 1] - ib->sn_nb_off[q] + 1;
@@ -1016,7 +1042,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     c->dv.df_new = c->dalloc<double>(np * K);
     c->dv.sdf = c->dalloc<double>(np * K * D);
     c->dv.sdl = c->dalloc<double>(np * K * D);
-    c->dv.flux = c->dalloc<double>(np * K);
+    c->dv.flux = nullptr;   // vs_data.flux exists only on the un-fused path: allocated on first use (ensure_flux)
     c->dv.w = c->dalloc<double>((size_t)c->n_cell * M);
     c->dv.prim = c->dalloc<double>((size_t)c->n_cell * M);
     c->dv.mflux = c->dalloc<double>((size_t)c->n_cell * M);
@@ -1029,7 +1055,6 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     CK(cudaMemsetAsync(c->dv.df_new, 0, np * K * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->dv.sdf, 0, np * K * D * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->dv.sdl, 0, np * K * D * sizeof(double), c->stream));
-    CK(cudaMemsetAsync(c->dv.flux, 0, np * K * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->dv.w, 0, (size_t)c->n_cell * M * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->dv.prim, 0, (size_t)c->n_cell * M * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->dv.mflux, 0, (size_t)c->n_cell * M * sizeof(double), c->stream));
@@ -1129,7 +1154,29 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         c->d_sendbuf = c->dalloc<double>((size_t)send_total);
         c->d_recvbuf = c->dalloc<double>((size_t)recv_total);
     }
+    if (getenv("KAMR_VERBOSE")) {
+        for (auto& b : c->bins) {
+            long long pts = 0;
+            for (int cell : b.cells) pts += c->cells[cell].n;
+            fprintf(stderr, "[kamr] phase bin: %zu cells, %lld points, smem %zu, %s%s%s\n", b.cells.size(), pts, b.smem,
+                    b.big ? "big " : "small ", b.regular ? "regular " : "general ", b.mapped ? "mapped" : "");
+        }
+        for (auto& st : c->slope_stages)
+            fprintf(stderr, "[kamr] slope stage %d: %zu regular, %zu regular-mapped, %zu general%s\n", st.wave,
+                    st.reg.size(), st.regm.size(), st.gen.size(), st.flags ? " (flags)" : "");
+        fprintf(stderr, "[kamr] %zu solid cells, %zu solid neighbours, %zu pair maps (%zu ints)\n", c->solid_tasks.size(),
+                c->sn_tasks.size(), c->rel_off.size(), c->pm_start.size());
+    }
     CK(cudaStreamSynchronize(c->stream));
+}
+
+// vs_data.flux (and the SolidNeighbor "reconstruction perturbance" kept in the same array) is only needed by
+// kamr_flux / kamr_iterate, CIP_Marching, Euler and the aux transfers; the fused CAIDVM step never touches it.
+void ensure_flux(kamr_ctx* c) {
+    if (c->dv.flux) return;
+    const size_t n = (size_t)c->npts_pad * c->K;
+    c->dv.flux = c->dalloc<double>(n);
+    CK(cudaMemsetAsync(c->dv.flux, 0, n * sizeof(double), c->stream));
 }
 
 // Synchronises the stream and turns a device-side give-up (DevView::err_flag) into a host error.
@@ -1407,6 +1454,7 @@ void do_ib(kamr_ctx* c, double* df2, cudaStream_t st = nullptr) {
 
 template <int D, int K>
 void do_flux(kamr_ctx* c, double dt) {
+    ensure_flux(c);
     do_ib<D, K>(c, nullptr);
     for (auto& b : c->bins) launch_phase<D, K, MODE_FLUX>(c, b, dt, 0);
     CK(cudaGetLastError());
@@ -1426,6 +1474,7 @@ void fetch_residual(kamr_ctx* c, int want, double* res_out) {
 
 template <int D, int K>
 void do_iterate(kamr_ctx* c, double dt, int want, double* res_out) {
+    ensure_flux(c);
     if (c->gas.marching == KAMR_MARCH_CIP) {
         if (!c->fluid_cells.empty()) {
             Launch L_(c, KID_UPDATE);
@@ -1624,7 +1673,7 @@ int kamr_upload_aux(kamr_ctx* c, const double* sdf, const double* flux, const do
             DISPATCH(c, run_limit, c, c->d_limit_cells, (int)c->limit_cells.size());
             c->raw_sdf_valid = true;
         }
-        if (flux) copy_points(c, c->dv.flux, nullptr, flux, c->K, true);
+        if (flux) { ensure_flux(c); copy_points(c, c->dv.flux, nullptr, flux, c->K, true); }
         if (mflux) CK(cudaMemcpyAsync(c->dv.mflux, mflux, (size_t)c->n_local * c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     });
@@ -1643,7 +1692,7 @@ int kamr_download_state(kamr_ctx* c, uint32_t mask, double* df, double* sdf, dou
                            "or set KAMR_OPT_KEEP_SDF before the step whose slopes the host needs");
             copy_points(c, c->dv.sdf, sdf, nullptr, c->K * D, false);
         }
-        if ((mask & KAMR_DL_FLUX) && flux) copy_points(c, c->dv.flux, flux, nullptr, c->K, false);
+        if ((mask & KAMR_DL_FLUX) && flux) { ensure_flux(c); copy_points(c, c->dv.flux, flux, nullptr, c->K, false); }
         const size_t nl = (size_t)c->n_local;
         if ((mask & KAMR_DL_W) && w) CK(cudaMemcpyAsync(w, c->dv.w, nl * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if ((mask & KAMR_DL_PRIM) && prim) CK(cudaMemcpyAsync(prim, c->dv.prim, nl * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1751,8 +1800,8 @@ int kamr_get_pair_map(kamr_ctx* c, int32_t ga, int32_t gb, int32_t* start, int32
     int rc = 0;
     int g = guarded(c, [&] {
         if (ga < 0 || gb < 0 || ga >= c->n_grid || gb >= c->n_grid) throw Fail("grid id out of range");
-        if (ga == gb) { rc = 1; return; }
-        auto it = c->rel_id.find(std::make_pair((int)ga, (int)gb));
+        if (c->grid_canon[ga] == c->grid_canon[gb]) { rc = 1; return; }
+        auto it = c->rel_id.find(std::make_pair(c->grid_canon[ga], c->grid_canon[gb]));
         if (it == c->rel_id.end()) throw Fail("no relation between these grids in the current topology");
         const int na = c->grid_n[ga];
         if (cap < na + 1) throw Fail("buffer too small");

@@ -342,3 +342,34 @@ def build_rank_view(forest: Forest, grids, cell_grid_global, bc_type, bc_prim, n
         peer_rank=i32(peers), send_off=i32(send_off), send_cells=i32(send_cells), recv_off=i32(recv_off),
         global_ids=gids, ib=host_ib,
     )
+
+
+def uniquify_grids(mesh: HostMesh) -> HostMesh:
+    """The same mesh with one velocity-grid copy per (local or ghost) cell, as a host holds them when every PsData
+    owns its VsData (Velocity_space/Types.jl:5-20) and nothing deduplicates: `cell_grid` becomes the identity.  A
+    SolidNeighbor keeps sharing its donor's grid (Boundary/Immersed_boundary.jl:290-298).  The library recognises
+    identical grids by content, so index maps are unchanged; only the statics stop being cache-resident."""
+    import dataclasses
+    D = mesh.dim
+    nlg = mesh.n_local + mesh.n_ghost
+    go = mesh.grid_off
+    g = mesh.cell_grid[:nlg].astype(np.int64)
+    n = (go[1:] - go[:-1])[g]
+    new_off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    total = int(new_off[-1])
+    within = np.arange(total, dtype=np.int64) - np.repeat(new_off[:-1], n)
+    src = np.repeat(go[g], n) + within
+    v_level = mesh.v_level[src]
+    v_weight = mesh.v_weight[src]
+    v_mid = np.empty(total * D, dtype=np.float64)
+    base_new = np.repeat(new_off[:-1] * D, n)
+    base_old = np.repeat(go[g] * D, n)
+    nn = np.repeat(n, n)
+    for d in range(D):
+        v_mid[base_new + d * nn + within] = mesh.v_mid[base_old + d * nn + within]
+    cell_grid = np.arange(mesh.n_cell, dtype=np.int32)
+    if mesh.n_solidnbr:
+        cell_grid[nlg:] = np.asarray(mesh.ib.sn_donor, dtype=np.int32)
+    return dataclasses.replace(mesh, cell_grid=np.ascontiguousarray(cell_grid), grid_off=new_off,
+                               v_level=np.ascontiguousarray(v_level), v_weight=np.ascontiguousarray(v_weight),
+                               v_mid=v_mid)

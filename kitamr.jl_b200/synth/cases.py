@@ -586,6 +586,11 @@ def airfoil_s3(ps_maxlevel=7, box_level=4, trees=(24, 32), vtrees=60, noise=0.01
 WORKLOADS = {
     "S2": cylinder_s2,
     "S2ib": lambda copies=1: cylinder_s2(copies=copies, ib=True),
+    # the same cases with the dynamically refined box one level finer (54 436 / 45 936 cells): the cell counts SURVEY.md
+    # §8d estimates for S2 / S3 (6e4 / 1e5).  The velocity spaces stay the configs' own (16x16 roots L<=3 -> mean vs_num
+    # 928, where the survey guessed ~1500; 60x60), so the phase-space sizes are 5.0e7 and 1.65e8, not 1e8 and 3.6e8.
+    "S2ib-big": lambda copies=1: cylinder_s2(copies=copies, ib=True, box_level=5),
+    "S3-big": lambda copies=1: airfoil_s3(box_level=5),
     "S4": sphere_s4,
     "S1": lambda copies=1: riemann_s1(),
     "S1caidvm": lambda copies=1: riemann_s1(marching=abi.MARCH_CAIDVM),

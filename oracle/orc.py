@@ -24,15 +24,45 @@ def build(force=False):
 
 
 _lib = None
+_parity_lib = None
+FAST_DIR = os.path.join(HERE, "_fast")
 
 
 def lib():
-    global _lib
+    global _lib, _parity_lib
     if _lib is None:
         build()
         _lib = C.CDLL(LIB)
         _lib.orc_get_tau.restype = C.c_double
+        _parity_lib = _lib
     return _lib
+
+
+def use_fast():
+    """Switch this process (and the workers it forks) to a build of the same source for SPEED: -O3 -march=native,
+    compiled on the machine it runs on.  Only bench.py's timed CPU legs call this; every comparison
+    uses the parity build (-O2 -ffp-contract=off).  Returns a note for the bench line."""
+    global _lib
+    lib()
+    os.makedirs(FAST_DIR, exist_ok=True)
+    out = os.path.join(FAST_DIR, "libkamr_oracle_fast.so")
+    flags = ["-O3", "-march=native", "-std=c99", "-fPIC", "-fno-fast-math"]
+    try:
+        subprocess.check_call([os.environ.get("CC", "gcc")] + flags + ["-shared", "-o", out,
+                                                                     os.path.join(HERE, "kamr_oracle.c"), "-lm"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        fast = C.CDLL(out)
+        fast.orc_get_tau.restype = C.c_double
+        _lib = fast
+        return "built " + " ".join(flags[:2]) + " on this box for the timed leg"
+    except Exception as e:  # pragma: no cover
+        return "fast build failed (%r): timed with the parity build -O2 -ffp-contract=off" % (e,)
+
+
+def use_parity():
+    global _lib
+    lib()
+    _lib = _parity_lib
 
 
 def _p(a):
