@@ -64,6 +64,87 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double* red) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// A physical cell is owned by a thread-block CLUSTER of C CTAs (C = 1, 2, 4, 8): CTA r of the cluster takes the
+// contiguous point range [r*P, (r+1)*P) of the cell, so a CTA never holds more than a few thousand points whatever
+// the size of the velocity grid (the convected f of its range is staged in its shared memory), the number of cells in
+// flight — and with it the L2 footprint of their neighbourhoods — stays bounded, and the three per-cell reductions of
+// the step (moments, heat flux, wall density) go through distributed shared memory.
+template <int C>
+struct Cluster {
+    static __device__ __forceinline__ unsigned rank() {
+        if (C == 1) return 0u;
+        unsigned r;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+        return r;
+    }
+    static __device__ __forceinline__ void sync() {
+        if (C > 1) {
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+    }
+    // the double at the same shared-memory address in CTA r of the cluster
+    static __device__ __forceinline__ double peer(const double* p, unsigned r) {
+        const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+        unsigned ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(r));
+        double v;
+        asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+        return v;
+    }
+};
+
+// Sum of NV doubles over all threads of all CTAs of the cluster, broadcast to every thread.  `xch` (NV doubles of
+// shared memory, a buffer of its own per call site) publishes this CTA's totals to its peers; the ranks are added in
+// rank order by every CTA, so all CTAs hold the same bits.  The caller ends the kernel with Cluster<C>::sync() so that
+// no CTA exits while a peer still reads its buffer.
+template <int NV, int C>
+__device__ __forceinline__ void cluster_reduce(double (&v)[NV], double* red, double* xch) {
+    block_reduce<NV>(v, red);
+    if (C == 1) return;
+    const int nwarp = (blockDim.x + 31) >> 5;
+    if ((int)threadIdx.x < NV) xch[threadIdx.x] = red[nwarp * NV + threadIdx.x];
+    Cluster<C>::sync();
+    if ((int)threadIdx.x < NV) {
+        double x = 0.0;
+#pragma unroll
+        for (int r = 0; r < C; ++r) x += Cluster<C>::peer(xch + threadIdx.x, (unsigned)r);
+        red[threadIdx.x] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = red[k];
+    __syncthreads();
+}
+
+// packed velocity-grid statics (DevView::v_pack / v_tab): tables staged in shared memory, one word per point
+template <int D>
+__device__ __forceinline__ void load_vtab(const DevView& g, double* tab) {
+    const int nw = D * g.n_vtab + VPK_LEVELS;
+    for (int t = threadIdx.x; t < nw; t += blockDim.x) tab[t] = g.v_tab[t];
+}
+template <int D>
+__device__ __forceinline__ void unpack_v(unsigned w, const double* __restrict__ tab, int ntab, double* v) {
+    constexpr unsigned MSK = (1u << VPK_BITS) - 1u;
+    v[0] = tab[w & MSK];
+    v[1] = tab[ntab + ((w >> VPK_BITS) & MSK)];
+    if (D == 3) v[2] = tab[2 * ntab + ((w >> (2 * VPK_BITS)) & MSK)];
+}
+template <int D>
+__device__ __forceinline__ double unpack_wt(unsigned w, const double* __restrict__ tab, int ntab) {
+    return tab[D * ntab + (w >> 27)];
+}
+// bit d = (v_d > 0): the side whose neighbour is upwind (see hot_flux)
+template <int D>
+__device__ __forceinline__ unsigned sign_bits(const double* v) {
+    unsigned sg = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) sg |= (v[d] > 0.) ? (1u << d) : 0u;
+    return sg;
+}
+__host__ __device__ inline size_t vtab_doubles(int D, int ntab) { return (size_t)D * ntab + VPK_LEVELS; }
+
+// ------------------------------------------------------------------------------------------------
 // kinetics (lib/KitCore)
 template <int D>
 __device__ __forceinline__ void get_prim(const double* w, double gamma, double* prim) {
@@ -442,54 +523,114 @@ __device__ __forceinline__ void hot_flux(const DevView& g, const FaceRec* hot, c
     }
 }
 
-// The neighbour-upwind half of fluid/fluid faces whose neighbour lives on a DIFFERENT velocity grid (pair-mapped
-// records, FaceRec::flags bit1 clear), gathered in the same pass as the identical-grid faces: update_micro_flux!,
-// Flux.jl:151-344 in gather form.  Point i of the own grid is covered by / covers points st[i] .. st[i+1]-1 of the
-// neighbour's grid (one entry when the neighbour is equal or coarser there):
-//   fl[k]  += area * micro (mean over the covering finer points / injection from the coarser point)
-//   mac[m] += area * w_j psi(v_j) micro_j      (the neighbour's share of fw, CAIDVM.jl:119)
+// One neighbour point of a pair-mapped gather: what is loaded ...
 template <int D, int K>
-__device__ __forceinline__ void mapped_flux(const DevView& g, const FaceRec* hot, const unsigned char* sb, int i,
-                                            unsigned sg, double dt, double wt, const int8_t* __restrict__ own_lev,
-                                            double* fl, double* mac) {
+struct MapPt {
+    unsigned w;          // packed statics of the neighbour's point
+    double f[K], s[K * D];
+};
+template <int D, int K>
+__device__ __forceinline__ void map_load(MapPt<D, K>& p, const double* __restrict__ nf, const double* __restrict__ nsl,
+                                         const unsigned* __restrict__ npk, int np, int j) {
+    p.w = npk[j];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        p.f[k] = ldg_stream(nf + k * np + j);
+#pragma unroll
+        for (int t = 0; t < D; ++t) p.s[k * D + t] = ldg_stream(nsl + (t * K + k) * np + j);
+    }
+}
+// ... and what it contributes: fl[k] += area * micro (mean over the covering finer points / injection from the coarser
+// point), mac[m] += area * w_j psi(v_j) micro_j (the neighbour's share of fw, CAIDVM.jl:119)
+template <int D, int K>
+__device__ __forceinline__ void map_apply(const MapPt<D, K>& p, const double* __restrict__ tab, int ntab, bool finer,
+                                          int li, const double* fmid, const double* nmid, int d, double A, double wt,
+                                          double dt, double* fl, double* mac) {
+    double vj[D], dx[D], m[K];
+    unpack_v<D>(p.w, tab, ntab, vj);
+#pragma unroll
+    for (int t = 0; t < D; ++t) dx[t] = face_dx(fmid[t], __dmul_rn(vj[t], dt), nmid[t]);
+    double scale = 1.0, wq = wt;
+    if (finer) {
+        scale = 1.0 / (double)(1 << (D * ((int)(p.w >> 27) - li)));
+        wq = unpack_wt<D>(p.w, tab, ntab);
+    }
+    const double vnj = pick<D>(vj, d);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s_dx = 0.0;
+#pragma unroll
+        for (int t = 0; t < D; ++t) s_dx += dx[t] * p.s[k * D + t];
+        m[k] = (p.f[k] + s_dx) * vnj;
+        fl[k] += (A * m[k]) * scale;
+    }
+    add_moments<D, K>(mac, A * wq, vj, m);
+}
+// The pair-mapped neighbour-upwind half of one face for own point i (update_micro_flux!, Flux.jl:151-344 in gather
+// form): the own point is covered by / covers points j0 .. j0+cnt-1 of the neighbour's grid (one entry when the
+// neighbour is equal or coarser there).  Neighbour points are taken two at a time, loads before arithmetic, so a
+// covering set of 2^DIM finer points costs half the memory round trips.
+template <int D, int K>
+__device__ __forceinline__ void mapped_gather(const DevView& g, const double* __restrict__ tab, int ntab,
+                                              const double* __restrict__ nf, const double* __restrict__ nsl,
+                                              long long ngoff, int np, int j0, int cnt, int li, const double* fmid,
+                                              const double* nmid, int d, double A, double wt, double dt, double* fl,
+                                              double* mac) {
+    const unsigned* __restrict__ npk = g.v_pack + ngoff;
+    const bool finer = cnt > 1;
+    for (int j = j0; j < j0 + cnt; j += 2) {
+        MapPt<D, K> a, b;
+        const bool two = j + 1 < j0 + cnt;
+        map_load<D, K>(a, nf, nsl, npk, np, j);
+        if (two) map_load<D, K>(b, nf, nsl, npk, np, j + 1);
+        map_apply<D, K>(a, tab, ntab, finer, li, fmid, nmid, d, A, wt, dt, fl, mac);
+        if (two) map_apply<D, K>(b, tab, ntab, finer, li, fmid, nmid, d, A, wt, dt, fl, mac);
+    }
+}
+
+// Work distribution of the pair-mapped pass: warps draw 32-point batches of the CTA's range from a shared counter, so
+// the points with long gathers (covered by 2^DIM or more finer neighbour points) do not leave the other warps waiting
+// at the next barrier.
+__device__ __forceinline__ int warp_next_batch(int* ctr) {
+    int b = 0;
+    if ((threadIdx.x & 31) == 0) b = atomicAdd(ctr, 32);
+    return __shfl_sync(0xffffffffu, b, 0);
+}
+
+// The macro flux of pair-mapped gathers is summed per 32-point batch with a fixed shuffle tree and kept in a
+// [D+2][batches] table in shared memory; the batches are added in index order afterwards.  The result therefore does
+// not depend on which warp drew which batch: the step stays bit-reproducible.
+template <int NV>
+__device__ __forceinline__ void warp_batch_add(double* mbat, int nb, int b, double (&mac)[NV]) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mac[k] += __shfl_down_sync(0xffffffffu, mac[k], off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) mbat[k * nb + b] += mac[k];
+    }
+}
+__host__ __device__ inline int batch_count(int P) { return (P + 31) / 32 + 1; }
+
+// The neighbour-upwind half of fluid/fluid faces whose neighbour lives on a DIFFERENT velocity grid (pair-mapped
+// records, FaceRec::flags bit1 clear), gathered in a pass of its own (pass A2) after the identical-grid faces.
+template <int D, int K>
+__device__ __forceinline__ void mapped_flux(const DevView& g, const double* __restrict__ tab, int ntab,
+                                            const FaceRec* hot, const unsigned char* sb, int i, unsigned sg, double dt,
+                                            double wt, int li, double* fl, double* mac) {
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const int sn = ((sg >> d) & 1u) ? 0 : 1;
         for (int q = sb[2 * d + sn]; q < sb[2 * d + sn + 1]; ++q) {
             const FaceRec& h = hot[q];
             if (h.flags & 2) continue;   // block-uniform
-            const double* __restrict__ nf = g.df + h.nf_off;
-            const double* __restrict__ nsl = g.sdl + h.nsl_off;
-            const double* __restrict__ nv = g.v_mid + h.ngoff * D;
-            const int np = h.np;
             const int* __restrict__ st = g.pm_start + h.rel_off;
             const int j0 = st[i];
             const int cnt = max(1, st[i + 1] - j0);
-            const double A = h.area;
-            const int li = (cnt > 1) ? (int)own_lev[i] : 0;
-            for (int j = j0; j < j0 + cnt; ++j) {
-                double vj[D], dx[D], m[K];
-#pragma unroll
-                for (int t = 0; t < D; ++t) {
-                    vj[t] = nv[t * np + j];
-                    dx[t] = face_dx(h.fmid[t], __dmul_rn(vj[t], dt), h.nbr_mid[t]);
-                }
-                const double vnj = vj[d];
-                double scale = 1.0, wq = wt;
-                if (cnt > 1) {
-                    scale = 1.0 / (double)(1 << (D * ((int)g.v_level[h.ngoff + j] - li)));
-                    wq = g.v_weight[h.ngoff + j];
-                }
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    double s_dx = 0.0;
-#pragma unroll
-                    for (int t = 0; t < D; ++t) s_dx += dx[t] * ldg_stream(nsl + (t * K + k) * np + j);
-                    m[k] = (ldg_stream(nf + k * np + j) + s_dx) * vnj;
-                    fl[k] += (A * m[k]) * scale;
-                }
-                add_moments<D, K>(mac, A * wq, vj, m);
-            }
+            mapped_gather<D, K>(g, tab, ntab, g.df + h.nf_off, g.sdl + h.nsl_off, h.ngoff, h.np, j0, cnt, li, h.fmid,
+                                h.nbr_mid, d, h.area, wt, dt, fl, mac);
         }
     }
 }
@@ -522,25 +663,32 @@ __device__ __forceinline__ void maxwell_c(const double* v, const double* prim, d
 }
 
 // The update half shared by the phase kernels: given the block-partial sums acc = [macro flux | moments of the
-// convected f] and the convected f staged in fs, finish iterate!(CAIDVM_Marching) (Theory/Iterate.jl:108-126).
-// The point loops of phases 2 and 3 request the velocity-grid statics of TAIL_B2 / TAIL_B3 points before touching any of them, so
-// a thread waits for one L1/L2 round trip per batch instead of one per point.
+// convected f] of this CTA's point range [p0, p1) and the convected f staged in fs, finish iterate!(CAIDVM_Marching)
+// (Theory/Iterate.jl:108-126).  The reductions run over the whole cluster that owns the cell.  The point loops of
+// phases 2 and 3 request the packed statics of TAIL_B2 / TAIL_B3 points before touching any of them, so a thread waits
+// for one round trip per batch instead of one per point.
 #ifndef KAMR_TAIL_B2
-#define KAMR_TAIL_B2 1
+#define KAMR_TAIL_B2 2
 #endif
 #ifndef KAMR_TAIL_B3
 #define KAMR_TAIL_B3 4
 #endif
 constexpr int TAIL_B2 = KAMR_TAIL_B2, TAIL_B3 = KAMR_TAIL_B3;
-template <int D, int K, int MODE, bool STAGE_SMEM, int NT>
-__device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas, int n, int np, double vol, int c,
+template <int D>
+struct TailXch { double a[2 * (D + 2)], q[D]; };   // per-CTA exchange buffers of the two cluster reductions
+
+template <int D, int K, int MODE, bool STAGE_SMEM, int NT, int C>
+__device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas, int p0, int p1, int np, double vol, int c,
                                             double dt, int want_residual, double (&acc)[2 * (D + 2)],
-                                            const double* __restrict__ gv, const double* __restrict__ gwt,
-                                            double* fs, int fstride, double* __restrict__ fout, double* dyn, double* red,
-                                            UpdateShared<D, K>& us, double* w_new, double* w0s) {
-    block_reduce<2 * (D + 2)>(acc, red);
+                                            const unsigned* __restrict__ pk, const double* __restrict__ tab,
+                                            double* fs, int fstride, int soff, double* __restrict__ fout, double* fch,
+                                            double* red, TailXch<D>& xch, UpdateShared<D, K>& us, double* w_new,
+                                            double* w0s) {
+    const int ntab = g.n_vtab;
+    cluster_reduce<2 * (D + 2), C>(acc, red, xch.a);
     // moments -> prim_c, prim, tau and the Maxwellian constants: two independent serial chains of fp64 divisions (and a
-    // pow); lane 0 of warp 0 takes the conserved state, lane 0 of warp 1 the convected one
+    // pow); lane 0 of warp 0 takes the conserved state, lane 0 of warp 1 the convected one.  Every CTA of the cluster
+    // evaluates them from the same bits.
     if (threadIdx.x == 0) {
         acc[D + 1] *= 0.5;
 #pragma unroll
@@ -568,10 +716,7 @@ __device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas,
 #pragma unroll
     for (int m = 0; m < D + 2; ++m) prim_c[m] = us.prim_c[m];
     const double coef_c = us.coef_c, cb_c = us.cb_c;
-    // h-component of M[prim_c]: staged beside f by the small-CTA instantiations; the big-CTA ones (cells of thousands
-    // of points) recompute it in phase 3 instead, which halves (3D1F) their shared memory and lets two cells share an SM
-    constexpr bool STAGE_FC = STAGE_SMEM && NT != PNT_BIG;
-    double* fch = dyn + (size_t)K * n;
+    constexpr bool STAGE_FC = STAGE_SMEM;   // h-component of M[prim_c] staged beside f, re-used by phase 3
     {
         double prim[D + 2];
 #pragma unroll
@@ -580,41 +725,39 @@ __device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas,
         double q[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) q[d] = 0.0;
-        for (int i0 = threadIdx.x; i0 < n; i0 += TAIL_B2 * NT) {
-            double vb[TAIL_B2][D], wb[TAIL_B2];
+        for (int i0 = p0 + threadIdx.x; i0 < p1; i0 += TAIL_B2 * NT) {
+            unsigned wb[TAIL_B2];
 #pragma unroll
             for (int u = 0; u < TAIL_B2; ++u) {
                 const int i = i0 + u * NT;
-                if (i < n) {
-#pragma unroll
-                    for (int t = 0; t < D; ++t) vb[u][t] = gv[t * np + i];
-                    wb[u] = gwt[i];
-                }
+                wb[u] = (i < p1) ? pk[i] : 0u;
             }
 #pragma unroll
             for (int u = 0; u < TAIL_B2; ++u) {
                 const int i = i0 + u * NT;
-                if (i < n) {
-                    double Fc[K], F[K], f[K];
-                    maxwell_c<D, K>(vb[u], prim_c, coef_c, cb_c, Fc);
-                    maxwell_c<D, K>(vb[u], prim, coef, cb, F);
+                if (i < p1) {
+                    double v[D], Fc[K], F[K], f[K];
+                    unpack_v<D>(wb[u], tab, ntab, v);
+                    const double wt = unpack_wt<D>(wb[u], tab, ntab);
+                    maxwell_c<D, K>(v, prim_c, coef_c, cb_c, Fc);
+                    maxwell_c<D, K>(v, prim, coef, cb, F);
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        f[k] = fs[k * fstride + i] + (Fc[k] - F[k]);
-                        fs[k * fstride + i] = f[k];
+                        f[k] = fs[k * fstride + (i - soff)] + (Fc[k] - F[k]);
+                        fs[k * fstride + (i - soff)] = f[k];
                     }
-                    if (STAGE_FC) fch[i] = Fc[0];
+                    if (STAGE_FC) fch[i - soff] = Fc[0];
                     // heat_flux (2D2F.jl:68-88, 3D1F.jl:41-72): q_d = 1/2 sum w c_d (c^2 h + b)
-                    const double gq = wb[u] * (c2_of<D>(vb[u], prim_c) * f[0] + ((K > 1) ? f[1] : 0.0));
+                    const double gq = wt * (c2_of<D>(v, prim_c) * f[0] + ((K > 1) ? f[1] : 0.0));
 #pragma unroll
-                    for (int d = 0; d < D; ++d) q[d] += (vb[u][d] - prim_c[1 + d]) * gq;
+                    for (int d = 0; d < D; ++d) q[d] += (v[d] - prim_c[1 + d]) * gq;
                 }
             }
         }
-        block_reduce<D>(q, red);
+        cluster_reduce<D, C>(q, red, xch.q);
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) { us.qf[d] = 0.5 * q[d]; g.qf[(size_t)c * D + d] = 0.5 * q[d]; }
+            for (int d = 0; d < D; ++d) us.qf[d] = 0.5 * q[d];
         }
         __syncthreads();
     }
@@ -626,36 +769,36 @@ __device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas,
         double qf[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) qf[d] = us.qf[d];
-        for (int i0 = threadIdx.x; i0 < n; i0 += TAIL_B3 * NT) {
-            double vb[TAIL_B3][D];
+        for (int i0 = p0 + threadIdx.x; i0 < p1; i0 += TAIL_B3 * NT) {
+            unsigned wb[TAIL_B3];
 #pragma unroll
             for (int u = 0; u < TAIL_B3; ++u) {
                 const int i = i0 + u * NT;
-                if (i < n) {
-#pragma unroll
-                    for (int t = 0; t < D; ++t) vb[u][t] = gv[t * np + i];
-                }
+                wb[u] = (i < p1) ? pk[i] : 0u;
             }
 #pragma unroll
             for (int u = 0; u < TAIL_B3; ++u) {
                 const int i = i0 + u * NT;
-                if (i < n) {
-                    double Fc[K], Fp[K];
+                if (i < p1) {
+                    double v[D], Fc[K], Fp[K];
+                    unpack_v<D>(wb[u], tab, ntab, v);
                     if (STAGE_FC) {
-                        Fc[0] = fch[i];
+                        Fc[0] = fch[i - soff];
                         if (K > 1) Fc[1] = Fc[0] * cb_c;
                     } else {
-                        maxwell_c<D, K>(vb[u], prim_c, coef_c, cb_c, Fc);
+                        maxwell_c<D, K>(v, prim_c, coef_c, cb_c, Fc);
                     }
-                    shakhov<D, K>(vb[u], Fc, prim_c, qf, gas.Pr, gas.K, Fp);
+                    shakhov<D, K>(v, Fc, prim_c, qf, gas.Pr, gas.K, Fp);
 #pragma unroll
-                    for (int k = 0; k < K; ++k) fout[k * np + i] = fs[k * fstride + i] * a + b * (Fc[k] + Fp[k]);
+                    for (int k = 0; k < K; ++k) fout[k * np + i] = fs[k * fstride + (i - soff)] * a + b * (Fc[k] + Fp[k]);
                 }
             }
         }
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && Cluster<C>::rank() == 0) {
         double* prim_old = g.prim + (size_t)c * (D + 2);
+#pragma unroll
+        for (int d = 0; d < D; ++d) g.qf[(size_t)c * D + d] = us.qf[d];
         if (want_residual) {  // residual_check!, Solver/Finalize.jl:5-11
 #pragma unroll
             for (int m = 0; m < D + 2; ++m) {
@@ -671,11 +814,33 @@ __device__ __forceinline__ void update_tail(const DevView& g, const GasPar& gas,
             g.mflux[(size_t)c * (D + 2) + m] = 0.0;
         }
     }
+    Cluster<C>::sync();   // no CTA leaves while a peer may still read its exchange buffers
 }
 
-template <int D, int K, int MODE, bool STAGE_SMEM, int NT, int MINB>
+// point range of CTA `rank` of a C-CTA cluster on a cell of n points: ranges are multiples of 4 points (32 B)
+template <int C>
+__device__ __forceinline__ void chunk_range(int n, unsigned rank, int& P, int& p0, int& p1) {
+    P = (C == 1) ? ((n + 3) & ~3) : ((((n + C - 1) / C) + 3) & ~3);
+    p0 = min((int)rank * P, n);
+    p1 = min(p0 + P, n);
+}
+__host__ __device__ inline int chunk_points(int n, int C) { return (C == 1) ? ((n + 3) & ~3) : ((((n + C - 1) / C) + 3) & ~3); }
+
+// dynamic shared memory of the phase kernels:
+//   [velocity tables | f: K planes of P | face flux: K planes of P (later the h-plane of M[prim_c]) | moment columns]
+// The fused kernels stage BOTH the cell's f and the gathered face flux of every point of the CTA's range, so the gather
+// loop carries no moment accumulators (they were the registers it spilled); the moments are taken afterwards in a
+// loop over the staged planes.  Kernels with pair-mapped gathers add a [D+2][batches] table for the neighbour-side
+// macro flux (its quadrature runs over the NEIGHBOUR's points, CAIDVM.jl:119), see warp_batch_add.
+template <int D, int K>
+__host__ __device__ inline size_t phase_smem_bytes(int ntab, int P, bool stage, bool mapped) {
+    return sizeof(double) * (((vtab_doubles(D, ntab) + 1) & ~(size_t)1) + (stage ? (size_t)(2 * K) * P : 0) +
+                             (mapped ? (size_t)(D + 2) * batch_count(P) : 0));
+}
+
+template <int D, int K, int MODE, bool STAGE_SMEM, int NT, int MINB, int C>
 __global__ void __launch_bounds__(NT, MINB)
-    phase_kernel(DevView g, GasPar gas, const int* __restrict__ cell_list, double dt, int want_residual) {
+    phase_kernel(DevView g, GasPar gas, const int* __restrict__ cell_list, double dt, int want_residual, int pf_dist) {
     extern __shared__ double dyn[];
     constexpr int NSLOT = (MODE == MODE_UPDATE) ? 1 : MaxSlots<D>::value;
     __shared__ Slot sh_slots[NSLOT];
@@ -685,11 +850,18 @@ __global__ void __launch_bounds__(NT, MINB)
     __shared__ double red[2 * (D + 2) * 33];
     __shared__ CellInfo ci;
     __shared__ UpdateShared<D, K> us;
+    __shared__ TailXch<D> xch;
     __shared__ double w_new[D + 2], w0s[D + 2];
-    const int c = cell_list[blockIdx.x];
+    __shared__ int s_next;
+    const int cidx = blockIdx.x / C;
+    const int c = cell_list[cidx];
     copy_words(g.cells + c, &ci, (int)(sizeof(CellInfo) / sizeof(int)));
+    double* tab = dyn;
+    load_vtab<D>(g, tab);
     __syncthreads();
-    const int n = ci.n, np = ci.np;
+    const int n = ci.n, np = ci.np, ntab = g.n_vtab;
+    int P, p0, p1;
+    chunk_range<C>(n, Cluster<C>::rank(), P, p0, p1);
     const int ns = (MODE == MODE_UPDATE) ? 0 : ci.slot_end - ci.slot_begin;
     const int nrare = (MODE == MODE_UPDATE) ? 0 : ci.rare_count;
     if (MODE != MODE_UPDATE) {
@@ -699,27 +871,43 @@ __global__ void __launch_bounds__(NT, MINB)
             copy_words(g.rare + ci.rare_begin, rare, nrare);
         }
         __syncthreads();
+        // (a reduction over ALL points of the cell: every CTA of the cluster evaluates it, boundary cells only)
         if (ci.flags & CELL_HAS_MAXWELL_WALL) wall_density<D, K>(g, ci, sh_slots, ns, dt, rho_w, red);
     }
     const CellPtr<D, K> own(g, ci);
+    const unsigned* __restrict__ pk = g.v_pack + ci.goff;
     const double dtv = dt / ci.vol;
     double* vflux = g.flux + ci.doff * K;
     double* fout = (MODE == MODE_FUSED ? g.df_new : g.df) + ci.doff * K;
-    double* fs = STAGE_SMEM ? dyn : fout;
-    const int fstride = STAGE_SMEM ? n : np;
+    double* fsm = dyn + ((vtab_doubles(D, ntab) + 1) & ~(size_t)1);
+    double* fs = STAGE_SMEM ? fsm : fout;
+    const int fstride = STAGE_SMEM ? P : np;
+    const int soff = STAGE_SMEM ? p0 : 0;
+    double* fls = fsm + (size_t)K * P;    // staged face flux (SPLIT); afterwards the h-plane of M[prim_c]
+    double* fch = fls;
+    // SPLIT: the fused kernel with shared-memory staging keeps f and the gathered flux of every point in shared memory
+    // and takes the moments in a loop of its own; the other instantiations accumulate them while they gather
+    constexpr bool SPLIT = MODE == MODE_FUSED && STAGE_SMEM;
+    double* mbat = fsm + (STAGE_SMEM ? (size_t)(2 * K) * P : 0);   // [D+2][NB] macro flux of pair-mapped gathers (SPLIT)
+    const int NB = batch_count(P);
 
     // ---- phase 1: face fluxes, convection, moments
     double acc[2 * (D + 2)];  // [0,D+2): macro flux, [D+2, 2D+4): moments of the convected f
 #pragma unroll
     for (int q = 0; q < 2 * (D + 2); ++q) acc[q] = 0.0;
-    const unsigned char* __restrict__ sgn = g.v_sign + ci.goff;
     const bool has_mapped = (ci.flags & CELL_HAS_MAPPED) != 0;
-    for (int i = threadIdx.x; i < n; i += NT) {  // pass A
+    const bool any_pair = MODE != MODE_UPDATE && (has_mapped || nrare > 0);
+    if (SPLIT && any_pair) {
+        for (int t = threadIdx.x; t < (D + 2) * NB; t += NT) mbat[t] = 0.0;
+    }
+    unsigned wnext = (p0 + (int)threadIdx.x < p1) ? pk[p0 + threadIdx.x] : 0u;
+    for (int i = p0 + threadIdx.x; i < p1; i += NT) {  // pass A
         double v[D], f[K], fl[K];
-        const unsigned sg = (MODE != MODE_UPDATE) ? sgn[i] : 0u;
-#pragma unroll
-        for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
-        const double wt = own.wt[i];
+        const unsigned wcur = wnext;
+        if (i + NT < p1) wnext = pk[i + NT];   // the next point's word travels while this point computes
+        unpack_v<D>(wcur, tab, ntab, v);
+        const double wt = unpack_wt<D>(wcur, tab, ntab);
+        const unsigned sg = sign_bits<D>(v);
 #pragma unroll
         for (int k = 0; k < K; ++k) { f[k] = ldg_stream(own.f + k * np + i); fl[k] = 0.0; }
         if (MODE != MODE_UPDATE) {
@@ -729,8 +917,7 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
                 for (int t = 0; t < D; ++t) s[k * D + t] = ldg_stream(own.sl + (t * K + k) * np + i);
             hot_flux<D, K>(g, hot, ci.side_begin, i, sg, dt, v, f, s, fl);
-            add_moments<D, K>(acc, wt, v, fl);
-            if (has_mapped) mapped_flux<D, K>(g, hot, ci.side_begin, i, sg, dt, wt, own.lev, fl, acc);
+            if (!SPLIT) add_moments<D, K>(acc, wt, v, fl);
         } else {
 #pragma unroll
             for (int k = 0; k < K; ++k) { fl[k] = vflux[k * np + i]; vflux[k * np + i] = 0.0; }
@@ -738,30 +925,93 @@ __global__ void __launch_bounds__(NT, MINB)
         if (MODE == MODE_FLUX) {
 #pragma unroll
             for (int k = 0; k < K; ++k) vflux[k * np + i] += fl[k];
+        } else if (SPLIT) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                fs[k * fstride + (i - soff)] = f[k];
+                fls[k * fstride + (i - soff)] = fl[k];
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 f[k] += dtv * fl[k];
-                fs[k * fstride + i] = f[k];
+                fs[k * fstride + (i - soff)] = f[k];
             }
             add_moments<D, K>(acc + (D + 2), wt, v, f);
         }
+    }
+    if (MODE != MODE_UPDATE && has_mapped) {   // pass A2 (block-uniform branch): pair-mapped neighbour-upwind halves
+        if (threadIdx.x == 0) s_next = p0;
+        __syncthreads();
+        for (;;) {
+            const int ib = warp_next_batch(&s_next);
+            if (ib >= p1) break;
+            const int i = ib + (int)(threadIdx.x & 31);
+            const bool on = i < p1;
+            double v[D], flm[K], mac[D + 2];
+            const unsigned wcur = on ? pk[i] : 0u;
+            unpack_v<D>(wcur, tab, ntab, v);
+            const double wt = unpack_wt<D>(wcur, tab, ntab);
+#pragma unroll
+            for (int k = 0; k < K; ++k) flm[k] = 0.0;
+#pragma unroll
+            for (int q = 0; q < D + 2; ++q) mac[q] = 0.0;
+            // the neighbour's share of fw is weighted with the neighbour's points: kept apart from the own-weighted flux
+            if (on) mapped_flux<D, K>(g, tab, ntab, hot, ci.side_begin, i, sign_bits<D>(v), dt, wt, (int)(wcur >> 27), flm, mac);
+            if (SPLIT) warp_batch_add<D + 2>(mbat, NB, (ib - p0) >> 5, mac);
+            if (!on) continue;
+            if (MODE == MODE_FLUX) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) vflux[k * np + i] += flm[k];
+#pragma unroll
+                for (int q = 0; q < D + 2; ++q) acc[q] += mac[q];
+            } else if (SPLIT) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) fs[k * fstride + (i - soff)] += dtv * flm[k];
+            } else {
+#pragma unroll
+                for (int q = 0; q < D + 2; ++q) acc[q] += mac[q];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    flm[k] *= dtv;
+                    fs[k * fstride + (i - soff)] += flm[k];
+                }
+                add_moments<D, K>(acc + (D + 2), wt, v, flm);
+            }
+        }
+        __syncthreads();
     }
     if (MODE != MODE_UPDATE && nrare > 0) {  // pass B (block-uniform branch)
         for (int qq = 0; qq < nrare; ++qq) {
             const Slot& sl = sh_slots[rare[qq]];
             const int kind = sl.kind;
-            for (int i = threadIdx.x; i < n; i += NT) {
-                double v[D], fl[K];
-#pragma unroll
-                for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
-                const double wt = own.wt[i];
+            const bool pair_slot = kind <= SLOT_NBR_SOLID && sl.rel_off >= 0;   // block-uniform
+            for (int ib = p0 + (int)(threadIdx.x & ~31u); ib < p1; ib += NT) {
+                const int i = ib + (int)(threadIdx.x & 31);
+                const bool on = i < p1;
+                double v[D], fl[K], mac[D + 2];
+                const unsigned wcur = on ? pk[i] : 0u;
+                unpack_v<D>(wcur, tab, ntab, v);
+                const double wt = unpack_wt<D>(wcur, tab, ntab);
 #pragma unroll
                 for (int k = 0; k < K; ++k) fl[k] = 0.0;
+#pragma unroll
+                for (int q = 0; q < D + 2; ++q) mac[q] = 0.0;
                 const double vn = pick<D>(v, sl.dir);
                 const double x = sl.rot * vn;
                 const bool own_up = sl.is_here ? (x <= 0.) : (x > 0.);
-                if (kind > SLOT_NBR_SOLID || (kind == SLOT_NBR_SOLID && own_up)) {
+                bool own_weighted = true;   // fl's macro flux is its own moment (false: pair_flux added the neighbour's)
+                bool paired = false;
+                if (SPLIT && pair_slot) {   // (all lanes of the warp: the batch sum below is a warp collective)
+                    paired = on && !own_up;
+                    if (paired) pair_flux<D, K>(g, sl, wt, (int)(wcur >> 27), i, dt, gas.flux_type == KAMR_FLUX_DVM_, fl, mac);
+                    warp_batch_add<D + 2>(mbat, NB, (ib - p0) >> 5, mac);
+                    if (paired) own_weighted = false;
+                }
+                if (!on) continue;
+                if (paired) {
+                    // gathered above
+                } else if (kind > SLOT_NBR_SOLID || (kind == SLOT_NBR_SOLID && own_up)) {
                     double f[K], s[K * D];  // raw (unlimited) slopes
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
@@ -781,7 +1031,7 @@ __global__ void __launch_bounds__(NT, MINB)
                             fl[k] += sl.area * ((f[k] + s_dx) * vn);
                         }
                     }
-                    add_moments<D, K>(acc, wt, v, fl);
+                    if (!SPLIT) add_moments<D, K>(acc, wt, v, fl);
                 } else if (own_up) {
                     continue;  // own half of a pair-mapped fluid slot was gathered in pass A
                 } else if (sl.rel_off < 0) {  // solid side, identical grids: f_wall v_n, CAIDVM.jl:111
@@ -802,22 +1052,59 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
                         for (int k = 0; k < K; ++k) fl[k] += sl.area * (nf[k * sl.nbr_np] * vn);
                     }
-                    add_moments<D, K>(acc, wt, v, fl);
+                    if (!SPLIT) add_moments<D, K>(acc, wt, v, fl);
                 } else {
-                    pair_flux<D, K>(g, sl, wt, own.lev[i], i, dt, gas.flux_type == KAMR_FLUX_DVM_, fl, acc);
+                    pair_flux<D, K>(g, sl, wt, (int)(wcur >> 27), i, dt, gas.flux_type == KAMR_FLUX_DVM_, fl, acc);
                 }
                 if (MODE == MODE_FLUX) {
 #pragma unroll
                     for (int k = 0; k < K; ++k) vflux[k * np + i] += fl[k];
+                } else if (SPLIT) {
+                    if (own_weighted) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) fls[k * fstride + (i - soff)] += fl[k];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) fs[k * fstride + (i - soff)] += dtv * fl[k];
+                    }
                 } else {
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         fl[k] *= dtv;
-                        fs[k * fstride + i] += fl[k];
+                        fs[k * fstride + (i - soff)] += fl[k];
                     }
                     add_moments<D, K>(acc + (D + 2), wt, v, fl);
                 }
             }
+        }
+    }
+    if (SPLIT) {   // moments of the staged planes: macro flux = <psi fl> (+ the pair-mapped batches), then f* = f + dt/V fl
+        if (any_pair) {   // (block-uniform) batches in index order; the energy slots hold un-halved sums like acc's
+            __syncthreads();
+            if ((int)threadIdx.x < D + 2) {
+                double x = 0.0;
+                for (int b = 0; b < NB; ++b) x += mbat[threadIdx.x * NB + b];
+                mbat[threadIdx.x * NB] = x;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int q = 0; q < D + 2; ++q) acc[q] = mbat[q * NB];
+            }
+        }
+        for (int i = p0 + threadIdx.x; i < p1; i += NT) {
+            double v[D], f[K], fl[K];
+            const unsigned wcur = pk[i];
+            unpack_v<D>(wcur, tab, ntab, v);
+            const double wt = unpack_wt<D>(wcur, tab, ntab);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                fl[k] = fls[k * fstride + (i - soff)];
+                f[k] = fs[k * fstride + (i - soff)] + dtv * fl[k];
+                fs[k * fstride + (i - soff)] = f[k];
+            }
+            add_moments<D, K>(acc, wt, v, fl);
+            add_moments<D, K>(acc + (D + 2), wt, v, f);
         }
     }
     if (MODE == MODE_FLUX) {
@@ -831,15 +1118,23 @@ __global__ void __launch_bounds__(NT, MINB)
         }
         return;
     }
-    if (PF_DIST > 0 && MODE == MODE_FUSED && threadIdx.x == NT - 1 && blockIdx.x + PF_DIST < gridDim.x) {
-        const CellInfo* __restrict__ nx = g.cells + cell_list[blockIdx.x + PF_DIST];
-        const long long nd = nx->doff;
-        const unsigned nb = (unsigned)nx->np * 8u;
-        l2_prefetch(g.df + nd * K, nb * K);
-        l2_prefetch(g.sdl + nd * (K * D), nb * (K * D));
+    if (MODE == MODE_FUSED && pf_dist > 0 && threadIdx.x == NT - 1 && (cidx + pf_dist) * C < (int)gridDim.x) {
+        // DRAM -> L2 prefetch of this CTA's point range of the cell pf_dist cells ahead in the launch
+        const CellInfo* __restrict__ nx = g.cells + cell_list[cidx + pf_dist];
+        int P2, q0, q1;
+        chunk_range<C>(nx->n, Cluster<C>::rank(), P2, q0, q1);
+        if (q1 > q0) {
+            const long long nd = nx->doff;
+            const long long nnp = nx->np;
+            const unsigned nb = (unsigned)((q1 - q0 + 1) & ~1) * 8u;
+#pragma unroll
+            for (int k = 0; k < K; ++k) l2_prefetch(g.df + nd * K + k * nnp + q0, nb);
+#pragma unroll
+            for (int k = 0; k < K * D; ++k) l2_prefetch(g.sdl + nd * (K * D) + k * nnp + q0, nb);
+        }
     }
-    update_tail<D, K, MODE, STAGE_SMEM, NT>(g, gas, n, np, ci.vol, c, dt, want_residual, acc, own.v, own.wt, fs, fstride,
-                                            fout, dyn, red, us, w_new, w0s);
+    update_tail<D, K, MODE, STAGE_SMEM, NT, C>(g, gas, p0, p1, np, ci.vol, c, dt, want_residual, acc, pk, tab, fs,
+                                               fstride, soff, fout, fch, red, xch, us, w_new, w0s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -847,58 +1142,67 @@ __global__ void __launch_bounds__(NT, MINB)
 // fluid/fluid face to a same-size neighbour on the same velocity grid, and the face / neighbour midpoints equal the
 // cell's own in the transverse coordinates bit for bit (checked at flatten time; the bulk of every mesh away from level
 // jumps, domain edges, velocity-grid changes and the body).  Same arithmetic as phase_kernel<FUSED> pass A with the
-// structure fixed at compile time: one RegCell record per CTA, no slot loops, no rare pass.  The side whose neighbour
-// is upwind comes from the point's sign byte (L1-resident, one per distinct velocity grid), so all global loads of a
+// structure fixed at compile time: one RegCell record per cluster, no slot loops, no rare pass.  The side whose
+// neighbour is upwind comes from the point's packed word (requested one iteration ahead), so all global loads of a
 // point are requested together; the transverse dx = (x_t - v_t dt) - x_t is formed once per point instead of once per
 // face.
-template <int D, int K, bool STAGE_SMEM, int NT, int MINB, bool MAPPED>
+template <int D, int K, bool STAGE_SMEM, int NT, int MINB, bool MAPPED, int C>
 __global__ void __launch_bounds__(NT, MINB)
-    phase_regular_kernel(DevView g, GasPar gas, const RegCell* __restrict__ recs, double dt, int want_residual) {
+    phase_regular_kernel(DevView g, GasPar gas, const RegCell* __restrict__ recs, double dt, int want_residual,
+                         int pf_dist) {
     extern __shared__ double dyn[];
     __shared__ RegCell rc;
     __shared__ double red[2 * (D + 2) * 33];
     __shared__ UpdateShared<D, K> us;
+    __shared__ TailXch<D> xch;
     __shared__ double w_new[D + 2], w0s[D + 2];
-    copy_words(recs + blockIdx.x, &rc, (int)(sizeof(RegCell) / sizeof(int)));
+    __shared__ int s_next;
+    const int cidx = blockIdx.x / C;
+    copy_words(recs + cidx, &rc, (int)(sizeof(RegCell) / sizeof(int)));
+    double* tab = dyn;
+    load_vtab<D>(g, tab);
     __syncthreads();
-    const int n = rc.n, np = rc.np, c = rc.cell;
-#ifdef KAMR_PF_SELF
-    if (threadIdx.x == NT - 1) {
-        l2_prefetch(g.df + rc.doff * K, (unsigned)np * 8u * K);
-        l2_prefetch(g.sdl + rc.doff * (K * D), (unsigned)np * 8u * (K * D));
-    }
-#endif
+    const int n = rc.n, np = rc.np, c = rc.cell, ntab = g.n_vtab;
+    int P, p0, p1;
+    chunk_range<C>(n, Cluster<C>::rank(), P, p0, p1);
     const double dtv = dt / rc.vol;
     double* __restrict__ fout = g.df_new + rc.doff * K;
-    double* fs = STAGE_SMEM ? dyn : fout;
-    const int fstride = STAGE_SMEM ? n : np;
+    double* fsm = dyn + ((vtab_doubles(D, ntab) + 1) & ~(size_t)1);
+    double* fs = STAGE_SMEM ? fsm : fout;
+    const int fstride = STAGE_SMEM ? P : np;
+    const int soff = STAGE_SMEM ? p0 : 0;
+    double* fls = fsm + (size_t)K * P;    // staged face flux (SPLIT); afterwards the h-plane of M[prim_c]
+    double* fch = fls;
+    constexpr bool SPLIT = STAGE_SMEM;    // see phase_kernel
+    double* mbat = fsm + (size_t)(2 * K) * P;   // [D+2][NB] macro flux of the pair-mapped gathers (MAPPED && SPLIT)
+    const int NB = batch_count(P);
     const double* __restrict__ gdf = g.df;
     const double* __restrict__ gsl = g.sdl;
-    const double* __restrict__ gv = g.v_mid + rc.goff * D;
-    const double* __restrict__ gwt = g.v_weight + rc.goff;
-    const unsigned char* __restrict__ sgn = g.v_sign + rc.goff;
+    const unsigned* __restrict__ pk = g.v_pack + rc.goff;
     const double* __restrict__ of = gdf + rc.doff * K;
     const double* __restrict__ os = gsl + rc.doff * K * D;
     double acc[2 * (D + 2)];
 #pragma unroll
     for (int q = 0; q < 2 * (D + 2); ++q) acc[q] = 0.0;
+    if (MAPPED && SPLIT) {
+        for (int t = threadIdx.x; t < (D + 2) * NB; t += NT) mbat[t] = 0.0;
+    }
+    unsigned wnext = (p0 + (int)threadIdx.x < p1) ? pk[p0 + threadIdx.x] : 0u;
 #pragma unroll UNROLL
-    for (int i = threadIdx.x; i < n; i += NT) {
+    for (int i = p0 + threadIdx.x; i < p1; i += NT) {
         double v[D], vdt[D], tdx[D], f[K], s[K * D], fl[K];
         double nfv[D][K], nsv[D][K * D];
         bool mapped[D];
-        int mj0[D], mj1[D];
-        const unsigned sg = sgn[i];
+        const unsigned wcur = wnext;
+        if (i + NT < p1) wnext = pk[i + NT];
+        unpack_v<D>(wcur, tab, ntab, v);
+        const double wt = unpack_wt<D>(wcur, tab, ntab);
+        const unsigned sg = sign_bits<D>(v);
 #pragma unroll
         for (int d = 0; d < D; ++d) {  // neighbour-upwind side: low face for v_d > 0, high face otherwise
             const RegSide& hs = rc.side[2 * d + (((sg >> d) & 1u) ? 0 : 1)];
             mapped[d] = MAPPED && hs.rel_off >= 0;
-            if (mapped[d]) {   // pair-mapped neighbour: gathered below; its index range is requested now, with the rest
-                const int* __restrict__ st = g.pm_start + hs.rel_off;
-                mj0[d] = st[i];
-                mj1[d] = st[i + 1];
-                continue;
-            }
+            if (mapped[d]) continue;   // pair-mapped neighbour: gathered in pass A2
             const long long nd = hs.ndoff;
             const double* __restrict__ nf = gdf + nd * K + i;
             const double* __restrict__ nsl = gsl + nd * (K * D) + i;
@@ -909,9 +1213,6 @@ __global__ void __launch_bounds__(NT, MINB)
                 for (int t = 0; t < D; ++t) nsv[d][k * D + t] = ldg_stream(nsl + (t * K + k) * np);
             }
         }
-#pragma unroll
-        for (int t = 0; t < D; ++t) v[t] = gv[t * np + i];
-        const double wt = gwt[i];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             f[k] = ldg_stream(of + k * np + i);
@@ -953,62 +1254,117 @@ __global__ void __launch_bounds__(NT, MINB)
                 }
             }
         }
-        add_moments<D, K>(acc, wt, v, fl);
-        if (MAPPED) {
-            // neighbour-upwind halves across faces to another velocity grid (update_micro_flux!, Flux.jl:151-344 in
-            // gather form, as mapped_flux): point i is covered by / covers points st[i] .. st[i+1]-1 over there
+        if (SPLIT) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                fs[k * fstride + (i - soff)] = f[k];
+                fls[k * fstride + (i - soff)] = fl[k];
+            }
+        } else {
+            add_moments<D, K>(acc, wt, v, fl);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                f[k] += dtv * fl[k];
+                fs[k * fstride + (i - soff)] = f[k];
+            }
+            add_moments<D, K>(acc + (D + 2), wt, v, f);
+        }
+    }
+    if (MAPPED) {
+        // pass A2: neighbour-upwind halves across faces to another velocity grid (update_micro_flux!, Flux.jl:151-344 in
+        // gather form): point i is covered by / covers points st[i] .. st[i+1]-1 over there.  Its macro flux is weighted
+        // with the NEIGHBOUR's points, so it is kept apart from the own-weighted flux (per-thread columns / acc).
+        if (threadIdx.x == 0) s_next = p0;
+        __syncthreads();
+        for (;;) {
+            const int ib = warp_next_batch(&s_next);
+            if (ib >= p1) break;
+            const int i = ib + (int)(threadIdx.x & 31);
+            const bool on = i < p1;
+            double v[D], flm[K], mac[D + 2];
+            const unsigned wcur = on ? pk[i] : 0u;
+            unpack_v<D>(wcur, tab, ntab, v);
+            const double wt = unpack_wt<D>(wcur, tab, ntab);
+            const unsigned sg = sign_bits<D>(v);
+#pragma unroll
+            for (int k = 0; k < K; ++k) flm[k] = 0.0;
+#pragma unroll
+            for (int q = 0; q < D + 2; ++q) mac[q] = 0.0;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                if (!mapped[d]) continue;
                 const RegSide& h = rc.side[2 * d + (((sg >> d) & 1u) ? 0 : 1)];
-                const double* __restrict__ nf = gdf + h.ndoff * K;
-                const double* __restrict__ nsl = gsl + h.ndoff * (K * D);
-                const double* __restrict__ nv = g.v_mid + h.ngoff * D;
-                const int nnp = h.np;
-                const int j0 = mj0[d];
-                const int cnt = max(1, mj1[d] - j0);
-                const double A = h.area;
-                const int li = (cnt > 1) ? (int)g.v_level[rc.goff + i] : 0;
-                for (int j = j0; j < j0 + cnt; ++j) {
-                    double vj[D], dx[D], m[K];
+                if (h.rel_off < 0 || !on) continue;
+                const int* __restrict__ st = g.pm_start + h.rel_off;
+                const int j0 = st[i];
+                const int cnt = max(1, st[i + 1] - j0);
+                double fm[D], nm[D];
 #pragma unroll
-                    for (int t = 0; t < D; ++t) {
-                        vj[t] = nv[t * nnp + j];
-                        dx[t] = face_dx(t == d ? h.fmid : rc.mid[t], __dmul_rn(vj[t], dt), t == d ? h.nmid : rc.mid[t]);
-                    }
-                    double scale = 1.0, wq = wt;
-                    if (cnt > 1) {
-                        scale = 1.0 / (double)(1 << (D * ((int)g.v_level[h.ngoff + j] - li)));
-                        wq = g.v_weight[h.ngoff + j];
-                    }
+                for (int t = 0; t < D; ++t) { fm[t] = (t == d) ? h.fmid : rc.mid[t]; nm[t] = (t == d) ? h.nmid : rc.mid[t]; }
+                mapped_gather<D, K>(g, tab, ntab, gdf + h.ndoff * K, gsl + h.ndoff * (K * D), h.ngoff, h.np, j0, cnt,
+                                    (int)(wcur >> 27), fm, nm, d, h.area, wt, dt, flm, mac);
+            }
+            if (SPLIT) warp_batch_add<D + 2>(mbat, NB, (ib - p0) >> 5, mac);
+            if (!on) continue;
+            if (SPLIT) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        double s_dx = 0.0;
+                for (int k = 0; k < K; ++k) fs[k * fstride + (i - soff)] += dtv * flm[k];
+            } else {
 #pragma unroll
-                        for (int t = 0; t < D; ++t) s_dx += dx[t] * nsl[(t * K + k) * nnp + j];
-                        m[k] = (nf[k * nnp + j] + s_dx) * vj[d];
-                        fl[k] += (A * m[k]) * scale;
-                    }
-                    add_moments<D, K>(acc, A * wq, vj, m);
+                for (int q = 0; q < D + 2; ++q) acc[q] += mac[q];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    flm[k] *= dtv;
+                    fs[k * fstride + (i - soff)] += flm[k];
                 }
+                add_moments<D, K>(acc + (D + 2), wt, v, flm);
             }
         }
+        __syncthreads();
+    }
+    if (SPLIT) {   // moments of the staged planes: macro flux = <psi fl> (+ the pair-mapped columns), then f* = f + dt/V fl
+        if (MAPPED) {   // batches in index order (the barrier at the end of pass A2 ordered the table)
+            if ((int)threadIdx.x < D + 2) {
+                double x = 0.0;
+                for (int b = 0; b < NB; ++b) x += mbat[threadIdx.x * NB + b];
+                mbat[threadIdx.x * NB] = x;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            f[k] += dtv * fl[k];
-            fs[k * fstride + i] = f[k];
+                for (int q = 0; q < D + 2; ++q) acc[q] = mbat[q * NB];
+            }
         }
-        add_moments<D, K>(acc + (D + 2), wt, v, f);
+        for (int i = p0 + threadIdx.x; i < p1; i += NT) {
+            double v[D], f[K], fl[K];
+            const unsigned wcur = pk[i];
+            unpack_v<D>(wcur, tab, ntab, v);
+            const double wt = unpack_wt<D>(wcur, tab, ntab);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                fl[k] = fls[k * fstride + (i - soff)];
+                f[k] = fs[k * fstride + (i - soff)] + dtv * fl[k];
+                fs[k * fstride + (i - soff)] = f[k];
+            }
+            add_moments<D, K>(acc, wt, v, fl);
+            add_moments<D, K>(acc + (D + 2), wt, v, f);
+        }
     }
-    if (PF_DIST > 0 && threadIdx.x == NT - 1 && blockIdx.x + PF_DIST < gridDim.x) {
-        const RegCell* __restrict__ nx = recs + blockIdx.x + PF_DIST;
-        const long long nd = nx->doff;
-        const unsigned nb = (unsigned)nx->np * 8u;
-        l2_prefetch(gdf + nd * K, nb * K);
-        l2_prefetch(gsl + nd * (K * D), nb * (K * D));
+    if (pf_dist > 0 && threadIdx.x == NT - 1 && (cidx + pf_dist) * C < (int)gridDim.x) {
+        const RegCell* __restrict__ nx = recs + cidx + pf_dist;
+        int P2, q0, q1;
+        chunk_range<C>(nx->n, Cluster<C>::rank(), P2, q0, q1);
+        if (q1 > q0) {
+            const long long nd = nx->doff;
+            const long long nnp = nx->np;
+            const unsigned nb = (unsigned)((q1 - q0 + 1) & ~1) * 8u;
+#pragma unroll
+            for (int k = 0; k < K; ++k) l2_prefetch(gdf + nd * K + k * nnp + q0, nb);
+#pragma unroll
+            for (int k = 0; k < K * D; ++k) l2_prefetch(gsl + nd * (K * D) + k * nnp + q0, nb);
+        }
     }
-    update_tail<D, K, MODE_FUSED, STAGE_SMEM, NT>(g, gas, n, np, rc.vol, c, dt, want_residual, acc, gv, gwt, fs, fstride,
-                                                  fout, dyn, red, us, w_new, w0s);
+    update_tail<D, K, MODE_FUSED, STAGE_SMEM, NT, C>(g, gas, p0, p1, np, rc.vol, c, dt, want_residual, acc, pk, tab, fs,
+                                                     fstride, soff, fout, fch, red, xch, us, w_new, w0s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1378,14 +1734,51 @@ __device__ __forceinline__ double minmod(double a, double b) {
     return pos ? m : (neg ? -m : 0.0);
 }
 
-// accumulated difference to the neighbours of one side
-template <int D, int K, bool GENERIC>
-__device__ __forceinline__ void side_sum(const DevView& g, const SlopeNbr* nb, int cnt, int i, int li,
-                                         const double* f, double* acc) {
+// N same-grid neighbours of one side, compile-time count: loads first, arithmetic after (a side of 2^(DIM-1) finer
+// neighbours costs one memory round trip instead of one per neighbour).  The raw slopes of a projecting neighbour are
+// requested with its value.
+template <int D, int K, int N>
+__device__ __forceinline__ void side_sum_fixed(const DevView& g, const SlopeNbr* nb, int i, const double* f, double* acc) {
+    double nfv[N][K], nsv[N][K][D];
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+        const double* __restrict__ nf = g.df + nb[a].doff * K + i;
+        const double* __restrict__ nsd = g.sdf + nb[a].doff * (K * D) + i;
+        const int np = nb[a].np;
+        const bool pj = nb[a].proj != 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            nfv[a][k] = nf[k * np];
+#pragma unroll
+            for (int t = 0; t < D; ++t) nsv[a][k][t] = pj ? nsd[(t * K + k) * np] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+        const bool pj = nb[a].proj != 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double proj = nfv[a][k];
+            if (pj) {
+#pragma unroll
+                for (int t = 0; t < D; ++t) proj += nb[a].dm[t] * nsv[a][k][t];
+            }
+            acc[k] += f[k] - proj;
+        }
+    }
+}
+
+// accumulated difference to the neighbours of one side: the general case (neighbours on other velocity grids, any count)
+template <int K> struct KVec { double v[K]; };
+template <int D, int K>
+__device__ __forceinline__ KVec<K> side_sum_slow(const DevView& g, const SlopeNbr* nb, int cnt, int i, int li, KVec<K> f) {
+    KVec<K> acc;
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc.v[k] = 0.0;
     for (int a = 0; a < cnt; ++a) {
         const SlopeNbr& e = nb[a];
         const int np = e.np;
-        if (!GENERIC || e.rel_off < 0) {
+        if (e.rel_off < 0) {
             const double* __restrict__ nf = g.df + e.doff * K + i;
             const double* __restrict__ nsd = g.sdf + e.doff * (K * D) + i;
 #pragma unroll
@@ -1395,7 +1788,7 @@ __device__ __forceinline__ void side_sum(const DevView& g, const SlopeNbr* nb, i
 #pragma unroll
                     for (int t = 0; t < D; ++t) proj += e.dm[t] * nsd[(t * K + k) * np];
                 }
-                acc[k] += f[k] - proj;
+                acc.v[k] += f.v[k] - proj;
             }
         } else {
             // pair-mapped neighbour (mismatched velocity grids): mean over the covering finer points or
@@ -1415,11 +1808,37 @@ __device__ __forceinline__ void side_sum(const DevView& g, const SlopeNbr* nb, i
 #pragma unroll
                         for (int t = 0; t < D; ++t) proj += e.dm[t] * nsd[(t * K + k) * np + j];
                     }
-                    acc[k] += (f[k] - proj) * scale;
+                    acc.v[k] += (f.v[k] - proj) * scale;
                 }
             }
         }
     }
+    return acc;
+}
+
+template <int D, int K, bool GENERIC>
+__device__ __forceinline__ void side_sum(const DevView& g, const SlopeNbr* nb, int cnt, int i, int li,
+                                         const double* f, double* acc) {
+    // Block-uniform fast path: every neighbour of the side lives on the cell's own velocity grid (point i <-> point i)
+    constexpr int MAXN = 1 << (D - 1);
+#ifdef KAMR_SLOPE_V2
+    bool same = cnt == 1 || cnt == MAXN;
+#else
+    bool same = false;
+#endif
+    if (GENERIC)
+        for (int a = 0; a < cnt; ++a) same = same && nb[a].rel_off < 0;
+    if (same) {
+        if (cnt == 1) side_sum_fixed<D, K, 1>(g, nb, i, f, acc);
+        else side_sum_fixed<D, K, MAXN>(g, nb, i, f, acc);
+        return;
+    }
+    KVec<K> fv;
+#pragma unroll
+    for (int k = 0; k < K; ++k) fv.v[k] = f[k];
+    const KVec<K> r = side_sum_slow<D, K>(g, nb, cnt, i, li, fv);
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] += r.v[k];
 }
 
 // Besides the reference's sdf (raw slopes) the kernel leaves the LIMITED slopes r*sdf in g.sdl, with
@@ -1439,8 +1858,13 @@ __device__ __forceinline__ void side_sum(const DevView& g, const SlopeNbr* nb, i
 // cannot deadlock under MPS, time-slicing or a debugger.  The spin is bounded all the same: on expiry the kernel
 // raises g.err_flag (surfaced by the next kamr_sync / download / residual read as an error) instead of hanging.
 constexpr unsigned SLOPE_SPIN_LIMIT = 1u << 25;   // x 64 ns sleep: seconds
+#ifdef KAMR_SLOPE_V2
+#define KAMR_SLOPE_THREADS 768
+#else
+#define KAMR_SLOPE_THREADS 1024
+#endif
 template <int D, int K, bool GENERIC, int NT>
-__global__ void __launch_bounds__(NT, 1024 / NT) slope_kernel(DevView g, const SlopeTask* __restrict__ tasks, int raw_all,
+__global__ void __launch_bounds__(NT, KAMR_SLOPE_THREADS / NT) slope_kernel(DevView g, const SlopeTask* __restrict__ tasks, int raw_all,
                                                    int epoch, unsigned* __restrict__ ticket, unsigned ticket_base) {
     __shared__ SlopeTask tk;
     __shared__ CellInfo ci;
@@ -1561,7 +1985,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) slope_kernel(DevView g, const S
 #pragma unroll
         for (int k = 0; k < K; ++k) f[k] = own.f[k * np + i];
         const int li = GENERIC ? (int)own.lev[i] : 0;
+        // (the direction loop stays rolled: s[d] is indexed at run time and lives in local memory, a few L1-resident
+        // bytes per point, in exchange for a kernel a third of the size — unrolled it overflowed the instruction cache)
+#ifdef KAMR_SLOPE_V2
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int d = 0; d < D; ++d) {
             const SlopeDir& sd = tk.d[d];
             const int mode = sd.mode;
@@ -1611,7 +2041,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) slope_kernel(DevView g, const S
 // side, all 2*DIM neighbour values requested up front.  MAPPED (SlopeRegMap): neighbours may live on other velocity
 // grids; their point indices come from the pair maps (mean over covering finer points, diff_vs! Slope.jl:29-64).
 template <int D, int K, int NT, bool MAPPED>
-__global__ void __launch_bounds__(NT) slope_regular_kernel(DevView g, const void* __restrict__ tasks_, int raw_all) {
+__global__ void __launch_bounds__(NT) slope_regular_kernel(DevView g, const void* __restrict__ tasks_, int raw_all,
+                                                           int pf_dist) {
     using Task = typename std::conditional<MAPPED, SlopeRegMap, SlopeReg>::type;
     const Task* __restrict__ tasks = reinterpret_cast<const Task*>(tasks_);
     __shared__ Task tkm;
@@ -1622,8 +2053,8 @@ __global__ void __launch_bounds__(NT) slope_regular_kernel(DevView g, const void
     const int n = tk.n, np = tk.np;
     const bool raw = raw_all || (tk.flags & 1);
     const double* __restrict__ df = g.df;
-    if (PF_DIST > 0 && threadIdx.x == NT - 1 && blockIdx.x + PF_DIST < gridDim.x) {
-        const SlopeReg* __restrict__ nx = reinterpret_cast<const SlopeReg*>(tasks + blockIdx.x + PF_DIST);
+    if (pf_dist > 0 && threadIdx.x == NT - 1 && blockIdx.x + pf_dist < gridDim.x) {
+        const SlopeReg* __restrict__ nx = reinterpret_cast<const SlopeReg*>(tasks + blockIdx.x + pf_dist);
         l2_prefetch(df + nx->doff * K, (unsigned)nx->np * 8u * K);
     }
     const double* __restrict__ own = df + tk.doff * K;
@@ -2033,6 +2464,44 @@ __global__ void __launch_bounds__(256) copy_segments_kernel(const CopySeg* __res
         const double* a = src + sg.src;
         double* b = dst + sg.dst;
         for (long long t = threadIdx.x; t < sg.len; t += blockDim.x) b[t] = a[t];
+    }
+}
+
+// One-sided halo: segments of a local array stored into the peers' arrays (peer pointers mapped with CUDA IPC; the
+// stores travel over NVLink).  One block per segment, grid-stride over segments; 128-bit stores (blocks are 32-byte
+// aligned and their lengths multiples of 4 doubles).
+__global__ void __launch_bounds__(256) put_segments_kernel(const PutSeg* __restrict__ segs, int nseg,
+                                                           const double* __restrict__ src, double* const* __restrict__ dst) {
+    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+        const PutSeg sg = segs[s];
+        const double2* a = reinterpret_cast<const double2*>(src + sg.src);
+        double2* b = reinterpret_cast<double2*>(dst[sg.peer] + sg.dst);
+        for (int t = threadIdx.x; t < sg.len / 2; t += blockDim.x) b[t] = a[t];
+    }
+}
+// After the puts of one message: make them visible system-wide, then raise the message's flag in every receiving
+// peer's memory (slot [my rank][kind] of its flag table) to `epoch`.  Stream order puts this after the put kernel.
+__global__ void halo_signal_kernel(int* const* __restrict__ peer_flags, const int* __restrict__ peer_sel, int nsel, int slot,
+                                   int epoch) {
+    if ((int)threadIdx.x < nsel) {
+        __threadfence_system();
+        volatile int* f = peer_flags[peer_sel[threadIdx.x]] + slot;
+        *f = epoch;
+    }
+}
+// Before the first kernel that reads a message's ghost blocks: wait until every sending peer has raised its flag.
+// Bounded: on expiry the kernel raises err_flag (surfaced at the next sync point) instead of hanging the device.
+constexpr unsigned HALO_SPIN_LIMIT = 1u << 26;
+__global__ void halo_wait_kernel(const int* __restrict__ flags, const int* __restrict__ slots, int nsel, int epoch,
+                                 int* err_flag) {
+    if ((int)threadIdx.x < nsel) {
+        const volatile int* f = flags + slots[threadIdx.x];
+        unsigned spins = 0;
+        while (*f - epoch < 0) {   // (monotone counters; wrap-safe comparison)
+            __nanosleep(100);
+            if (++spins > HALO_SPIN_LIMIT) { atomicExch(err_flag, 2); break; }
+        }
+        __threadfence_system();
     }
 }
 

@@ -57,15 +57,28 @@ struct DBuf {
     size_t n = 0;
 };
 
-constexpr size_t BIG_SMEM = 32 << 10;   // a cell whose staged block (f + M[prim_c]) exceeds this is "big"
+#ifndef KAMR_SMALL_N
+#define KAMR_SMALL_N 1024
+#endif
+#ifndef KAMR_CHUNK_BYTES
+#define KAMR_CHUNK_BYTES 65536
+#endif
+constexpr int SMALL_N = KAMR_SMALL_N;   // cells up to this many points: one 128-thread CTA
+constexpr int CHUNK_BYTES = KAMR_CHUNK_BYTES;   // larger cells: 256-thread CTAs whose staged f + flux planes take at most
+                                                // this much shared memory (2D2F: 2048 points, 3D1F: 4096), 1..8 per cell
 
+// One launch of a phase kernel: cells of one kernel class whose point ranges per CTA fall in one size class.
 struct Bin {
     std::vector<int> cells;
     int* d_cells = nullptr;
-    size_t smem = 0;     // dynamic shared memory per block (0 => global staging)
-    bool big = false;      // cells of thousands of points: large CTAs, M[prim_c] not staged
+    int C = 1;             // CTAs per cell (thread-block cluster size): 1, 2, 4 or 8
+    int P = 0;             // largest point range of one CTA in this bin (sizes the staging area)
+    bool wide = false;     // 256-thread CTAs (cells of more than SMALL_N points), else 128-thread CTAs
+    bool stage = true;     // convected f staged in shared memory (false: in the output array; only giant cells)
     bool regular = false;  // all cells are CELL_REGULAR / CELL_REGULAR_MAPPED: phase_regular_kernel
     bool mapped = false;   // ... CELL_REGULAR_MAPPED: the MAPPED instantiation
+    bool halo = false;     // cells that read ghost data: launched after the halo has arrived
+    int pf_dist = 0;       // L2 prefetch distance in cells of this launch
     RegCell* d_recs = nullptr;  // regular bins: one record per cell, in launch order
 };
 
@@ -97,6 +110,28 @@ struct PeerPlan {
     unsigned long long early = 0;             // waves whose slopes this pair exchanges right after the wave
     Lvl solid;                                // df of solid ghost cells, mid-flux (Boundary/Parallel.jl:138-259)
     long long send_base = 0, recv_base = 0;  // offsets of this peer's region in the staging buffers
+};
+
+// One-sided halo over NVLink.  Message kinds; a peer raises flag [sender rank][kind] in the receiver's
+// flag table when its puts of that kind have landed.
+enum { HK_DF = 0, HK_SOLID = 1, HK_SDF_FINAL = 2, HK_SDF_EARLY = 3, HK_SLOTS = 3 + 64 };
+struct HaloMsg {
+    std::vector<PutSeg> segs;      // what this rank stores where
+    PutSeg* d_segs = nullptr;
+    std::vector<int> to;           // peer indices that receive this kind from this rank
+    int* d_to = nullptr;
+    std::vector<int> from;         // flag slots of the peers this rank receives this kind from
+    int* d_from = nullptr;
+    int epoch = 0;                 // messages of this kind sent so far (all ranks count alike)
+};
+struct P2P {
+    bool on = false;
+    int* d_flags = nullptr;                  // [nranks][HK_SLOTS], written by the peers
+    std::vector<void*> opened;               // cudaIpcOpenMemHandle results (closed at the next re-flatten)
+    double** d_pdf[2] = {nullptr, nullptr};  // per peer: its two df allocations
+    double** d_psdf = nullptr;               // per peer: its raw-slope array
+    int** d_pflags = nullptr;                // per peer: its flag table
+    std::map<int, HaloMsg> msg;
 };
 
 }  // namespace
@@ -137,6 +172,8 @@ struct kamr_ctx {
         SlopeRegMap* d_regm = nullptr;
         SlopeTask* d_gen = nullptr;
         bool flags = false;   // gen tasks carry dependency lists
+        int pf_reg = 0, pf_regm = 0;   // L2 prefetch distances (tasks) of the two regular launches
+        int reg_int = 0, regm_int = 0, gen_int = 0;   // leading tasks of each list that read no ghost data ("interior")
     };
     std::vector<SlopeStage> slope_stages;
     std::vector<int> slope_deps;
@@ -177,6 +214,12 @@ struct kamr_ctx {
     size_t d_stage_doubles = 0;
     long long* d_host_off = nullptr;
     // halo
+    P2P p2p;
+    int df_parity = 0;             // which of the two df allocations is current (peers swap in lockstep)
+    bool df_wait_pending = false;  // the df halo of the last step was sent; its arrival has not been waited for yet
+    cudaStream_t comm_stream = nullptr;   // puts run here, beside the kernels of the main stream
+    cudaEvent_t ev_put_ready = nullptr, ev_put_done = nullptr;
+    bool put_in_flight = false;
     ncclComm_t comm = nullptr;
     std::vector<PeerPlan> peers;
     double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
@@ -208,6 +251,7 @@ struct kamr_ctx {
     }
     void free_topology() {
         if (stream) cudaStreamSynchronize(stream);
+        if (comm_stream) cudaStreamSynchronize(comm_stream);
         for (void* p : allocs) cudaFree(p);
         allocs.clear();
         device_bytes = 0;
@@ -220,6 +264,9 @@ struct kamr_ctx {
         d_res = nullptr; d_sendbuf = d_recvbuf = nullptr; d_fluid_cells = nullptr; d_limit_cells = nullptr;
         limit_cells.clear(); raw_sdf_valid = false;
         peer_early.clear(); early_mask = 0; d_ghost_fluid = nullptr; n_ghost_fluid = 0; merged_segs.clear();
+        for (void* q : p2p.opened) cudaIpcCloseMemHandle(q);
+        p2p = P2P{};
+        df_parity = 0; df_wait_pending = false; put_in_flight = false;
         solid_tasks.clear(); sn_tasks.clear(); ib_nb.clear(); d_solid_tasks = nullptr; d_sn_tasks = nullptr;
     }
 };
@@ -442,6 +489,8 @@ void transverse_dir(kamr_ctx* c, const kamr_mesh* m, int cell, int dir, SlopeDir
     }
 }
 
+void setup_p2p(kamr_ctx* c, const kamr_mesh* m);
+
 void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     const int D = c->D, K = c->K, M = c->M;
     c->free_topology();
@@ -547,6 +596,59 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             for (int i = 0; i < np; ++i)
                 for (int d = 0; d < D; ++d)
                     if (vm[go * D + (size_t)d * np + i] > 0.) sg[go + i] |= (unsigned char)(1u << d);
+        }
+        {   // packed statics: per-axis tables of the distinct coordinates, weight by level, one word per point
+            std::vector<std::vector<double>> tab(D);
+            for (int d = 0; d < D; ++d) {
+                std::vector<double>& t = tab[d];
+                for (int g = 0; g < m->n_grid; ++g) {
+                    if (c->grid_canon[g] != g) continue;
+                    const double* p = vm.data() + c->grid_goff[g] * D + (size_t)d * c->grid_np[g];
+                    t.insert(t.end(), p, p + c->grid_n[g]);
+                    std::sort(t.begin(), t.end());
+                    t.erase(std::unique(t.begin(), t.end()), t.end());
+                }
+                if ((int)t.size() > (1 << VPK_BITS))
+                    throw Fail("more than " + std::to_string(1 << VPK_BITS) + " distinct velocity coordinates on one axis");
+            }
+            int ntab = 1;
+            for (int d = 0; d < D; ++d) ntab = std::max<int>(ntab, (int)tab[d].size());
+            ntab = (int)round_up(ntab, 2);
+            std::vector<double> vt((size_t)D * ntab + VPK_LEVELS, 0.0);
+            for (int d = 0; d < D; ++d) std::copy(tab[d].begin(), tab[d].end(), vt.begin() + (size_t)d * ntab);
+            std::vector<char> have(VPK_LEVELS, 0);
+            std::vector<unsigned> pk(gpts_d, 0u);
+            for (int g = 0; g < m->n_grid; ++g) {
+                const int np = c->grid_np[g];
+                const long long go = c->grid_goff[g];
+                const int cg = c->grid_canon[g];
+                if (cg != g) {   // identical contents: copy the words
+                    std::copy(pk.begin() + c->grid_goff[cg], pk.begin() + c->grid_goff[cg] + np, pk.begin() + go);
+                    continue;
+                }
+                for (int i = 0; i < np; ++i) {
+                    const int l = lv[go + i];
+                    if (l < 0 || l >= VPK_LEVELS) throw Fail("velocity level out of range (0..15)");
+                    unsigned w = (unsigned)l << 27;
+                    for (int d = 0; d < D; ++d) {
+                        const double x = vm[go * D + (size_t)d * np + i];
+                        const int k = (int)(std::lower_bound(tab[d].begin(), tab[d].end(), x) - tab[d].begin());
+                        w |= (unsigned)k << (VPK_BITS * d);
+                    }
+                    pk[go + i] = w;
+                    if (i < c->grid_n[g]) {
+                        const double wgt = wt[go + i];
+                        if (!have[l]) { have[l] = 1; vt[(size_t)D * ntab + l] = wgt; }
+                        else if (vt[(size_t)D * ntab + l] != wgt)
+                            throw Fail("velocity weights are not a function of the level (VsData.weight = root weight / "
+                                       "2^(DIM*level), Velocity_space/Rebuild.jl:60)");
+                    }
+                }
+            }
+            c->dv.v_pack = c->dupload(pk);
+            c->dv.v_tab = c->dupload(vt);
+            c->dv.n_vtab = ntab;
+            CK(cudaStreamSynchronize(c->stream));
         }
         c->dv.v_sign = c->dupload(sg);
         c->dv.v_level = c->dupload(lv);
@@ -860,7 +962,35 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         std::vector<char> in_gen(tasks.size(), 0);
         for (int ti : order)
             in_gen[ti] = !((by_level || wave[ti] == 0) && (is_regular(tasks[ti]) || is_regmapped(tasks[ti])));
+        // With peers every launch list is split into tasks that can run before the df halo of the previous step has
+        // arrived ("interior") and tasks that read a ghost cell's df, or project the slopes of a task that does
+        // ("halo"): the interior part overlaps the transfer (the structure of flux!(p4est, ka), Flux.jl:461-485).
+        std::vector<char> bnd(tasks.size(), 0);
+        if (m->n_peer > 0) {
+            const int g0 = c->n_local, g1 = c->n_local + c->n_ghost;
+            for (int ti : order) {   // ascending wave: the tasks a task depends on come first
+                bool b = false;
+                for (int d = 0; d < D && !b; ++d)
+                    for (int a = 0; a < tasks[ti].d[d].nA + tasks[ti].d[d].nB && !b; ++a) {
+                        const int nc = cell_of_doff[c->slope_nb[tasks[ti].d[d].nb_begin + a].doff];
+                        b = nc >= g0 && nc < g1;
+                    }
+                for (int tgt : deps[ti]) {
+                    const int tj = (tgt < c->n_local) ? task_of[tgt] : -1;
+                    if (tj >= 0 && bnd[tj]) b = true;
+                }
+                bnd[ti] = b ? 1 : 0;
+            }
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1)
+            for (auto& kv : stages) {
+                kv.second.reg_int = (int)kv.second.reg.size();
+                kv.second.regm_int = (int)kv.second.regm.size();
+                kv.second.gen_int = (int)kv.second.gen.size();
+            }
         for (int ti : order) {
+            if ((int)bnd[ti] != pass) continue;
             const int sidx = by_level ? stage_of_task(ti) : 0;
             kamr_ctx::SlopeStage& st = stages[sidx];
             st.wave = sidx;
@@ -891,7 +1021,27 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             }
             st.gen.push_back(t);
         }
+        }
         for (auto& kv : stages) {
+            if (m->n_peer == 0) {
+                kv.second.reg_int = (int)kv.second.reg.size();
+                kv.second.regm_int = (int)kv.second.regm.size();
+                kv.second.gen_int = (int)kv.second.gen.size();
+            }
+        }
+        for (auto& kv : stages) {
+            {   // prefetch distance of the regular launches: pf_mb of df ahead
+                const double pf_mb = getenv("KAMR_PF_MB") ? atof(getenv("KAMR_PF_MB")) : 24.0;
+                auto dist = [&](double pts, size_t cnt) {
+                    if (!cnt || pf_mb <= 0.0) return 0;
+                    return (int)std::min(512.0, std::max(1.0, pf_mb * 1048576.0 / (pts / cnt * 8.0 * K * (1 + D))));
+                };
+                double pr = 0, pm = 0;
+                for (auto& r : kv.second.reg) pr += r.np;
+                for (auto& r : kv.second.regm) pm += r.r.np;
+                kv.second.pf_reg = dist(pr, kv.second.reg.size());
+                kv.second.pf_regm = dist(pm, kv.second.regm.size());
+            }
             kv.second.d_reg = c->dupload(kv.second.reg);
             kv.second.d_regm = c->dupload(kv.second.regm);
             kv.second.d_gen = c->dupload(kv.second.gen);
@@ -917,27 +1067,53 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         if (c->cells[i].bound_enc >= 0) c->limit_cells.push_back(i);
     c->d_limit_cells = c->dupload(c->limit_cells);
     {
-        // dynamic shared memory classes.  Small cells (<= BIG_SMEM with M[prim_c] staged): K planes of convected f + 1
-        // plane of M[prim_c], 128-thread CTAs.  Big cells: K planes only, PNT_BIG-thread CTAs, MINB_BIG per SM.
-        const size_t big_max = (size_t)(227 << 10) / MINB_BIG - (8 << 10);
-        const size_t caps[] = {8 << 10, 16 << 10, 24 << 10, 32 << 10, 48 << 10, 64 << 10, 80 << 10, 96 << 10,
-                               std::min(big_max, (size_t)c->max_smem_optin - (12 << 10))};
-        const int ncap = (int)(sizeof(caps) / sizeof(caps[0]));
-        std::vector<Bin> bins(6 * (ncap + 1));
+        // Launch classes.  A cell of n points is owned by C CTAs (a thread-block cluster), each with a contiguous range of
+        // at most CHUNK_N points whose convected f (+ the h-plane of M[prim_c]) it stages in shared memory; giant cells
+        // whose range does not fit even with C = 8 stage in the output array.  Ranges are grouped in steps of 256 points
+        // so that a launch sizes its shared memory for what its cells need.
+        const size_t smem_avail = (size_t)c->max_smem_optin - (14 << 10);   // static shared memory of the kernels
+        std::map<std::vector<int>, Bin> bmap;
         c->fused_cells = 0;
+        const double pf_mb = getenv("KAMR_PF_MB") ? atof(getenv("KAMR_PF_MB")) : 24.0;
         for (int cell : c->fluid_cells) {
             const CellInfo& ci = c->cells[cell];
-            const bool big = (size_t)ci.n * (K + 1) * sizeof(double) > BIG_SMEM;
-            const size_t need = (size_t)ci.n * (big ? K : K + 1) * sizeof(double);
-            int q = 0;
-            while (q < ncap && need > caps[q]) ++q;
+            int C = 1;
+            const int chunk_n = CHUNK_BYTES / (2 * K * (int)sizeof(double));
+            while (C < 8 && (ci.n + C - 1) / C > (ci.n <= SMALL_N ? SMALL_N : chunk_n)) C *= 2;
+            const int P = chunk_points(ci.n, C);
+            const bool stage = sizeof(double) * ((size_t)(2 * K) * P + vtab_doubles(D, c->dv.n_vtab) + 2 +
+                                                 (size_t)(D + 2) * batch_count(P)) <= smem_avail;
             const bool mapped = (ci.flags & CELL_REGULAR_MAPPED) != 0;
             const bool regular = mapped || (ci.flags & CELL_REGULAR) != 0;
-            Bin& b = bins[6 * q + 3 * (big ? 1 : 0) + (mapped ? 2 : (regular ? 1 : 0))];
-            b.regular = regular; b.mapped = mapped; b.big = big;
-            b.smem = (q < ncap) ? std::max(b.smem, need) : 0;
+            const int pclass = stage ? (P + 255) / 256 : 0;
+            // with peers: cells that read ghost data (a ghost across a face) or wall data that depends on it (donors)
+            // are launched after the halo has arrived, everything else while it is in flight
+            bool halo = false;
+            if (m->n_peer > 0) {
+                halo = ci.bound_enc > 0;
+                for (int q = ci.slot_begin; q < ci.slot_end && !halo; ++q) {
+                    const int nb = c->slots[q].nbr;
+                    halo = nb >= c->n_local && nb < c->n_local + c->n_ghost;
+                }
+            }
+            Bin& b = bmap[{halo ? 1 : 0, regular ? (mapped ? 2 : 1) : 0, ci.n > SMALL_N ? 1 : 0, C, pclass}];
+            b.halo = halo;
+            b.C = C; b.wide = ci.n > SMALL_N; b.stage = stage; b.regular = regular; b.mapped = mapped;
+            b.P = std::max(b.P, P);
             b.cells.push_back(cell);
-            if (q < ncap) c->fused_cells++;
+            if (stage) c->fused_cells++;
+        }
+        std::vector<Bin> bins;
+        // launch order: regular classes first (the wall kernels run beside them), then the rest
+        for (int pass = 0; pass < 2; ++pass)
+            for (auto& kv : bmap)
+                if ((kv.first[1] != 0) == (pass == 0)) bins.push_back(std::move(kv.second));
+        for (auto& b : bins) {   // DRAM -> L2 prefetch distance: pf_mb of cell state ahead in the launch
+            double bytes = 0.0;
+            for (int cell : b.cells) bytes += (double)c->cells[cell].np * 8.0 * K * (1 + D);
+            bytes /= (double)b.cells.size();
+            b.pf_dist = (int)std::min(512.0, std::max(1.0, pf_mb * 1048576.0 / bytes));
+            if (pf_mb <= 0.0) b.pf_dist = 0;
         }
         for (auto& b : bins) {
             if (b.cells.empty()) continue;
@@ -1154,12 +1330,14 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         c->d_sendbuf = c->dalloc<double>((size_t)send_total);
         c->d_recvbuf = c->dalloc<double>((size_t)recv_total);
     }
+    setup_p2p(c, m);
     if (getenv("KAMR_VERBOSE")) {
         for (auto& b : c->bins) {
             long long pts = 0;
             for (int cell : b.cells) pts += c->cells[cell].n;
-            fprintf(stderr, "[kamr] phase bin: %zu cells, %lld points, smem %zu, %s%s%s\n", b.cells.size(), pts, b.smem,
-                    b.big ? "big " : "small ", b.regular ? "regular " : "general ", b.mapped ? "mapped" : "");
+            fprintf(stderr, "[kamr] phase bin: %zu cells, %lld points, C %d, P %d, %s, %s%s%s, prefetch %d cells\n",
+                    b.cells.size(), pts, b.C, b.P, b.stage ? "smem" : "global", b.wide ? "256 thr " : "128 thr ",
+                    b.regular ? "regular " : "general ", b.mapped ? "mapped" : "", b.pf_dist);
         }
         for (auto& st : c->slope_stages)
             fprintf(stderr, "[kamr] slope stage %d: %zu regular, %zu regular-mapped, %zu general%s\n", st.wave,
@@ -1168,6 +1346,168 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
                 c->sn_tasks.size(), c->rel_off.size(), c->pm_start.size());
     }
     CK(cudaStreamSynchronize(c->stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-sided halo: at re-flatten time every pair of neighbouring ranks swaps the CUDA IPC handles of the arrays the
+// other side writes into (both df allocations, the raw slopes, the flag table) and the block offsets of its ghost
+// cells; a mirror cell's block is then STORED straight into the peer's ghost block over NVLink by a put kernel on a
+// side stream, followed by a flag the receiver's stream waits on right before the first kernel that reads the ghosts.
+// No rendezvous: a sender never waits, a receiver only when it reads.  p4est's mirror order of a pair equals the
+// peer's ghost order (Parallel/Ghost.jl:221-264), so the k-th mirror sent to a peer lands in its k-th ghost from us.
+void setup_p2p(kamr_ctx* c, const kamr_mesh* m) {
+    if (m->n_peer == 0 || !c->comm) return;
+    if (const char* h = getenv("KAMR_HALO")) if (!strcmp(h, "nccl")) return;   // two-sided NCCL path (debugging)
+    const int K = c->K, D = c->D, np = m->n_peer, nr = c->cfg.nranks;
+    P2P& pp = c->p2p;
+    pp.d_flags = c->dalloc<int>((size_t)nr * HK_SLOTS);
+    CK(cudaMemsetAsync(pp.d_flags, 0, sizeof(int) * (size_t)nr * HK_SLOTS, c->stream));
+    constexpr int HW = 4 * (int)sizeof(cudaIpcMemHandle_t) / 8;   // handle block in 8-byte words
+    cudaIpcMemHandle_t mine[4];
+    CK(cudaIpcGetMemHandle(&mine[0], c->dv.df));
+    CK(cudaIpcGetMemHandle(&mine[1], c->dv.df_new));
+    CK(cudaIpcGetMemHandle(&mine[2], c->dv.sdf));
+    CK(cudaIpcGetMemHandle(&mine[3], pp.d_flags));
+    std::vector<long long> soff(np + 1, 0), roff(np + 1, 0);
+    for (int p = 0; p < np; ++p) {
+        soff[p + 1] = soff[p] + HW + (m->recv_off[p + 1] - m->recv_off[p]);   // what we tell p: handles + OUR ghost offsets
+        roff[p + 1] = roff[p] + HW + (m->send_off[p + 1] - m->send_off[p]);   // what p tells us: handles + ITS ghost offsets
+    }
+    std::vector<long long> sx(soff[np]), rx(roff[np]);
+    for (int p = 0; p < np; ++p) {
+        memcpy(&sx[soff[p]], mine, sizeof(mine));
+        for (int gq = m->recv_off[p]; gq < m->recv_off[p + 1]; ++gq) sx[soff[p] + HW + gq - m->recv_off[p]] = c->cells[c->n_local + gq].doff;
+    }
+    long long* d_sx = c->dalloc<long long>(sx.size());
+    long long* d_rx = c->dalloc<long long>(rx.size());
+    CK(cudaMemcpyAsync(d_sx, sx.data(), sizeof(long long) * sx.size(), cudaMemcpyHostToDevice, c->stream));
+    NCK(nccl().GroupStart());
+    for (int p = 0; p < np; ++p) {
+        NCK(nccl().Send(d_sx + soff[p], (size_t)(soff[p + 1] - soff[p]), ncclFloat64, m->peer_rank[p], c->comm, c->stream));
+        NCK(nccl().Recv(d_rx + roff[p], (size_t)(roff[p + 1] - roff[p]), ncclFloat64, m->peer_rank[p], c->comm, c->stream));
+    }
+    NCK(nccl().GroupEnd());
+    CK(cudaMemcpyAsync(rx.data(), d_rx, sizeof(long long) * rx.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<double*> pdf0(np), pdf1(np), psdf(np);
+    std::vector<int*> pfl(np);
+    for (int p = 0; p < np; ++p) {
+        cudaIpcMemHandle_t h[4];
+        memcpy(h, &rx[roff[p]], sizeof(h));
+        void* q[4];
+        for (int a = 0; a < 4; ++a) {
+            cudaError_t e = cudaIpcOpenMemHandle(&q[a], h[a], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+                throw Fail(std::string("cudaIpcOpenMemHandle (peer rank ") + std::to_string(m->peer_rank[p]) + "): " +
+                           cudaGetErrorString(e) + " — set KAMR_HALO=nccl to use the two-sided NCCL halo instead");
+            pp.opened.push_back(q[a]);
+        }
+        pdf0[p] = (double*)q[0]; pdf1[p] = (double*)q[1]; psdf[p] = (double*)q[2]; pfl[p] = (int*)q[3];
+    }
+    pp.d_pdf[0] = c->dupload(pdf0); pp.d_pdf[1] = c->dupload(pdf1);
+    pp.d_psdf = c->dupload(psdf); pp.d_pflags = c->dupload(pfl);
+    // put lists and flag slots per message kind
+    for (int p = 0; p < np; ++p) {
+        const PeerPlan& pl = c->peers[p];
+        const long long* rd = &rx[roff[p] + HW];
+        auto kind_of_level = [&](int wv) { return (pl.early >> std::min(63, wv) & 1ull) ? HK_SDF_EARLY + std::min(63, wv) : HK_SDF_FINAL; };
+        std::map<int, bool> sends, recvs;
+        for (int q = m->send_off[p]; q < m->send_off[p + 1]; ++q) {
+            const CellInfo& ci = c->cells[m->send_cells[q]];
+            const long long r = rd[q - m->send_off[p]];
+            pp.msg[HK_DF].segs.push_back(PutSeg{ci.doff * K, r * K, ci.np * K, p});
+            sends[HK_DF] = true;
+            if (ci.bound_enc < 0) {
+                pp.msg[HK_SOLID].segs.push_back(PutSeg{ci.doff * K, r * K, ci.np * K, p});
+                sends[HK_SOLID] = true;
+            } else {
+                const int kd = kind_of_level(std::max(0, ci.ps_level - m->ps_minlevel));
+                pp.msg[kd].segs.push_back(PutSeg{ci.doff * K * D, r * K * D, ci.np * K * D, p});
+                sends[kd] = true;
+            }
+        }
+        for (int gq = m->recv_off[p]; gq < m->recv_off[p + 1]; ++gq) {
+            const CellInfo& ci = c->cells[c->n_local + gq];
+            recvs[HK_DF] = true;
+            if (ci.bound_enc < 0) recvs[HK_SOLID] = true;
+            else recvs[kind_of_level(std::max(0, ci.ps_level - m->ps_minlevel))] = true;
+        }
+        for (auto& kv : sends) pp.msg[kv.first].to.push_back(p);
+        for (auto& kv : recvs) pp.msg[kv.first].from.push_back(m->peer_rank[p] * HK_SLOTS + kv.first);
+    }
+    for (auto& kv : pp.msg) {
+        kv.second.d_segs = c->dupload(kv.second.segs);
+        kv.second.d_to = c->dupload(kv.second.to);
+        kv.second.d_from = c->dupload(kv.second.from);
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    pp.on = true;
+}
+
+void exchange(kamr_ctx* c, int what, int level);
+
+// the (what, level) of the two-sided path for a message kind
+inline void kind_to_what(int kind, int& what, int& level) {
+    level = 0;
+    if (kind == HK_DF) what = 0;
+    else if (kind == HK_SOLID) what = 2;
+    else if (kind == HK_SDF_FINAL) what = 3;
+    else { what = 1; level = kind - HK_SDF_EARLY; }
+}
+
+// Send this rank's part of a message: the mirrors' blocks are stored into the peers' ghost blocks by a put kernel on
+// the communication stream, then the flags go up.  Two-sided path: nothing yet (the exchange runs at the wait).
+void halo_put(kamr_ctx* c, int kind) {
+    if (c->peers.empty() || !c->p2p.on) return;
+    auto it = c->p2p.msg.find(kind);
+    if (it == c->p2p.msg.end()) return;
+    HaloMsg& ms = it->second;
+    ms.epoch++;
+    if (ms.to.empty()) return;
+    const bool is_df = kind == HK_DF || kind == HK_SOLID;
+    CK(cudaEventRecord(c->ev_put_ready, c->stream));
+    CK(cudaStreamWaitEvent(c->comm_stream, c->ev_put_ready, 0));
+    {
+        Launch L_(c, KID_PACK, c->comm_stream);
+        put_segments_kernel<<<std::min<int>((int)ms.segs.size(), 148 * 4), 256, 0, c->comm_stream>>>(
+            ms.d_segs, (int)ms.segs.size(), is_df ? c->dv.df : c->dv.sdf,
+            is_df ? c->p2p.d_pdf[c->df_parity] : c->p2p.d_psdf);
+    }
+    halo_signal_kernel<<<1, (int)round_up((long long)ms.to.size(), 32), 0, c->comm_stream>>>(
+        c->p2p.d_pflags, ms.d_to, (int)ms.to.size(), c->cfg.rank * HK_SLOTS + kind, ms.epoch);
+    CK(cudaEventRecord(c->ev_put_done, c->comm_stream));
+    c->put_in_flight = true;
+    CK(cudaGetLastError());
+}
+// The main stream may not overwrite what a put in flight still reads (nor exit a step with one pending)
+void halo_join_puts(kamr_ctx* c) {
+    if (!c->put_in_flight) return;
+    CK(cudaStreamWaitEvent(c->stream, c->ev_put_done, 0));
+    c->put_in_flight = false;
+}
+// Before the first kernel that reads the ghosts of a message: wait for the peers' flags (one-sided) or run the
+// pack / ncclSend+ncclRecv / unpack exchange here (two-sided).
+void halo_wait(kamr_ctx* c, int kind) {
+    if (c->peers.empty()) return;
+    if (!c->p2p.on) {
+        int what, level;
+        kind_to_what(kind, what, level);
+        exchange(c, what, level);
+        return;
+    }
+    auto it = c->p2p.msg.find(kind);
+    if (it == c->p2p.msg.end() || it->second.from.empty()) return;
+    HaloMsg& ms = it->second;
+    Launch L_(c, KID_UNPACK);
+    halo_wait_kernel<<<1, (int)round_up((long long)ms.from.size(), 32), 0, c->stream>>>(
+        c->p2p.d_flags, ms.d_from, (int)ms.from.size(), ms.epoch, c->dv.err_flag);
+    CK(cudaGetLastError());
+}
+// the df halo of the previous step is waited for lazily, right before the first kernel that reads a ghost's df
+void halo_finish_df(kamr_ctx* c) {
+    if (!c->df_wait_pending) return;
+    c->df_wait_pending = false;
+    halo_wait(c, HK_DF);
 }
 
 // vs_data.flux (and the SolidNeighbor "reconstruction perturbance" kept in the same array) is only needed by
@@ -1184,9 +1524,11 @@ void sync_and_check(kamr_ctx* c) {
     if (c->dv.err_flag) CK(cudaMemcpyAsync(c->h_err, c->dv.err_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (c->dv.err_flag && *c->h_err) {
+        const int code = *c->h_err;
         *c->h_err = 0;
         CK(cudaMemsetAsync(c->dv.err_flag, 0, sizeof(int), c->stream));
-        throw Fail("slope dependency sweep timed out waiting for another CTA (the results of this step are invalid)");
+        throw Fail(code == 2 ? "halo wait timed out: a peer never raised its flag (the results of this step are invalid)"
+                             : "slope dependency sweep timed out waiting for another CTA (the results of this step are invalid)");
     }
 }
 
@@ -1299,29 +1641,38 @@ void exchange(kamr_ctx* c, int what, int level) {
 #endif
 constexpr int NT = KAMR_NT;      // threads per CTA of the slope kernel (one CTA per physical cell)
 constexpr int PNT = KAMR_PNT;
-static_assert(KAMR_PNT != KAMR_PNT_BIG, "small- and big-cell CTA sizes must differ (STAGE_FC is keyed on the CTA size)");    // threads per CTA of the phase kernel: small CTAs keep many cells in flight per SM,
-                                 // so one cell's barriers and serial moments->prim step hide behind the others
+// threads per CTA of the phase kernel for small cells: small CTAs keep many cells in flight per SM, so one cell's barriers
+// and serial moments->prim step hide behind the others
 #ifndef KAMR_MINB_GEN
 #define KAMR_MINB_GEN KAMR_MINB
 #endif
 constexpr int MINB_GEN = KAMR_MINB_GEN;  // same for the general phase kernel (more live state: slot loops, pair-mapped gather)
 constexpr int MINB = KAMR_MINB;  // CTAs per SM the phase kernel is register-budgeted for
 
+// part 0: the tasks that read no ghost data, part 1: the rest, part 2: both
 template <int D, int K>
-void launch_slope_stage(kamr_ctx* c, const kamr_ctx::SlopeStage& st, int raw_all) {
-    if (!st.reg.empty()) {
+void launch_slope_stage(kamr_ctx* c, const kamr_ctx::SlopeStage& st, int raw_all, int part = 2) {
+    auto range = [&](int total, int n_int, int& first, int& count) {
+        first = part == 1 ? n_int : 0;
+        count = part == 0 ? n_int : (part == 1 ? total - n_int : total);
+    };
+    int f0, n0;
+    range((int)st.reg.size(), st.reg_int, f0, n0);
+    if (n0 > 0) {
         Launch L_(c, KID_SLOPE_REGULAR);
-        slope_regular_kernel<D, K, NT, false><<<(int)st.reg.size(), NT, 0, c->stream>>>(c->dv, st.d_reg, raw_all);
+        slope_regular_kernel<D, K, NT, false><<<n0, NT, 0, c->stream>>>(c->dv, st.d_reg + f0, raw_all, st.pf_reg);
     }
-    if (!st.regm.empty()) {
+    range((int)st.regm.size(), st.regm_int, f0, n0);
+    if (n0 > 0) {
         Launch L_(c, KID_SLOPE_REGMAP);
-        slope_regular_kernel<D, K, NT, true><<<(int)st.regm.size(), NT, 0, c->stream>>>(c->dv, st.d_regm, raw_all);
+        slope_regular_kernel<D, K, NT, true><<<n0, NT, 0, c->stream>>>(c->dv, st.d_regm + f0, raw_all, st.pf_regm);
     }
-    if (!st.gen.empty()) {
+    range((int)st.gen.size(), st.gen_int, f0, n0);
+    if (n0 > 0) {
         Launch L_(c, KID_SLOPE);
-        slope_kernel<D, K, true, NT_SLOPE><<<(int)st.gen.size(), NT_SLOPE, 0, c->stream>>>(
-            c->dv, st.d_gen, raw_all, st.flags ? c->slope_epoch : 0, c->d_slope_ticket, c->slope_ticket_base);
-        if (st.flags) c->slope_ticket_base += (unsigned)st.gen.size();   // tickets drawn by this launch (wraps with the counter)
+        slope_kernel<D, K, true, NT_SLOPE><<<n0, NT_SLOPE, 0, c->stream>>>(
+            c->dv, st.d_gen + f0, raw_all, st.flags ? c->slope_epoch : 0, c->d_slope_ticket, c->slope_ticket_base);
+        if (st.flags) c->slope_ticket_base += (unsigned)n0;   // tickets drawn by this launch (wraps with the counter)
     }
 }
 
@@ -1339,15 +1690,27 @@ void run_macro_slope(kamr_ctx* c) {
     macro_slope_kernel<D, K><<<(int)c->fluid_cells.size(), 256, 0, c->stream>>>(c->dv, c->d_fluid_cells);
 }
 
+// the slope halo of the mirrors not exchanged early has been sent; wait for the peers' and limit the ghosts' slopes
+template <int D, int K>
+void finish_slope_halo(kamr_ctx* c) {
+    if (c->peers.empty()) return;
+    halo_wait(c, HK_SDF_FINAL);
+    run_limit<D, K>(c, c->d_ghost_fluid, c->n_ghost_fluid);
+}
+
 // slope!(p4est, ka).  raw_all: every cell's reference sdf is written (public kamr_slope, KAMR_OPT_KEEP_SDF);
 // otherwise only where a kernel reads it, and the limited slopes everywhere.
+// With peers: the tasks that read no ghost data are launched first; then the stream waits for the df halo of the
+// previous step, the remaining tasks follow, and the mirrors' slopes are put.  defer_final: the caller overlaps the
+// final slope message with work that reads no ghost slopes and calls finish_slope_halo itself.
 template <int D, int K>
-void do_slope(kamr_ctx* c, bool with_sw, bool raw_all) {
+void do_slope(kamr_ctx* c, bool with_sw, bool raw_all, bool defer_final = false) {
     raw_all = raw_all || c->keep_sdf;
     c->slope_epoch = c->slope_epoch == 0x7fffffff ? 1 : c->slope_epoch + 1;
     if (c->peers.empty()) {
         for (auto& st : c->slope_stages) launch_slope_stage<D, K>(c, st, raw_all);
     } else {
+        halo_join_puts(c);   // (the slope kernels overwrite what the previous step's slope puts read)
         // stage s = the waves up to and including the s-th early wave; it is followed by that wave's exchange between
         // the pairs that project each other's slopes of that level (slope_exchange_level!, Parallel/Ghost.jl:896).
         // Everything else travels in one message per pair after the last stage, then the ghosts' limited slopes.
@@ -1358,11 +1721,17 @@ void do_slope(kamr_ctx* c, bool with_sw, bool raw_all) {
         for (auto& st : c->slope_stages) nst = std::max(nst, (size_t)st.wave + 1);
         for (size_t sidx = 0; sidx < nst; ++sidx) {
             for (auto& st : c->slope_stages)
-                if ((size_t)st.wave == sidx) launch_slope_stage<D, K>(c, st, raw_all);
-            if (sidx < early.size()) exchange(c, 1, early[sidx]);
+                if ((size_t)st.wave == sidx) launch_slope_stage<D, K>(c, st, raw_all, 0);
+            if (sidx == 0) halo_finish_df(c);
+            for (auto& st : c->slope_stages)
+                if ((size_t)st.wave == sidx) launch_slope_stage<D, K>(c, st, raw_all, 1);
+            if (sidx < early.size()) {
+                halo_put(c, HK_SDF_EARLY + early[sidx]);
+                halo_wait(c, HK_SDF_EARLY + early[sidx]);
+            }
         }
-        exchange(c, 3, 0);
-        run_limit<D, K>(c, c->d_ghost_fluid, c->n_ghost_fluid);
+        halo_put(c, HK_SDF_FINAL);
+        if (!defer_final) finish_slope_halo<D, K>(c);
     }
     c->raw_sdf_valid = raw_all;
     CK(cudaGetLastError());
@@ -1374,16 +1743,35 @@ template <class Kern>
 void prepare_kernel(Kern kern, int max_dyn) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
     // no carve-out preference: the driver sizes shared memory for the resident CTAs and leaves the rest of the 256 KB to
-    // L1, which serves the velocity-grid statics every pass re-reads (forcing MaxShared cost 12 % of the step, r01_i)
+    // L1 (forcing MaxShared cost 12 % of the step, r01_i)
 }
 
-// cells whose staged block needs more than 32 KB of shared memory (n > ~1300 points in 2D2F, ~2000 in 3D1F) take
-// 1024-thread CTAs: one or two of them fill an SM, and a cell's points still spread over 32 warps
+// launches `kern` on ncell cells with C CTAs per cell (a thread-block cluster when C > 1)
+template <class Kern, class... Args>
+void launch_cells(kamr_ctx* c, Kern kern, int ncell, int C, int nt, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)ncell * C, 1, 1);
+    cfg.blockDim = dim3(nt, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = C > 1 ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kern, args...));
+}
 
+#ifndef KAMR_MINB_WIDE
+#define KAMR_MINB_WIDE 3
+#endif
+constexpr int PNT_WIDE = 256;              // threads per CTA for point ranges of more than SMALL_N points
+constexpr int MINB_WIDE = KAMR_MINB_WIDE;  // CTAs per SM those kernels are register-budgeted for
 
-template <int D, int K, int MODE, bool STAGE, int PT, int MB>
+template <int D, int K, int MODE, bool STAGE, int PT, int MB, int C>
 void launch_phase_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want, int kid) {
-    auto kern = phase_kernel<D, K, MODE, STAGE, PT, MB>;
+    auto kern = phase_kernel<D, K, MODE, STAGE, PT, MB, C>;
     static bool prepared = false;  // per instantiation; attributes are per device function
     if (!prepared) {
         cudaFuncAttributes fa;
@@ -1392,12 +1780,12 @@ void launch_phase_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int wa
         prepared = true;
     }
     Launch L_(c, kid);
-    kern<<<(int)b.cells.size(), PT, smem, c->stream>>>(c->dv, c->gas, b.d_cells, dt, want);
+    launch_cells(c, kern, (int)b.cells.size(), C, PT, smem, c->dv, c->gas, (const int*)b.d_cells, dt, want, b.pf_dist);
 }
 
-template <int D, int K, bool STAGE, int PT, int MB, bool MAPPED>
+template <int D, int K, bool STAGE, int PT, int MB, bool MAPPED, int C>
 void launch_regular_inst2(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want) {
-    auto kern = phase_regular_kernel<D, K, STAGE, PT, MB, MAPPED>;
+    auto kern = phase_regular_kernel<D, K, STAGE, PT, MB, MAPPED, C>;
     static bool prepared = false;
     if (!prepared) {
         cudaFuncAttributes fa;
@@ -1406,33 +1794,47 @@ void launch_regular_inst2(kamr_ctx* c, const Bin& b, size_t smem, double dt, int
         prepared = true;
     }
     Launch L_(c, MAPPED ? KID_STEP_REGMAP : KID_STEP_REGULAR);
-    kern<<<(int)b.cells.size(), PT, smem, c->stream>>>(c->dv, c->gas, b.d_recs, dt, want);
+    launch_cells(c, kern, (int)b.cells.size(), C, PT, smem, c->dv, c->gas, (const RegCell*)b.d_recs, dt, want, b.pf_dist);
 }
-template <int D, int K, bool STAGE, int PT, int MB>
+template <int D, int K, bool STAGE, int PT, int MB, int C>
 void launch_regular_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want) {
-    if (b.mapped) launch_regular_inst2<D, K, STAGE, PT, MB, true>(c, b, smem, dt, want);
-    else launch_regular_inst2<D, K, STAGE, PT, MB, false>(c, b, smem, dt, want);
+    if (b.mapped) launch_regular_inst2<D, K, STAGE, PT, MB, true, C>(c, b, smem, dt, want);
+    else launch_regular_inst2<D, K, STAGE, PT, MB, false, C>(c, b, smem, dt, want);
 }
 
+// the fused step of one bin: the instantiation follows the bin's CTA width, cluster size and staging area
+template <int D, int K>
+void launch_fused(kamr_ctx* c, const Bin& b, double dt, int want) {
+    const size_t smem = phase_smem_bytes<D, K>(c->dv.n_vtab, b.P, b.stage, !b.regular || b.mapped);
+#define KAMR_FUSED(STAGE, PT, MB, CC)                                                                       \
+    do {                                                                                                    \
+        if (b.regular) launch_regular_inst<D, K, STAGE, PT, MB, CC>(c, b, smem, dt, want);                  \
+        else launch_phase_inst<D, K, MODE_FUSED, STAGE, PT, MB, CC>(c, b, smem, dt, want, KID_STEP);        \
+    } while (0)
+    if (!b.wide) { KAMR_FUSED(true, PNT, MINB, 1); return; }
+    if (!b.stage) { KAMR_FUSED(false, PNT_WIDE, MINB_WIDE, 8); return; }
+    switch (b.C) {
+        case 1: KAMR_FUSED(true, PNT_WIDE, MINB_WIDE, 1); break;
+        case 2: KAMR_FUSED(true, PNT_WIDE, MINB_WIDE, 2); break;
+        case 4: KAMR_FUSED(true, PNT_WIDE, MINB_WIDE, 4); break;
+        default: KAMR_FUSED(true, PNT_WIDE, MINB_WIDE, 8); break;
+    }
+#undef KAMR_FUSED
+}
+
+// flux!(p4est, ka) / iterate!(CAIDVM_Marching) one call at a time: one CTA per cell over all its points; the update
+// stages in shared memory when the whole cell fits
 template <int D, int K, int MODE>
-void launch_phase(kamr_ctx* c, const Bin& b, double dt, int want) {
-    const bool big = b.big;
-    if (MODE == MODE_FUSED && b.regular) {
-        if (b.smem == 0) launch_regular_inst<D, K, false, PNT_BIG, MINB_BIG>(c, b, 0, dt, want);
-        else if (big) launch_regular_inst<D, K, true, PNT_BIG, MINB_BIG>(c, b, b.smem, dt, want);
-        else launch_regular_inst<D, K, true, PNT, MINB>(c, b, b.smem, dt, want);
-        return;
-    }
-    const int kid = MODE == MODE_FUSED ? KID_STEP : (MODE == MODE_FLUX ? KID_FLUX : KID_UPDATE);
-    const bool stage = (MODE != MODE_FLUX) && b.smem > 0;
-    if (stage) {
-        if (big) launch_phase_inst<D, K, MODE, true, PNT_BIG, MINB_BIG>(c, b, b.smem, dt, want, kid);
-        else launch_phase_inst<D, K, MODE, true, PNT, MINB_GEN>(c, b, b.smem, dt, want, kid);
-    } else {
-        // (MODE_FLUX stages nothing: its CTA size follows the cell size only)
-        if (big) launch_phase_inst<D, K, MODE, false, PNT_BIG, MINB_BIG>(c, b, 0, dt, want, kid);
-        else launch_phase_inst<D, K, MODE, false, PNT, MINB_GEN>(c, b, 0, dt, want, kid);
-    }
+void launch_unfused(kamr_ctx* c, const Bin& b, double dt, int want) {
+    const int kid = MODE == MODE_FLUX ? KID_FLUX : KID_UPDATE;
+    int nmax = 0;
+    for (int cell : b.cells) nmax = std::max(nmax, c->cells[cell].n);
+    const int P = chunk_points(nmax, 1);
+    const bool stage = MODE == MODE_UPDATE &&
+                       phase_smem_bytes<D, K>(c->dv.n_vtab, P, true, false) + (14 << 10) <= (size_t)c->max_smem_optin;
+    const size_t smem = phase_smem_bytes<D, K>(c->dv.n_vtab, P, stage, false);
+    if (stage) launch_phase_inst<D, K, MODE, true, PNT_WIDE, MINB_WIDE, 1>(c, b, smem, dt, want, kid);
+    else launch_phase_inst<D, K, MODE, false, PNT_WIDE, MINB_WIDE, 1>(c, b, smem, dt, want, kid);
 }
 
 // the wall half of flux!(p4est, ka) (Flux.jl:463-481): update_solid_cell!, the solid halo, update_solid_neighbor!.
@@ -1444,7 +1846,10 @@ void do_ib(kamr_ctx* c, double* df2, cudaStream_t st = nullptr) {
         Launch L_(c, KID_SOLID_CELL, st);
         solid_cell_kernel<D, K><<<(int)c->solid_tasks.size(), 256, 0, st>>>(c->dv, c->gas, c->d_solid_tasks, df2);
     }
-    if (st == c->stream) exchange(c, 2, 0);   // (callers use the side stream only when no solid cell crosses ranks)
+    if (st == c->stream) {   // (callers use the side stream only on a rank without peers)
+        halo_put(c, HK_SOLID);
+        halo_wait(c, HK_SOLID);
+    }
     if (!c->sn_tasks.empty()) {
         Launch L_(c, KID_SOLID_NBR, st);
         solid_neighbor_kernel<D, K><<<(int)c->sn_tasks.size(), 256, 0, st>>>(c->dv, c->gas, c->d_sn_tasks, df2);
@@ -1455,8 +1860,9 @@ void do_ib(kamr_ctx* c, double* df2, cudaStream_t st = nullptr) {
 template <int D, int K>
 void do_flux(kamr_ctx* c, double dt) {
     ensure_flux(c);
+    halo_finish_df(c);
     do_ib<D, K>(c, nullptr);
-    for (auto& b : c->bins) launch_phase<D, K, MODE_FLUX>(c, b, dt, 0);
+    for (auto& b : c->bins) launch_unfused<D, K, MODE_FLUX>(c, b, dt, 0);
     CK(cudaGetLastError());
 }
 
@@ -1472,9 +1878,19 @@ void fetch_residual(kamr_ctx* c, int want, double* res_out) {
     if (res_out) memcpy(res_out, c->h_res, 2 * M * sizeof(double));
 }
 
+// data_exchange! (Parallel/Ghost.jl:841) after the update: the mirrors' new df goes out now; its arrival is waited for
+// by the first kernel of the next call that reads a ghost's df
+void send_df_halo(kamr_ctx* c) {
+    if (c->peers.empty()) return;
+    halo_join_puts(c);
+    halo_put(c, HK_DF);
+    c->df_wait_pending = true;
+}
+
 template <int D, int K>
 void do_iterate(kamr_ctx* c, double dt, int want, double* res_out) {
     ensure_flux(c);
+    halo_finish_df(c);
     if (c->gas.marching == KAMR_MARCH_CIP) {
         if (!c->fluid_cells.empty()) {
             Launch L_(c, KID_UPDATE);
@@ -1488,11 +1904,11 @@ void do_iterate(kamr_ctx* c, double dt, int want, double* res_out) {
                                                                                           dt, want);
         }
     } else {
-        for (auto& b : c->bins) launch_phase<D, K, MODE_UPDATE>(c, b, dt, want);
+        for (auto& b : c->bins) launch_unfused<D, K, MODE_UPDATE>(c, b, dt, want);
     }
     CK(cudaGetLastError());
+    send_df_halo(c);
     fetch_residual<D, K>(c, want, res_out);
-    exchange(c, 0, 0);
 }
 
 template <int D, int K>
@@ -1503,30 +1919,38 @@ void do_step(kamr_ctx* c, double dt, int want, double* res_out) {
         do_iterate<D, K>(c, dt, want, res_out);
         return;
     }
-    do_slope<D, K>(c, false, false);
-    // The wall kernels feed the donor cells only, and a donor is never a regular cell: they run on the side stream
-    // while the regular cells' phase kernel runs here (the overlap flux!(p4est, ka) has between the solid halo and the
-    // non-IB faces, Flux.jl:461-485).  With solid cells in the halo the exchange keeps them on the main stream.
-    bool solid_halo = false;
-    for (auto& pp : c->peers) solid_halo = solid_halo || !pp.solid.send.empty() || !pp.solid.recv.empty();
-    const bool side = !solid_halo && (!c->solid_tasks.empty() || !c->sn_tasks.empty());
-    if (side) {
-        CK(cudaEventRecord(c->ev_fork, c->stream));
-        CK(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
-        do_ib<D, K>(c, c->dv.df_new, c->side_stream);
-        CK(cudaEventRecord(c->ev_join, c->side_stream));
+    if (c->peers.empty()) {
+        do_slope<D, K>(c, false, false);
+        // The wall kernels feed the donor cells only, and a donor is never a regular cell: they run on the side stream
+        // while the regular cells' phase kernels run here (the overlap flux!(p4est, ka) has between the solid halo and
+        // the non-IB faces, Flux.jl:461-485).
+        const bool side = !c->solid_tasks.empty() || !c->sn_tasks.empty();
+        if (side) {
+            CK(cudaEventRecord(c->ev_fork, c->stream));
+            CK(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+            do_ib<D, K>(c, c->dv.df_new, c->side_stream);
+            CK(cudaEventRecord(c->ev_join, c->side_stream));
+        }
+        for (auto& b : c->bins) if (b.regular) launch_fused<D, K>(c, b, dt, want);
+        if (side) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        for (auto& b : c->bins) if (!b.regular) launch_fused<D, K>(c, b, dt, want);
     } else {
+        // With peers (the order of flux!(p4est, ka), Flux.jl:461-485, with more of it overlapped): slopes; the final
+        // slope message goes out; the cells that read no ghost data are updated while it travels; then the ghosts'
+        // slopes, the wall kernels around the solid-cell halo, and the cells along the partition boundary.
+        do_slope<D, K>(c, false, false, true);
+        for (auto& b : c->bins) if (!b.halo) launch_fused<D, K>(c, b, dt, want);
+        finish_slope_halo<D, K>(c);
         do_ib<D, K>(c, c->dv.df_new);
+        for (auto& b : c->bins) if (b.halo) launch_fused<D, K>(c, b, dt, want);
     }
-    for (auto& b : c->bins) if (b.regular) launch_phase<D, K, MODE_FUSED>(c, b, dt, want);
-    if (side) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-    for (auto& b : c->bins) if (!b.regular) launch_phase<D, K, MODE_FUSED>(c, b, dt, want);
     CK(cudaGetLastError());
     // cells that are not updated (solid ghost cells, ghosts) are refreshed in the new buffer by the IB
     // kernels / the halo exchange below
     std::swap(c->dv.df, c->dv.df_new);
+    c->df_parity ^= 1;
+    send_df_halo(c);
     fetch_residual<D, K>(c, want, res_out);
-    exchange(c, 0, 0);
 }
 
 template <class F>
@@ -1589,6 +2013,13 @@ int kamr_create(const kamr_config* cfg, kamr_ctx** out) {
             CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
             CK(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi));
         }
+        {
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+        }
+        CK(cudaEventCreateWithFlags(&c->ev_put_ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_put_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         CK(cudaMallocHost((void**)&c->h_res, 64 * sizeof(double)));
@@ -1614,6 +2045,9 @@ int kamr_destroy(kamr_ctx* c) {
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
+    if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); }
+    if (c->ev_put_ready) cudaEventDestroy(c->ev_put_ready);
+    if (c->ev_put_done) cudaEventDestroy(c->ev_put_done);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -1648,6 +2082,11 @@ int kamr_upload_topology(kamr_ctx* c, const kamr_mesh* m) {
         if (!m) throw Fail("null mesh");
         CK(cudaSetDevice(c->cfg.device));
         struct Clear { kamr_ctx* c; ~Clear() { c->h_vmid = nullptr; } } clear_{c};   // the host array is the caller's
+        if (!c->cells.empty()) {   // the peers' last puts into the arrays about to be freed must have landed
+            halo_finish_df(c);
+            halo_join_puts(c);
+            CK(cudaStreamSynchronize(c->stream));
+        }
         build_topology(c, m);
     });
 }
@@ -1656,6 +2095,8 @@ int kamr_upload_state(kamr_ctx* c, const double* df, const double* w, const doub
     return guarded(c, [&] {
         CK(cudaSetDevice(c->cfg.device));
         if (c->cells.empty()) throw Fail("upload_topology first");
+        halo_finish_df(c);
+        halo_join_puts(c);
         if (df) copy_points(c, c->dv.df, nullptr, df, c->K, true);
         const size_t nb = (size_t)c->n_local * c->M * sizeof(double);
         if (w) CK(cudaMemcpyAsync(c->dv.w, w, nb, cudaMemcpyHostToDevice, c->stream));
@@ -1685,6 +2126,8 @@ int kamr_download_state(kamr_ctx* c, uint32_t mask, double* df, double* sdf, dou
         CK(cudaSetDevice(c->cfg.device));
         if (c->cells.empty()) throw Fail("upload_topology first");
         const int M = c->M, D = c->D;
+        halo_finish_df(c);
+        halo_join_puts(c);
         if ((mask & KAMR_DL_DF) && df) copy_points(c, c->dv.df, df, nullptr, c->K, false);
         if ((mask & KAMR_DL_SDF) && sdf) {
             if (!c->raw_sdf_valid)
@@ -1716,10 +2159,14 @@ int kamr_step(kamr_ctx* c, double dt, int32_t want_residual, double* res_out) {
     return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_step, c, dt, want_residual, res_out); });
 }
 int kamr_exchange_df(kamr_ctx* c) {
-    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); exchange(c, 0, 0); });
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->cfg.device));
+        send_df_halo(c);
+        halo_finish_df(c);
+    });
 }
 int kamr_sync(kamr_ctx* c) {
-    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); sync_and_check(c); });
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); halo_finish_df(c); halo_join_puts(c); sync_and_check(c); });
 }
 
 int kamr_get_stats(kamr_ctx* c, kamr_stats* out) {

@@ -13,6 +13,9 @@ constexpr int MAX_SLOTS = MaxSlots<MAXD>::value;
 constexpr int MAX_SLOPE_NB = 24;  // DIM dirs x 2 sides x 2^(DIM-1) neighbours
 constexpr int PAD = 4;          // planes padded to 4 doubles (32 B) so 128-bit loads stay aligned
 
+constexpr int VPK_BITS = 9;       // <= 512 distinct coordinates per axis
+constexpr int VPK_LEVELS = 16;    // velocity refinement levels 0..15
+
 constexpr double EPS_KIT = 1e-12;                   // src/Abstract/Types.jl:3
 constexpr double EPS_MACH = 2.220446049250313e-16;  // Julia eps(), Flux/CAIDVM.jl:137
 
@@ -171,6 +174,14 @@ struct CopySeg {
     long long len;
 };
 
+// One-sided halo over NVLink: a mirror cell's block is stored straight into the peer's ghost block
+// (the peer's arrays are mapped through CUDA IPC at re-flatten time).
+struct PutSeg {
+    long long src, dst;   // offsets in doubles in the local / the peer's array
+    int len;              // doubles
+    int peer;             // index into the per-peer base-pointer table
+};
+
 // Device pointers handed to the kernels.
 struct DevView {
     const CellInfo* cells;
@@ -185,6 +196,14 @@ struct DevView {
     const unsigned char* v_sign; // per point: bit d = (v_d > 0)
     const double* v_weight;
     const double* v_mid;
+    // Packed velocity-grid statics: the coordinates of all velocity points of a run take few distinct
+    // values per axis (root index x refinement offsets), and a point's weight is a function of its level alone
+    // (Velocity_space/Rebuild.jl:60), so one 32-bit word per point — an index into a per-axis table of the actual
+    // doubles plus the level — replaces DIM+1 doubles.  The hot kernels stage the tables in shared memory and read
+    // 4 bytes per point and pass instead of 8*(DIM+1); values are bit-identical to v_mid / v_weight by construction.
+    const unsigned* v_pack;     // per point: axis d index in bits [VPK_BITS*d, +VPK_BITS), level in bits [27, 31)
+    const double* v_tab;        // [DIM][n_vtab] coordinate tables, then [VPK_LEVELS] weights by level
+    int n_vtab;
     const int* pm_start;        // concatenated pair maps
     const IbNbr* ib_nb;
     const int* cvc_index;       // cut velocity cells of all SolidNeighbors

@@ -2,10 +2,10 @@
 # usage: tools/sweep.sh <outdir> [bench args...]  -- runs bench.py once per library variant under csrc/variants/
 out=$1; shift
 mkdir -p "$out"
-python bench.py --no-cpu --steps 30 --warmup 5 "$@" > "$out/base.json" 2> "$out/base.err"
+python bench.py --no-cpu --steps 10 --warmup 3 --no-parity --no-workloads "$@" > "$out/base.json" 2> "$out/base.err"
 for so in kitamr.jl_b200/csrc/variants/libkamr_*.so; do
   tag=$(basename "$so" .so); tag=${tag#libkamr_}
-  KAMR_LIB=$PWD/$so python bench.py --no-cpu --steps 30 --warmup 5 "$@" > "$out/$tag.json" 2> "$out/$tag.err"
+  KAMR_LIB=$PWD/$so python bench.py --no-cpu --steps 10 --warmup 3 --no-parity --no-workloads "$@" > "$out/$tag.json" 2> "$out/$tag.err"
 done
 python - "$out" <<'P'
 import json, sys, glob, os
