@@ -35,6 +35,8 @@
  *      sdf [ (P*NDF*DIM)  + (d*NDF + k)*n + i ]  == VsData.sdf[i,k,d]
  *      flux[ (P*NDF)      + k*n + i ]            == VsData.flux[i,k]
  *   per-cell:  w,prim,mflux [c*(DIM+2)+m];  qf [c*DIM+d];  sw [c*(DIM+2)*DIM + d*(DIM+2)+m]
+ *              (downloads cover the local cells; sw also the ghost cells behind them: kamr_slope ships the mirrors'
+ *               macro slopes as sw_exchange! does, Parallel/Ghost.jl:867, for the host's Löhner sensor)
  *   velocity grids are shared: cell c uses grid g = cell_grid[c]; grid g has
  *   n_g = grid_off[g+1]-grid_off[g] points at Q = grid_off[g]:
  *      v_level [Q+i]  (Int8, VsData.level)     v_weight[Q+i] (VsData.weight)
@@ -56,8 +58,8 @@ extern "C" {
 enum { KAMR_FLUX_CAIDVM = 0, KAMR_FLUX_DVM = 1 };
 /* time marching: Solver.time_marching (src/Solver/Types.jl:71).
  *   CAIDVM  iterate!(::Type{CAIDVM_Marching}), Theory/Iterate.jl:96   (kamr_step fuses flux! + iterate!)
- *   CIP     iterate!(::Type{CIP_Marching}),    Theory/I-projection.jl:161 (Newton I-projection per cell; refused by
- *           kamr_upload_topology on meshes with immersed-boundary donor cells: positivity_preserving_ib! is not built)
+ *   CIP     iterate!(::Type{CIP_Marching}),    Theory/I-projection.jl:161 (Newton I-projection per cell; on donor cells
+ *           of an immersed boundary preceded by positivity_preserving_ib!, Boundary/Positivity.jl:1)
  *   EULER   iterate!(::Type{Euler}),           Theory/Iterate.jl:131 */
 enum { KAMR_MARCH_CAIDVM = 0, KAMR_MARCH_CIP = 1, KAMR_MARCH_EULER = 2 };
 /* face kinds (src/Physical_space/Types.jl:157-219, src/Boundary/Types.jl:27-33).

@@ -1454,8 +1454,7 @@ __global__ void __launch_bounds__(256) euler_update_kernel(DevView g, GasPar gas
 // backtracking; every Newton sum and every line-search objective is one block reduction), Shakhov relaxation.
 // One CTA per cell, in place on g.df from the stored g.flux.  Every thread carries lambda and takes the (identical)
 // scalar decisions from the broadcast reduction results, so the loop needs no extra broadcast.
-// positivity_preserving_ib! (Boundary/Positivity.jl) is not on the device: the host refuses CIP_Marching on meshes with
-// donor cells (kamr_upload_topology).
+// Donor cells of an immersed boundary first take positivity_preserving_ib! (Boundary/Positivity.jl).
 template <int NV>
 __device__ __forceinline__ void block_min(double (&v)[NV], double* red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
@@ -1545,6 +1544,82 @@ __global__ void __launch_bounds__(256) cip_update_kernel(DevView g, GasPar gas, 
 #pragma unroll
         for (int m = 0; m < M; ++m)
             w_new[m] = g.w[(size_t)c * M + m] + g.mflux[(size_t)c * M + m] * dt / ci.vol;
+    }
+    if (ci.sn_count > 0) {
+        // positivity_preserving_ib! (Boundary/Positivity.jl:1-43), donor cells only (block-uniform): the slope-
+        // extrapolated correction of every SolidNeighbor face, micro = (sn.flux + ndx . sn.sdf) v_n A on the points the
+        // wall side is upwind for (rot v_dir > 0), enters w and vs_data.flux limited by theta = min(theta_rho, theta_e)
+        // so that density and internal energy of w stay positive
+        __shared__ double theta_s;
+        double we[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) we[m] = 0.0;
+        for (int q = 0; q < ci.sn_count; ++q) {
+            const DonorSn e = g.donor_sn[ci.sn_begin + q];
+            const double* __restrict__ snflux = g.flux + e.doff * K;
+            const double* __restrict__ snsdf = g.sdf + e.doff * (K * D);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                double v[D], mic[K];
+#pragma unroll
+                for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+                const double vn = pick<D>(v, e.dir);
+                if (!(e.rot * vn > 0.)) continue;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    double dot = 0.0;
+#pragma unroll
+                    for (int t = 0; t < D; ++t) dot += (e.fmid[t] - v[t] * dt - e.snmid[t]) * snsdf[(t * K + k) * np + i];
+                    mic[k] = (snflux[k * np + i] + dot) * vn * e.area;
+                }
+                add_moments<D, K>(we, own.wt[i], v, mic);
+            }
+        }
+        block_reduce<M>(we, red);
+        if (threadIdx.x == 0) {
+            we[M - 1] *= 0.5;
+#pragma unroll
+            for (int m = 0; m < M; ++m) we[m] *= dt / ci.vol;
+            const double delta = 1e-3;
+            const double th_rho = we[0] > 0 ? 1.0 : fmin(1.0, (1 - delta) * w_new[0] / (fabs(we[0]) + EPS_MACH));
+            double rub2 = 0.0, rube = 0.0, rue2 = 0.0;
+#pragma unroll
+            for (int d = 1; d <= D; ++d) { rub2 += w_new[d] * w_new[d]; rube += w_new[d] * we[d]; rue2 += we[d] * we[d]; }
+            const double eb = w_new[M - 1] - rub2 / (2 * w_new[0]);
+            const double ee = we[M - 1] - rube / w_new[0];
+            const double gam = rue2 / (2 * w_new[0]);
+            const double th_e = fmin(1.0, 2 * (1 - delta) * eb / (sqrt(ee * ee + 4 * gam * (1 - delta) * eb) - ee + EPS_MACH));
+            const double th = fmin(th_rho, th_e);
+#pragma unroll
+            for (int m = 0; m < M; ++m) w_new[m] += th * we[m];
+            theta_s = th;
+        }
+        __syncthreads();
+        const double th = theta_s;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            double v[D], tot[K];
+#pragma unroll
+            for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+#pragma unroll
+            for (int k = 0; k < K; ++k) tot[k] = 0.0;
+            for (int q = 0; q < ci.sn_count; ++q) {
+                const DonorSn& e = g.donor_sn[ci.sn_begin + q];
+                const double vn = pick<D>(v, e.dir);
+                if (!(e.rot * vn > 0.)) continue;
+                const double* __restrict__ snflux = g.flux + e.doff * K;
+                const double* __restrict__ snsdf = g.sdf + e.doff * (K * D);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    double dot = 0.0;
+#pragma unroll
+                    for (int t = 0; t < D; ++t) dot += (e.fmid[t] - v[t] * dt - e.snmid[t]) * snsdf[(t * K + k) * np + i];
+                    tot[k] += (snflux[k * np + i] + dot) * vn * e.area;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) vflux[k * np + i] += th * tot[k];
+        }
+    }
+    if (threadIdx.x == 0) {
         get_prim<D>(w_new, gas.gamma, us.prim_c);
         us.tau = gas.mu_ref * 2.0 * pow(us.prim_c[D + 1], 1 - gas.omega) / us.prim_c[0];
         us.coef_c = maxwell_coef<D>(us.prim_c);
@@ -2478,6 +2553,14 @@ __global__ void __launch_bounds__(256) put_segments_kernel(const PutSeg* __restr
         double2* b = reinterpret_cast<double2*>(dst[sg.peer] + sg.dst);
         for (int t = threadIdx.x; t < sg.len / 2; t += blockDim.x) b[t] = a[t];
     }
+}
+// the same for short blocks of any length (macro slopes: (DIM+2)*DIM doubles per cell): 8 segments per block
+__global__ void __launch_bounds__(256) put_small_kernel(const PutSeg* __restrict__ segs, int nseg,
+                                                        const double* __restrict__ src, double* const* __restrict__ dst) {
+    const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (s >= nseg) return;
+    const PutSeg sg = segs[s];
+    for (int t = threadIdx.x & 31; t < sg.len; t += 32) dst[sg.peer][sg.dst + t] = src[sg.src + t];
 }
 // After the puts of one message: make them visible system-wide, then raise the message's flag in every receiving
 // peer's memory (slot [my rank][kind] of its flag table) to `epoch`.  Stream order puts this after the put kernel.

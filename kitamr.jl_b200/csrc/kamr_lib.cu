@@ -109,12 +109,13 @@ struct PeerPlan {
     Lvl sdf_final;                            // all levels this pair does not exchange early, in one message
     unsigned long long early = 0;             // waves whose slopes this pair exchanges right after the wave
     Lvl solid;                                // df of solid ghost cells, mid-flux (Boundary/Parallel.jl:138-259)
+    Lvl sw;                                   // macro slopes of the mirrors (sw_exchange!, Parallel/Ghost.jl:867)
     long long send_base = 0, recv_base = 0;  // offsets of this peer's region in the staging buffers
 };
 
 // One-sided halo over NVLink.  Message kinds; a peer raises flag [sender rank][kind] in the receiver's
 // flag table when its puts of that kind have landed.
-enum { HK_DF = 0, HK_SOLID = 1, HK_SDF_FINAL = 2, HK_SDF_EARLY = 3, HK_SLOTS = 3 + 64 };
+enum { HK_DF = 0, HK_SOLID = 1, HK_SDF_FINAL = 2, HK_SW = 3, HK_SDF_EARLY = 4, HK_SLOTS = 4 + 64 };
 struct HaloMsg {
     std::vector<PutSeg> segs;      // what this rank stores where
     PutSeg* d_segs = nullptr;
@@ -130,6 +131,7 @@ struct P2P {
     std::vector<void*> opened;               // cudaIpcOpenMemHandle results (closed at the next re-flatten)
     double** d_pdf[2] = {nullptr, nullptr};  // per peer: its two df allocations
     double** d_psdf = nullptr;               // per peer: its raw-slope array
+    double** d_psw = nullptr;                // per peer: its macro-slope array
     int** d_pflags = nullptr;                // per peer: its flag table
     std::map<int, HaloMsg> msg;
 };
@@ -527,9 +529,6 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         for (int q = 0; q < ib->n_sn; ++q)
             if (ib->sn_donor[q] < 0 || ib->sn_donor[q] >= m->n_local) throw Fail("sn_donor must be a local cell");
     }
-    if (c->gas.marching == KAMR_MARCH_CIP)   // positivity_preserving_ib! (Boundary/Positivity.jl) is not on the device
-        for (int i = 0; i < m->n_local; ++i)
-            if (m->bound_enc[i] > 0) throw Fail("CIP_Marching with immersed-boundary donor cells is not supported");
     // ---- grids
     c->grid_n.resize(m->n_grid); c->grid_np.resize(m->n_grid);
     c->grid_goff.resize(m->n_grid + 1); c->grid_hoff.resize(m->n_grid + 1);
@@ -1193,6 +1192,32 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             for (int k = 0; k < M; ++k) t.bc[k] = ib->sn_bc[(size_t)q * M + k];
             c->sn_tasks.push_back(t);
         }
+        {   // per donor cell: its SolidNeighbor faces (positivity_preserving_ib!, CIP_Marching)
+            std::vector<std::vector<int>> of_donor(c->n_local);
+            for (int q = 0; q < ib->n_sn; ++q) of_donor[ib->sn_donor[q]].push_back(q);
+            std::vector<DonorSn> dsn;
+            for (int i = 0; i < c->n_local; ++i) {
+                CellInfo& ci = c->cells[i];
+                ci.sn_begin = (int)dsn.size();
+                for (int q : of_donor[i]) {
+                    DonorSn e;
+                    memset(&e, 0, sizeof(e));
+                    const CellInfo& sn = c->cells[sn0 + q];
+                    e.doff = sn.doff; e.dir = ib->sn_faceid[q] / 2;
+                    e.rot = (ib->sn_faceid[q] % 2 == 0) ? 1.0 : -1.0;   // get_rot, Theory/Math.jl:2
+                    e.area = e.rot;
+                    for (int t = 0; t < D; ++t) {
+                        e.fmid[t] = ci.mid[t];
+                        e.snmid[t] = sn.mid[t];
+                        if (t != e.dir) e.area *= ci.ds[t];
+                    }
+                    e.fmid[e.dir] -= 0.5 * e.rot * ci.ds[e.dir];
+                    dsn.push_back(e);
+                }
+                ci.sn_count = (int)dsn.size() - ci.sn_begin;
+            }
+            c->dv.donor_sn = c->dupload(dsn);
+        }
         const int ncvc = ib->n_sn ? ib->cvc_off[ib->n_sn] : 0;
         cvc_index.assign(ib->cvc_index, ib->cvc_index + ncvc);
         cvc_gw.assign(ib->cvc_gas_w, ib->cvc_gas_w + ncvc);
@@ -1255,6 +1280,10 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
                 pp.solid.send_len += (long long)ci.np * K;
             }
             pos += (long long)ci.np * K;
+            {   // sw of every mirror (fluid or not: the reference ships the block of every mirror, Ghost.jl:795-808)
+                pp.sw.send.push_back(CopySeg{(long long)m->send_cells[q] * M * D, pp.send_base + pp.sw.send_len, (long long)M * D});
+                pp.sw.send_len += (long long)M * D;
+            }
             if (ci.bound_enc >= 0) {  // solid cells carry no slopes
                 const int wv = std::max(0, ci.ps_level - m->ps_minlevel);
                 auto& lv = pp.sdf[wv];
@@ -1275,6 +1304,8 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         long long rpos_max = 0;
         for (int gidx = g0; gidx < g1; ++gidx) {
             const CellInfo& ci = c->cells[gidx];
+            pp.sw.recv.push_back(CopySeg{pp.recv_base + pp.sw.recv_len, (long long)gidx * M * D, (long long)M * D});
+            pp.sw.recv_len += (long long)M * D;
             if (ci.bound_enc < 0) {
                 pp.solid.recv.push_back(CopySeg{pp.recv_base + pp.solid.recv_len, ci.doff * K, (long long)ci.np * K});
                 pp.solid.recv_len += (long long)ci.np * K;
@@ -1310,8 +1341,8 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         }
         pp.sdf_final.d_send = c->dupload(pp.sdf_final.send);
         pp.sdf_final.d_recv = c->dupload(pp.sdf_final.recv);
-        spos_max = std::max(spos_max, pp.sdf_final.send_len);
-        rpos_max = std::max(rpos_max, pp.sdf_final.recv_len);
+        spos_max = std::max(spos_max, std::max(pp.sdf_final.send_len, pp.sw.send_len));
+        rpos_max = std::max(rpos_max, std::max(pp.sdf_final.recv_len, pp.sw.recv_len));
         pp.d_df_send = c->dupload(pp.df_send);
         pp.solid.d_send = c->dupload(pp.solid.send);
         pp.solid.d_recv = c->dupload(pp.solid.recv);
@@ -1362,12 +1393,14 @@ void setup_p2p(kamr_ctx* c, const kamr_mesh* m) {
     P2P& pp = c->p2p;
     pp.d_flags = c->dalloc<int>((size_t)nr * HK_SLOTS);
     CK(cudaMemsetAsync(pp.d_flags, 0, sizeof(int) * (size_t)nr * HK_SLOTS, c->stream));
-    constexpr int HW = 4 * (int)sizeof(cudaIpcMemHandle_t) / 8;   // handle block in 8-byte words
-    cudaIpcMemHandle_t mine[4];
+    constexpr int NH = 5;
+    constexpr int HW = NH * (int)sizeof(cudaIpcMemHandle_t) / 8 + 1;   // handle block in 8-byte words + first ghost id
+    cudaIpcMemHandle_t mine[NH];
     CK(cudaIpcGetMemHandle(&mine[0], c->dv.df));
     CK(cudaIpcGetMemHandle(&mine[1], c->dv.df_new));
     CK(cudaIpcGetMemHandle(&mine[2], c->dv.sdf));
     CK(cudaIpcGetMemHandle(&mine[3], pp.d_flags));
+    CK(cudaIpcGetMemHandle(&mine[4], c->dv.sw));
     std::vector<long long> soff(np + 1, 0), roff(np + 1, 0);
     for (int p = 0; p < np; ++p) {
         soff[p + 1] = soff[p] + HW + (m->recv_off[p + 1] - m->recv_off[p]);   // what we tell p: handles + OUR ghost offsets
@@ -1376,6 +1409,7 @@ void setup_p2p(kamr_ctx* c, const kamr_mesh* m) {
     std::vector<long long> sx(soff[np]), rx(roff[np]);
     for (int p = 0; p < np; ++p) {
         memcpy(&sx[soff[p]], mine, sizeof(mine));
+        sx[soff[p] + HW - 1] = c->n_local + m->recv_off[p];   // cell id of our first ghost from p (per-cell arrays)
         for (int gq = m->recv_off[p]; gq < m->recv_off[p + 1]; ++gq) sx[soff[p] + HW + gq - m->recv_off[p]] = c->cells[c->n_local + gq].doff;
     }
     long long* d_sx = c->dalloc<long long>(sx.size());
@@ -1389,13 +1423,13 @@ void setup_p2p(kamr_ctx* c, const kamr_mesh* m) {
     NCK(nccl().GroupEnd());
     CK(cudaMemcpyAsync(rx.data(), d_rx, sizeof(long long) * rx.size(), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    std::vector<double*> pdf0(np), pdf1(np), psdf(np);
+    std::vector<double*> pdf0(np), pdf1(np), psdf(np), psw(np);
     std::vector<int*> pfl(np);
     for (int p = 0; p < np; ++p) {
-        cudaIpcMemHandle_t h[4];
+        cudaIpcMemHandle_t h[NH];
         memcpy(h, &rx[roff[p]], sizeof(h));
-        void* q[4];
-        for (int a = 0; a < 4; ++a) {
+        void* q[NH];
+        for (int a = 0; a < NH; ++a) {
             cudaError_t e = cudaIpcOpenMemHandle(&q[a], h[a], cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess)
                 throw Fail(std::string("cudaIpcOpenMemHandle (peer rank ") + std::to_string(m->peer_rank[p]) + "): " +
@@ -1403,18 +1437,23 @@ void setup_p2p(kamr_ctx* c, const kamr_mesh* m) {
             pp.opened.push_back(q[a]);
         }
         pdf0[p] = (double*)q[0]; pdf1[p] = (double*)q[1]; psdf[p] = (double*)q[2]; pfl[p] = (int*)q[3];
+        psw[p] = (double*)q[4];
     }
     pp.d_pdf[0] = c->dupload(pdf0); pp.d_pdf[1] = c->dupload(pdf1);
-    pp.d_psdf = c->dupload(psdf); pp.d_pflags = c->dupload(pfl);
+    pp.d_psdf = c->dupload(psdf); pp.d_pflags = c->dupload(pfl); pp.d_psw = c->dupload(psw);
     // put lists and flag slots per message kind
     for (int p = 0; p < np; ++p) {
         const PeerPlan& pl = c->peers[p];
         const long long* rd = &rx[roff[p] + HW];
         auto kind_of_level = [&](int wv) { return (pl.early >> std::min(63, wv) & 1ull) ? HK_SDF_EARLY + std::min(63, wv) : HK_SDF_FINAL; };
         std::map<int, bool> sends, recvs;
+        const long long rcell0 = rx[roff[p] + HW - 1];   // the peer's cell id of its first ghost from us
+        const int MD = (D + 2) * D;
         for (int q = m->send_off[p]; q < m->send_off[p + 1]; ++q) {
             const CellInfo& ci = c->cells[m->send_cells[q]];
             const long long r = rd[q - m->send_off[p]];
+            pp.msg[HK_SW].segs.push_back(PutSeg{(long long)m->send_cells[q] * MD, (rcell0 + q - m->send_off[p]) * MD, MD, p});
+            sends[HK_SW] = true;
             pp.msg[HK_DF].segs.push_back(PutSeg{ci.doff * K, r * K, ci.np * K, p});
             sends[HK_DF] = true;
             if (ci.bound_enc < 0) {
@@ -1429,6 +1468,7 @@ void setup_p2p(kamr_ctx* c, const kamr_mesh* m) {
         for (int gq = m->recv_off[p]; gq < m->recv_off[p + 1]; ++gq) {
             const CellInfo& ci = c->cells[c->n_local + gq];
             recvs[HK_DF] = true;
+            recvs[HK_SW] = true;
             if (ci.bound_enc < 0) recvs[HK_SOLID] = true;
             else recvs[kind_of_level(std::max(0, ci.ps_level - m->ps_minlevel))] = true;
         }
@@ -1452,6 +1492,7 @@ inline void kind_to_what(int kind, int& what, int& level) {
     if (kind == HK_DF) what = 0;
     else if (kind == HK_SOLID) what = 2;
     else if (kind == HK_SDF_FINAL) what = 3;
+    else if (kind == HK_SW) what = 4;
     else { what = 1; level = kind - HK_SDF_EARLY; }
 }
 
@@ -1467,7 +1508,11 @@ void halo_put(kamr_ctx* c, int kind) {
     const bool is_df = kind == HK_DF || kind == HK_SOLID;
     CK(cudaEventRecord(c->ev_put_ready, c->stream));
     CK(cudaStreamWaitEvent(c->comm_stream, c->ev_put_ready, 0));
-    {
+    if (kind == HK_SW) {   // (D+2)*D doubles per cell: scalar stores
+        Launch L_(c, KID_PACK, c->comm_stream);
+        put_small_kernel<<<((int)ms.segs.size() + 7) / 8, 256, 0, c->comm_stream>>>(ms.d_segs, (int)ms.segs.size(), c->dv.sw,
+                                                                                   c->p2p.d_psw);
+    } else {
         Launch L_(c, KID_PACK, c->comm_stream);
         put_segments_kernel<<<std::min<int>((int)ms.segs.size(), 148 * 4), 256, 0, c->comm_stream>>>(
             ms.d_segs, (int)ms.segs.size(), is_df ? c->dv.df : c->dv.sdf,
@@ -1566,6 +1611,7 @@ void copy_points(kamr_ctx* c, double* dev, double* host_rw, const double* host_r
 PeerPlan::Lvl* halo_level(PeerPlan& pp, int what, int level) {
     if (what == 2) return (pp.solid.send.empty() && pp.solid.recv.empty()) ? nullptr : &pp.solid;
     if (what == 3) return (pp.sdf_final.send.empty() && pp.sdf_final.recv.empty()) ? nullptr : &pp.sdf_final;
+    if (what == 4) return (pp.sw.send.empty() && pp.sw.recv.empty()) ? nullptr : &pp.sw;
     if (!(pp.early >> std::min(63, level) & 1ull)) return nullptr;   // this pair sends that level in the final message
     auto it = pp.sdf.find(level);
     return it == pp.sdf.end() ? nullptr : &it->second;
@@ -1573,11 +1619,11 @@ PeerPlan::Lvl* halo_level(PeerPlan& pp, int what, int level) {
 
 // what: 0 df of all mirrors (data_exchange!), 1 sdf of one level for the pairs that need it early
 // (slope_exchange_level!), 2 df of solid ghost cells (solid_exchange_begin!/finish!), 3 sdf of every level not sent
-// early, one message per pair
+// early, one message per pair, 4 macro slopes sw of all mirrors (sw_exchange!)
 void exchange(kamr_ctx* c, int what, int level) {
     if (c->peers.empty()) return;
     if (!c->comm) throw Fail("mesh has peers but kamr_comm_init was not called");
-    double* src = (what == 1 || what == 3) ? c->dv.sdf : c->dv.df;
+    double* src = (what == 1 || what == 3) ? c->dv.sdf : (what == 4 ? c->dv.sw : c->dv.df);
     double* dst = src;
     // one pack and one unpack launch per exchange: the segment lists of all peers taking part, concatenated once
     auto key = std::make_pair(what, what == 1 ? level : 0);
@@ -1735,7 +1781,14 @@ void do_slope(kamr_ctx* c, bool with_sw, bool raw_all, bool defer_final = false)
     }
     c->raw_sdf_valid = raw_all;
     CK(cudaGetLastError());
-    if (with_sw) run_macro_slope<D, K>(c);
+    if (with_sw) {
+        run_macro_slope<D, K>(c);
+        if (!c->peers.empty()) {   // sw_exchange!, Parallel/Ghost.jl:867: the ghosts' sw feed the host's Löhner sensor
+            halo_join_puts(c);
+            halo_put(c, HK_SW);
+            halo_wait(c, HK_SW);
+        }
+    }
     CK(cudaGetLastError());
 }
 
@@ -2140,7 +2193,8 @@ int kamr_download_state(kamr_ctx* c, uint32_t mask, double* df, double* sdf, dou
         if ((mask & KAMR_DL_W) && w) CK(cudaMemcpyAsync(w, c->dv.w, nl * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if ((mask & KAMR_DL_PRIM) && prim) CK(cudaMemcpyAsync(prim, c->dv.prim, nl * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if ((mask & KAMR_DL_QF) && qf) CK(cudaMemcpyAsync(qf, c->dv.qf, nl * D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        if ((mask & KAMR_DL_SW) && sw) CK(cudaMemcpyAsync(sw, c->dv.sw, nl * M * D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if ((mask & KAMR_DL_SW) && sw)   // local cells and, behind them, the ghosts (filled by kamr_slope's sw halo)
+            CK(cudaMemcpyAsync(sw, c->dv.sw, (nl + (size_t)c->n_ghost) * M * D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if ((mask & KAMR_DL_MFLUX) && mflux) CK(cudaMemcpyAsync(mflux, c->dv.mflux, nl * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         sync_and_check(c);
     });

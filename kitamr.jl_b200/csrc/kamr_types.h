@@ -32,8 +32,18 @@ struct CellInfo {
     int hot_begin;                 // first FaceRec of the cell; records sorted by (direction, side)
     int rare_begin, rare_count;    // cell-relative indices of the slots pass B visits
     unsigned char side_begin[8];   // [2*d + side] .. [2*d + side + 1]: FaceRec range of that side; [2*DIM]: total
+    int sn_begin, sn_count;        // donor cells: their SolidNeighbor faces in DevView::donor_sn (positivity_preserving_ib!)
     int pad_;
     double ds[MAXD], mid[MAXD], vol;
+};
+// A SolidNeighbor face as its donor cell sees it in positivity_preserving_ib! (Boundary/Positivity.jl:11-27)
+struct DonorSn {
+    long long doff;      // the SolidNeighbor pseudo-cell's block (its vs_data.flux / .sdf live there)
+    int dir, pad_;
+    double rot;          // get_rot(faceid)
+    double area;         // rot * prod_{t != dir} ds_t of the donor
+    double fmid[MAXD];   // face midpoint: donor midpoint shifted by -rot ds_dir / 2 along dir
+    double snmid[MAXD];  // SolidNeighbor.midpoint (= its solid cell's)
 };
 enum CellFlags : int {
     CELL_HAS_MAXWELL_WALL = 1,
@@ -206,6 +216,7 @@ struct DevView {
     int n_vtab;
     const int* pm_start;        // concatenated pair maps
     const IbNbr* ib_nb;
+    const DonorSn* donor_sn;
     const int* cvc_index;       // cut velocity cells of all SolidNeighbors
     const double* cvc_gas_w;
     const double* cvc_solid_w;

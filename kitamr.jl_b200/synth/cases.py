@@ -318,7 +318,7 @@ def uniform_case(dim=2, trees=64, maxlevel=0, vtrees=60, name=None, seed=3, refi
 
 # ---------------------------------------------------------------------- bench workloads
 def cylinder_s2(copies=1, ps_maxlevel=7, box_level=4, vs_maxlevel=3, vtrees=16, trees=25, noise=0.01,
-                ib=False) -> Case:
+                ib=False, Ma=5.0) -> Case:
     """S2 cylinder2d (example/cylinder/cylinder.jl:5-47): 25x25 roots on [-16,16]^2, level `box_level`
     in max-norm(x)<5 (the converged dynamic-AMR region, cylinder_udf.jl:9-15), level `ps_maxlevel`
     within search_coeffi*ds_min = 4*ds_min of the r=1 circle; velocity grids 16x16 roots on
@@ -332,7 +332,6 @@ def cylinder_s2(copies=1, ps_maxlevel=7, box_level=4, vs_maxlevel=3, vtrees=16, 
     geo = (-16.0, -16.0 + W * copies, -16.0, 16.0)
     centers = np.array([[W * k, 0.0] for k in range(copies)])
     ds_min = W / trees / 2 ** ps_maxlevel
-    Ma = 5.0
 
     def rel(mid):
         d = mid[:, None, :] - centers[None, :, :]
@@ -382,7 +381,7 @@ def cylinder_s2(copies=1, ps_maxlevel=7, box_level=4, vs_maxlevel=3, vtrees=16, 
 
 
 def sphere_s4(copies=1, ps_maxlevel=4, trees=16, vtrees=16, vs_maxlevel=2, noise=0.01, ib=True,
-              shell=1.5) -> Case:
+              shell=1.5, Ma=3.834) -> Case:
     """S4 sphere3d (example/sphere/sphere.jl:5-47, sphere_udf.jl): trees^3 roots on [-4,4]^3, static refinement
     to level L-2 in max-norm(x) < 1.2 and L-1 in < 0.8 outside the body (shock_wave_region), level L within
     search_coeffi*ds_min = 1.5*ds_min of the r = 0.5 sphere; velocity grids vtrees^3 roots on [-7.28,7.28]^3 refined to
@@ -394,7 +393,6 @@ def sphere_s4(copies=1, ps_maxlevel=4, trees=16, vtrees=16, vs_maxlevel=2, noise
     centers = np.array([[W * k, 0.0, 0.0] for k in range(copies)])
     L = ps_maxlevel
     ds_min = W / trees / 2 ** L
-    Ma = 3.834
     Tw = 1.0 + (5 / 3 - 1) * 0.5 * Ma ** 2
 
     def rel(mid):

@@ -68,6 +68,12 @@ def _cases():
         "s1_small": lambda: cases.riemann_s1(ps_level=1, band_level=2, trees=4, vtrees=8, vs_maxlevel=2),
         # S3 (example/airfoil): one uniform velocity grid, InterpolatedOutflow on three sides
         "s3_small": lambda: cases.airfoil_s3(ps_maxlevel=3, box_level=2, trees=(6, 8), vtrees=12),
+        # CIP_Marching on immersed-boundary meshes: positivity_preserving_ib! on the donor cells (Boundary/Positivity.jl).
+        # Subsonic (Ma 0.3): the Ma 5 / Ma 3.8 impulsive starts of the bench cases leave the ORACLE's Newton projection
+        # with NaN after three CIP steps, so they are no parity cases.
+        "cip_ib2d": lambda: _cip(cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True,
+                                                   Ma=0.3)),
+        "cip_ib3d": lambda: _cip(cases.sphere_s4(trees=4, ps_maxlevel=2, vtrees=6, vs_maxlevel=1, Ma=0.3)),
         # DVM flux (Flux/DVM.jl:79-99; Solver.flux = DVM): micro flux only, hanging faces + mismatched grids; the domain
         # BCs exclude the Maxwellian wall, which cannot run in the reference under DVM (DVM.jl:12)
         "dvm2d": lambda: _dvm(cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=8, vs_maxlevel=2, ragged=True, seed=41,
@@ -78,6 +84,12 @@ def _cases():
         "dvm_ib2d": lambda: _dvm(cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True)),
         "dvm_ib3d": lambda: _dvm(cases.sphere_s4(trees=4, ps_maxlevel=2, vtrees=4, vs_maxlevel=1)),
     }
+
+
+def _cip(case):
+    from kitamr_jl_b200 import abi
+    case.marching = abi.MARCH_CIP
+    return case
 
 
 def _dvm(case):

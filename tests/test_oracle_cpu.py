@@ -612,8 +612,8 @@ def test_cip_and_caidvm_agree_to_first_order():
 
 
 def test_cip_with_immersed_boundary_keeps_density_and_energy_positive():
-    """positivity_preserving_ib! (Boundary/Positivity.jl, restated in the ORACLE only — libkamr refuses CIP_Marching on a
-    mesh with donor cells): the slope-extrapolated wall correction enters w and vs_data.flux scaled by
+    """positivity_preserving_ib! (Boundary/Positivity.jl; device parity: tests/test_gpu_parity.py cip_ib2d / cip_ib3d):
+    the slope-extrapolated wall correction enters w and vs_data.flux scaled by
     theta = min(theta_rho, theta_e) <= 1, chosen so that rho and the internal energy of the updated w stay positive."""
     case = cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True)
     case.marching = abi.MARCH_CIP
