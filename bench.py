@@ -625,19 +625,27 @@ def parity_check(args, case, mesh, st0, ctx, rank, world, local, stream, dt):
         dist.barrier()
         ref_df = ref_w = None
         full = None
+        err = None
         if rank == 0:
-            full = case.rank_mesh()
-            stf = case.init_state(full)
-            c1 = api.Context(case.config(device=local, rank=0, nranks=1, stream=stream.cuda_stream))
             try:
-                c1.upload_topology(full)
-                c1.upload_state(stf, aux=False)
-                for _ in range(steps):
-                    c1.step(dt, False)
-                stf = c1.download_state(stf, abi.DL_DF | abi.DL_W)
-            finally:
-                c1.close()
-            ref_df, ref_w = stf.df, stf.w
+                full = case.rank_mesh()
+                stf = case.init_state(full)
+                c1 = api.Context(case.config(device=local, rank=0, nranks=1, stream=stream.cuda_stream))
+                try:
+                    c1.upload_topology(full)
+                    c1.upload_state(stf, aux=False)
+                    for _ in range(steps):
+                        c1.step(dt, False)
+                    stf = c1.download_state(stf, abi.DL_DF | abi.DL_W)
+                finally:
+                    c1.close()
+                ref_df, ref_w = stf.df, stf.w
+            except Exception as e:   # e.g. the whole forest does not fit one GPU: every rank must learn it
+                err = repr(e)
+        okf = torch.tensor([0 if err else 1], dtype=torch.int64, device="cuda")
+        dist.broadcast(okf, src=0)
+        if int(okf.item()) == 0:
+            return {"error": err or "single-rank reference run failed on rank 0", "steps": steps}
         # every rank's local cells are a contiguous range of the whole forest's cell list (Morton partition)
         g0 = int(mesh.global_ids[0]); g1 = int(mesh.global_ids[nl - 1])
         rng = torch.tensor([g0, g1], dtype=torch.int64, device="cuda")

@@ -833,9 +833,10 @@ __host__ __device__ inline int chunk_points(int n, int C) { return (C == 1) ? ((
 // loop over the staged planes.  Kernels with pair-mapped gathers add a [D+2][batches] table for the neighbour-side
 // macro flux (its quadrature runs over the NEIGHBOUR's points, CAIDVM.jl:119), see warp_batch_add.
 template <int D, int K>
-__host__ __device__ inline size_t phase_smem_bytes(int ntab, int P, bool stage, bool mapped) {
-    return sizeof(double) * (((vtab_doubles(D, ntab) + 1) & ~(size_t)1) + (stage ? (size_t)(2 * K) * P : 0) +
-                             (mapped ? (size_t)(D + 2) * batch_count(P) : 0));
+__host__ __device__ inline size_t phase_smem_bytes(int ntab, int P, bool stage, bool split, bool mapped) {
+    return sizeof(double) * (((vtab_doubles(D, ntab) + 1) & ~(size_t)1) +
+                             (stage ? (size_t)(split ? 2 * K : K + 1) * P : 0) +
+                             (mapped && split ? (size_t)(D + 2) * batch_count(P) : 0));
 }
 
 template <int D, int K, int MODE, bool STAGE_SMEM, int NT, int MINB, int C>
@@ -888,7 +889,7 @@ __global__ void __launch_bounds__(NT, MINB)
     // SPLIT: the fused kernel with shared-memory staging keeps f and the gathered flux of every point in shared memory
     // and takes the moments in a loop of its own; the other instantiations accumulate them while they gather
     constexpr bool SPLIT = MODE == MODE_FUSED && STAGE_SMEM;
-    double* mbat = fsm + (STAGE_SMEM ? (size_t)(2 * K) * P : 0);   // [D+2][NB] macro flux of pair-mapped gathers (SPLIT)
+    double* mbat = fsm + (size_t)(2 * K) * P;   // [D+2][NB] macro flux of pair-mapped gathers (SPLIT only)
     const int NB = batch_count(P);
 
     // ---- phase 1: face fluxes, convection, moments
@@ -943,8 +944,11 @@ __global__ void __launch_bounds__(NT, MINB)
     if (MODE != MODE_UPDATE && has_mapped) {   // pass A2 (block-uniform branch): pair-mapped neighbour-upwind halves
         if (threadIdx.x == 0) s_next = p0;
         __syncthreads();
+        int ib_static = p0 + (int)(threadIdx.x & ~31u);
         for (;;) {
-            const int ib = warp_next_batch(&s_next);
+            // (without the batch table the sums live in per-thread accumulators: a fixed assignment keeps them reproducible)
+            int ib;
+            if (SPLIT) ib = warp_next_batch(&s_next); else { ib = ib_static; ib_static += NT; }
             if (ib >= p1) break;
             const int i = ib + (int)(threadIdx.x & 31);
             const bool on = i < p1;
@@ -1173,7 +1177,9 @@ __global__ void __launch_bounds__(NT, MINB)
     const int soff = STAGE_SMEM ? p0 : 0;
     double* fls = fsm + (size_t)K * P;    // staged face flux (SPLIT); afterwards the h-plane of M[prim_c]
     double* fch = fls;
-    constexpr bool SPLIT = STAGE_SMEM;    // see phase_kernel
+    // see phase_kernel; the regular small-cell kernel (128-thread CTAs) keeps the moments in its gather loop: there the
+    // extra pass costs more than the few spilled accumulators (measured on S2: 0.42 -> 0.38 ms)
+    constexpr bool SPLIT = STAGE_SMEM && NT > 128;
     double* mbat = fsm + (size_t)(2 * K) * P;   // [D+2][NB] macro flux of the pair-mapped gathers (MAPPED && SPLIT)
     const int NB = batch_count(P);
     const double* __restrict__ gdf = g.df;
@@ -1276,8 +1282,10 @@ __global__ void __launch_bounds__(NT, MINB)
         // with the NEIGHBOUR's points, so it is kept apart from the own-weighted flux (per-thread columns / acc).
         if (threadIdx.x == 0) s_next = p0;
         __syncthreads();
+        int ib_static = p0 + (int)(threadIdx.x & ~31u);
         for (;;) {
-            const int ib = warp_next_batch(&s_next);
+            int ib;
+            if (SPLIT) ib = warp_next_batch(&s_next); else { ib = ib_static; ib_static += NT; }
             if (ib >= p1) break;
             const int i = ib + (int)(threadIdx.x & 31);
             const bool on = i < p1;

@@ -1386,6 +1386,11 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
 // side stream, followed by a flag the receiver's stream waits on right before the first kernel that reads the ghosts.
 // No rendezvous: a sender never waits, a receiver only when it reads.  p4est's mirror order of a pair equals the
 // peer's ghost order (Parallel/Ghost.jl:221-264), so the k-th mirror sent to a peer lands in its k-th ghost from us.
+#ifndef KAMR_PUT_CTAS
+#define KAMR_PUT_CTAS 96
+#endif
+constexpr int PUT_CTAS = KAMR_PUT_CTAS;
+
 void setup_p2p(kamr_ctx* c, const kamr_mesh* m) {
     if (m->n_peer == 0 || !c->comm) return;
     if (const char* h = getenv("KAMR_HALO")) if (!strcmp(h, "nccl")) return;   // two-sided NCCL path (debugging)
@@ -1498,15 +1503,16 @@ inline void kind_to_what(int kind, int& what, int& level) {
 
 // Send this rank's part of a message: the mirrors' blocks are stored into the peers' ghost blocks by a put kernel on
 // the communication stream, then the flags go up.  Two-sided path: nothing yet (the exchange runs at the wait).
-void halo_put(kamr_ctx* c, int kind) {
+void halo_put(kamr_ctx* c, int kind, cudaStream_t after = nullptr) {
     if (c->peers.empty() || !c->p2p.on) return;
+    if (!after) after = c->stream;
     auto it = c->p2p.msg.find(kind);
     if (it == c->p2p.msg.end()) return;
     HaloMsg& ms = it->second;
     ms.epoch++;
     if (ms.to.empty()) return;
     const bool is_df = kind == HK_DF || kind == HK_SOLID;
-    CK(cudaEventRecord(c->ev_put_ready, c->stream));
+    CK(cudaEventRecord(c->ev_put_ready, after));
     CK(cudaStreamWaitEvent(c->comm_stream, c->ev_put_ready, 0));
     if (kind == HK_SW) {   // (D+2)*D doubles per cell: scalar stores
         Launch L_(c, KID_PACK, c->comm_stream);
@@ -1514,7 +1520,9 @@ void halo_put(kamr_ctx* c, int kind) {
                                                                                    c->p2p.d_psw);
     } else {
         Launch L_(c, KID_PACK, c->comm_stream);
-        put_segments_kernel<<<std::min<int>((int)ms.segs.size(), 148 * 4), 256, 0, c->comm_stream>>>(
+        // (a modest grid: the NVLink stores need few CTAs to saturate the link, and every CTA of this high-priority
+        // stream displaces one of the step's own kernels)
+        put_segments_kernel<<<std::min<int>((int)ms.segs.size(), PUT_CTAS), 256, 0, c->comm_stream>>>(
             ms.d_segs, (int)ms.segs.size(), is_df ? c->dv.df : c->dv.sdf,
             is_df ? c->p2p.d_pdf[c->df_parity] : c->p2p.d_psdf);
     }
@@ -1532,8 +1540,9 @@ void halo_join_puts(kamr_ctx* c) {
 }
 // Before the first kernel that reads the ghosts of a message: wait for the peers' flags (one-sided) or run the
 // pack / ncclSend+ncclRecv / unpack exchange here (two-sided).
-void halo_wait(kamr_ctx* c, int kind) {
+void halo_wait(kamr_ctx* c, int kind, cudaStream_t on = nullptr) {
     if (c->peers.empty()) return;
+    if (!on) on = c->stream;
     if (!c->p2p.on) {
         int what, level;
         kind_to_what(kind, what, level);
@@ -1543,8 +1552,8 @@ void halo_wait(kamr_ctx* c, int kind) {
     auto it = c->p2p.msg.find(kind);
     if (it == c->p2p.msg.end() || it->second.from.empty()) return;
     HaloMsg& ms = it->second;
-    Launch L_(c, KID_UNPACK);
-    halo_wait_kernel<<<1, (int)round_up((long long)ms.from.size(), 32), 0, c->stream>>>(
+    Launch L_(c, KID_UNPACK, on);
+    halo_wait_kernel<<<1, (int)round_up((long long)ms.from.size(), 32), 0, on>>>(
         c->p2p.d_flags, ms.d_from, (int)ms.from.size(), ms.epoch, c->dv.err_flag);
     CK(cudaGetLastError());
 }
@@ -1858,7 +1867,7 @@ void launch_regular_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int 
 // the fused step of one bin: the instantiation follows the bin's CTA width, cluster size and staging area
 template <int D, int K>
 void launch_fused(kamr_ctx* c, const Bin& b, double dt, int want) {
-    const size_t smem = phase_smem_bytes<D, K>(c->dv.n_vtab, b.P, b.stage, !b.regular || b.mapped);
+    const size_t smem = phase_smem_bytes<D, K>(c->dv.n_vtab, b.P, b.stage, b.wide || !b.regular, !b.regular || b.mapped);
 #define KAMR_FUSED(STAGE, PT, MB, CC)                                                                       \
     do {                                                                                                    \
         if (b.regular) launch_regular_inst<D, K, STAGE, PT, MB, CC>(c, b, smem, dt, want);                  \
@@ -1884,8 +1893,8 @@ void launch_unfused(kamr_ctx* c, const Bin& b, double dt, int want) {
     for (int cell : b.cells) nmax = std::max(nmax, c->cells[cell].n);
     const int P = chunk_points(nmax, 1);
     const bool stage = MODE == MODE_UPDATE &&
-                       phase_smem_bytes<D, K>(c->dv.n_vtab, P, true, false) + (14 << 10) <= (size_t)c->max_smem_optin;
-    const size_t smem = phase_smem_bytes<D, K>(c->dv.n_vtab, P, stage, false);
+                       phase_smem_bytes<D, K>(c->dv.n_vtab, P, true, false, false) + (14 << 10) <= (size_t)c->max_smem_optin;
+    const size_t smem = phase_smem_bytes<D, K>(c->dv.n_vtab, P, stage, false, false);
     if (stage) launch_phase_inst<D, K, MODE, true, PNT_WIDE, MINB_WIDE, 1>(c, b, smem, dt, want, kid);
     else launch_phase_inst<D, K, MODE, false, PNT_WIDE, MINB_WIDE, 1>(c, b, smem, dt, want, kid);
 }
@@ -1899,9 +1908,9 @@ void do_ib(kamr_ctx* c, double* df2, cudaStream_t st = nullptr) {
         Launch L_(c, KID_SOLID_CELL, st);
         solid_cell_kernel<D, K><<<(int)c->solid_tasks.size(), 256, 0, st>>>(c->dv, c->gas, c->d_solid_tasks, df2);
     }
-    if (st == c->stream) {   // (callers use the side stream only on a rank without peers)
-        halo_put(c, HK_SOLID);
-        halo_wait(c, HK_SOLID);
+    if (st == c->stream || c->p2p.on) {   // (the two-sided exchange lives on the main stream)
+        halo_put(c, HK_SOLID, st);
+        halo_wait(c, HK_SOLID, st);
     }
     if (!c->sn_tasks.empty()) {
         Launch L_(c, KID_SOLID_NBR, st);
@@ -1960,7 +1969,13 @@ void do_iterate(kamr_ctx* c, double dt, int want, double* res_out) {
         for (auto& b : c->bins) launch_unfused<D, K, MODE_UPDATE>(c, b, dt, want);
     }
     CK(cudaGetLastError());
-    send_df_halo(c);
+    // The update ran IN PLACE: unlike the fused step, whose ghosts of the new time level land in the other df buffer, a
+    // one-sided put here could overwrite ghost blocks a slower peer is still reading.  data_exchange! therefore stays a
+    // two-sided pack / ncclSend+ncclRecv on this path (a rendezvous at the same program point of both ranks).
+    if (!c->peers.empty()) {
+        halo_join_puts(c);
+        exchange(c, 0, 0);
+    }
     fetch_residual<D, K>(c, want, res_out);
 }
 
@@ -1992,9 +2007,21 @@ void do_step(kamr_ctx* c, double dt, int want, double* res_out) {
         // slope message goes out; the cells that read no ghost data are updated while it travels; then the ghosts'
         // slopes, the wall kernels around the solid-cell halo, and the cells along the partition boundary.
         do_slope<D, K>(c, false, false, true);
+        const bool walls = !c->solid_tasks.empty() || !c->sn_tasks.empty();
+        const bool side = walls && c->p2p.on;
+        if (side) {
+            // one-sided halo: the wall chain (ghost slopes -> solid cells -> solid halo -> solid neighbours) runs on the
+            // side stream beside the cells that read no ghost data, as on a single rank
+            CK(cudaEventRecord(c->ev_fork, c->stream));
+            CK(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+            halo_wait(c, HK_SDF_FINAL, c->side_stream);   // (the wall kernels read the ghosts' RAW slopes)
+            do_ib<D, K>(c, c->dv.df_new, c->side_stream);
+            CK(cudaEventRecord(c->ev_join, c->side_stream));
+        }
         for (auto& b : c->bins) if (!b.halo) launch_fused<D, K>(c, b, dt, want);
         finish_slope_halo<D, K>(c);
-        do_ib<D, K>(c, c->dv.df_new);
+        if (side) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        else do_ib<D, K>(c, c->dv.df_new);
         for (auto& b : c->bins) if (b.halo) launch_fused<D, K>(c, b, dt, want);
     }
     CK(cudaGetLastError());

@@ -234,11 +234,11 @@ def _dedup_grids(per_cell_grids):
 
 
 # ---------------------------------------------------------------------- cases
-def smoke_s0(noise=0.01, trees=16, vtrees=16) -> Case:
+def smoke_s0(noise=0.01, trees=16, vtrees=16, tree_order="morton") -> Case:
     """test/runtests.jl:4-41: 2-D, NDF=2, 16x16 cells, 16x16 velocity points, Maxwellian walls in x
     (xmax wall moving with U=sqrt(5/6)), periodic in y, CAIDVM + CAIDVM_Marching."""
     geo = (-0.5, 0.5, -0.5, 0.5)
-    forest = Forest.build(2, geo, (trees, trees), 0, periodic=(False, True))
+    forest = Forest.build(2, geo, (trees, trees), 0, periodic=(False, True), tree_order=tree_order)
     quad = (-5.0, 5.0, -5.0, 5.0)
     g = vg.root_grid(quad, (vtrees, vtrees))
     gas = Gas(K=0.0, Kn=0.075, omega=0.81, omega_r=0.81)
@@ -297,13 +297,13 @@ def amr_case(dim=2, trees=4, maxlevel=2, vtrees=6, vs_maxlevel=2, ragged=True, p
 
 
 def uniform_case(dim=2, trees=64, maxlevel=0, vtrees=60, name=None, seed=3, refine_fn=None,
-                 geometry=None, quadrature=None, U0=None) -> Case:
+                 geometry=None, quadrature=None, U0=None, tree_order="morton") -> Case:
     """Bench-shaped case: one shared uniform velocity grid (example/airfoil: 60x60, VS level 0) on a
     (optionally geometry-refined) physical mesh, supersonic inflow at xmin and outflow elsewhere."""
     ndf = 2 if dim == 2 else 1
     geo = geometry or tuple([-0.5, 0.5] * dim)
     trees_t = trees if isinstance(trees, tuple) else (trees,) * dim
-    forest = Forest.build(dim, geo, trees_t, maxlevel, refine_fn)
+    forest = Forest.build(dim, geo, trees_t, maxlevel, refine_fn, tree_order=tree_order)
     quad = quadrature or tuple([-6.0, 6.0] * dim)
     vt = vtrees if isinstance(vtrees, tuple) else (vtrees,) * dim
     g = vg.root_grid(quad, vt)

@@ -136,18 +136,18 @@ def test_pair_map_rejects_non_covering():
 # ------------------------------------------------------------------------------------------------ twin
 def _twin_cases():
     return {
-        "S0": lambda: cases.smoke_s0(trees=8, vtrees=12),
-        "inflow2d": lambda: cases.uniform_case(dim=2, trees=6, vtrees=10),
+        "S0": lambda: cases.smoke_s0(trees=8, vtrees=12, tree_order="lex"),
+        "inflow2d": lambda: cases.uniform_case(dim=2, trees=6, vtrees=10, tree_order="lex"),
         "periodic2d": lambda: _periodic_uniform(2),
-        "inflow3d": lambda: cases.uniform_case(dim=3, trees=4, vtrees=6),
-        "euler2d": lambda: _with(cases.uniform_case(dim=2, trees=5, vtrees=8), marching=abi.MARCH_EULER),
+        "inflow3d": lambda: cases.uniform_case(dim=3, trees=4, vtrees=6, tree_order="lex"),
+        "euler2d": lambda: _with(cases.uniform_case(dim=2, trees=5, vtrees=8, tree_order="lex"), marching=abi.MARCH_EULER),
         "interp_outflow2d": lambda: _interp_case(),
-        "cip2d": lambda: _with(cases.uniform_case(dim=2, trees=5, vtrees=10), marching=abi.MARCH_CIP),
-        "cip3d": lambda: _with(cases.uniform_case(dim=3, trees=3, vtrees=6), marching=abi.MARCH_CIP),
+        "cip2d": lambda: _with(cases.uniform_case(dim=2, trees=5, vtrees=10, tree_order="lex"), marching=abi.MARCH_CIP),
+        "cip3d": lambda: _with(cases.uniform_case(dim=3, trees=3, vtrees=6, tree_order="lex"), marching=abi.MARCH_CIP),
         # DVM flux (Flux/DVM.jl:79-99): the same micro fluxes, no macro flux, so w stays put under every marching (the
         # Euler MicroFlux branch, Theory/Iterate.jl:144, tests a Type against a Union of types and is never taken)
-        "dvm2d": lambda: _with(cases.uniform_case(dim=2, trees=6, vtrees=10), flux_type=abi.FLUX_DVM),
-        "dvm3d_euler": lambda: _with(cases.uniform_case(dim=3, trees=3, vtrees=6), flux_type=abi.FLUX_DVM,
+        "dvm2d": lambda: _with(cases.uniform_case(dim=2, trees=6, vtrees=10, tree_order="lex"), flux_type=abi.FLUX_DVM),
+        "dvm3d_euler": lambda: _with(cases.uniform_case(dim=3, trees=3, vtrees=6, tree_order="lex"), flux_type=abi.FLUX_DVM,
                                      marching=abi.MARCH_EULER),
     }
 
@@ -160,13 +160,13 @@ def _with(case, **kw):
 
 def _periodic_uniform(dim):
     from kitamr_jl_b200.synth.forest import Forest
-    c = cases.uniform_case(dim=dim, trees=5, vtrees=8)
-    c.forest = Forest.build(dim, c.forest.geometry, c.forest.trees_num, 0, periodic=(True,) * dim)
+    c = cases.uniform_case(dim=dim, trees=5, vtrees=8, tree_order="lex")
+    c.forest = Forest.build(dim, c.forest.geometry, c.forest.trees_num, 0, periodic=(True,) * dim, tree_order="lex")
     return c
 
 
 def _interp_case():
-    c = cases.uniform_case(dim=2, trees=6, vtrees=8)
+    c = cases.uniform_case(dim=2, trees=6, vtrees=8, tree_order="lex")
     c.bc_type = np.array([abi.BC_SUPERSONIC_INFLOW, abi.BC_INTERPOLATED_OUTFLOW, abi.BC_MAXWELLIAN,
                           abi.BC_INTERPOLATED_OUTFLOW], dtype=np.int32)
     return c
