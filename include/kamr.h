@@ -163,11 +163,17 @@ int  kamr_version(void);
 
 /* multi-GPU: nccl_unique_id points at the 128-byte ncclUniqueId obtained on
  * rank 0 via kamr_comm_unique_id and distributed by the host (MPI_Bcast in the
- * Julia shim).  Not needed for nranks == 1. */
+ * Julia shim).  Not needed for nranks == 1.  NCCL carries the set-up handshakes; the per-step halo is one-sided
+ * (mirror blocks stored into the peer's ghost blocks over NVLink through CUDA IPC mappings), or
+ * two-sided ncclSend/ncclRecv with KAMR_HALO=nccl in the environment. */
 int  kamr_comm_unique_id(void* id128);
 int  kamr_comm_init(kamr_ctx* ctx, const void* id128);
 
-/* re-flatten: after initialize / restart / every amr_recover! (Solver/AMR.jl:54) */
+/* re-flatten: after initialize / restart / every amr_recover! (Solver/AMR.jl:54).
+ * On a mesh with peers (n_peer > 0) this call is COLLECTIVE over the communicator, as amr_recover! is over MPI: every rank
+ * must have called kamr_comm_init first and must call kamr_upload_topology too (the ranks swap their slope-halo
+ * schedule and, for the one-sided halo, the CUDA IPC handles and ghost offsets of their arrays); a mesh with peers
+ * without a communicator is refused.  All index arrays are range-checked; a malformed mesh is an error, not a crash. */
 int  kamr_upload_topology(kamr_ctx* ctx, const kamr_mesh* mesh);
 /* state in host layout; df for all n_cell cells (ghost / solid-neighbour blocks may be anything),
  * w and prim for local cells [n_local*(DIM+2)].  NULL pointers are skipped. */
@@ -193,7 +199,7 @@ int  kamr_iterate(kamr_ctx* ctx, double dt, int32_t want_residual, double* res_o
 /* slope + flux + iterate with the flux kept on chip (DESIGN.md "fused step") */
 int  kamr_step(kamr_ctx* ctx, double dt, int32_t want_residual, double* res_out);
 /* halo of df after the update (data_exchange!, Parallel/Ghost.jl:841); called by kamr_iterate/kamr_step
- * internally, exported for host-driven sequences */
+ * internally, exported for host-driven sequences (after kamr_upload_state on a mesh with peers) */
 int  kamr_exchange_df(kamr_ctx* ctx);
 int  kamr_sync(kamr_ctx* ctx);
 

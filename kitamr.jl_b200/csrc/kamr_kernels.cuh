@@ -502,6 +502,49 @@ __device__ __forceinline__ void hot_flux(const DevView& g, const FaceRec* hot, c
             }
         }
         const int sn = 1 - so;
+#ifndef KAMR_HANG_SERIAL
+        // further sub-faces of a hanging side (2^(DIM-1) - 1 of them): all their neighbour values are requested before
+        // any is used, so the side costs one more memory round trip, not one per sub-face
+        constexpr int XN = (1 << (D - 1)) - 1;
+        const int qb = sb[2 * d + sn] + 1, qe = sb[2 * d + sn + 1];
+        if (qb < qe) {
+            double xf[XN][K], xs[XN][K * D];
+#pragma unroll
+            for (int r = 0; r < XN; ++r) {
+                const int q = qb + r;
+                if (q < qe && (hot[q].flags & 2)) {
+                    const FaceRec& h = hot[q];
+                    const double* __restrict__ nf = g.df + h.nf_off + i;
+                    const double* __restrict__ nsl = g.sdl + h.nsl_off + i;
+                    const int np = h.np;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        xf[r][k] = ldg_stream(nf + k * np);
+#pragma unroll
+                        for (int t = 0; t < D; ++t) xs[r][k * D + t] = ldg_stream(nsl + (t * K + k) * np);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < XN; ++r) {
+                const int q = qb + r;
+                if (q < qe && (hot[q].flags & 2)) {
+                    const FaceRec& h = hot[q];
+                    const double Avn = h.area * vn;
+                    double dx[D];
+#pragma unroll
+                    for (int t = 0; t < D; ++t) dx[t] = face_dx(h.fmid[t], vdt[t], h.nbr_mid[t]);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        double val = xf[r][k];
+#pragma unroll
+                        for (int t = 0; t < D; ++t) val += dx[t] * xs[r][k * D + t];
+                        fl[k] += val * Avn;
+                    }
+                }
+            }
+        }
+#else
         for (int q = sb[2 * d + sn] + 1; q < sb[2 * d + sn + 1]; ++q) {   // further sub-faces of a hanging side
             const FaceRec& h = hot[q];
             if (!(h.flags & 2)) continue;
@@ -520,6 +563,7 @@ __device__ __forceinline__ void hot_flux(const DevView& g, const FaceRec* hot, c
                 fl[k] += val * Avn;
             }
         }
+#endif
     }
 }
 
@@ -1904,7 +1948,7 @@ __device__ __forceinline__ void side_sum(const DevView& g, const SlopeNbr* nb, i
                                          const double* f, double* acc) {
     // Block-uniform fast path: every neighbour of the side lives on the cell's own velocity grid (point i <-> point i)
     constexpr int MAXN = 1 << (D - 1);
-#ifdef KAMR_SLOPE_V2
+#if defined(KAMR_SLOPE_V2) || defined(KAMR_SLOPE_FIXED)
     bool same = cnt == 1 || cnt == MAXN;
 #else
     bool same = false;
@@ -1941,10 +1985,12 @@ __device__ __forceinline__ void side_sum(const DevView& g, const SlopeNbr* nb, i
 // cannot deadlock under MPS, time-slicing or a debugger.  The spin is bounded all the same: on expiry the kernel
 // raises g.err_flag (surfaced by the next kamr_sync / download / residual read as an error) instead of hanging.
 constexpr unsigned SLOPE_SPIN_LIMIT = 1u << 25;   // x 64 ns sleep: seconds
+#ifndef KAMR_SLOPE_THREADS
 #ifdef KAMR_SLOPE_V2
 #define KAMR_SLOPE_THREADS 768
 #else
 #define KAMR_SLOPE_THREADS 1024
+#endif
 #endif
 template <int D, int K, bool GENERIC, int NT>
 __global__ void __launch_bounds__(NT, KAMR_SLOPE_THREADS / NT) slope_kernel(DevView g, const SlopeTask* __restrict__ tasks, int raw_all,
@@ -2070,7 +2116,7 @@ __global__ void __launch_bounds__(NT, KAMR_SLOPE_THREADS / NT) slope_kernel(DevV
         const int li = GENERIC ? (int)own.lev[i] : 0;
         // (the direction loop stays rolled: s[d] is indexed at run time and lives in local memory, a few L1-resident
         // bytes per point, in exchange for a kernel a third of the size — unrolled it overflowed the instruction cache)
-#ifdef KAMR_SLOPE_V2
+#if defined(KAMR_SLOPE_V2) || defined(KAMR_SLOPE_ROLL)
 #pragma unroll 1
 #else
 #pragma unroll

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <functional>
 #include <map>
 #include <stdexcept>
@@ -495,7 +496,16 @@ void setup_p2p(kamr_ctx* c, const kamr_mesh* m);
 
 void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     const int D = c->D, K = c->K, M = c->M;
+    const bool verbose = getenv("KAMR_VERBOSE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {   // KAMR_VERBOSE: where a re-flatten spends its time
+        if (!verbose) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[kamr] re-flatten %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     c->free_topology();
+    lap("free old topology");
     c->n_local = m->n_local; c->n_ghost = m->n_ghost; c->n_sn = m->n_solidnbr;
     c->n_cell = m->n_local + m->n_ghost + m->n_solidnbr;
     c->n_grid = m->n_grid;
@@ -655,6 +665,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         c->dv.v_mid = c->dupload(vm);
         CK(cudaStreamSynchronize(c->stream));
     }
+    lap("grids + packed statics");
     // ---- cells
     c->cells.resize(c->n_cell);
     c->host_off.resize(c->n_cell + 1);
@@ -681,6 +692,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         if (i < c->n_local && ci.bound_enc >= 0) c->n_phase_local += ci.n;
     }
     c->npts_pad = doff; c->npts_host = c->host_off[c->n_cell];
+    lap("cells");
     // ---- slots (cell-centric view of the face list)
     std::vector<std::vector<Slot>> per_cell(c->n_local);
     for (int f = 0; f < m->n_face; ++f) {
@@ -785,6 +797,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         }
         if (regular) ci.flags |= any_mapped ? CELL_REGULAR_MAPPED : CELL_REGULAR;
     }
+    lap("slots");
     // ---- slope tasks in dependency waves (slope!, Slope.jl:1047-1070).  The reference sweeps the levels
     // coarse to fine because a fine cell next to a coarse one projects the coarse cell's FINISHED slopes
     // (Slope.jl:165-175).  Only those cells depend on anything: a cell none of whose stencils projects
@@ -1056,6 +1069,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         CK(cudaMemsetAsync(c->dv.err_flag, 0, sizeof(int), c->stream));
         c->slope_ticket_base = 0;
     }
+    lap("slope tasks");
     // ---- fluid cell list (Morton order: neighbours in space are neighbours in the launch, so the blocks
     // resident at one time share their neighbour reads through L2) and the phase-kernel bins
     for (int i = 0; i < c->n_local; ++i)
@@ -1142,6 +1156,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
             c->bins.push_back(b);
         }
     }
+    lap("bins");
     // ---- immersed boundary tables (kernel d)
     std::vector<int> cvc_index;
     std::vector<double> cvc_gw, cvc_sw;
@@ -1231,6 +1246,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     c->dv.cvc_index = c->dupload(cvc_index);
     c->dv.cvc_gas_w = c->dupload(cvc_gw);
     c->dv.cvc_solid_w = c->dupload(cvc_sw);
+    lap("ib tables");
     // ---- device state
     const size_t np = (size_t)c->npts_pad;
     c->dv.cells = c->dupload(c->cells);
@@ -1262,6 +1278,7 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     CK(cudaMemsetAsync(c->dv.qf, 0, (size_t)c->n_cell * D * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->dv.sw, 0, (size_t)c->n_cell * M * D * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->dv.res_cell, 0, (size_t)c->n_local * 2 * M * sizeof(double), c->stream));
+    lap("device arrays");
     // ---- halo plan (Parallel/Ghost.jl:133-145, 203-284)
     c->halo_bytes_step = 0;
     long long send_total = 0, recv_total = 0;
@@ -1361,7 +1378,9 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         c->d_sendbuf = c->dalloc<double>((size_t)send_total);
         c->d_recvbuf = c->dalloc<double>((size_t)recv_total);
     }
+    lap("halo plan");
     setup_p2p(c, m);
+    lap("one-sided halo set-up");
     if (getenv("KAMR_VERBOSE")) {
         for (auto& b : c->bins) {
             long long pts = 0;
