@@ -183,6 +183,14 @@ int  kamr_upload_aux(kamr_ctx* ctx, const double* sdf, const double* flux, const
 int  kamr_download_state(kamr_ctx* ctx, uint32_t mask, double* df, double* sdf, double* flux,
                          double* w, double* prim, double* qf, double* sw, double* mflux);
 
+/* Selective transfer of whole cells, packed on the device: what partition migration ships per migrating cell
+ * (Parallel/Partition.jl:339-388: w and df; level / midpoint are host-known statics) and what an adapt event reads of
+ * the flagged cells (Physical_space/AMR.jl:633-703).  cells[q] are local cell ids; df holds the cells' VsData.df blocks
+ * back to back in the given order (n(c)*NDF doubles each, host layout), w the (DIM+2)-vectors.  NULL pointers are
+ * skipped.  kamr_unpack_cells is the receiving side (after kamr_upload_topology of the new partition). */
+int  kamr_pack_cells(kamr_ctx* ctx, int32_t n, const int32_t* cells, double* df, double* w);
+int  kamr_unpack_cells(kamr_ctx* ctx, int32_t n, const int32_t* cells, const double* df, const double* w);
+
 /* options.  KAMR_OPT_KEEP_SDF (default 0): kamr_step keeps the limited slopes r*sdf on the device and
  * writes the reference's raw VsData.sdf only for the cells a kernel reads them from; with the option on,
  * every step also writes the raw sdf of every cell so that kamr_download_state(KAMR_DL_SDF) is valid after

@@ -86,7 +86,7 @@ EXPORTS = [
     "kamr_upload_topology", "kamr_upload_state", "kamr_upload_aux", "kamr_download_state",
     "kamr_slope", "kamr_flux", "kamr_iterate", "kamr_step", "kamr_exchange_df", "kamr_sync",
     "kamr_get_stats", "kamr_get_pair_map", "kamr_get_cell_slots", "kamr_profile_enable", "kamr_profile_read", "kamr_set_option",
-    "kamr_debug_exp_nonpos",
+    "kamr_debug_exp_nonpos", "kamr_pack_cells", "kamr_unpack_cells",
 ]
 
 _lib = None
@@ -128,6 +128,8 @@ def load(path: str | None = None):
     lib.kamr_profile_enable.argtypes = [vp, C.c_int32]
     lib.kamr_profile_read.argtypes = [vp, C.POINTER(KamrKernelTime), C.c_int32, c_i32p]
     lib.kamr_debug_exp_nonpos.argtypes = [vp, c_f64p, c_f64p, C.c_int64]
+    lib.kamr_pack_cells.argtypes = [vp, C.c_int32, c_i32p, c_f64p, c_f64p]
+    lib.kamr_unpack_cells.argtypes = [vp, C.c_int32, c_i32p, c_f64p, c_f64p]
     for name in EXPORTS:
         if name != "kamr_last_error":
             getattr(lib, name).restype = C.c_int

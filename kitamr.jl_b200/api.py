@@ -112,6 +112,22 @@ class Context:
         self._ck(self.lib.kamr_profile_read(self.h, buf, 32, C.byref(n)))
         return {buf[i].name.decode(): (int(buf[i].launches), float(buf[i].total_ms)) for i in range(n.value)}
 
+    def pack_cells(self, cells):
+        """(df, w) of the listed local cells, packed on the device (partition migration, Parallel/Partition.jl:339-388)"""
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        n_of = self.mesh.cell_n()[cells].astype(np.int64)
+        df = np.empty(int(n_of.sum()) * self.K)
+        w = np.empty(len(cells) * self.M)
+        self._ck(self.lib.kamr_pack_cells(self.h, len(cells), cells.ctypes.data_as(abi.c_i32p),
+                                          df.ctypes.data_as(abi.c_f64p), w.ctypes.data_as(abi.c_f64p)))
+        return df, w
+
+    def unpack_cells(self, cells, df, w):
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        df = np.ascontiguousarray(df, dtype=np.float64); w = np.ascontiguousarray(w, dtype=np.float64)
+        self._ck(self.lib.kamr_unpack_cells(self.h, len(cells), cells.ctypes.data_as(abi.c_i32p),
+                                            df.ctypes.data_as(abi.c_f64p), w.ctypes.data_as(abi.c_f64p)))
+
     def debug_exp_nonpos(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.empty_like(x)

@@ -2657,6 +2657,23 @@ __global__ void __launch_bounds__(256) repack_kernel(const CellInfo* __restrict_
     }
 }
 
+// the same for a list of cells: packed block q holds cell list[q] (partition migration, selective download)
+__global__ void __launch_bounds__(256) repack_list_kernel(const CellInfo* __restrict__ cells, const int* __restrict__ list,
+                                                          const long long* __restrict__ list_off, int nlist, int comps,
+                                                          double* __restrict__ padded, double* __restrict__ packed,
+                                                          int to_padded) {
+    for (int q = blockIdx.x; q < nlist; q += gridDim.x) {
+        const CellInfo& ci = cells[list[q]];
+        const long long doff = ci.doff * comps, hoff = list_off[q] * comps;
+        const int n = ci.n, np = ci.np;
+        for (int t = threadIdx.x; t < comps * n; t += blockDim.x) {
+            const int p = t / n, i = t - p * n;
+            if (to_padded) padded[doff + (long long)p * np + i] = packed[hoff + t];
+            else packed[hoff + t] = padded[doff + (long long)p * np + i];
+        }
+    }
+}
+
 __global__ void exp_nonpos_kernel(const double* __restrict__ x, double* __restrict__ y, long long n) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
         y[t] = exp_nonpos(x[t]);

@@ -2246,6 +2246,59 @@ int kamr_download_state(kamr_ctx* c, uint32_t mask, double* df, double* sdf, dou
     });
 }
 
+// partition migration / selective download: the listed cells' df blocks packed back to back on the device, one transfer
+static void transfer_cells(kamr_ctx* c, int n, const int32_t* cells, double* df_rw, const double* df_ro, double* w_rw,
+                           const double* w_ro, bool to_device) {
+    if (n <= 0) return;
+    if (c->cells.empty()) throw Fail("upload_topology first");
+    const int K = c->K, M = c->M;
+    std::vector<long long> off(n + 1, 0);
+    for (int q = 0; q < n; ++q) {
+        if (cells[q] < 0 || cells[q] >= c->n_local) throw Fail("cell id out of range (local cells only)");
+        off[q + 1] = off[q] + c->cells[cells[q]].n;
+    }
+    halo_finish_df(c);
+    halo_join_puts(c);
+    const size_t total = (size_t)off[n] * K;
+    int* d_list = nullptr; long long* d_off = nullptr; double* d_pack = nullptr; double* d_w = nullptr;
+    struct Free { int*& a; long long*& b; double*& p; double*& w; ~Free() { cudaFree(a); cudaFree(b); cudaFree(p); cudaFree(w); } } fr{d_list, d_off, d_pack, d_w};
+    CK(cudaMalloc((void**)&d_list, sizeof(int) * n));
+    CK(cudaMalloc((void**)&d_off, sizeof(long long) * (n + 1)));
+    CK(cudaMemcpyAsync(d_list, cells, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, c->stream));
+    const int grid = std::min(n, 148 * 16);
+    if ((df_rw || df_ro) && total) {
+        CK(cudaMalloc((void**)&d_pack, sizeof(double) * total));
+        if (to_device) {
+            CK(cudaMemcpyAsync(d_pack, df_ro, sizeof(double) * total, cudaMemcpyHostToDevice, c->stream));
+            repack_list_kernel<<<grid, 256, 0, c->stream>>>(c->dv.cells, d_list, d_off, n, K, c->dv.df, d_pack, 1);
+        } else {
+            repack_list_kernel<<<grid, 256, 0, c->stream>>>(c->dv.cells, d_list, d_off, n, K, c->dv.df, d_pack, 0);
+            CK(cudaMemcpyAsync(df_rw, d_pack, sizeof(double) * total, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    if (w_rw || w_ro) {   // (DIM+2) doubles per cell: gathered on the host side of one small transfer
+        std::vector<double> hw((size_t)c->n_local * M);
+        CK(cudaMemcpyAsync(hw.data(), c->dv.w, sizeof(double) * hw.size(), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (to_device) {
+            for (int q = 0; q < n; ++q) memcpy(&hw[(size_t)cells[q] * M], w_ro + (size_t)q * M, sizeof(double) * M);
+            CK(cudaMemcpyAsync(c->dv.w, hw.data(), sizeof(double) * hw.size(), cudaMemcpyHostToDevice, c->stream));
+        } else {
+            for (int q = 0; q < n; ++q) memcpy(w_rw + (size_t)q * M, &hw[(size_t)cells[q] * M], sizeof(double) * M);
+        }
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+}
+
+int kamr_pack_cells(kamr_ctx* c, int32_t n, const int32_t* cells, double* df, double* w) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); transfer_cells(c, n, cells, df, nullptr, w, nullptr, false); });
+}
+int kamr_unpack_cells(kamr_ctx* c, int32_t n, const int32_t* cells, const double* df, const double* w) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); transfer_cells(c, n, cells, nullptr, df, nullptr, w, true); });
+}
+
 int kamr_slope(kamr_ctx* c) {
     return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_slope, c, true, true); });
 }

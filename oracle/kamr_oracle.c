@@ -1070,10 +1070,18 @@ int orc_small_solve(int M, double* A, double* b, double* x) {
     return 0;
 }
 /* dual_objective :31-47 without the - lambda.W term */
+/* Test hook: the order in which the Newton sums of solve_I_projection run over the velocity points.  The algorithm's
+ * exits (|G| < 1e-10 max(1,|W|), the stall test, the Armijo comparison of objectives that differ by less than their
+ * rounding error near convergence) make WHICH iterate it returns depend on the rounding of these sums; running the same
+ * CPU code with the points in reverse order measures how well the result is defined (tests/test_oracle_cpu.py). */
+static int g_cip_reverse = 0;
+void orc_set_cip_sum_order(int reverse) { g_cip_reverse = reverse; }
+
 static double dual_sum(int D, int n, const double* vm, const double* f, const double* wt, const double* lam) {
     const int M = D + 2;
     double acc = 0.0, psi[MAXM];
-    for (int k = 0; k < n; ++k) {
+    for (int kk = 0; kk < n; ++kk) {
+        const int k = g_cip_reverse ? n - 1 - kk : kk;
         psi_of(D, vm, n, k, psi);
         double lp = 0.0;
         for (int i = 0; i < M; ++i) lp += lam[i] * psi[i];
@@ -1107,7 +1115,8 @@ int orc_solve_I_projection(int D, int n, const double* vm, double* f, const doub
     for (int it = 0; it < maxiter; ++it) {
         for (int i = 0; i < M; ++i) G[i] = 0.0;
         for (int i = 0; i < M * M; ++i) J[i] = 0.0;
-        for (int k = 0; k < n; ++k) {
+        for (int kk = 0; kk < n; ++kk) {
+            const int k = g_cip_reverse ? n - 1 - kk : kk;
             psi_of(D, vm, n, k, psi);
             double lp = 0.0;
             for (int i = 0; i < M; ++i) lp += lam[i] * psi[i];

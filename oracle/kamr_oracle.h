@@ -39,6 +39,8 @@ int orc_iterate(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, doubl
                 double* res_out);
 int orc_step(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt, int want_residual,
              double* res_out);
+/* test hook: order of the Newton sums of solve_I_projection over the velocity points (0 forward, 1 reverse) */
+void orc_set_cip_sum_order(int reverse);
 #ifdef __cplusplus
 }
 #endif

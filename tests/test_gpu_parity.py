@@ -367,3 +367,40 @@ def test_1000_steps(kamr_lib, name):
         print(f"{name}: rel L2 (df, w) by step: {worst}")
     finally:
         ctx.close()
+
+
+def test_pack_and_unpack_cells_round_trip(kamr_lib):
+    """partition migration payload from device memory (Parallel/Partition.jl:339-445): the df blocks and w of a list
+    of cells packed on the device equal the slices of a full download, and unpacking them into another context's cells
+    reproduces the state bit for bit."""
+    from kitamr_jl_b200 import abi, api
+    from kitamr_jl_b200.synth import cases
+    case = cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=8, vs_maxlevel=2, ragged=True, seed=51)
+    mesh = case.rank_mesh()
+    st = case.init_state(mesh)
+    K, M = mesh.ndf, mesh.dim + 2
+    off = mesh.vs_off()
+    rng = np.random.default_rng(3)
+    cells = rng.permutation(mesh.n_local)[: mesh.n_local // 3].astype(np.int32)
+    a = api.Context(case.config(device=0)); b = api.Context(case.config(device=0))
+    try:
+        a.upload_topology(mesh); a.upload_state(st)
+        for _ in range(2):
+            a.step(case.dt(), False)
+        full = a.download_state(st.copy(), abi.DL_DF | abi.DL_W)
+        df, w = a.pack_cells(cells)
+        exp_df = np.concatenate([full.df[off[c] * K: off[c + 1] * K] for c in cells])
+        exp_w = np.concatenate([full.w[c * M:(c + 1) * M] for c in cells])
+        assert np.array_equal(df, exp_df) and np.array_equal(w, exp_w)
+        b.upload_topology(mesh); b.upload_state(st)
+        b.unpack_cells(cells, df, w)
+        got = b.download_state(st.copy(), abi.DL_DF | abi.DL_W)
+        want = st.copy()
+        for c in cells:
+            want.df[off[c] * K: off[c + 1] * K] = full.df[off[c] * K: off[c + 1] * K]
+            want.w[c * M:(c + 1) * M] = full.w[c * M:(c + 1) * M]
+        nl = mesh.n_local
+        assert np.array_equal(got.df[: off[nl] * K], want.df[: off[nl] * K])
+        assert np.array_equal(got.w[: nl * M], want.w[: nl * M])
+    finally:
+        a.close(); b.close()
