@@ -502,7 +502,7 @@ __device__ __forceinline__ void hot_flux(const DevView& g, const FaceRec* hot, c
             }
         }
         const int sn = 1 - so;
-#ifndef KAMR_HANG_SERIAL
+#ifdef KAMR_HANG_BATCH   // (measured on S4: 11.0 ms against 9.65 ms for the plain loop below: the extra live registers cost more)
         // further sub-faces of a hanging side (2^(DIM-1) - 1 of them): all their neighbour values are requested before
         // any is used, so the side costs one more memory round trip, not one per sub-face
         constexpr int XN = (1 << (D - 1)) - 1;
@@ -1185,6 +1185,52 @@ __global__ void __launch_bounds__(NT, MINB)
                                                fstride, soff, fout, fch, red, xch, us, w_new, w0s);
 }
 
+// The face flux of one point of a REGULAR cell from its loaded values (the arithmetic of phase_regular_kernel's gather
+// loop as a function, used by the two-points-per-thread path): own-upwind face and neighbour-upwind face per direction,
+// transverse dx = (x_t - v_t dt) - x_t formed once.
+template <int D, int K>
+__device__ __forceinline__ void regular_point_flux(const RegCell& rc, const double* v, unsigned sg, double dt,
+                                                   const double* f, const double* s /*[K][D]*/,
+                                                   const double (*nfv)[K], const double (*nsv)[K * D], double* fl) {
+    double vdt[D], tdx[D];
+#pragma unroll
+    for (int t = 0; t < D; ++t) {
+        vdt[t] = __dmul_rn(v[t], dt);
+        tdx[t] = face_dx(rc.mid[t], vdt[t], rc.mid[t]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) fl[k] = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const double vn = v[d];
+        const int sn = ((sg >> d) & 1u) ? 0 : 1;
+        {   // own-upwind face: the other side of this direction
+            const RegSide& h = rc.side[2 * d + (sn ^ 1)];
+            const double Avn = h.area * vn;
+            const double dxd = face_dx(h.fmid, vdt[d], rc.mid[d]);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double val = f[k];
+#pragma unroll
+                for (int t = 0; t < D; ++t) val += (t == d ? dxd : tdx[t]) * s[k * D + t];
+                fl[k] += val * Avn;
+            }
+        }
+        {   // neighbour-upwind face
+            const RegSide& h = rc.side[2 * d + sn];
+            const double Avn = h.area * vn;
+            const double dxd = face_dx(h.fmid, vdt[d], h.nmid);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double val = nfv[d][k];
+#pragma unroll
+                for (int t = 0; t < D; ++t) val += (t == d ? dxd : tdx[t]) * nsv[d][k * D + t];
+                fl[k] += val * Avn;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // phase_regular_kernel: the fused flux + update for REGULAR cells — every one of the 2*DIM sides is a single
 // fluid/fluid face to a same-size neighbour on the same velocity grid, and the face / neighbour midpoints equal the
@@ -1237,9 +1283,94 @@ __global__ void __launch_bounds__(NT, MINB)
     if (MAPPED && SPLIT) {
         for (int t = threadIdx.x; t < (D + 2) * NB; t += NT) mbat[t] = 0.0;
     }
-    unsigned wnext = (p0 + (int)threadIdx.x < p1) ? pk[p0 + threadIdx.x] : 0u;
+#ifdef KAMR_PAIRS   // (measured slower, see DESIGN.md section 6 "tried and not adopted")
+    constexpr bool PAIRS = !MAPPED;
+#else
+    constexpr bool PAIRS = false;
+#endif
+    if (PAIRS) {
+        // Two points per thread (i even): 128-bit loads of the cell's own planes and, where both points take the same
+        // upwind neighbour in a direction (sign runs of v_d are long: the exception is a pair that straddles a run
+        // boundary), of the neighbour's; 64-bit otherwise.  Planes are 32-byte aligned and padded to a multiple of 4
+        // points, so the partner of the last point of an odd cell is padding that exists in memory; it is computed
+        // and staged like a point but never enters a moment or the output.
+        for (int i = p0 + 2 * (int)threadIdx.x; i < p1; i += 2 * NT) {
+            const bool two = i + 1 < p1;
+            const uint2 w2 = *reinterpret_cast<const uint2*>(pk + i);
+            double v0[D], v1[D];
+            unpack_v<D>(w2.x, tab, ntab, v0);
+            unpack_v<D>(w2.y, tab, ntab, v1);
+            const unsigned sg0 = sign_bits<D>(v0), sg1 = sign_bits<D>(v1);
+            double nf0[D][K], nf1[D][K], ns0[D][K * D], ns1[D][K * D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const RegSide& ha = rc.side[2 * d + (((sg0 >> d) & 1u) ? 0 : 1)];
+                const RegSide& hb = rc.side[2 * d + (((sg1 >> d) & 1u) ? 0 : 1)];
+                const double* __restrict__ fa = gdf + ha.ndoff * K + i;
+                const double* __restrict__ sa = gsl + ha.ndoff * (K * D) + i;
+                if ((((sg0 ^ sg1) >> d) & 1u) == 0u) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const double2 x = *reinterpret_cast<const double2*>(fa + k * np);
+                        nf0[d][k] = x.x; nf1[d][k] = x.y;
+#pragma unroll
+                        for (int t = 0; t < D; ++t) {
+                            const double2 y = *reinterpret_cast<const double2*>(sa + (t * K + k) * np);
+                            ns0[d][k * D + t] = y.x; ns1[d][k * D + t] = y.y;
+                        }
+                    }
+                } else {
+                    const double* __restrict__ fb = gdf + hb.ndoff * K + i + 1;
+                    const double* __restrict__ sb2 = gsl + hb.ndoff * (K * D) + i + 1;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        nf0[d][k] = ldg_stream(fa + k * np); nf1[d][k] = ldg_stream(fb + k * np);
+#pragma unroll
+                        for (int t = 0; t < D; ++t) {
+                            ns0[d][k * D + t] = ldg_stream(sa + (t * K + k) * np);
+                            ns1[d][k * D + t] = ldg_stream(sb2 + (t * K + k) * np);
+                        }
+                    }
+                }
+            }
+            double f0[K], f1[K], s0[K * D], s1[K * D], fl0[K], fl1[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double2 x = *reinterpret_cast<const double2*>(of + k * np + i);
+                f0[k] = x.x; f1[k] = x.y;
+#pragma unroll
+                for (int t = 0; t < D; ++t) {
+                    const double2 y = *reinterpret_cast<const double2*>(os + (t * K + k) * np + i);
+                    s0[k * D + t] = y.x; s1[k * D + t] = y.y;
+                }
+            }
+            regular_point_flux<D, K>(rc, v0, sg0, dt, f0, s0, nf0, ns0, fl0);
+            regular_point_flux<D, K>(rc, v1, sg1, dt, f1, s1, nf1, ns1, fl1);
+            const int j = i - soff;
+            if (SPLIT) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    *reinterpret_cast<double2*>(fs + k * fstride + j) = make_double2(f0[k], f1[k]);
+                    *reinterpret_cast<double2*>(fls + k * fstride + j) = make_double2(fl0[k], fl1[k]);
+                }
+            } else {
+                const double wt0 = unpack_wt<D>(w2.x, tab, ntab), wt1 = unpack_wt<D>(w2.y, tab, ntab);
+                add_moments<D, K>(acc, wt0, v0, fl0);
+#pragma unroll
+                for (int k = 0; k < K; ++k) { f0[k] += dtv * fl0[k]; fs[k * fstride + j] = f0[k]; }
+                add_moments<D, K>(acc + (D + 2), wt0, v0, f0);
+                if (two) {
+                    add_moments<D, K>(acc, wt1, v1, fl1);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { f1[k] += dtv * fl1[k]; fs[k * fstride + j + 1] = f1[k]; }
+                    add_moments<D, K>(acc + (D + 2), wt1, v1, f1);
+                }
+            }
+        }
+    }
+    unsigned wnext = (!PAIRS && p0 + (int)threadIdx.x < p1) ? pk[p0 + threadIdx.x] : 0u;
 #pragma unroll UNROLL
-    for (int i = p0 + threadIdx.x; i < p1; i += NT) {
+    for (int i = p0 + threadIdx.x; i < (PAIRS ? p0 : p1); i += NT) {
         double v[D], vdt[D], tdx[D], f[K], s[K * D], fl[K];
         double nfv[D][K], nsv[D][K * D];
         bool mapped[D];
@@ -2189,6 +2320,58 @@ __global__ void __launch_bounds__(NT) slope_regular_kernel(DevView g, const void
     const double* __restrict__ own = df + tk.doff * K;
     double* sdf = g.sdf + tk.doff * K * D;
     double* sdl = g.sdl + tk.doff * K * D;
+#ifdef KAMR_PAIRS   // (measured slower, see DESIGN.md section 6 "tried and not adopted")
+    if (!MAPPED) {
+        // Identical grids on all sides: point i of every neighbour is point i.  A thread takes the points i, i+1 with
+        // 128-bit loads and stores (planes are 32-byte aligned and padded to a multiple of 4 points, so i+1 exists in
+        // memory even when it is padding): half the load / store instructions and address arithmetic per point.
+        for (int i = 2 * threadIdx.x; i < n; i += 2 * NT) {
+            double2 f2[K], nf2[2 * D][K];
+#pragma unroll
+            for (int q = 0; q < 2 * D; ++q) {
+                const double* __restrict__ p = df + tk.nb_doff[q] * K + i;
+#pragma unroll
+                for (int k = 0; k < K; ++k) nf2[q][k] = *reinterpret_cast<const double2*>(p + k * np);
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) f2[k] = *reinterpret_cast<const double2*>(own + k * np + i);
+            double2 s2[D][K], l2[D][K];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double f[K], s[D][K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) f[k] = h ? f2[k].y : f2[k].x;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const double a = 0.0 + (f[k] - (h ? nf2[2 * d][k].y : nf2[2 * d][k].x));
+                        const double b = 0.0 + (f[k] - (h ? nf2[2 * d + 1][k].y : nf2[2 * d + 1][k].x));
+                        s[d][k] = minmod(a * tk.inv[2 * d], b * tk.inv[2 * d + 1]);
+                        if (h) s2[d][k].y = s[d][k]; else s2[d][k].x = s[d][k];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    double s_abs = 0.0;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) s_abs += tk.ds[d] * fabs(s[d][k]);
+                    const double r = limiter(f[k], s_abs);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) { if (h) l2[d][k].y = r * s[d][k]; else l2[d][k].x = r * s[d][k]; }
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (raw) *reinterpret_cast<double2*>(sdf + (d * K + k) * np + i) = s2[d][k];
+                    *reinterpret_cast<double2*>(sdl + (d * K + k) * np + i) = l2[d][k];
+                }
+        }
+        return;
+    }
+#endif
     for (int i = threadIdx.x; i < n; i += NT) {
         double f[K], nf[2 * D][K], s[D][K];
         int j0[2 * D], cn[2 * D];

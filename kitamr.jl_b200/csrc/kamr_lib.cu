@@ -1091,7 +1091,11 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         for (int cell : c->fluid_cells) {
             const CellInfo& ci = c->cells[cell];
             int C = 1;
-            const int chunk_n = CHUNK_BYTES / (2 * K * (int)sizeof(double));
+            // staged planes per CTA: ~64 KB for the regular kernels (4 KB of static shared memory: 3 CTAs per SM), ~48 KB
+            // for the general kernel (12 KB of slot / face records besides: at 64 KB only 2 CTAs fit, measured 9.65 vs
+            // 8.5 ms on S4)
+            const bool regular_cell = (ci.flags & (CELL_REGULAR | CELL_REGULAR_MAPPED)) != 0;
+            const int chunk_n = (regular_cell ? CHUNK_BYTES : CHUNK_BYTES * 3 / 4) / (2 * K * (int)sizeof(double));
             while (C < 8 && (ci.n + C - 1) / C > (ci.n <= SMALL_N ? SMALL_N : chunk_n)) C *= 2;
             const int P = chunk_points(ci.n, C);
             const bool stage = sizeof(double) * ((size_t)(2 * K) * P + vtab_doubles(D, c->dv.n_vtab) + 2 +
@@ -1877,10 +1881,20 @@ void launch_regular_inst2(kamr_ctx* c, const Bin& b, size_t smem, double dt, int
     Launch L_(c, MAPPED ? KID_STEP_REGMAP : KID_STEP_REGULAR);
     launch_cells(c, kern, (int)b.cells.size(), C, PT, smem, c->dv, c->gas, (const RegCell*)b.d_recs, dt, want, b.pf_dist);
 }
+#ifndef KAMR_PAIR_THREADS
+#define KAMR_PAIR_THREADS 512
+#endif
 template <int D, int K, bool STAGE, int PT, int MB, int C>
 void launch_regular_inst(kamr_ctx* c, const Bin& b, size_t smem, double dt, int want) {
+    // -DKAMR_PAIRS: the plain regular kernel takes two points per thread (128-bit loads): twice the live values, so it
+    // is register-budgeted for KAMR_PAIR_THREADS resident threads per SM (128 registers at 512) instead of 768
+#ifdef KAMR_PAIRS
+    constexpr int MBP = KAMR_PAIR_THREADS / PT;
+#else
+    constexpr int MBP = MB;
+#endif
     if (b.mapped) launch_regular_inst2<D, K, STAGE, PT, MB, true, C>(c, b, smem, dt, want);
-    else launch_regular_inst2<D, K, STAGE, PT, MB, false, C>(c, b, smem, dt, want);
+    else launch_regular_inst2<D, K, STAGE, PT, MBP, false, C>(c, b, smem, dt, want);
 }
 
 // the fused step of one bin: the instantiation follows the bin's CTA width, cluster size and staging area
