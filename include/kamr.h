@@ -191,6 +191,53 @@ int  kamr_download_state(kamr_ctx* ctx, uint32_t mask, double* df, double* sdf, 
 int  kamr_pack_cells(kamr_ctx* ctx, int32_t n, const int32_t* cells, double* df, double* w);
 int  kamr_unpack_cells(kamr_ctx* ctx, int32_t n, const int32_t* cells, const double* df, const double* w);
 
+/* update_criterion!(ka), Physical_space/AMR.jl:256-341: the physical-space adaptation sensor on the device.  For every
+ * local fluid cell and direction the Löhner estimator of Physical_space/Criteria.jl:25-200 over the primitive state
+ * of the two sides (mean of the neighbours' conserved state; ds, 0.75 ds or 1.5 ds by the side's level, AMR.jl:5-157;
+ * the coarser side shifted to the cell's transverse position with its sw) with the vorticity estimator in row 2, then
+ * the one-cell buffer apply_amr_buffer! (AMR.jl:296-341: an unflagged cell with a flagged fluid face neighbour gets
+ * lohner .= 2*threshold; the mirrors' decisions travel to the peers as lohner_flag_exchange! does,
+ * Parallel/Ghost.jl:939-978).  threshold = ADAPT_COEFFI_PS.  A SolidNeighbor side enters with w = sw = 0 as in the
+ * reference (Boundary/Immersed_boundary.jl:300-302), so donor cells see a density jump there; solid cells get zeros.
+ * Precondition: kamr_slope since the last change of state (ps_adaptive_mesh_refinement! runs slope! first,
+ * AMR.jl:1109-1111) — the call fails otherwise.  Collective over the communicator when the mesh has peers.
+ * lohner_out: [n_local][DIM][DIM+2] (PsData.lohner, column-major as in Julia); sensor_out: [n_local] ps_sensor
+ * (Criteria.jl:14-23), all the host's ps_refine_flag / ps_coarsen_flag read (:69-101).  NULL pointers are skipped. */
+int  kamr_ps_criterion(kamr_ctx* ctx, double threshold, double* lohner_out, double* sensor_out);
+
+/* Velocity-space adaptation inputs on the device: the per-velocity-point decisions of vs_refine! and
+ * vs_coarsen! (Velocity_space/AMR.jl:26-115) evaluated where df and sdf live, so that an adapt event downloads one
+ * byte per point and decision instead of df + sdf.  The grid surgery itself (refine_grid_stream!,
+ * coarsen_grid_stream!, Velocity_space/Rebuild.jl:44,96) stays on the host. */
+typedef struct kamr_vs_adapt {
+    int32_t mode;           /* ADAPT_VS_MODE: 0 :lohner (default, Solver/Types.jl:99), 1 contribution */
+    int32_t maxlevel;       /* AMR_VS_MAXLEVEL */
+    int32_t trees[3];       /* config.vs_trees_num */
+    int32_t pad_;
+    double  vmin[3], vmax[3];   /* config.quadrature = [vmin1, vmax1, vmin2, vmax2, ...] */
+    double  coeff_lohner;   /* ADAPT_COEFFI_VS_LOHNER */
+    double  coeff_local;    /* ADAPT_COEFFI_VS_LOCAL */
+    double  coeff_global;   /* ADAPT_COEFFI_VS_GLOBAL */
+    double  vr_density, vr_energy;   /* Velocity_Resolution after the MPI max (contribution mode only) */
+} kamr_vs_adapt;
+/* vs_resolution(trees, kinfo) before its two MPI.Allreduce(MAX) (Velocity_space/AMR.jl:139-166): out[0] = max over the
+ * local fluid cells of maximum(df) * weight, out[1] = the same for the peculiar-energy density; weight is the volume
+ * of a finest-level velocity cell.  The host takes the max over the ranks and passes it back in kamr_vs_adapt. */
+int  kamr_vs_resolution(kamr_ctx* ctx, const kamr_vs_adapt* par, double out[2]);
+/* refine_flag[p] / coarsen_ok[p] for every velocity point of every local cell (host point order, one byte each):
+ * the `refine_flags[c]` of vs_refine! (:56-64) and the `coarsen_ok[c]` of vs_coarsen! (:102-110), both evaluated on
+ * the grid and state resident on the device.  The criterion distribution is df + max_d |sdf ds_d|
+ * (_criterion_cell!, :8-21) with the slopes resident on the device (those of the last kamr_slope, or of the last step
+ * under KAMR_OPT_KEEP_SDF — like the reference, which reads whatever VsData.sdf holds); the call fails if no raw
+ * slopes are resident.  :lohner mode: vs_lohner_indicator (Velocity_space/Criteria.jl:259-287) over the same-or-coarser
+ * face neighbours of vs_face_neighbor (Velocity_space/Neighbor.jl:181-204; the table is built per distinct velocity
+ * grid at the first call after a re-flatten), with local_contribution_{refine,coarsen}_flag (Criteria.jl:19-49);
+ * contribution mode: contribution_refine_flag / local && global coarsen flags (Criteria.jl:4-6, 55-84).
+ * NOTE: the reference evaluates coarsen_ok AFTER refine_grid_stream! has run; for a cell whose grid that pass changed,
+ * the host re-evaluates vs_coarsen! on its own (it needs that cell's df only: refinement copies df to the children and
+ * zeroes sdf, Rebuild.jl:69,81) — kamr_pack_cells fetches it.  NULL pointers are skipped. */
+int  kamr_vs_criterion(kamr_ctx* ctx, const kamr_vs_adapt* par, uint8_t* refine_flag, uint8_t* coarsen_ok);
+
 /* options.  KAMR_OPT_KEEP_SDF (default 0): kamr_step keeps the limited slopes r*sdf on the device and
  * writes the reference's raw VsData.sdf only for the cells a kernel reads them from; with the option on,
  * every step also writes the raw sdf of every cell so that kamr_download_state(KAMR_DL_SDF) is valid after

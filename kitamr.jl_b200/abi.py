@@ -68,6 +68,34 @@ class KamrStats(C.Structure):
     ]
 
 
+class KamrVsAdapt(C.Structure):
+    """== kamr_vs_adapt (include/kamr.h): parameters of vs_refine! / vs_coarsen!, Velocity_space/AMR.jl:26-115"""
+    _fields_ = [
+        ("mode", C.c_int32), ("maxlevel", C.c_int32), ("trees", C.c_int32 * 3), ("pad_", C.c_int32),
+        ("vmin", C.c_double * 3), ("vmax", C.c_double * 3),
+        ("coeff_lohner", C.c_double), ("coeff_local", C.c_double), ("coeff_global", C.c_double),
+        ("vr_density", C.c_double), ("vr_energy", C.c_double),
+    ]
+
+
+VS_MODE_LOHNER, VS_MODE_CONTRIBUTION = 0, 1
+
+
+def vs_adapt(case, mode=VS_MODE_LOHNER, coeff_lohner=0.6, coeff_local=1e-2, coeff_global=0.125,
+             vr_density=0.0, vr_energy=0.0) -> "KamrVsAdapt":
+    """kamr_vs_adapt of a synthetic case with the reference's default coefficients (Solver/Types.jl:96-100)"""
+    D = case.dim
+    p = KamrVsAdapt()
+    p.mode, p.maxlevel = int(mode), int(case.vs_maxlevel)
+    for d in range(3):
+        p.trees[d] = int(case.vs_trees_num[d]) if d < D else 1
+        p.vmin[d] = float(case.quadrature[2 * d]) if d < D else 0.0
+        p.vmax[d] = float(case.quadrature[2 * d + 1]) if d < D else 1.0
+    p.coeff_lohner, p.coeff_local, p.coeff_global = coeff_lohner, coeff_local, coeff_global
+    p.vr_density, p.vr_energy = vr_density, vr_energy
+    return p
+
+
 class KamrKernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
@@ -86,7 +114,8 @@ EXPORTS = [
     "kamr_upload_topology", "kamr_upload_state", "kamr_upload_aux", "kamr_download_state",
     "kamr_slope", "kamr_flux", "kamr_iterate", "kamr_step", "kamr_exchange_df", "kamr_sync",
     "kamr_get_stats", "kamr_get_pair_map", "kamr_get_cell_slots", "kamr_profile_enable", "kamr_profile_read", "kamr_set_option",
-    "kamr_debug_exp_nonpos", "kamr_pack_cells", "kamr_unpack_cells",
+    "kamr_debug_exp_nonpos", "kamr_pack_cells", "kamr_unpack_cells", "kamr_ps_criterion",
+    "kamr_vs_resolution", "kamr_vs_criterion",
 ]
 
 _lib = None
@@ -130,6 +159,9 @@ def load(path: str | None = None):
     lib.kamr_debug_exp_nonpos.argtypes = [vp, c_f64p, c_f64p, C.c_int64]
     lib.kamr_pack_cells.argtypes = [vp, C.c_int32, c_i32p, c_f64p, c_f64p]
     lib.kamr_unpack_cells.argtypes = [vp, C.c_int32, c_i32p, c_f64p, c_f64p]
+    lib.kamr_ps_criterion.argtypes = [vp, C.c_double, c_f64p, c_f64p]
+    lib.kamr_vs_resolution.argtypes = [vp, C.POINTER(KamrVsAdapt), c_f64p]
+    lib.kamr_vs_criterion.argtypes = [vp, C.POINTER(KamrVsAdapt), C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
     for name in EXPORTS:
         if name != "kamr_last_error":
             getattr(lib, name).restype = C.c_int

@@ -128,6 +128,31 @@ class Context:
         self._ck(self.lib.kamr_unpack_cells(self.h, len(cells), cells.ctypes.data_as(abi.c_i32p),
                                             df.ctypes.data_as(abi.c_f64p), w.ctypes.data_as(abi.c_f64p)))
 
+    def ps_criterion(self, threshold, want_lohner=True):
+        """update_criterion!(ka) (Physical_space/AMR.jl:256-341) after slope(): (lohner [n_local, DIM, DIM+2] or None,
+        ps_sensor [n_local])"""
+        n = self.mesh.n_local
+        loh = np.empty((n, self.D, self.M)) if want_lohner else None
+        sen = np.empty(n)
+        self._ck(self.lib.kamr_ps_criterion(self.h, float(threshold),
+                                            loh.ctypes.data_as(abi.c_f64p) if want_lohner else None,
+                                            sen.ctypes.data_as(abi.c_f64p)))
+        return loh, sen
+
+    def vs_resolution(self, par):
+        """local maxima of vs_resolution(ps_data, kinfo) (Velocity_space/AMR.jl:139-166): [density, energy]"""
+        out = np.zeros(2)
+        self._ck(self.lib.kamr_vs_resolution(self.h, C.byref(par), out.ctypes.data_as(abi.c_f64p)))
+        return out
+
+    def vs_criterion(self, par):
+        """(refine_flag, coarsen_ok) per local velocity point, host order (vs_refine! / vs_coarsen!, AMR.jl:26-115)"""
+        npts = int(self.mesh.vs_off()[self.mesh.n_local])
+        rf = np.zeros(npts, dtype=np.uint8); co = np.zeros(npts, dtype=np.uint8)
+        u8 = C.POINTER(C.c_uint8)
+        self._ck(self.lib.kamr_vs_criterion(self.h, C.byref(par), rf.ctypes.data_as(u8), co.ctypes.data_as(u8)))
+        return rf, co
+
     def debug_exp_nonpos(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.empty_like(x)

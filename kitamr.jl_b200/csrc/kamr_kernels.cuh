@@ -2867,4 +2867,454 @@ __global__ void fill_kernel(double* p, long long n, double v) {
         p[t] = v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Physical-space adaptation sensor: update_criterion!(ka), Physical_space/AMR.jl:256-341, with the
+// Löhner estimator of Physical_space/Criteria.jl:14-200.  Event-driven (once per adaptation pass), macroscopic fields
+// only: one thread per physical cell.  Every operation is an explicitly rounded one (no FMA contraction), so equal
+// inputs give the oracle's bits and a flag never flips on a borderline sensor value.
+namespace sensor {
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
+// Julia's max: NaN if either argument is NaN
+__device__ __forceinline__ double jmax(double a, double b) {
+    if (a != a || b != b) return CUDART_NAN;
+    return a > b ? a : b;
+}
+constexpr double LOHNER_ABS_FLOOR = 1e-4;          // Criteria.jl:2
+constexpr double PRIMITIVE_REL_JUMP_FLOOR = 1e-3;  // Criteria.jl:3
+constexpr double VORTICITY_JUMP_FLOOR = 2e-2;      // Criteria.jl:4
+
+template <int D>
+__device__ __forceinline__ void prim_of(const double* w, double gamma, double* prim) {   // lib/KitCore get_prim
+    prim[0] = w[0];
+    double m2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { prim[1 + d] = dvd(w[1 + d], w[0]); m2 = add(m2, mul(w[1 + d], w[1 + d])); }
+    prim[D + 1] = dvd(dvd(mul(0.5, w[0]), sub(gamma, 1.0)), sub(w[D + 1], dvd(mul(0.5, m2), w[0])));
+}
+// lohner_value, Criteria.jl:25-31
+__device__ __forceinline__ double lohner_value(double l, double c, double r, double dsL, double dsR, double eps) {
+    const double scale = add(add(mul(dsR, fabs(l)), mul(add(dsL, dsR), fabs(c))), mul(dsL, fabs(r)));
+    if (scale < mul(LOHNER_ABS_FLOOR, dsL < dsR ? dsL : dsR)) return 0.0;
+    const double denom = add(add(mul(dsR, fabs(sub(l, c))), mul(dsL, fabs(sub(r, c)))), mul(eps, scale));
+    if (denom <= 0.0) return 0.0;
+    return dvd(fabs(add(sub(mul(dsR, l), mul(add(dsL, dsR), c)), mul(dsL, r))), denom);
+}
+__device__ __forceinline__ bool amplitude_ok(double l, double c, double r) {   // Criteria.jl:33-37
+    const double jump = jmax(fabs(sub(l, c)), fabs(sub(r, c)));
+    const double scale = jmax(fabs(c), LOHNER_ABS_FLOOR);
+    return jump >= mul(PRIMITIVE_REL_JUMP_FLOOR, scale);
+}
+// sw is [dir][row]; velocity_slope + vorticity, Criteria.jl:39-53
+template <int D>
+__device__ __forceinline__ double vslope(const double* sw, const double* prim, int comp, int dir) {
+    return dvd(sub(sw[dir * (D + 2) + comp], mul(prim[comp], sw[dir * (D + 2)])), prim[0]);
+}
+template <int D>
+__device__ __forceinline__ double vorticity(const double* sw, const double* prim) {
+    if (D == 2) return sub(vslope<D>(sw, prim, 1, 1), vslope<D>(sw, prim, 2, 0));
+    const double c1 = sub(vslope<D>(sw, prim, 2, 2), vslope<D>(sw, prim, 3, 1));
+    const double c2 = sub(vslope<D>(sw, prim, 3, 0), vslope<D>(sw, prim, 1, 2));
+    const double c3 = sub(vslope<D>(sw, prim, 1, 1), vslope<D>(sw, prim, 2, 0));
+    return __dsqrt_rn(add(add(mul(c1, c1), mul(c2, c2)), mul(c3, c3)));
+}
+template <int D>
+__device__ __forceinline__ bool vorticity_ok(double l, double c, double r, const double* prim, double h) {   // :55-67
+    const double omega = jmax(fabs(l), jmax(fabs(c), fabs(r)));
+    double speed2 = 0.0;
+#pragma unroll
+    for (int i = 1; i <= D; ++i) speed2 = add(speed2, mul(prim[i], prim[i]));
+    const double lambda = jmax(fabs(prim[D + 1]), EPS_MACH);
+    const double vscale = jmax(__dsqrt_rn(speed2), dvd(1.0, __dsqrt_rn(lambda)));
+    return mul(omega, h) >= mul(VORTICITY_JUMP_FLOOR, vscale);
+}
+// one side of update_Lohner_inner_ps!, Criteria.jl:124-160.  Ids >= n_real are SolidNeighbor pseudo-cells, whose
+// w and sw are zero in the reference (Boundary/Immersed_boundary.jl:300-302).
+template <int D>
+__device__ __forceinline__ void side(const CellInfo* __restrict__ cells, const double* __restrict__ w,
+                                     const double* __restrict__ sw, const int* __restrict__ ids, int cnt, int n_real,
+                                     const double* mid, int dir, bool coarser, double gamma, double* prim_out,
+                                     double* sw_out) {
+    constexpr int M = D + 2;
+    double ws[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) ws[j] = 0.0;
+#pragma unroll
+    for (int q = 0; q < M * D; ++q) sw_out[q] = 0.0;
+    for (int k = 0; k < cnt; ++k) {
+        const int id = ids[k];
+        const bool real = id < n_real;
+#pragma unroll
+        for (int j = 0; j < M; ++j) ws[j] = add(ws[j], real ? w[(size_t)id * M + j] : 0.0);
+#pragma unroll
+        for (int q = 0; q < M * D; ++q) sw_out[q] = add(sw_out[q], real ? sw[(size_t)id * M * D + q] : 0.0);
+    }
+    if (coarser) {
+        const int id = ids[0];
+        const bool real = id < n_real;
+        const CellInfo& nb = cells[id];
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            double acc = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int t = 0; t < D; ++t) {
+                if (t == dir) continue;
+                const double term = mul(sub(mid[t], nb.mid[t]), real ? sw[(size_t)id * M * D + t * M + j] : 0.0);
+                acc = first ? term : add(acc, term);
+                first = false;
+            }
+            ws[j] = add(ws[j], acc);
+        }
+    }
+    const double inv_n = (double)cnt;
+#pragma unroll
+    for (int j = 0; j < M; ++j) ws[j] = dvd(ws[j], inv_n);
+#pragma unroll
+    for (int q = 0; q < M * D; ++q) sw_out[q] = dvd(sw_out[q], inv_n);
+    prim_of<D>(ws, gamma, prim_out);
+}
+template <int D>
+__device__ __forceinline__ double sensor_of(const double* loh) {   // ps_sensor, Criteria.jl:14-23
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { a = jmax(a, loh[d * (D + 2)]); b = jmax(b, loh[d * (D + 2) + D + 1]); }
+    return jmax(a, b);
+}
+}  // namespace sensor
+
+// lohner[c][dir][row] of every local cell and above[c] = (ps_sensor > threshold) as a double (1.0 / 0.0) so that the
+// mirrors' decisions travel like any other per-cell field (lohner_flag_exchange!, Parallel/Ghost.jl:939-978)
+template <int D>
+__global__ void __launch_bounds__(128) ps_lohner_kernel(const CellInfo* __restrict__ cells,
+                                                        const int* __restrict__ nb_state, const int* __restrict__ nb_off,
+                                                        const int* __restrict__ nb_ids, const double* __restrict__ w,
+                                                        const double* __restrict__ prim_all,
+                                                        const double* __restrict__ sw_all, int n_local, int n_real,
+                                                        double gamma, double threshold, double* __restrict__ lohner,
+                                                        double* __restrict__ above) {
+    constexpr int M = D + 2;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_local) return;
+    double loh[M * D];
+#pragma unroll
+    for (int q = 0; q < M * D; ++q) loh[q] = 0.0;
+    const CellInfo& ci = cells[c];
+    bool fluid = ci.bound_enc >= 0;   // AMR.jl:264-265
+    if (fluid) {
+        double prim[M], sw[M * D], mid[D];
+#pragma unroll
+        for (int j = 0; j < M; ++j) prim[j] = prim_all[(size_t)c * M + j];
+#pragma unroll
+        for (int q = 0; q < M * D; ++q) sw[q] = sw_all[(size_t)c * M * D + q];
+#pragma unroll
+        for (int t = 0; t < D; ++t) mid[t] = ci.mid[t];
+        const double omega = sensor::vorticity<D>(sw, prim);
+#pragma unroll
+        for (int dir = 0; dir < D; ++dir) {
+            const int e = c * 2 * D + 2 * dir;
+            const int sL = nb_state[e], sR = nb_state[e + 1];
+            if (sL == 0 || sR == 0) continue;   // AMR.jl:160-255
+            const double ds = ci.ds[dir];
+            // AMR.jl:5-157: same level ds, finer 0.75 ds, coarser 1.5 ds
+            const double dsL = sL == 1 ? ds : (sL > 1 ? sensor::mul(0.75, ds) : sensor::mul(1.5, ds));
+            const double dsR = sR == 1 ? ds : (sR > 1 ? sensor::mul(0.75, ds) : sensor::mul(1.5, ds));
+            double pL[M], pR[M], swL[M * D], swR[M * D];
+            sensor::side<D>(cells, w, sw_all, nb_ids + nb_off[e], nb_off[e + 1] - nb_off[e], n_real, mid, dir, dsL > ds,
+                            gamma, pL, swL);
+            sensor::side<D>(cells, w, sw_all, nb_ids + nb_off[e + 1], nb_off[e + 2] - nb_off[e + 1], n_real, mid, dir,
+                            dsR > ds, gamma, pR, swR);
+            const double oL = sensor::vorticity<D>(swL, pL), oR = sensor::vorticity<D>(swR, pR);
+            const bool use_vort = sensor::vorticity_ok<D>(oL, omega, oR, prim, dsL > dsR ? dsL : dsR);
+            const double eps_l = sensor::mul(0.2, ds);
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                if (j == 1)
+                    loh[dir * M + j] = use_vort ? sensor::lohner_value(oL, omega, oR, dsL, dsR, eps_l) : 0.0;
+                else
+                    loh[dir * M + j] = sensor::amplitude_ok(pL[j], prim[j], pR[j])
+                                           ? sensor::lohner_value(pL[j], prim[j], pR[j], dsL, dsR, eps_l) : 0.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < M * D; ++q) lohner[(size_t)c * M * D + q] = loh[q];
+    above[c] = (fluid && sensor::sensor_of<D>(loh) > threshold) ? 1.0 : 0.0;
+}
+
+// apply_amr_buffer!, AMR.jl:296-341: an unflagged fluid cell with a flagged fluid face neighbour (local or ghost) gets
+// lohner .= 2 threshold.  Decisions are read from `above` (un-inflated), so the buffer stays one cell thick.
+template <int D>
+__global__ void __launch_bounds__(128) ps_buffer_kernel(const CellInfo* __restrict__ cells,
+                                                        const int* __restrict__ nb_state, const int* __restrict__ nb_off,
+                                                        const int* __restrict__ nb_ids, int n_local, int n_real,
+                                                        double threshold, const double* __restrict__ above,
+                                                        double* __restrict__ lohner, double* __restrict__ sensor_out) {
+    constexpr int M = D + 2;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_local) return;
+    bool flagged = false;
+    if (cells[c].bound_enc >= 0 && above[c] == 0.0) {
+        for (int f = 0; f < 2 * D && !flagged; ++f) {
+            const int e = c * 2 * D + f;
+            if (nb_state[e] == 0) continue;
+            for (int k = nb_off[e]; k < nb_off[e + 1] && !flagged; ++k) {
+                const int id = nb_ids[k];
+                if (id >= n_real || cells[id].bound_enc < 0) continue;
+                flagged = above[id] != 0.0;
+            }
+        }
+    }
+    double loh[M * D];
+#pragma unroll
+    for (int q = 0; q < M * D; ++q) {
+        loh[q] = flagged ? sensor::mul(2.0, threshold) : lohner[(size_t)c * M * D + q];
+        if (flagged) lohner[(size_t)c * M * D + q] = loh[q];
+    }
+    sensor_out[c] = sensor::sensor_of<D>(loh);
+}
+
+// rows of `width` doubles of a per-cell array: gather the rows of a list of cells into a contiguous buffer
+__global__ void __launch_bounds__(256) gather_rows_kernel(const int* __restrict__ list, int n, int width,
+                                                          const double* __restrict__ src, double* __restrict__ dst) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)n * width;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(t / width), j = (int)(t - (long long)q * width);
+        dst[t] = src[(size_t)list[q] * width + j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Velocity-space adaptation inputs: vs_refine! / vs_coarsen! decisions per velocity point,
+// Velocity_space/AMR.jl:26-115 with Velocity_space/Criteria.jl; the face-neighbour search of
+// Velocity_space/Neighbor.jl as a painted finest-level lattice instead of sorted Morton keys.
+struct VsPar {
+    int mode, maxlevel;
+    int gmax[MAXD];          // finest-level lattice extent: vs_trees_num << maxlevel
+    double vmin[MAXD], h_fine[MAXD];
+    double coeff_lohner, coeff_local, coeff_global, vr_density, vr_energy;
+    double cell_weight;      // volume of a finest-level velocity cell (vs_resolution, AMR.jl:163)
+};
+struct VsGridTask {
+    long long goff;          // velocity-grid statics of the grid
+    long long nb_off;        // its face-neighbour table [n][DIM][2] in ints
+    int n, np;
+};
+
+// One CTA per distinct velocity grid: every leaf paints its id over the finest-level lattice cells it covers
+// (_corner_index, Neighbor.jl:63-66), then every leaf probes half a finest cell across each face on its centre line
+// (vs_face_neighbor, Neighbor.jl:181-204) and reads the owner.  -1: velocity-domain boundary (vacuum).
+template <int D>
+__global__ void __launch_bounds__(256) vs_neighbors_kernel(const VsGridTask* __restrict__ tasks, VsPar par,
+                                                           const double* __restrict__ v_mid,
+                                                           const int8_t* __restrict__ v_level,
+                                                           int* __restrict__ lattice_all, long long lattice_size,
+                                                           int* __restrict__ nbt, int* __restrict__ err_flag) {
+    const VsGridTask t = tasks[blockIdx.x];
+    int* lat = lattice_all + (long long)blockIdx.x * lattice_size;
+    for (long long q = threadIdx.x; q < lattice_size; q += blockDim.x) lat[q] = -1;
+    __syncthreads();
+    const double* v = v_mid + t.goff * D;
+    const int8_t* lev = v_level + t.goff;
+    for (int i = threadIdx.x; i < t.n; i += blockDim.x) {
+        const int span = 1 << (par.maxlevel - lev[i]);
+        int g[D];
+        bool ok = true;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const double cell = __dmul_rn(par.h_fine[d], (double)span);
+            const double x = __ddiv_rn(__dsub_rn(__dsub_rn(v[(size_t)d * t.np + i], __dmul_rn(0.5, cell)), par.vmin[d]),
+                                       par.h_fine[d]);
+            g[d] = (int)llrint(x);
+            ok = ok && g[d] >= 0 && g[d] + span <= par.gmax[d];
+        }
+        if (!ok) { *err_flag = 3; continue; }
+        const int cnt = D == 2 ? span * span : span * span * span;
+        for (int o = 0; o < cnt; ++o) {
+            long long lin = 0;
+            int rem = o;
+#pragma unroll
+            for (int d = D - 1; d >= 0; --d) {
+                const int od = d == 0 ? rem : rem / (d == 1 ? span : span * span);
+                if (d > 0) rem -= od * (d == 1 ? span : span * span);
+                lin = lin * par.gmax[d] + (g[d] + od);
+            }
+            lat[lin] = i;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < t.n; i += blockDim.x) {
+        const int span = 1 << (par.maxlevel - lev[i]);
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) {
+            const double cell = __dmul_rn(par.h_fine[dim], (double)span);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const double dir = s ? 1.0 : -1.0;
+                long long lin = 0;
+                bool inside = true;
+#pragma unroll
+                for (int d = D - 1; d >= 0; --d) {
+                    double coord = v[(size_t)d * t.np + i];
+                    if (d == dim)
+                        coord = __dadd_rn(coord, __dmul_rn(dir, __dadd_rn(__dmul_rn(0.5, cell), __dmul_rn(0.5, par.h_fine[d]))));
+                    const double q = floor(__ddiv_rn(__dsub_rn(coord, par.vmin[d]), par.h_fine[d]));
+                    inside = inside && q >= 0.0 && q < (double)par.gmax[d];
+                    lin = lin * par.gmax[d] + (long long)(inside ? q : 0.0);
+                }
+                nbt[t.nb_off + ((long long)i * D + dim) * 2 + s] = inside ? lat[lin] : -1;
+            }
+        }
+    }
+}
+
+namespace vsadapt {
+using sensor::add; using sensor::sub; using sensor::mul; using sensor::dvd; using sensor::jmax;
+constexpr double EPS_FLT = 1e-2, EPS_ABS = 1e-3, COARSEN_RATIO = 0.3;   // Criteria.jl:213-217
+// _lohner_ratio, Criteria.jl:222-228
+__device__ __forceinline__ double ratio(double L, double C, double R, double dsL, double dsR, double scale) {
+    const double both = add(dsL, dsR);
+    const double num = fabs(add(sub(mul(dsR, L), mul(both, C)), mul(dsL, R)));
+    const double den = add(add(add(mul(dsR, fabs(sub(L, C))), mul(dsL, fabs(sub(R, C)))),
+                               mul(EPS_FLT, add(add(mul(dsR, fabs(L)), mul(both, fabs(C))), mul(dsL, fabs(R))))),
+                           mul(mul(EPS_ABS, scale), both));
+    return den > 0 ? dvd(num, den) : 0.0;
+}
+}  // namespace vsadapt
+
+// block-wide max of two values (result broadcast)
+__device__ __forceinline__ void block_max2(double& a, double& b, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+        a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    __syncthreads();
+    if (lane == 0) { red[warp] = a; red[32 + warp] = b; }
+    __syncthreads();
+    a = red[0]; b = red[32];
+    for (int q = 1; q < nwarp; ++q) { a = fmax(a, red[q]); b = fmax(b, red[32 + q]); }
+}
+
+// One CTA per local cell.  refine_flag / coarsen_ok in the host's point order (host_off[c] + i).
+template <int D, int K>
+__global__ void __launch_bounds__(256) vs_criterion_kernel(DevView g, VsPar par, const long long* __restrict__ host_off,
+                                                           const long long* __restrict__ nb_off_of_grid,
+                                                           const int* __restrict__ nbt,
+                                                           unsigned char* __restrict__ refine_flag,
+                                                           unsigned char* __restrict__ coarsen_ok) {
+    using namespace vsadapt;
+    constexpr int M = D + 2;
+    __shared__ double red[64];
+    const int c = blockIdx.x;
+    const CellInfo& ci = g.cells[c];
+    const CellPtr<D, K> own(g, ci);
+    const int n = ci.n, np = ci.np;
+    const bool lohner = par.mode == 0;
+    double s1 = 0.0, s2 = 0.0;
+    if (lohner) {   // vs_lohner_scales, Criteria.jl:238-248 (values are never NaN: fmax is max)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            s1 = fmax(s1, fabs(own.f[i]));
+            if (K == 2) s2 = fmax(s2, fabs(own.f[np + i]));
+        }
+        block_max2(s1, s2, red);
+    }
+    double w[M], U[D], ds[D];
+#pragma unroll
+    for (int j = 0; j < M; ++j) w[j] = g.w[(size_t)c * M + j];
+    double U2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { U[d] = g.prim[(size_t)c * M + 1 + d]; ds[d] = ci.ds[d]; U2 = add(U2, mul(U[d], U[d])); }
+    const double eden = sub(w[M - 1], mul(mul(0.5, w[0]), U2));   // w[end] - 0.5 w[1] sum(U.^2)
+    const double two_d = (double)(1 << D);
+    const int* nb_tab = lohner ? nbt + nb_off_of_grid[ci.grid] : nullptr;
+    const long long out0 = host_off[c];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double f[K], cdf[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {   // _criterion_cell!, AMR.jl:8-21
+            f[k] = own.f[k * np + i];
+            double mx = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const double a = fabs(mul(own.s[(d * K + k) * np + i], ds[d]));
+                if (a > mx) mx = a;
+            }
+            cdf[k] = add(f[k], mx);
+        }
+        double S = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) { const double t = sub(U[d], own.v[d * np + i]); S = add(S, mul(t, t)); }
+        const double wgt = own.wt[i];
+        const int level = own.lev[i];
+        // local_contribution_refine_flag / _coarsen_flag, Criteria.jl:19-49 (note the different association for NDF = 1)
+        const double e2 = K == 2 ? mul(mul(0.5, add(mul(S, cdf[0]), cdf[K - 1])), wgt) : 0.0;
+        const double e_ref = K == 2 ? fabs(e2) : fabs(mul(mul(mul(0.5, S), cdf[0]), wgt));
+        const double e_co = K == 2 ? e2 : mul(mul(0.5, mul(S, cdf[0])), wgt);
+        const double mass = dvd(mul(cdf[0], wgt), w[0]);
+        const bool local_refine = jmax(dvd(e_ref, eden), mass) > par.coeff_local;
+        const bool local_coarsen = jmax(dvd(e_co, eden), mass) < dvd(par.coeff_local, two_d);
+        bool base_refine, ok;
+        if (lohner) {   // vs_lohner_indicator, Criteria.jl:259-287
+            double eta = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const double hi = mul(par.h_fine[d], (double)(1 << (par.maxlevel - level)));
+                const int Ln = nb_tab[((long long)i * D + d) * 2], Rn = nb_tab[((long long)i * D + d) * 2 + 1];
+                const double dsL = Ln < 0 ? hi : mul(0.5, add(hi, mul(par.h_fine[d], (double)(1 << (par.maxlevel - own.lev[Ln])))));
+                const double dsR = Rn < 0 ? hi : mul(0.5, add(hi, mul(par.h_fine[d], (double)(1 << (par.maxlevel - own.lev[Rn])))));
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const double fL = Ln < 0 ? 0.0 : own.f[k * np + Ln], fR = Rn < 0 ? 0.0 : own.f[k * np + Rn];
+                    eta = jmax(eta, ratio(fL, f[k], fR, dsL, dsR, k == 0 ? s1 : s2));
+                }
+            }
+            base_refine = eta > par.coeff_lohner || local_refine;
+            ok = eta < mul(COARSEN_RATIO, par.coeff_lohner) && local_coarsen;
+        } else {   // global_contribution_{refine,coarsen}_flag, Criteria.jl:55-84
+            const double e_gl = K == 2 ? e2 : e_co;
+            const double m0 = mul(cdf[0], wgt);
+            const bool global_refine = m0 > mul(par.coeff_global, par.vr_density) || e_gl > mul(par.vr_energy, par.coeff_global);
+            const bool global_coarsen = m0 < dvd(mul(par.coeff_global, par.vr_density), two_d) &&
+                                        e_gl < dvd(mul(par.vr_energy, par.coeff_global), two_d);
+            base_refine = local_refine || global_refine;
+            ok = local_coarsen && global_coarsen;
+        }
+        if (refine_flag) refine_flag[out0 + i] = (unsigned char)(level < par.maxlevel && base_refine);
+        if (coarsen_ok) coarsen_ok[out0 + i] = (unsigned char)ok;
+    }
+}
+
+// vs_resolution(ps_data, kinfo), AMR.jl:154-166: per local cell (density_max, energy_max) * weight; solid cells give 0
+template <int D, int K>
+__global__ void __launch_bounds__(256) vs_resolution_kernel(DevView g, VsPar par, double* __restrict__ out) {
+    __shared__ double red[64];
+    const int c = blockIdx.x;
+    const CellInfo& ci = g.cells[c];
+    const CellPtr<D, K> own(g, ci);
+    const int n = ci.n, np = ci.np;
+    double U[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) U[d] = g.prim[(size_t)c * (D + 2) + 1 + d];
+    double dmax = -CUDART_INF, emax = -CUDART_INF;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double c2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) { const double t = sensor::sub(U[d], own.v[d * np + i]); c2 = sensor::add(c2, sensor::mul(t, t)); }
+        const double f0 = own.f[i];
+        dmax = fmax(dmax, f0);
+        double e = sensor::mul(f0, c2);
+        if (K == 2) { const double f1 = own.f[np + i]; dmax = fmax(dmax, f1); e = sensor::add(e, f1); }
+        emax = fmax(emax, e);
+    }
+    block_max2(dmax, emax, red);
+    if (threadIdx.x == 0) {
+        const bool fluid = ci.bound_enc >= 0;
+        out[2 * c] = fluid ? sensor::mul(dmax, par.cell_weight) : 0.0;
+        out[2 * c + 1] = fluid ? sensor::mul(sensor::mul(0.5, emax), par.cell_weight) : 0.0;
+    }
+}
+
 }  // namespace kamr

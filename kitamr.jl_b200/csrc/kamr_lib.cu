@@ -85,13 +85,13 @@ struct Bin {
 
 enum KernelId { KID_SLOPE = 0, KID_MACRO_SLOPE, KID_FLUX, KID_UPDATE, KID_STEP, KID_RESIDUAL, KID_PACK, KID_UNPACK,
                 KID_LIMIT, KID_SOLID_CELL, KID_SOLID_NBR, KID_STEP_REGULAR, KID_SLOPE_REGULAR, KID_STEP_REGMAP,
-                KID_SLOPE_REGMAP, KID_COUNT };
+                KID_SLOPE_REGMAP, KID_PS_SENSOR, KID_COUNT };
 const char* const kKernelNames[KID_COUNT] = {"slope_kernel", "macro_slope_kernel", "phase_kernel<FLUX>",
                                              "phase_kernel<UPDATE>", "phase_kernel<FUSED>", "residual_reduce_kernel",
                                              "pack_kernel", "unpack_kernel", "limit_kernel", "solid_cell_kernel",
                                              "solid_neighbor_kernel", "phase_regular_kernel",
                                              "slope_regular_kernel", "phase_regular_kernel<MAPPED>",
-                                             "slope_regular_kernel<MAPPED>"};
+                                             "slope_regular_kernel<MAPPED>", "adaptation criteria (ps / vs)"};
 
 struct PeerPlan {
     int rank;
@@ -112,6 +112,8 @@ struct PeerPlan {
     Lvl solid;                                // df of solid ghost cells, mid-flux (Boundary/Parallel.jl:138-259)
     Lvl sw;                                   // macro slopes of the mirrors (sw_exchange!, Parallel/Ghost.jl:867)
     long long send_base = 0, recv_base = 0;  // offsets of this peer's region in the staging buffers
+    int mirror_first = 0, mirror_count = 0;  // this peer's mirrors in kamr_ctx::d_send_cells
+    int ghost_first = 0, ghost_count = 0;    // its ghost cells (contiguous cell ids)
 };
 
 // One-sided halo over NVLink.  Message kinds; a peer raises flag [sender rank][kind] in the receiver's
@@ -187,6 +189,7 @@ struct kamr_ctx {
     int max_smem_optin = 0;
     bool keep_sdf = false;        // KAMR_OPT_KEEP_SDF: fused steps also write the raw slopes of every cell
     bool raw_sdf_valid = false;   // g.sdf holds the reference's sdf for every local cell
+    bool sw_valid = false;        // g.sw holds the macro slopes of the current state (local cells and ghosts)
     std::vector<int> limit_cells; // local fluid + ghost fluid cells (limit_kernel after upload_aux)
     int* d_limit_cells = nullptr;
     struct MergedSegs { CopySeg *d_send = nullptr, *d_recv = nullptr; int n_send = 0, n_recv = 0; };
@@ -227,6 +230,19 @@ struct kamr_ctx {
     std::vector<PeerPlan> peers;
     double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
     long long halo_bytes_step = 0;
+    // physical-space adaptation sensor (kamr_ps_criterion): the neighbour lists of the host mesh, per-cell work arrays
+    int *d_nb_state = nullptr, *d_nb_off = nullptr, *d_nb_ids = nullptr, *d_send_cells = nullptr;
+    double *d_ps_lohner = nullptr, *d_ps_above = nullptr, *d_ps_sensor = nullptr;
+    // velocity-space adaptation inputs (kamr_vs_criterion): face-neighbour tables per distinct velocity grid
+    struct VsCache {
+        bool valid = false;
+        int maxlevel = 0, trees[3] = {0, 0, 0};
+        double vmin[3] = {0, 0, 0}, vmax[3] = {0, 0, 0};
+        int* d_nbt = nullptr;
+        long long* d_nb_off = nullptr;
+    } vs_cache;
+    unsigned char* d_vs_flags = nullptr;   // refine_flag | coarsen_ok of the local points (host order)
+    double* d_vs_res = nullptr;
     // per-kernel timing (kamr_profile_enable)
     bool profiling = false;
     struct ProfRec { int kid; cudaEvent_t a, b; };
@@ -265,7 +281,10 @@ struct kamr_ctx {
         d_host_off = nullptr;
         d_slope_ticket = nullptr;
         d_res = nullptr; d_sendbuf = d_recvbuf = nullptr; d_fluid_cells = nullptr; d_limit_cells = nullptr;
-        limit_cells.clear(); raw_sdf_valid = false;
+        d_nb_state = d_nb_off = d_nb_ids = d_send_cells = nullptr;
+        d_ps_lohner = d_ps_above = d_ps_sensor = nullptr;
+        vs_cache = VsCache{}; d_vs_flags = nullptr; d_vs_res = nullptr;
+        limit_cells.clear(); raw_sdf_valid = false; sw_valid = false;
         peer_early.clear(); early_mask = 0; d_ghost_fluid = nullptr; n_ghost_fluid = 0; merged_segs.clear();
         for (void* q : p2p.opened) cudaIpcCloseMemHandle(q);
         p2p = P2P{};
@@ -1291,6 +1310,8 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
         PeerPlan pp;
         pp.rank = m->peer_rank[p];
         pp.send_base = send_total; pp.recv_base = recv_total;
+        pp.mirror_first = m->send_off[p]; pp.mirror_count = m->send_off[p + 1] - m->send_off[p];
+        pp.ghost_first = c->n_local + m->recv_off[p]; pp.ghost_count = m->recv_off[p + 1] - m->recv_off[p];
         long long pos = 0, spos_max = 0;
         std::map<int, long long> lpos;
         for (int q = m->send_off[p]; q < m->send_off[p + 1]; ++q) {
@@ -1381,6 +1402,14 @@ void build_topology(kamr_ctx* c, const kamr_mesh* m) {
     if (m->n_peer > 0) {
         c->d_sendbuf = c->dalloc<double>((size_t)send_total);
         c->d_recvbuf = c->dalloc<double>((size_t)recv_total);
+        c->d_send_cells = c->dupload(std::vector<int>(m->send_cells, m->send_cells + m->send_off[m->n_peer]));
+    }
+    {   // neighbour lists as the host mesh holds them (PsData.neighbor), for the adaptation sensor
+        const int ne = c->n_local * 2 * D;
+        c->d_nb_state = c->dupload(std::vector<int>(m->nb_state, m->nb_state + ne));
+        c->d_nb_off = c->dupload(std::vector<int>(m->nb_off, m->nb_off + ne + 1));
+        c->d_nb_ids = c->dupload(std::vector<int>(m->nb_ids, m->nb_ids + m->nb_off[ne]));
+        CK(cudaStreamSynchronize(c->stream));   // the temporaries above
     }
     lap("halo plan");
     setup_p2p(c, m);
@@ -1706,6 +1735,190 @@ void exchange(kamr_ctx* c, int what, int level) {
     CK(cudaGetLastError());
 }
 
+// Two-sided exchange of the mirrors' rows of a per-cell array (`width` doubles per cell, width <= (DIM+2)*DIM so that
+// the sw message's staging region fits): gathered per peer, received straight into the peer's contiguous ghost rows.
+// Event-driven users only (the adaptation sensor): the per-step halo is the one-sided path above.
+void exchange_rows(kamr_ctx* c, double* arr, int width) {
+    if (c->peers.empty()) return;
+    if (!c->comm) throw Fail("mesh has peers but kamr_comm_init was not called");
+    for (auto& pp : c->peers) {
+        if (!pp.mirror_count) continue;
+        Launch L_(c, KID_PACK);
+        const long long total = (long long)pp.mirror_count * width;
+        gather_rows_kernel<<<(int)std::min<long long>((total + 255) / 256, 1024), 256, 0, c->stream>>>(
+            c->d_send_cells + pp.mirror_first, pp.mirror_count, width, arr, c->d_sendbuf + pp.send_base);
+    }
+    CK(cudaGetLastError());
+    NCK(nccl().GroupStart());
+    for (auto& pp : c->peers) {
+        if (pp.mirror_count)
+            NCK(nccl().Send(c->d_sendbuf + pp.send_base, (size_t)pp.mirror_count * width, ncclFloat64, pp.rank, c->comm, c->stream));
+        if (pp.ghost_count)
+            NCK(nccl().Recv(arr + (size_t)pp.ghost_first * width, (size_t)pp.ghost_count * width, ncclFloat64, pp.rank, c->comm, c->stream));
+    }
+    NCK(nccl().GroupEnd());
+}
+
+// update_criterion!(ka), Physical_space/AMR.jl:256-341.  The slopes are current (kamr_slope, as
+// ps_adaptive_mesh_refinement! runs slope! first, AMR.jl:1109-1111): sw of local and ghost cells is on the device;
+// the ghosts' w travels here (in the reference it rides in the df message, Parallel/Ghost.jl:1).
+template <int D, int K>
+void do_ps_criterion(kamr_ctx* c, double threshold, double* lohner_out, double* sensor_out) {
+    constexpr int M = D + 2;
+    if (!c->sw_valid)
+        throw Fail("kamr_ps_criterion needs the macro slopes of the current state: call kamr_slope first "
+                   "(ps_adaptive_mesh_refinement! runs slope! before update_criterion!)");
+    halo_finish_df(c);
+    halo_join_puts(c);
+    if (!c->d_ps_lohner) {
+        c->d_ps_lohner = c->dalloc<double>((size_t)c->n_local * M * D);
+        c->d_ps_above = c->dalloc<double>((size_t)c->n_cell);
+        c->d_ps_sensor = c->dalloc<double>((size_t)c->n_local);
+        CK(cudaMemsetAsync(c->d_ps_above, 0, (size_t)c->n_cell * sizeof(double), c->stream));
+    }
+    exchange_rows(c, c->dv.w, M);
+    const int n_real = c->n_local + c->n_ghost;
+    const int grid = (c->n_local + 127) / 128;
+    if (grid > 0) {
+        Launch L_(c, KID_PS_SENSOR);
+        ps_lohner_kernel<D><<<grid, 128, 0, c->stream>>>(c->dv.cells, c->d_nb_state, c->d_nb_off, c->d_nb_ids, c->dv.w,
+                                                         c->dv.prim, c->dv.sw, c->n_local, n_real, c->gas.gamma, threshold,
+                                                         c->d_ps_lohner, c->d_ps_above);
+    }
+    exchange_rows(c, c->d_ps_above, 1);   // lohner_flag_exchange!, Parallel/Ghost.jl:939-978
+    if (grid > 0) {
+        Launch L_(c, KID_PS_SENSOR);
+        ps_buffer_kernel<D><<<grid, 128, 0, c->stream>>>(c->dv.cells, c->d_nb_state, c->d_nb_off, c->d_nb_ids, c->n_local,
+                                                         n_real, threshold, c->d_ps_above, c->d_ps_lohner, c->d_ps_sensor);
+    }
+    CK(cudaGetLastError());
+    if (lohner_out)
+        CK(cudaMemcpyAsync(lohner_out, c->d_ps_lohner, (size_t)c->n_local * M * D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (sensor_out)
+        CK(cudaMemcpyAsync(sensor_out, c->d_ps_sensor, (size_t)c->n_local * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    sync_and_check(c);
+}
+
+// ---- velocity-space adaptation inputs
+VsPar make_vs_par(kamr_ctx* c, const kamr_vs_adapt* p) {
+    if (!p) throw Fail("kamr_vs_adapt is NULL");
+    if (p->mode != 0 && p->mode != 1) throw Fail("kamr_vs_adapt.mode: 0 (:lohner) or 1 (contribution)");
+    if (p->maxlevel < 0 || p->maxlevel >= VPK_LEVELS) throw Fail("kamr_vs_adapt.maxlevel out of range");
+    VsPar v{};
+    v.mode = p->mode; v.maxlevel = p->maxlevel;
+    double du = 1.0, nt = 1.0;
+    for (int d = 0; d < c->D; ++d) {
+        if (p->trees[d] <= 0 || !(p->vmax[d] > p->vmin[d])) throw Fail("kamr_vs_adapt: trees / quadrature invalid");
+        const double ds0 = (p->vmax[d] - p->vmin[d]) / p->trees[d];   // Velocity_space/AMR.jl:29-30
+        v.vmin[d] = p->vmin[d];
+        v.h_fine[d] = ds0 / std::ldexp(1.0, p->maxlevel);             // Neighbor.jl:83
+        const long long gm = (long long)p->trees[d] << p->maxlevel;
+        if (gm > (1 << 20)) throw Fail("kamr_vs_adapt: finest-level velocity lattice too large");
+        v.gmax[d] = (int)gm;
+        du *= p->vmax[d] - p->vmin[d];
+        nt *= (double)p->trees[d];
+    }
+    v.coeff_lohner = p->coeff_lohner; v.coeff_local = p->coeff_local; v.coeff_global = p->coeff_global;
+    v.vr_density = p->vr_density; v.vr_energy = p->vr_energy;
+    v.cell_weight = du / nt / std::ldexp(1.0, c->D * p->maxlevel);    // AMR.jl:163
+    return v;
+}
+
+// face-neighbour tables of every distinct velocity grid, built on the device (one CTA per grid, a finest-level
+// lattice per CTA in a scratch buffer, grids taken in batches that keep the scratch under 256 MB)
+template <int D, int K>
+void ensure_vs_neighbors(kamr_ctx* c, const kamr_vs_adapt* p, const VsPar& vp) {
+    auto& vc = c->vs_cache;
+    bool same = vc.valid && vc.maxlevel == p->maxlevel;
+    for (int d = 0; d < D && same; ++d)
+        same = vc.trees[d] == p->trees[d] && vc.vmin[d] == p->vmin[d] && vc.vmax[d] == p->vmax[d];
+    if (same) return;
+    const int ng = (int)c->grid_n.size();
+    std::vector<VsGridTask> tasks;
+    std::vector<long long> nb_off(ng, 0);
+    long long total = 0;
+    for (int g = 0; g < ng; ++g) {
+        if (c->grid_canon[g] != g) continue;
+        nb_off[g] = total;
+        tasks.push_back(VsGridTask{c->grid_goff[g], total, c->grid_n[g], c->grid_np[g]});
+        total += (long long)c->grid_n[g] * D * 2;
+    }
+    for (int g = 0; g < ng; ++g) nb_off[g] = nb_off[c->grid_canon[g]];
+    vc.d_nbt = c->dalloc<int>((size_t)total);
+    vc.d_nb_off = c->dupload(nb_off);
+    VsGridTask* d_tasks = c->dupload(tasks);
+    long long lattice = 1;
+    for (int d = 0; d < D; ++d) lattice *= vp.gmax[d];
+    const int batch = (int)std::max<long long>(1, std::min<long long>((long long)tasks.size(), (256ll << 20) / (lattice * 4)));
+    int* d_lattice = nullptr;
+    CK(cudaMalloc((void**)&d_lattice, (size_t)batch * lattice * sizeof(int)));
+    for (size_t first = 0; first < tasks.size(); first += batch) {
+        const int nb = (int)std::min<size_t>(batch, tasks.size() - first);
+        Launch L_(c, KID_PS_SENSOR);
+        vs_neighbors_kernel<D><<<nb, 256, 0, c->stream>>>(d_tasks + first, vp, c->dv.v_mid, c->dv.v_level, d_lattice,
+                                                          lattice, vc.d_nbt, c->dv.err_flag);
+    }
+    cudaError_t e = cudaGetLastError();
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_lattice);
+    CK(e);
+    CK(cudaMemcpy(c->h_err, c->dv.err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (*c->h_err == 3) {
+        *c->h_err = 0;
+        CK(cudaMemset(c->dv.err_flag, 0, sizeof(int)));
+        throw Fail("kamr_vs_adapt does not describe the velocity grids on the device (a velocity cell lies outside "
+                   "quadrature / vs_trees_num / AMR_VS_MAXLEVEL)");
+    }
+    vc.valid = true; vc.maxlevel = p->maxlevel;
+    for (int d = 0; d < D; ++d) { vc.trees[d] = p->trees[d]; vc.vmin[d] = p->vmin[d]; vc.vmax[d] = p->vmax[d]; }
+}
+
+template <int D, int K>
+void do_vs_criterion(kamr_ctx* c, const kamr_vs_adapt* p, uint8_t* refine_flag, uint8_t* coarsen_ok) {
+    const VsPar vp = make_vs_par(c, p);
+    if (!c->raw_sdf_valid)
+        throw Fail("kamr_vs_criterion reads the raw slopes (criterion distribution df + max_d |sdf ds_d|): none are "
+                   "resident — call kamr_slope, or set KAMR_OPT_KEEP_SDF before the last step");
+    if (c->n_local == 0) return;
+    halo_finish_df(c);
+    halo_join_puts(c);
+    if (vp.mode == 0) ensure_vs_neighbors<D, K>(c, p, vp);
+    const long long npts = c->host_off[c->n_local];
+    if (!c->d_vs_flags) c->d_vs_flags = c->dalloc<unsigned char>((size_t)2 * npts);
+    if (!c->d_host_off) c->d_host_off = c->dupload(c->host_off);
+    {
+        Launch L_(c, KID_PS_SENSOR);
+        vs_criterion_kernel<D, K><<<c->n_local, 256, 0, c->stream>>>(c->dv, vp, c->d_host_off, c->vs_cache.d_nb_off,
+                                                                     c->vs_cache.d_nbt, c->d_vs_flags, c->d_vs_flags + npts);
+    }
+    CK(cudaGetLastError());
+    if (refine_flag) CK(cudaMemcpyAsync(refine_flag, c->d_vs_flags, (size_t)npts, cudaMemcpyDeviceToHost, c->stream));
+    if (coarsen_ok) CK(cudaMemcpyAsync(coarsen_ok, c->d_vs_flags + npts, (size_t)npts, cudaMemcpyDeviceToHost, c->stream));
+    sync_and_check(c);
+}
+
+template <int D, int K>
+void do_vs_resolution(kamr_ctx* c, const kamr_vs_adapt* p, double* out) {
+    const VsPar vp = make_vs_par(c, p);
+    out[0] = out[1] = 0.0;
+    if (c->n_local == 0) return;
+    halo_finish_df(c);
+    halo_join_puts(c);
+    if (!c->d_vs_res) c->d_vs_res = c->dalloc<double>((size_t)2 * c->n_local);
+    {
+        Launch L_(c, KID_PS_SENSOR);
+        vs_resolution_kernel<D, K><<<c->n_local, 256, 0, c->stream>>>(c->dv, vp, c->d_vs_res);
+    }
+    CK(cudaGetLastError());
+    std::vector<double> h((size_t)2 * c->n_local);
+    CK(cudaMemcpyAsync(h.data(), c->d_vs_res, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    sync_and_check(c);
+    for (int i = 0; i < c->n_local; ++i) {   // density_res = max(density_res_i, density_res), AMR.jl:146-147
+        out[0] = std::max(h[2 * i], out[0]);
+        out[1] = std::max(h[2 * i + 1], out[1]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch sequences
 #ifndef KAMR_NT
@@ -1813,6 +2026,7 @@ void do_slope(kamr_ctx* c, bool with_sw, bool raw_all, bool defer_final = false)
     }
     c->raw_sdf_valid = raw_all;
     CK(cudaGetLastError());
+    c->sw_valid = with_sw;
     if (with_sw) {
         run_macro_slope<D, K>(c);
         if (!c->peers.empty()) {   // sw_exchange!, Parallel/Ghost.jl:867: the ghosts' sw feed the host's Löhner sensor
@@ -1984,6 +2198,7 @@ void send_df_halo(kamr_ctx* c) {
 
 template <int D, int K>
 void do_iterate(kamr_ctx* c, double dt, int want, double* res_out) {
+    c->sw_valid = false;
     ensure_flux(c);
     halo_finish_df(c);
     if (c->gas.marching == KAMR_MARCH_CIP) {
@@ -2014,6 +2229,7 @@ void do_iterate(kamr_ctx* c, double dt, int want, double* res_out) {
 
 template <int D, int K>
 void do_step(kamr_ctx* c, double dt, int want, double* res_out) {
+    c->sw_valid = false;
     if (c->gas.marching != KAMR_MARCH_CAIDVM) {  // only CAIDVM_Marching has the fused kernel
         do_slope<D, K>(c, false, false);
         do_flux<D, K>(c, dt);
@@ -2210,6 +2426,7 @@ int kamr_upload_state(kamr_ctx* c, const double* df, const double* w, const doub
         if (c->cells.empty()) throw Fail("upload_topology first");
         halo_finish_df(c);
         halo_join_puts(c);
+        c->sw_valid = false;
         if (df) copy_points(c, c->dv.df, nullptr, df, c->K, true);
         const size_t nb = (size_t)c->n_local * c->M * sizeof(double);
         if (w) CK(cudaMemcpyAsync(c->dv.w, w, nb, cudaMemcpyHostToDevice, c->stream));
@@ -2226,6 +2443,7 @@ int kamr_upload_aux(kamr_ctx* c, const double* sdf, const double* flux, const do
             copy_points(c, c->dv.sdf, nullptr, sdf, c->K * c->D, true);
             DISPATCH(c, run_limit, c, c->d_limit_cells, (int)c->limit_cells.size());
             c->raw_sdf_valid = true;
+            c->sw_valid = false;
         }
         if (flux) { ensure_flux(c); copy_points(c, c->dv.flux, nullptr, flux, c->K, true); }
         if (mflux) CK(cudaMemcpyAsync(c->dv.mflux, mflux, (size_t)c->n_local * c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -2315,6 +2533,15 @@ int kamr_unpack_cells(kamr_ctx* c, int32_t n, const int32_t* cells, const double
 
 int kamr_slope(kamr_ctx* c) {
     return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_slope, c, true, true); });
+}
+int kamr_ps_criterion(kamr_ctx* c, double threshold, double* lohner_out, double* sensor_out) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_ps_criterion, c, threshold, lohner_out, sensor_out); });
+}
+int kamr_vs_resolution(kamr_ctx* c, const kamr_vs_adapt* par, double* out) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_vs_resolution, c, par, out); });
+}
+int kamr_vs_criterion(kamr_ctx* c, const kamr_vs_adapt* par, uint8_t* refine_flag, uint8_t* coarsen_ok) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_vs_criterion, c, par, refine_flag, coarsen_ok); });
 }
 int kamr_flux(kamr_ctx* c, double dt) {
     return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_flux, c, dt); });

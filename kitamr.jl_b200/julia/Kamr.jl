@@ -458,6 +458,69 @@ function download!(ctx::Context, mask::UInt32 = DL_DF | DL_W | DL_PRIM | DL_QF; 
 end
 
 """
+    update_criterion!(ctx, ka)
+
+Drop-in for `update_criterion!(ka)` (Physical_space/AMR.jl:256-286, including `apply_amr_buffer!` and its
+`lohner_flag_exchange!`): the Löhner sensor of every local cell is evaluated on the device from the resident
+`w` / `prim` / `sw` and only `PsData.lohner` ((DIM+2)×DIM per cell) comes back — no `df`, `sdf` or ghost data is
+downloaded for a physical-space adaptation pass.  Runs `kamr_slope` first, as `ps_adaptive_mesh_refinement!` runs
+`slope!` (AMR.jl:1109-1111).  `ps_refine_flag` / `ps_coarsen_flag` (Criteria.jl:69-101) then read `ps_data.lohner`
+on the host unchanged.
+"""
+function update_criterion!(ctx::Context, ka::KA{DIM}) where {DIM}
+    f = ctx.flat
+    M = DIM + 2
+    slope!(ctx)
+    lohner = Vector{Float64}(undef, f.n_local * M * DIM)
+    check(ctx, ccall((:kamr_ps_criterion, LIB), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Float64}, Ptr{Float64}),
+                     ctx.h, ka.kinfo.config.solver.ADAPT_COEFFI_PS, lohner, C_NULL))
+    for c in 1:f.n_local
+        x = f.cells[c]
+        x.bound_enc < 0 && continue                                   # solid cells keep theirs (AMR.jl:265)
+        vec(x.lohner) .= @view lohner[(c-1)*M*DIM+1:c*M*DIM]           # column-major [(DIM+2) × DIM] == the ABI layout
+    end
+    return nothing
+end
+
+struct CVsAdapt                        # == kamr_vs_adapt (include/kamr.h)
+    mode::Int32; maxlevel::Int32; trees::NTuple{3,Int32}; pad_::Int32
+    vmin::NTuple{3,Float64}; vmax::NTuple{3,Float64}
+    coeff_lohner::Float64; coeff_local::Float64; coeff_global::Float64
+    vr_density::Float64; vr_energy::Float64
+end
+
+function CVsAdapt(ka::KA{DIM}, vr_density = 0.0, vr_energy = 0.0) where {DIM}
+    cfg = ka.kinfo.config; s = cfg.solver; q = cfg.quadrature
+    t3(f, fill) = ntuple(d -> d <= DIM ? f(d) : fill, 3)
+    CVsAdapt(s.ADAPT_VS_MODE === :lohner ? 0 : 1, s.AMR_VS_MAXLEVEL, t3(d -> Int32(cfg.vs_trees_num[d]), Int32(1)), 0,
+             t3(d -> Float64(q[2d-1]), 0.0), t3(d -> Float64(q[2d]), 1.0),
+             s.ADAPT_COEFFI_VS_LOHNER, s.ADAPT_COEFFI_VS_LOCAL, s.ADAPT_COEFFI_VS_GLOBAL, vr_density, vr_energy)
+end
+
+"""
+    vs_flags(ctx, ka) -> (refine_flags, coarsen_ok)
+
+The per-velocity-point decisions of `vs_refine!` / `vs_coarsen!` (Velocity_space/AMR.jl:26-115) evaluated on the
+device: one byte per point and decision comes back instead of `df` + `sdf`.  Both vectors are in the flat point order
+(`flat.vs_off[c] + i`).  `vs_resolution` (AMR.jl:139-152) is evaluated on the device too; its two `MPI.Allreduce(MAX)`
+stay here.  The host then runs `refine_grid_stream!` with `refine_flags`, and `coarsen_grid_stream!` with `coarsen_ok`
+for the cells whose grid the refinement pass left alone; a cell whose grid changed re-evaluates `vs_coarsen!`'s loop
+body on the host after fetching its `df` with `kamr_pack_cells` (the reference evaluates `coarsen_ok` on the refined
+grid, whose `sdf` is zero, Rebuild.jl:81).
+"""
+function vs_flags(ctx::Context, ka::KA{DIM}) where {DIM}
+    f = ctx.flat
+    res = zeros(2)
+    check(ctx, ccall((:kamr_vs_resolution, LIB), Cint, (Ptr{Cvoid}, Ref{CVsAdapt}, Ptr{Float64}), ctx.h, CVsAdapt(ka), res))
+    res[1] = MPI.Allreduce(res[1], MPI.MAX, MPI.COMM_WORLD); res[2] = MPI.Allreduce(res[2], MPI.MAX, MPI.COMM_WORLD)
+    npts = f.vs_off[f.n_local+1]
+    refine = Vector{UInt8}(undef, npts); coarsen = Vector{UInt8}(undef, npts)
+    check(ctx, ccall((:kamr_vs_criterion, LIB), Cint, (Ptr{Cvoid}, Ref{CVsAdapt}, Ptr{UInt8}, Ptr{UInt8}),
+                     ctx.h, CVsAdapt(ka, res[1], res[2]), refine, coarsen))
+    return refine, coarsen
+end
+
+"""
 The `solve!`-shaped loop with the device in it (compare Solver/Solver.jl:44-87).  The adapt events keep their cadence;
 each one is bracketed by a download (what it reads) and a re-flatten (what it changed).
 """

@@ -1362,3 +1362,390 @@ int orc_step(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double d
     if (rc) return rc;
     return orc_iterate(cfg, m, st, dt, want_residual, res_out);
 }
+
+/* ------------------------------------------------------------------ physical-space adaptation sensor
+ * update_criterion!(ka) of Physical_space/AMR.jl:256-286 with the Löhner estimator of
+ * Physical_space/Criteria.jl:14-200 and the one-cell buffer apply_amr_buffer! (AMR.jl:296-341).
+ * The caller has run slope! (orc_slope) first, as ps_adaptive_mesh_refinement! does (AMR.jl:1109-1111). */
+
+/* Julia's max(a, b) returns NaN when either argument is NaN (C's fmax does not) */
+static inline double jl_max(double a, double b) {
+    if (a != a || b != b) return NAN;
+    return a > b ? a : b;
+}
+#define PS_LOHNER_ABS_FLOOR 1e-4          /* Criteria.jl:2 */
+#define PS_PRIMITIVE_REL_JUMP_FLOOR 1e-3  /* Criteria.jl:3 */
+#define PS_VORTICITY_JUMP_FLOOR 2e-2      /* Criteria.jl:4 */
+
+/* lohner_value, Criteria.jl:25-31 */
+static double lohner_value(double left, double center, double right, double dsL, double dsR, double eps) {
+    double scale = dsR * fabs(left) + (dsL + dsR) * fabs(center) + dsL * fabs(right);
+    if (scale < PS_LOHNER_ABS_FLOOR * (dsL < dsR ? dsL : dsR)) return 0.0;
+    double denom = dsR * fabs(left - center) + dsL * fabs(right - center) + eps * scale;
+    if (denom <= 0.0) return 0.0;
+    return fabs(dsR * left - (dsL + dsR) * center + dsL * right) / denom;
+}
+/* primitive_amplitude_ok, Criteria.jl:33-37 */
+static int primitive_amplitude_ok(double left, double center, double right) {
+    double jump = jl_max(fabs(left - center), fabs(right - center));
+    double scale = jl_max(fabs(center), PS_LOHNER_ABS_FLOOR);
+    return jump >= PS_PRIMITIVE_REL_JUMP_FLOOR * scale;
+}
+/* velocity_slope, Criteria.jl:39-42; sw is [dir][row] */
+static inline double velocity_slope(int M, const double* sw, const double* prim, int component, int dir) {
+    return (sw[dir * M + component] - prim[component] * sw[dir * M + 0]) / prim[0];
+}
+/* vorticity, Criteria.jl:44-53 (components 1-based there) */
+static double vorticity(int D, int M, const double* sw, const double* prim) {
+    if (D == 2) return velocity_slope(M, sw, prim, 1, 1) - velocity_slope(M, sw, prim, 2, 0);
+    double c1 = velocity_slope(M, sw, prim, 2, 2) - velocity_slope(M, sw, prim, 3, 1);
+    double c2 = velocity_slope(M, sw, prim, 3, 0) - velocity_slope(M, sw, prim, 1, 2);
+    double c3 = velocity_slope(M, sw, prim, 1, 1) - velocity_slope(M, sw, prim, 2, 0);
+    return sqrt(c1 * c1 + c2 * c2 + c3 * c3);
+}
+/* velocity_scale + vorticity_amplitude_ok, Criteria.jl:55-67 */
+static int vorticity_amplitude_ok(int M, double left, double center, double right, const double* prim, double h) {
+    double omega = jl_max(fabs(left), jl_max(fabs(center), fabs(right)));
+    double speed2 = 0.0;
+    for (int i = 1; i < M - 1; ++i) speed2 += prim[i] * prim[i];
+    double lambda = jl_max(fabs(prim[M - 1]), 2.220446049250313e-16);
+    double vscale = jl_max(sqrt(speed2), 1.0 / sqrt(lambda));
+    return omega * h >= PS_VORTICITY_JUMP_FLOOR * vscale;
+}
+
+/* one side of update_Lohner_inner_ps!, Criteria.jl:124-160: the mean conserved state (plus the transverse shift
+ * when the neighbour is coarser) turned into primitives, and the mean macro slopes.  Neighbours that are
+ * SolidNeighbor pseudo-cells carry w = sw = 0 (Boundary/Immersed_boundary.jl:300-302). */
+static void lohner_side(const octx* o, const orc_state* st, int c, nlist nb, int dir, int coarser, double* prim_out,
+                        double* sw_out) {
+    const int D = o->D, M = o->M;
+    const kamr_mesh* m = o->m;
+    const int n_real = m->n_local + m->n_ghost;
+    double ws[MAXM];
+    for (int j = 0; j < M; ++j) ws[j] = 0.0;
+    for (int q = 0; q < M * D; ++q) sw_out[q] = 0.0;
+    for (int k = 0; k < nb.cnt; ++k) {
+        int id = nb.ids[k];
+        for (int j = 0; j < M; ++j) ws[j] += id < n_real ? st->w[(size_t)id * M + j] : 0.0;
+        for (int q = 0; q < M * D; ++q) sw_out[q] += id < n_real ? st->sw[(size_t)id * M * D + q] : 0.0;
+    }
+    if (coarser) {   /* dot(dx, sw[j, FAT[DIM-1][dir]]) over the transverse directions in ascending order */
+        int id = nb.ids[0];
+        for (int j = 0; j < M; ++j) {
+            double acc = 0.0;
+            int first = 1;
+            for (int t = 0; t < D; ++t) {
+                if (t == dir) continue;
+                double dx = m->mid[(size_t)c * D + t] - m->mid[(size_t)id * D + t];
+                double s = id < n_real ? st->sw[(size_t)id * M * D + t * M + j] : 0.0;
+                if (first) { acc = dx * s; first = 0; } else acc += dx * s;
+            }
+            ws[j] += acc;
+        }
+    }
+    for (int j = 0; j < M; ++j) ws[j] /= (double)nb.cnt;
+    for (int q = 0; q < M * D; ++q) sw_out[q] /= (double)nb.cnt;
+    orc_get_prim(D, ws, o->cfg->gamma, prim_out);
+}
+
+static double ps_sensor_of(int D, int M, const double* loh) {   /* ps_sensor, Criteria.jl:14-23 */
+    double a = 0.0, b = 0.0;
+    for (int d = 0; d < D; ++d) { a = jl_max(a, loh[d * M + 0]); b = jl_max(b, loh[d * M + M - 1]); }
+    return jl_max(a, b);
+}
+
+/* ghost_flag: [n_ghost] the owner's "sensor > threshold" per ghost cell (lohner_flag_exchange!,
+ * Parallel/Ghost.jl:939-978), NULL on a single rank.  lohner_out: [n_local][DIM][DIM+2]; sensor_out: [n_local]
+ * ps_sensor after the buffer; flag_out: [n_local] the pre-buffer decision (what a rank sends for its mirrors). */
+int orc_ps_criterion(const kamr_config* cfg, const kamr_mesh* m, const orc_state* st, double threshold,
+                     const int32_t* ghost_flag, double* lohner_out, double* sensor_out, int32_t* flag_out) {
+    octx o;
+    if (octx_init(&o, cfg, m)) return 1;
+    const int D = o.D, M = o.M;
+    double primL[MAXM], primR[MAXM], swL[MAXM * MAXD], swR[MAXM * MAXD];
+    int32_t* above = (int32_t*)calloc((size_t)m->n_local, sizeof(int32_t));
+    for (int c = 0; c < m->n_local; ++c) {
+        double* loh = lohner_out + (size_t)c * M * D;
+        for (int q = 0; q < M * D; ++q) loh[q] = 0.0;
+        if (skip_cell(&o, c)) continue;   /* AMR.jl:264-265 */
+        const double* prim = st->prim + (size_t)c * M;
+        const double* sw = st->sw + (size_t)c * M * D;
+        for (int dir = 0; dir < D; ++dir) {
+            int sL = m->nb_state[c * 2 * D + 2 * dir], sR = m->nb_state[c * 2 * D + 2 * dir + 1];
+            if (sL == 0 || sR == 0) continue;   /* AMR.jl:160-255: a domain side zeroes the direction */
+            double ds = m->ds[(size_t)c * D + dir];
+            /* AMR.jl:5-157: same level ds, finer 0.75 ds, coarser 1.5 ds */
+            double dsL = sL == 1 ? ds : (sL > 1 ? 0.75 * ds : 1.5 * ds);
+            double dsR = sR == 1 ? ds : (sR > 1 ? 0.75 * ds : 1.5 * ds);
+            lohner_side(&o, st, c, nb_list(&o, c, 2 * dir), dir, dsL > ds, primL, swL);
+            lohner_side(&o, st, c, nb_list(&o, c, 2 * dir + 1), dir, dsR > ds, primR, swR);
+            double omegaL = vorticity(D, M, swL, primL), omegaR = vorticity(D, M, swR, primR);
+            double omega = vorticity(D, M, sw, prim);
+            int use_vort = vorticity_amplitude_ok(M, omegaL, omega, omegaR, prim, dsL > dsR ? dsL : dsR);
+            double eps_l = 0.2 * ds;
+            for (int j = 0; j < M; ++j) {
+                if (j == 1)
+                    loh[dir * M + j] = use_vort ? lohner_value(omegaL, omega, omegaR, dsL, dsR, eps_l) : 0.0;
+                else
+                    loh[dir * M + j] = primitive_amplitude_ok(primL[j], prim[j], primR[j])
+                                           ? lohner_value(primL[j], prim[j], primR[j], dsL, dsR, eps_l) : 0.0;
+            }
+        }
+        above[c] = ps_sensor_of(D, M, loh) > threshold;
+    }
+    /* apply_amr_buffer!, AMR.jl:296-341: decide with the un-inflated sensors, then inflate */
+    for (int c = 0; c < m->n_local; ++c) {
+        if (flag_out) flag_out[c] = above[c];
+        if (skip_cell(&o, c) || above[c]) continue;
+        int flagged = 0;
+        for (int f = 0; f < 2 * D && !flagged; ++f) {
+            if (m->nb_state[c * 2 * D + f] == 0) continue;
+            nlist nb = nb_list(&o, c, f);
+            for (int k = 0; k < nb.cnt && !flagged; ++k) {
+                int id = nb.ids[k];
+                if (id >= m->n_local + m->n_ghost) continue;   /* SolidNeighbor: neither PsData nor GhostPsData */
+                if (m->bound_enc[id] < 0) continue;
+                if (id < m->n_local) flagged = above[id] == 1;   /* decide-then-apply: never a buffered cell */
+                else flagged = ghost_flag ? ghost_flag[id - m->n_local] != 0 : 0;
+            }
+        }
+        if (flagged) above[c] = 2;
+    }
+    for (int c = 0; c < m->n_local; ++c) {
+        double* loh = lohner_out + (size_t)c * M * D;
+        if (above[c] == 2)
+            for (int q = 0; q < M * D; ++q) loh[q] = 2.0 * threshold;
+        if (sensor_out) sensor_out[c] = ps_sensor_of(D, M, loh);
+    }
+    free(above);
+    octx_free(&o);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ velocity-space adaptation inputs
+ * vs_resolution (Velocity_space/AMR.jl:139-166), the refine_flags of vs_refine! (:26-69) and the coarsen_ok of
+ * vs_coarsen! (:73-115) with the criteria of Velocity_space/Criteria.jl and the face-neighbour search of
+ * Velocity_space/Neighbor.jl.  The neighbour search here is a different algorithm with the same answer: instead of
+ * the reference's sorted Morton keys + predecessor search, the leaf owning a finest-level lattice point is found by
+ * looking its ancestors' corners up, level by level, in a sorted table of (level, corner) keys. */
+
+typedef struct { uint64_t key; int leaf; } vkey;
+static int vkey_cmp(const void* a, const void* b) {
+    uint64_t x = ((const vkey*)a)->key, y = ((const vkey*)b)->key;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+/* 4 bits of level, 20 bits per finest-level lattice coordinate */
+static inline uint64_t vkey_pack(int D, int level, const long long* g) {
+    uint64_t k = (uint64_t)level;
+    for (int d = 0; d < D; ++d) k = (k << 20) | (uint64_t)g[d];
+    return k;
+}
+typedef struct {
+    int D, n, maxlevel;
+    double vmin[MAXD], h_fine[MAXD];
+    long long gmax[MAXD];
+    vkey* keys;
+} vindex;
+
+static int vindex_build(vindex* ix, int D, int n, const double* vmid, const int8_t* level, const kamr_vs_adapt* par) {
+    ix->D = D; ix->n = n; ix->maxlevel = par->maxlevel;
+    if (par->maxlevel > 15) return 1;
+    for (int d = 0; d < D; ++d) {
+        double ds0 = (par->vmax[d] - par->vmin[d]) / par->trees[d];   /* AMR.jl:29-30 */
+        ix->vmin[d] = par->vmin[d];
+        ix->h_fine[d] = ds0 / pow2i(par->maxlevel);                   /* Neighbor.jl:83 */
+        ix->gmax[d] = (long long)par->trees[d] << par->maxlevel;
+        if (ix->gmax[d] >= (1 << 20)) return 1;
+    }
+    ix->keys = (vkey*)malloc(sizeof(vkey) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; ++i) {
+        long long g[MAXD];
+        int L = level[i];
+        for (int d = 0; d < D; ++d) {   /* _corner_index, Neighbor.jl:63-66 */
+            double cell = ix->h_fine[d] * (double)(1 << (par->maxlevel - L));
+            g[d] = llround((vmid[(size_t)d * n + i] - 0.5 * cell - ix->vmin[d]) / ix->h_fine[d]);
+        }
+        ix->keys[i].key = vkey_pack(D, L, g);
+        ix->keys[i].leaf = i;
+    }
+    qsort(ix->keys, (size_t)n, sizeof(vkey), vkey_cmp);
+    return 0;
+}
+/* leaf owning the finest-level lattice point g, -1 if none */
+static int vindex_locate(const vindex* ix, const long long* g) {
+    for (int L = ix->maxlevel; L >= 0; --L) {
+        long long c[MAXD];
+        int sh = ix->maxlevel - L;
+        for (int d = 0; d < ix->D; ++d) c[d] = (g[d] >> sh) << sh;
+        vkey probe = { vkey_pack(ix->D, L, c), 0 };
+        const vkey* hit = (const vkey*)bsearch(&probe, ix->keys, (size_t)ix->n, sizeof(vkey), vkey_cmp);
+        if (hit) return hit->leaf;
+    }
+    return -1;
+}
+/* vs_face_neighbor, Neighbor.jl:181-204: probe half a finest cell across the face, on the cell's centre line */
+static int vindex_face_neighbor(const vindex* ix, const double* vmid, const int8_t* level, int i, int dim, int dir) {
+    long long g[MAXD];
+    int L = level[i];
+    double cell = ix->h_fine[dim] * (double)(1 << (ix->maxlevel - L));
+    for (int d = 0; d < ix->D; ++d) {
+        double coord = vmid[(size_t)d * ix->n + i];
+        if (d == dim) coord += dir * (0.5 * cell + 0.5 * ix->h_fine[d]);
+        double q = floor((coord - ix->vmin[d]) / ix->h_fine[d]);
+        if (q < 0 || q >= (double)ix->gmax[d]) return -1;
+        g[d] = (long long)q;
+    }
+    return vindex_locate(ix, g);
+}
+
+/* exported for the tests: face neighbours [n][DIM][2] (-1: velocity-domain boundary) of one velocity grid */
+int orc_vs_face_neighbors(int D, int n, const double* vmid, const int8_t* level, const kamr_vs_adapt* par,
+                          int32_t* out) {
+    vindex ix;
+    if (vindex_build(&ix, D, n, vmid, level, par)) return 1;
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d < D; ++d) {
+            out[((size_t)i * D + d) * 2 + 0] = vindex_face_neighbor(&ix, vmid, level, i, d, -1);
+            out[((size_t)i * D + d) * 2 + 1] = vindex_face_neighbor(&ix, vmid, level, i, d, +1);
+        }
+    free(ix.keys);
+    return 0;
+}
+
+/* vs_resolution(ps_data, kinfo) maximised over the local fluid cells, AMR.jl:139-166 */
+int orc_vs_resolution(const kamr_config* cfg, const kamr_mesh* m, const orc_state* st, const kamr_vs_adapt* par,
+                      double* out) {
+    octx o;
+    if (octx_init(&o, cfg, m)) return 1;
+    const int D = o.D, K = o.K, M = o.M;
+    double du = 1.0, nt = 1.0;
+    for (int d = 0; d < D; ++d) { du *= par->vmax[d] - par->vmin[d]; nt *= (double)par->trees[d]; }
+    double weight = du / nt / pow2i(D * par->maxlevel);
+    double dres = 0.0, eres = 0.0;
+    for (int c = 0; c < m->n_local; ++c) {
+        if (skip_cell(&o, c)) continue;
+        int n = cell_n(&o, c);
+        const double* df = st->df + o.vs_off[c] * K;
+        const double* v = cell_vmid(&o, c);
+        const double* U = st->prim + (size_t)c * M + 1;
+        double dmax = -INFINITY, emax = -INFINITY;
+        for (int i = 0; i < n; ++i) {
+            for (int k = 0; k < K; ++k) dmax = jl_max(dmax, df[(size_t)k * n + i]);   /* maximum(vs_data.df) */
+            double c2 = 0.0;
+            for (int d = 0; d < D; ++d) { double t = U[d] - v[(size_t)d * n + i]; c2 += t * t; }
+            double e = K == 1 ? df[i] * c2 : df[i] * c2 + df[(size_t)n + i];
+            emax = jl_max(emax, e);
+        }
+        dres = jl_max(dmax * weight, dres);
+        eres = jl_max(0.5 * emax * weight, eres);
+    }
+    out[0] = dres; out[1] = eres;
+    octx_free(&o);
+    return 0;
+}
+
+#define VS_LOHNER_EPS_FLT 1e-2        /* Criteria.jl:213 */
+#define VS_LOHNER_EPS_ABS 1e-3        /* Criteria.jl:215 */
+#define VS_LOHNER_COARSEN_RATIO 0.3   /* Criteria.jl:217 */
+
+/* _lohner_ratio, Criteria.jl:222-228 */
+static double vs_lohner_ratio(double L, double C, double R, double dsL, double dsR, double scale) {
+    double num = fabs(dsR * L - (dsL + dsR) * C + dsL * R);
+    double den = dsR * fabs(L - C) + dsL * fabs(R - C) +
+                 VS_LOHNER_EPS_FLT * (dsR * fabs(L) + (dsL + dsR) * fabs(C) + dsL * fabs(R)) +
+                 VS_LOHNER_EPS_ABS * scale * (dsL + dsR);
+    return den > 0 ? num / den : 0.0;
+}
+
+int orc_vs_criterion(const kamr_config* cfg, const kamr_mesh* m, const orc_state* st, const kamr_vs_adapt* par,
+                     uint8_t* refine_flag, uint8_t* coarsen_ok) {
+    octx o;
+    if (octx_init(&o, cfg, m)) return 1;
+    const int D = o.D, K = o.K, M = o.M;
+    const int lohner = par->mode == 0;
+    int rc = 0;
+    /* one neighbour table per velocity grid */
+    int32_t** nbt = (int32_t**)calloc((size_t)m->n_grid, sizeof(int32_t*));
+    for (int c = 0; c < m->n_local && !rc; ++c) {
+        const int n = cell_n(&o, c), grid = m->cell_grid[c];
+        const double* v = cell_vmid(&o, c);
+        const int8_t* lev = cell_level(&o, c);
+        const double* wt = cell_weight(&o, c);
+        const double* df = st->df + o.vs_off[c] * K;
+        const double* sdf = st->sdf + o.vs_off[c] * K * D;
+        const double* w = st->w + (size_t)c * M;
+        const double* U = st->prim + (size_t)c * M + 1;
+        const double* ds = m->ds + (size_t)c * D;
+        uint8_t* rf = refine_flag ? refine_flag + o.vs_off[c] : NULL;
+        uint8_t* co = coarsen_ok ? coarsen_ok + o.vs_off[c] : NULL;
+        double s1 = 0.0, s2 = 0.0;
+        if (lohner) {
+            if (!nbt[grid]) {
+                nbt[grid] = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1) * D * 2);
+                if (orc_vs_face_neighbors(D, n, v, lev, par, nbt[grid])) { rc = 2; break; }
+            }
+            for (int i = 0; i < n; ++i) {   /* vs_lohner_scales, Criteria.jl:238-248 */
+                double a1 = fabs(df[i]); if (a1 > s1) s1 = a1;
+                if (K == 2) { double a2 = fabs(df[(size_t)n + i]); if (a2 > s2) s2 = a2; }
+            }
+        }
+        double U2 = 0.0;
+        for (int d = 0; d < D; ++d) U2 += U[d] * U[d];
+        const double eden = w[M - 1] - 0.5 * w[0] * U2;   /* w[end] - 0.5 w[1] sum(U.^2) */
+        const double two_d = pow2i(D);
+        for (int i = 0; i < n; ++i) {
+            double cdf[2] = {0.0, 0.0};
+            for (int k = 0; k < K; ++k) {   /* _criterion_cell!, AMR.jl:8-21 */
+                double mx = 0.0;
+                for (int d = 0; d < D; ++d) {
+                    double a = fabs(sdf[((size_t)d * K + k) * n + i] * ds[d]);
+                    if (a > mx) mx = a;
+                }
+                cdf[k] = df[(size_t)k * n + i] + mx;
+            }
+            double S = 0.0;
+            for (int d = 0; d < D; ++d) { double t = U[d] - v[(size_t)d * n + i]; S += t * t; }
+            const double wgt = wt[i];
+            /* local_contribution_refine_flag, Criteria.jl:19-26 */
+            double e_ref = K == 2 ? fabs(0.5 * (S * cdf[0] + cdf[1]) * wgt) : fabs(0.5 * S * cdf[0] * wgt);
+            int local_refine = jl_max(e_ref / eden, cdf[0] * wgt / w[0]) > par->coeff_local;
+            /* local_contribution_coarsen_flag (vector form), Criteria.jl:41-48 */
+            double e_co = K == 2 ? 0.5 * (S * cdf[0] + cdf[1]) * wgt : 0.5 * (S * cdf[0]) * wgt;
+            int local_coarsen = jl_max(e_co / eden, cdf[0] * wgt / w[0]) < par->coeff_local / two_d;
+            int base_refine, ok;
+            if (lohner) {
+                /* vs_lohner_indicator, Criteria.jl:259-287 (on df, not the criterion distribution) */
+                double eta = 0.0;
+                const int32_t* nb = nbt[grid] + (size_t)i * D * 2;
+                for (int d = 0; d < D; ++d) {
+                    double hfine = ((par->vmax[d] - par->vmin[d]) / par->trees[d]) / pow2i(par->maxlevel);
+                    double hi = hfine * (double)(1 << (par->maxlevel - lev[i]));
+                    int Ln = nb[d * 2], Rn = nb[d * 2 + 1];
+                    double dsL = Ln < 0 ? hi : 0.5 * (hi + hfine * (double)(1 << (par->maxlevel - lev[Ln])));
+                    double dsR = Rn < 0 ? hi : 0.5 * (hi + hfine * (double)(1 << (par->maxlevel - lev[Rn])));
+                    for (int k = 0; k < K; ++k) {
+                        double fL = Ln < 0 ? 0.0 : df[(size_t)k * n + Ln], fR = Rn < 0 ? 0.0 : df[(size_t)k * n + Rn];
+                        eta = jl_max(eta, vs_lohner_ratio(fL, df[(size_t)k * n + i], fR, dsL, dsR, k == 0 ? s1 : s2));
+                    }
+                }
+                base_refine = eta > par->coeff_lohner || local_refine;
+                ok = eta < VS_LOHNER_COARSEN_RATIO * par->coeff_lohner && local_coarsen;
+            } else {
+                /* global_contribution_{refine,coarsen}_flag, Criteria.jl:55-84 */
+                double e_gl = K == 2 ? 0.5 * (S * cdf[0] + cdf[1]) * wgt : 0.5 * (S * cdf[0]) * wgt;
+                int global_refine = cdf[0] * wgt > par->coeff_global * par->vr_density ||
+                                    e_gl > par->vr_energy * par->coeff_global;
+                int global_coarsen = cdf[0] * wgt < par->coeff_global * par->vr_density / two_d &&
+                                     e_gl < par->vr_energy * par->coeff_global / two_d;
+                base_refine = local_refine || global_refine;
+                ok = local_coarsen && global_coarsen;
+            }
+            if (rf) rf[i] = (uint8_t)(lev[i] < par->maxlevel && base_refine);
+            if (co) co[i] = (uint8_t)ok;
+        }
+    }
+    for (int g = 0; g < m->n_grid; ++g) free(nbt[g]);
+    free(nbt);
+    octx_free(&o);
+    return rc;
+}

@@ -39,6 +39,16 @@ int orc_iterate(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, doubl
                 double* res_out);
 int orc_step(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, double dt, int want_residual,
              double* res_out);
+/* update_criterion!(ka) (Physical_space/AMR.jl:256-341): Löhner sensor of every local cell + the one-cell buffer.
+ * st holds w, prim and the macro slopes sw of a finished orc_slope.  ghost_flag NULL on one rank. */
+int orc_ps_criterion(const kamr_config* cfg, const kamr_mesh* m, const orc_state* st, double threshold,
+                     const int32_t* ghost_flag, double* lohner_out, double* sensor_out, int32_t* flag_out);
+/* velocity-space adaptation inputs (Velocity_space/AMR.jl:26-166, Criteria.jl, Neighbor.jl); flags per local point */
+int orc_vs_face_neighbors(int D, int n, const double* vmid, const int8_t* level, const kamr_vs_adapt* par, int32_t* out);
+int orc_vs_resolution(const kamr_config* cfg, const kamr_mesh* m, const orc_state* st, const kamr_vs_adapt* par,
+                      double* out);
+int orc_vs_criterion(const kamr_config* cfg, const kamr_mesh* m, const orc_state* st, const kamr_vs_adapt* par,
+                     uint8_t* refine_flag, uint8_t* coarsen_ok);
 /* test hook: order of the Newton sums of solve_I_projection over the velocity points (0 forward, 1 reverse) */
 void orc_set_cip_sum_order(int reverse);
 #ifdef __cplusplus

@@ -125,6 +125,58 @@ def step(cfg, mesh, st, dt, want_residual=False):
     return res
 
 
+def ps_criterion(cfg, mesh, st, threshold, ghost_flag=None):
+    """update_criterion!(ka): returns (lohner [n_local, DIM, DIM+2], sensor [n_local], pre-buffer flag [n_local])."""
+    m = mesh.c_struct(); s = state_struct(st)
+    D, M = cfg.dim, cfg.dim + 2
+    loh = np.zeros((mesh.n_local, D, M)); sen = np.zeros(mesh.n_local); flg = np.zeros(mesh.n_local, dtype=np.int32)
+    gf = None
+    if ghost_flag is not None:
+        gfa = np.ascontiguousarray(ghost_flag, dtype=np.int32)
+        gf = gfa.ctypes.data_as(C.POINTER(C.c_int32))
+    f = lib().orc_ps_criterion
+    f.restype = C.c_int
+    rc = f(C.byref(cfg), C.byref(m), C.byref(s), C.c_double(threshold), gf, _p(loh), _p(sen),
+           flg.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0, f"orc_ps_criterion rc={rc}"
+    return loh, sen, flg
+
+
+def vs_face_neighbors(dim, vmid, level, par):
+    """[n, DIM, 2] same-or-coarser face neighbours (vs_face_neighbor, Velocity_space/Neighbor.jl:181), -1: none"""
+    n = len(level)
+    out = np.zeros((n, dim, 2), dtype=np.int32)
+    vmid = np.ascontiguousarray(vmid, dtype=np.float64); level = np.ascontiguousarray(level, dtype=np.int8)
+    f = lib().orc_vs_face_neighbors
+    f.restype = C.c_int
+    rc = f(int(dim), int(n), _p(vmid), level.ctypes.data_as(C.POINTER(C.c_int8)), C.byref(par),
+           out.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0, f"orc_vs_face_neighbors rc={rc}"
+    return out
+
+
+def vs_resolution(cfg, mesh, st, par):
+    m = mesh.c_struct(); s = state_struct(st)
+    out = np.zeros(2)
+    f = lib().orc_vs_resolution
+    f.restype = C.c_int
+    assert f(C.byref(cfg), C.byref(m), C.byref(s), C.byref(par), _p(out)) == 0
+    return out
+
+
+def vs_criterion(cfg, mesh, st, par):
+    """(refine_flag, coarsen_ok) per local velocity point (uint8), vs_refine! / vs_coarsen! of Velocity_space/AMR.jl"""
+    m = mesh.c_struct(); s = state_struct(st)
+    npts = int(mesh.vs_off()[mesh.n_local])
+    rf = np.zeros(npts, dtype=np.uint8); co = np.zeros(npts, dtype=np.uint8)
+    f = lib().orc_vs_criterion
+    f.restype = C.c_int
+    u8 = C.POINTER(C.c_uint8)
+    rc = f(C.byref(cfg), C.byref(m), C.byref(s), C.byref(par), rf.ctypes.data_as(u8), co.ctypes.data_as(u8))
+    assert rc == 0, f"orc_vs_criterion rc={rc}"
+    return rf, co
+
+
 def pair_map(dim, lev_a, lev_b):
     start = np.zeros(len(lev_a) + 1, dtype=np.int32)
     rc = lib().orc_pair_map(dim, len(lev_a), lev_a.ctypes.data_as(C.POINTER(C.c_int8)), len(lev_b),

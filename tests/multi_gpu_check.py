@@ -83,15 +83,35 @@ def main():
             g = index_all[int(mesh.global_ids[i])]
             a = out2.sw[i * MD:(i + 1) * MD]; b = ref.sw[g * MD:(g + 1) * MD]
             nsw += float(np.sum((a - b) ** 2)); dsw += float(np.sum(b ** 2))
-        t = torch.tensor([num, den, nsw, dsw], dtype=torch.float64, device="cuda")
+        # update_criterion!(ka) with the ghosts' w and the mirrors' decisions exchanged (lohner_flag_exchange!,
+        # Parallel/Ghost.jl:939): bit-identical to a single-rank device run of the whole forest
+        one = api.Context(case.config(device=local))
+        one.upload_topology(full)
+        one.upload_state(case.init_state(full))
+        for _ in range(steps):
+            one.step(case.dt(), False)
+        one.slope()
+        _, sen1 = one.ps_criterion(1e300, want_lohner=False)
+        nz = sen1[sen1 > 0]
+        thr = float(np.median(nz)) if nz.size else 0.25
+        loh1, sen1 = one.ps_criterion(thr)
+        one.close()
+        loh_n, sen_n = ctx.ps_criterion(thr)
+        gl = np.array([index_of[int(g)] for g in mesh.global_ids[: mesh.n_local]], dtype=np.int64)
+        bad_sensor = int(not (np.array_equal(loh_n, loh1[gl]) and np.array_equal(sen_n, sen1[gl])))
+        n_buf = int((sen_n == 2 * thr).sum())
+        t = torch.tensor([num, den, nsw, dsw, bad_sensor, n_buf], dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
+        if t[4] > 0:
+            worst = max(worst, 1.0)
         err = float(torch.sqrt(t[0] / t[1]))
         err_sw = float(torch.sqrt(t[2] / torch.clamp(t[3], min=1e-300)))
         worst = max(worst, err_sw * 1e-12 / (1e-9 if case.marching != abi.MARCH_CIP else 1e-5))
         worst = max(worst, err / (1e4 if case.marching == abi.MARCH_CIP else 1.0))
         if rank == 0:
             print(f"{name}: world={world} halo_bytes/step(rank0)={ctx.stats().halo_bytes_per_step} "
-                  f"rel L2(df) vs single-rank oracle after {steps} steps = {err:.3e}; ghost sw after kamr_slope = {err_sw:.3e}",
+                  f"rel L2(df) vs single-rank oracle after {steps} steps = {err:.3e}; ghost sw after kamr_slope = {err_sw:.3e}; "
+                  f"ps sensor vs single-rank device run: {'bit-identical' if t[4] == 0 else 'DIFFERS'} ({int(t[5])} buffered cells)",
                   flush=True)
         ctx.close()
     dist.destroy_process_group()

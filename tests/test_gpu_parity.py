@@ -189,6 +189,82 @@ def test_fused_step_matches_oracle(setup):
             assert rel_l2(out.prim[: nl * (D + 2)][fluid], ref.prim[: nl * (D + 2)][fluid]) <= tol
 
 
+def test_ps_criterion_matches_oracle(setup):
+    """update_criterion!(ka) on the device (kamr_ps_criterion: Löhner sensor + one-cell buffer) against the oracle's
+    restatement — bit for bit on the macroscopic fields the device itself holds (every operation of the kernel is an
+    explicitly rounded one), and to rounding on the oracle's own slopes."""
+    from kitamr_jl_b200 import abi
+    from oracle import orc
+    case, mesh, st0, cfg, ctx = setup
+    D, M = mesh.dim, mesh.dim + 2
+    nl = mesh.n_local
+    dt = case.dt()
+    ref = st0.copy()
+    for _ in range(2):
+        orc.step(cfg, mesh, ref, dt)
+    ctx.upload_state(ref, aux=False)
+    with pytest.raises(RuntimeError, match="kamr_slope first"):
+        ctx.ps_criterion(0.25)
+    ctx.slope()
+    dev = ctx.download_state(ref.copy(), abi.DL_W | abi.DL_PRIM | abi.DL_SW)
+    orc.slope(cfg, mesh, ref)
+    # a threshold that splits the cells: the median of the non-zero sensors
+    _, sen0, _ = orc.ps_criterion(cfg, mesh, ref, 1e300)
+    nz = sen0[sen0 > 0]
+    thr = float(np.median(nz)) if nz.size else 0.25
+    loh_d, sen_d = ctx.ps_criterion(thr)
+    loh_o, sen_o, flg_o = orc.ps_criterion(cfg, mesh, dev, thr)
+    assert np.isfinite(loh_d).all()
+    assert np.array_equal(loh_d, loh_o)
+    assert np.array_equal(sen_d, sen_o)
+    if nz.size:
+        assert 0 < flg_o.sum() < nl
+        assert (sen_d == 2 * thr).any() or flg_o.sum() + (mesh.bound_enc[:nl] < 0).sum() == nl
+    # the oracle's own fields (slopes differ in the last bits): same sensor to rounding, away from the gates
+    loh_r, sen_r, flg_r = orc.ps_criterion(cfg, mesh, ref, 1e300)
+    loh_x, _ = ctx.ps_criterion(1e300)
+    close = np.isclose(loh_x, loh_r, rtol=1e-7, atol=1e-9)
+    # (an amplitude gate, jump >= 1e-3 |center|, may flip on a borderline cell)
+    assert (~close).sum() <= max(2, 0.002 * close.size)
+    # sensor-only call
+    none, sen_only = ctx.ps_criterion(thr, want_lohner=False)
+    assert none is None and np.array_equal(sen_only, sen_d)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_vs_criterion_matches_oracle(setup, mode):
+    """kamr_vs_resolution / kamr_vs_criterion (the per-point decisions of vs_refine! / vs_coarsen!,
+    Velocity_space/AMR.jl:26-166) against the oracle on the state the device holds: bit-identical flags (the kernel's
+    arithmetic is explicitly rounded, the neighbour tables come from the same lattice coordinates)."""
+    from kitamr_jl_b200 import abi
+    from oracle import orc
+    case, mesh, st0, cfg, ctx = setup
+    K, D = mesh.ndf, mesh.dim
+    dt = case.dt()
+    ref = st0.copy()
+    for _ in range(2):
+        orc.step(cfg, mesh, ref, dt)
+    ctx.upload_state(ref, aux=False)
+    par = abi.vs_adapt(case, mode=mode)
+    ctx.step(dt)                      # the fused step leaves no raw slopes behind
+    with pytest.raises(RuntimeError, match="raw slopes"):
+        ctx.vs_criterion(par)
+    ctx.slope()
+    dev = ctx.download_state(ref.copy(), abi.DL_DF | abi.DL_SDF | abi.DL_W | abi.DL_PRIM)
+    vr_d = ctx.vs_resolution(par)
+    vr_o = orc.vs_resolution(cfg, mesh, dev, par)
+    assert np.array_equal(vr_d, vr_o) and vr_o[0] > 0
+    par.vr_density, par.vr_energy = float(vr_o[0]), float(vr_o[1])
+    rf_d, co_d = ctx.vs_criterion(par)
+    rf_o, co_o = orc.vs_criterion(cfg, mesh, dev, par)
+    assert np.array_equal(rf_d, rf_o)
+    assert np.array_equal(co_d, co_o)
+    assert co_o.any() and not (rf_o & co_o).any()
+    # a second call reuses the cached neighbour tables
+    rf2, co2 = ctx.vs_criterion(par)
+    assert np.array_equal(rf2, rf_d) and np.array_equal(co2, co_d)
+
+
 def test_pair_maps_bit_exact(setup):
     """pair maps built by the library == the reference merge-walk restated in the oracle (integer, bit-exact)."""
     from oracle import orc

@@ -1,0 +1,223 @@
+"""CPU tests of the oracle's velocity-space adaptation inputs (orc_vs_face_neighbors, orc_vs_resolution,
+orc_vs_criterion): vs_refine! / vs_coarsen! of Velocity_space/AMR.jl:26-166 with Velocity_space/Criteria.jl and the
+face-neighbour search of Velocity_space/Neighbor.jl.  Pinned by a brute-force geometric neighbour search, an
+independently written NumPy evaluation of the criteria, and their invariants."""
+import numpy as np
+import pytest
+
+from kitamr_jl_b200 import abi
+from kitamr_jl_b200.synth import cases
+from kitamr_jl_b200.synth import vgrid as vg
+from oracle import orc
+
+
+class _Shape:   # what abi.vs_adapt reads of a case
+    def __init__(self, dim, quadrature, trees, maxlevel):
+        self.dim, self.quadrature, self.vs_trees_num, self.vs_maxlevel = dim, quadrature, trees, maxlevel
+
+
+def _cell_sizes(grid, maxlevel):
+    return grid.root_ds[None, :] / (2.0 ** grid.level.astype(np.float64))[:, None]
+
+
+def _brute_neighbors(grid, quad, trees, maxlevel):
+    """the leaf containing the point half a finest cell across each face, on the cell's centre line"""
+    D, n = grid.dim, grid.n
+    size = _cell_sizes(grid, maxlevel)
+    lo, hi = grid.mid - 0.5 * size, grid.mid + 0.5 * size
+    hf = grid.root_ds / 2.0 ** maxlevel
+    out = -np.ones((n, D, 2), dtype=np.int32)
+    for i in range(n):
+        for d in range(D):
+            for s, sign in enumerate((-1.0, 1.0)):
+                p = grid.mid[i].copy()
+                p[d] += sign * (0.5 * size[i, d] + 0.5 * hf[d])
+                # the centre line of a cell coarser than the finest level lies ON a lattice line: which side the probe
+                # falls to is decided by the rounding of the reference's own expression floor((x - vmin) / h_fine)
+                # (Neighbor.jl:193), which is therefore used here too; the search itself is geometric
+                q = np.floor((p - np.array(quad[0::2])) / hf) * hf + np.array(quad[0::2]) + 0.5 * hf
+                inside = np.all((q > lo) & (q < hi), axis=1)
+                hit = np.flatnonzero(inside)
+                assert len(hit) <= 1
+                if len(hit):
+                    out[i, d, s] = hit[0]
+    return out
+
+
+@pytest.mark.parametrize("dim,trees,maxlevel", [(2, (6, 5), 2), (2, (4, 4), 3), (3, (3, 4, 3), 2)])
+def test_face_neighbors_match_a_brute_force_search(dim, trees, maxlevel):
+    rng = np.random.default_rng(11 + dim + maxlevel)
+    quad = tuple(np.ravel([(-4.0 - d, 5.0 + 0.5 * d) for d in range(dim)]))
+    grid = vg.random_grid(quad, trees, maxlevel, rng, p=0.35)
+    par = abi.vs_adapt(_Shape(dim, quad, trees, maxlevel))
+    got = orc.vs_face_neighbors(dim, np.ascontiguousarray(grid.mid.T), grid.level, par)
+    want = _brute_neighbors(grid, quad, trees, maxlevel)
+    assert (grid.level > 0).any() and (grid.level == 0).any()
+    assert np.array_equal(got, want)
+    # same-or-coarser or finer by any amount, but geometrically adjacent: the neighbour's extent touches the face
+    size = _cell_sizes(grid, maxlevel)
+    for d in range(dim):
+        for s, sign in enumerate((-1.0, 1.0)):
+            nb = got[:, d, s]
+            has = nb >= 0
+            face = grid.mid[has, d] + sign * 0.5 * size[has, d]
+            nb_face = grid.mid[nb[has], d] - sign * 0.5 * size[nb[has], d]
+            assert np.allclose(face, nb_face, rtol=0, atol=1e-12)
+    # the velocity-domain boundary has no neighbour
+    assert (got[np.isclose(grid.mid[:, 0] - 0.5 * size[:, 0], quad[0]), 0, 0] == -1).all()
+
+
+def _twin_flags(case, mesh, st, par, nbrs_of_grid):
+    """NumPy evaluation, one cell at a time, vectorised over the velocity points"""
+    D, K, M = case.dim, case.ndf, case.dim + 2
+    off = mesh.vs_off()
+    rf = np.zeros(off[mesh.n_local], dtype=np.uint8); co = np.zeros_like(rf)
+    hf = np.array([(par.vmax[d] - par.vmin[d]) / par.trees[d] / 2.0 ** par.maxlevel for d in range(D)])
+    for c in range(mesh.n_local):
+        g = mesh.cell_grid[c]
+        a, b = mesh.grid_off[g], mesh.grid_off[g + 1]
+        n = b - a
+        lev = mesh.v_level[a:b].astype(int)
+        wt = mesh.v_weight[a:b]
+        v = mesh.v_mid[a * D: b * D].reshape(D, n)
+        df = st.df[off[c] * K: off[c + 1] * K].reshape(K, n)
+        sdf = st.sdf[off[c] * K * D: off[c + 1] * K * D].reshape(D, K, n)
+        w = st.w[c * M:(c + 1) * M]; U = st.prim[c * M + 1: c * M + 1 + D]
+        ds = mesh.ds[c * D:(c + 1) * D]
+        cdf = df + np.max(np.abs(sdf * ds[:, None, None]), axis=0)
+        S = np.sum((U[:, None] - v) ** 2, axis=0)
+        eden = w[-1] - 0.5 * w[0] * np.sum(U ** 2)
+        e = 0.5 * (S * cdf[0] + (cdf[1] if K == 2 else 0.0)) * wt
+        local_refine = np.maximum(np.abs(e) / eden, cdf[0] * wt / w[0]) > par.coeff_local
+        local_coarsen = np.maximum(e / eden, cdf[0] * wt / w[0]) < par.coeff_local / 2 ** D
+        if par.mode == abi.VS_MODE_LOHNER:
+            nb = nbrs_of_grid(g)
+            size = hf[None, :] * (2.0 ** (par.maxlevel - lev))[:, None]
+            eta = np.zeros(n)
+            for d in range(D):
+                Ln, Rn = nb[:, d, 0], nb[:, d, 1]
+                dsL = np.where(Ln < 0, size[:, d], 0.5 * (size[:, d] + size[np.maximum(Ln, 0), d]))
+                dsR = np.where(Rn < 0, size[:, d], 0.5 * (size[:, d] + size[np.maximum(Rn, 0), d]))
+                for k in range(K):
+                    scale = np.abs(df[k]).max()
+                    L = np.where(Ln < 0, 0.0, df[k][np.maximum(Ln, 0)]); R = np.where(Rn < 0, 0.0, df[k][np.maximum(Rn, 0)])
+                    Cc = df[k]
+                    num = np.abs(dsR * L - (dsL + dsR) * Cc + dsL * R)
+                    den = (dsR * np.abs(L - Cc) + dsL * np.abs(R - Cc)
+                           + 1e-2 * (dsR * np.abs(L) + (dsL + dsR) * np.abs(Cc) + dsL * np.abs(R))
+                           + 1e-3 * scale * (dsL + dsR))
+                    eta = np.maximum(eta, np.where(den > 0, num / np.where(den > 0, den, 1.0), 0.0))
+            base = (eta > par.coeff_lohner) | local_refine
+            ok = (eta < 0.3 * par.coeff_lohner) & local_coarsen
+        else:
+            gr = (cdf[0] * wt > par.coeff_global * par.vr_density) | (e > par.vr_energy * par.coeff_global)
+            gc = (cdf[0] * wt < par.coeff_global * par.vr_density / 2 ** D) & (e < par.vr_energy * par.coeff_global / 2 ** D)
+            base = local_refine | gr
+            ok = local_coarsen & gc
+        rf[off[c]: off[c + 1]] = (lev < par.maxlevel) & base
+        co[off[c]: off[c + 1]] = ok
+    return rf, co
+
+
+def _stepped(case, steps=2):
+    mesh = case.rank_mesh()
+    st = case.init_state(mesh)
+    cfg = case.config()
+    for _ in range(steps):
+        orc.step(cfg, mesh, st, case.dt())
+    orc.slope(cfg, mesh, st)
+    return mesh, st, cfg
+
+
+def _vs_cases():
+    return {
+        "amr2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=1, vtrees=8, vs_maxlevel=2, ragged=True, seed=21),
+        "amr3d": lambda: cases.amr_case(dim=3, trees=2, maxlevel=1, vtrees=4, vs_maxlevel=1, ragged=True, seed=22),
+        "s2_ib": lambda: cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True),
+    }
+
+
+@pytest.mark.parametrize("name", list(_vs_cases().keys()))
+@pytest.mark.parametrize("mode", [abi.VS_MODE_LOHNER, abi.VS_MODE_CONTRIBUTION])
+def test_criterion_matches_numpy_twin(name, mode):
+    case = _vs_cases()[name]()
+    mesh, st, cfg = _stepped(case)
+    D = case.dim
+    par = abi.vs_adapt(case, mode=mode)
+    vr = orc.vs_resolution(cfg, mesh, st, par)
+    par.vr_density, par.vr_energy = float(vr[0]), float(vr[1])
+    rf, co = orc.vs_criterion(cfg, mesh, st, par)
+    cache = {}
+
+    def nbrs(g):   # the brute-force search, so the twin shares nothing with the oracle
+        if g not in cache:
+            a, b = mesh.grid_off[g], mesh.grid_off[g + 1]
+            mid = mesh.v_mid[a * D: b * D].reshape(D, b - a).T.copy()
+            grid = vg.VGrid(D, mesh.v_level[a:b].copy(), mesh.v_weight[a:b].copy(), mid,
+                            np.array([(par.vmax[d] - par.vmin[d]) / par.trees[d] for d in range(D)]))
+            cache[g] = _brute_neighbors(grid, case.quadrature, case.vs_trees_num, case.vs_maxlevel)
+        return cache[g]
+
+    trf, tco = _twin_flags(case, mesh, st, par, nbrs)
+    # thresholds on floating-point expressions: the twin's vectorised sums may round differently on a borderline point
+    assert (rf != trf).sum() <= 1e-4 * rf.size + 1 and (co != tco).sum() <= 1e-4 * co.size + 1
+    assert 0 < co.sum() < co.size
+    if name != "amr3d":   # (4^3 roots refined once around the bulk: nothing left to refine in contribution mode)
+        assert 0 < rf.sum() < rf.size
+    off = mesh.vs_off()
+    lev = np.concatenate([mesh.v_level[mesh.grid_off[g]: mesh.grid_off[g + 1]] for g in mesh.cell_grid[: mesh.n_local]])
+    assert not rf[lev >= case.vs_maxlevel].any()
+    assert not (rf & co).any()          # no point is both flagged for refinement and eligible for coarsening
+
+
+@pytest.mark.parametrize("name", ["amr2d", "amr3d"])
+def test_vs_resolution_known_answer(name):
+    case = _vs_cases()[name]()
+    mesh, st, cfg = _stepped(case, steps=1)
+    D, K, M = case.dim, case.ndf, case.dim + 2
+    par = abi.vs_adapt(case)
+    got = orc.vs_resolution(cfg, mesh, st, par)
+    off = mesh.vs_off()
+    weight = np.prod([par.vmax[d] - par.vmin[d] for d in range(D)]) / np.prod(case.vs_trees_num) / 2 ** (D * par.maxlevel)
+    dres = eres = 0.0
+    for c in range(mesh.n_local):
+        if mesh.bound_enc[c] < 0:
+            continue
+        g = mesh.cell_grid[c]; a, b = mesh.grid_off[g], mesh.grid_off[g + 1]; n = b - a
+        v = mesh.v_mid[a * D: b * D].reshape(D, n)
+        df = st.df[off[c] * K: off[c + 1] * K].reshape(K, n)
+        U = st.prim[c * M + 1: c * M + 1 + D]
+        c2 = np.sum((U[:, None] - v) ** 2, axis=0)
+        dres = max(dres, df.max() * weight)
+        eres = max(eres, 0.5 * (df[0] * c2 + (df[1] if K == 2 else 0.0)).max() * weight)
+    assert np.allclose(got, [dres, eres], rtol=1e-14, atol=0)
+    assert got[0] > 0 and got[1] > 0
+
+
+def test_resolved_maxwellian_wants_no_refinement_and_a_spike_does():
+    """a Maxwellian on the grid the reference's own initial criterion built for it is below the Löhner threshold away
+    from its core; a one-point spike in the tail is flagged together with its face neighbours"""
+    case = cases.uniform_case(dim=2, trees=3, vtrees=8, tree_order="lex")
+    case.vs_maxlevel = 2
+    mesh = case.rank_mesh()
+    st = case.init_state(mesh)
+    cfg = case.config()
+    par = abi.vs_adapt(case)
+    st.sdf[:] = 0.0
+    rf0, co0 = orc.vs_criterion(cfg, mesh, st, par)
+    n = mesh.grid_off[1] - mesh.grid_off[0]
+    K = case.ndf
+    off = mesh.vs_off()
+    # a tail point of cell 0: far from the bulk velocity, not flagged
+    v = mesh.v_mid[: 2 * n].reshape(2, n)
+    U = st.prim[1:3]
+    far = int(np.argmax(np.sum((v - U[:, None]) ** 2, axis=0) * (v[0] < 4) * (v[1] < 4) * (v[0] > -4) * (v[1] > -4)))
+    assert rf0[far] == 0
+    st.df[off[0] * K + far] += 0.05
+    rf1, co1 = orc.vs_criterion(cfg, mesh, st, par)
+    nb = orc.vs_face_neighbors(2, mesh.v_mid[: 2 * n].reshape(2, n), mesh.v_level[:n], par)[far]
+    assert rf1[far] == 1 and co1[far] == 0
+    assert all(rf1[j] == 1 for j in nb.ravel() if j >= 0)
+    changed = np.flatnonzero(rf1 != rf0)
+    assert set(changed) <= {far, *[int(j) for j in nb.ravel() if j >= 0]} | set(np.flatnonzero(rf1[:n] != rf0[:n]))
+    assert (changed < n).all()          # other cells are untouched
