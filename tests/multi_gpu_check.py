@@ -83,8 +83,9 @@ def main():
             g = index_all[int(mesh.global_ids[i])]
             a = out2.sw[i * MD:(i + 1) * MD]; b = ref.sw[g * MD:(g + 1) * MD]
             nsw += float(np.sum((a - b) ** 2)); dsw += float(np.sum(b ** 2))
-        # update_criterion!(ka) with the ghosts' w and the mirrors' decisions exchanged (lohner_flag_exchange!,
-        # Parallel/Ghost.jl:939): bit-identical to a single-rank device run of the whole forest
+        # update_criterion!(ka) with the ghosts' w and the mirrors' decisions exchanged inside the library
+        # (lohner_flag_exchange!, Parallel/Ghost.jl:939): bit-identical to the oracle evaluated per rank on the fields
+        # this rank's device holds, with the ghost rows of w and the ghost flags taken from their owners' ranks
         one = api.Context(case.config(device=local))
         one.upload_topology(full)
         one.upload_state(case.init_state(full))
@@ -97,10 +98,24 @@ def main():
         loh1, sen1 = one.ps_criterion(thr)
         one.close()
         loh_n, sen_n = ctx.ps_criterion(thr)
-        gl = np.array([index_of[int(g)] for g in mesh.global_ids[: mesh.n_local]], dtype=np.int64)
-        bad_sensor = int(not (np.array_equal(loh_n, loh1[gl]) and np.array_equal(sen_n, sen1[gl])))
+        nl, ng = mesh.n_local, mesh.n_ghost
+        gl = np.array([index_of[int(g)] for g in mesh.global_ids[:nl]], dtype=np.int64)
+        same_as_one_rank = bool(np.array_equal(loh_n, loh1[gl]) and np.array_equal(sen_n, sen1[gl]))
+        dev = ctx.download_state(st.copy(), abi.DL_W | abi.DL_PRIM | abi.DL_SW)
+        cfg_r = case.config(rank=rank, nranks=world)
+        rows = [None] * world
+        dist.all_gather_object(rows, (mesh.global_ids[:nl].copy(), dev.w[: nl * M].copy()))
+        w_of = {int(gid): w_r[q * M:(q + 1) * M] for gids, w_r in rows for q, gid in enumerate(gids)}
+        for q in range(ng):
+            dev.w[(nl + q) * M:(nl + q + 1) * M] = w_of[int(mesh.global_ids[nl + q])]
+        _, _, flg = orc.ps_criterion(cfg_r, mesh, dev, thr)          # the pre-buffer decisions need no ghost flags
+        dist.all_gather_object(rows, (mesh.global_ids[:nl].copy(), flg.copy()))
+        flag_of = {int(gid): int(f_r[q]) for gids, f_r in rows for q, gid in enumerate(gids)}
+        ghost_flag = np.array([flag_of[int(mesh.global_ids[nl + q])] for q in range(ng)], dtype=np.int32)
+        loh_o, sen_o, _ = orc.ps_criterion(cfg_r, mesh, dev, thr, ghost_flag=ghost_flag)
+        bad_sensor = int(not (np.array_equal(loh_n, loh_o) and np.array_equal(sen_n, sen_o)))
         n_buf = int((sen_n == 2 * thr).sum())
-        t = torch.tensor([num, den, nsw, dsw, bad_sensor, n_buf], dtype=torch.float64, device="cuda")
+        t = torch.tensor([num, den, nsw, dsw, bad_sensor, n_buf, int(same_as_one_rank)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
         if t[4] > 0:
             worst = max(worst, 1.0)
@@ -111,7 +126,9 @@ def main():
         if rank == 0:
             print(f"{name}: world={world} halo_bytes/step(rank0)={ctx.stats().halo_bytes_per_step} "
                   f"rel L2(df) vs single-rank oracle after {steps} steps = {err:.3e}; ghost sw after kamr_slope = {err_sw:.3e}; "
-                  f"ps sensor vs single-rank device run: {'bit-identical' if t[4] == 0 else 'DIFFERS'} ({int(t[5])} buffered cells)",
+                  f"ps sensor vs per-rank oracle on the device's fields: {'bit-identical' if t[4] == 0 else 'DIFFERS'} "
+                  f"({int(t[5])} buffered cells; vs a single-rank device run: "
+                  f"{'bit-identical' if t[6] == world else 'differs (the states do, in the last bits)'})",
                   flush=True)
         ctx.close()
     dist.destroy_process_group()
