@@ -238,6 +238,13 @@ int  kamr_vs_resolution(kamr_ctx* ctx, const kamr_vs_adapt* par, double out[2]);
  * zeroes sdf, Rebuild.jl:69,81) — kamr_pack_cells fetches it.  NULL pointers are skipped. */
 int  kamr_vs_criterion(kamr_ctx* ctx, const kamr_vs_adapt* par, uint8_t* refine_flag, uint8_t* coarsen_ok);
 
+/* vs_conserved_correction! (Velocity_space/AMR.jl:120-133): conserved_I_porjection!(vs_data, ps_data.w)
+ * (Theory/I-projection.jl:144-159) on the listed local cells — the cells whose velocity grid an adaptation pass changed,
+ * after the re-flatten and the upload of their regridded df (kamr_unpack_cells).  The h-component of df is projected
+ * onto the cell's w by the Newton iteration of solve_I_projection (the same code CIP_Marching runs every step); solid
+ * cells in the list are skipped.  In place; on a mesh with peers follow it with kamr_exchange_df. */
+int  kamr_project_cells(kamr_ctx* ctx, int32_t n, const int32_t* cells);
+
 /* options.  KAMR_OPT_KEEP_SDF (default 0): kamr_step keeps the limited slopes r*sdf on the device and
  * writes the reference's raw VsData.sdf only for the cells a kernel reads them from; with the option on,
  * every step also writes the raw sdf of every cell so that kamr_download_state(KAMR_DL_SDF) is valid after

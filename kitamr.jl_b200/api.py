@@ -139,6 +139,11 @@ class Context:
                                             sen.ctypes.data_as(abi.c_f64p)))
         return loh, sen
 
+    def project_cells(self, cells):
+        """conserved_I_porjection! of the listed local cells (vs_conserved_correction!, Velocity_space/AMR.jl:120-133)"""
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        self._ck(self.lib.kamr_project_cells(self.h, len(cells), cells.ctypes.data_as(abi.c_i32p)))
+
     def vs_resolution(self, par):
         """local maxima of vs_resolution(ps_data, kinfo) (Velocity_space/AMR.jl:139-166): [density, energy]"""
         out = np.zeros(2)

@@ -1707,6 +1707,112 @@ __device__ __forceinline__ void psi_of(const double* v, double* psi) {
     psi[D + 1] = s2 / 2;
 }
 
+// solve_I_projection, Theory/I-projection.jl:55-141, on the h-component plane `f` of one cell (one CTA): negative
+// values shaved (:73-83) given the block minima mn = {min f, min positive f}, then the Newton iteration on the dual with
+// Armijo backtracking (:88-136).  `lam` returns the multipliers; f_h *= exp(lam . psi) is left to the caller.  Each thread
+// revisits only the points it owns (threadIdx.x + k blockDim.x), so no barrier is needed around the shave pass.
+template <int D, int K>
+__device__ __forceinline__ void solve_projection(const CellPtr<D, K>& own, double* __restrict__ f, int n, int np,
+                                                 const double (&W)[D + 2], const double (&mn)[2], double* red,
+                                                 double (&lam)[D + 2]) {
+    constexpr int M = D + 2, NJ = M * (M + 1) / 2, NV = M + NJ;
+    // ---- shave negative values (:73-83)
+    const double f_min = 1.1 * mn[0];
+    if (f_min < 0.) {
+        const double fp = mn[1], dd = fp - f_min;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const double x = f[i];
+            if (x < 0.) f[i] = (x - f_min) / dd * fp;
+        }
+    }
+    // ---- Newton iteration on the dual (:88-136); each thread revisits only the points it wrote, so no barrier is needed
+    // between the shave pass and the sums
+#pragma unroll
+    for (int m = 0; m < M; ++m) lam[m] = 0.0;
+    {
+        double nW = 0.0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) nW += W[m] * W[m];
+        nW = sqrt(nW);
+        const double tol_eff = 1e-10 * fmax(1.0, nW);
+        double G_prev = CUDART_INF;
+        int stall = 0;
+        for (int it = 0; it < 10; ++it) {
+            double a[NV];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) a[q] = 0.0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                double v[D], psi[M];
+#pragma unroll
+                for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+                psi_of<D>(v, psi);
+                double lp = 0.0;
+#pragma unroll
+                for (int m = 0; m < M; ++m) lp += lam[m] * psi[m];
+                const double cc = own.wt[i] * f[i] * exp(lp);
+                int q = M;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const double cm = cc * psi[m];
+                    a[m] += cm;
+#pragma unroll
+                    for (int j = m; j < M; ++j) a[q++] += cm * psi[j];
+                }
+            }
+            block_reduce<NV>(a, red);
+            const double Phi_sum = a[0];
+            double G[M], Gn = 0.0;
+#pragma unroll
+            for (int m = 0; m < M; ++m) { G[m] = a[m] - W[m]; Gn += G[m] * G[m]; }
+            Gn = sqrt(Gn);
+            if (Gn < tol_eff) break;
+            if (Gn > 0.9 * G_prev) {
+                if (++stall >= 2) break;
+            } else {
+                stall = 0;
+            }
+            G_prev = Gn;
+            double A[M * M], b[M], dl[M];
+            {
+                int q = M;
+#pragma unroll
+                for (int m = 0; m < M; ++m)
+#pragma unroll
+                    for (int j = m; j < M; ++j) { A[m * M + j] = a[q]; A[j * M + m] = a[q]; ++q; }
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) b[m] = G[m];
+            if (!small_solve<M>(A, b, dl)) break;
+            double lW = 0.0, slope = 0.0;
+#pragma unroll
+            for (int m = 0; m < M; ++m) { dl[m] = -dl[m]; lW += lam[m] * W[m]; slope += G[m] * dl[m]; }
+            const double Phi0 = Phi_sum - lW;
+            double alpha = 1.0;
+            for (int ls = 0; ls < 10; ++ls) {
+                double lt[M], ltW = 0.0;
+#pragma unroll
+                for (int m = 0; m < M; ++m) { lt[m] = lam[m] + alpha * dl[m]; ltW += lt[m] * W[m]; }
+                double ph[1] = {0.0};
+                for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                    double v[D], psi[M];
+#pragma unroll
+                    for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+                    psi_of<D>(v, psi);
+                    double lp = 0.0;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) lp += lt[m] * psi[m];
+                    ph[0] += own.wt[i] * f[i] * exp(lp);
+                }
+                block_reduce<1>(ph, red);
+                if (ph[0] - ltW <= Phi0 + 1e-4 * alpha * slope) break;
+                alpha *= 0.5;
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) lam[m] += alpha * dl[m];
+        }
+    }
+}
+
 template <int D, int K>
 __global__ void __launch_bounds__(256) cip_update_kernel(DevView g, GasPar gas, const int* __restrict__ cell_list,
                                                          double dt, int want_residual) {
@@ -1843,102 +1949,8 @@ __global__ void __launch_bounds__(256) cip_update_kernel(DevView g, GasPar gas, 
 #pragma unroll
     for (int d = 0; d < D; ++d) qf[d] = 0.5 * qe[d];
     if (K > 1) W[M - 1] -= qe[D] / 2;
-    // ---- shave negative values (:73-83)
-    const double f_min = 1.1 * mn[0];
-    if (f_min < 0.) {
-        const double fp = mn[1], dd = fp - f_min;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const double x = f[i];
-            if (x < 0.) f[i] = (x - f_min) / dd * fp;
-        }
-    }
-    // ---- Newton iteration on the dual (:88-136); each thread revisits only the points it wrote, so no barrier is needed
-    // between the shave pass and the sums
     double lam[M];
-#pragma unroll
-    for (int m = 0; m < M; ++m) lam[m] = 0.0;
-    {
-        double nW = 0.0;
-#pragma unroll
-        for (int m = 0; m < M; ++m) nW += W[m] * W[m];
-        nW = sqrt(nW);
-        const double tol_eff = 1e-10 * fmax(1.0, nW);
-        double G_prev = CUDART_INF;
-        int stall = 0;
-        for (int it = 0; it < 10; ++it) {
-            double a[NV];
-#pragma unroll
-            for (int q = 0; q < NV; ++q) a[q] = 0.0;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                double v[D], psi[M];
-#pragma unroll
-                for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
-                psi_of<D>(v, psi);
-                double lp = 0.0;
-#pragma unroll
-                for (int m = 0; m < M; ++m) lp += lam[m] * psi[m];
-                const double cc = own.wt[i] * f[i] * exp(lp);
-                int q = M;
-#pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    const double cm = cc * psi[m];
-                    a[m] += cm;
-#pragma unroll
-                    for (int j = m; j < M; ++j) a[q++] += cm * psi[j];
-                }
-            }
-            block_reduce<NV>(a, red);
-            const double Phi_sum = a[0];
-            double G[M], Gn = 0.0;
-#pragma unroll
-            for (int m = 0; m < M; ++m) { G[m] = a[m] - W[m]; Gn += G[m] * G[m]; }
-            Gn = sqrt(Gn);
-            if (Gn < tol_eff) break;
-            if (Gn > 0.9 * G_prev) {
-                if (++stall >= 2) break;
-            } else {
-                stall = 0;
-            }
-            G_prev = Gn;
-            double A[M * M], b[M], dl[M];
-            {
-                int q = M;
-#pragma unroll
-                for (int m = 0; m < M; ++m)
-#pragma unroll
-                    for (int j = m; j < M; ++j) { A[m * M + j] = a[q]; A[j * M + m] = a[q]; ++q; }
-            }
-#pragma unroll
-            for (int m = 0; m < M; ++m) b[m] = G[m];
-            if (!small_solve<M>(A, b, dl)) break;
-            double lW = 0.0, slope = 0.0;
-#pragma unroll
-            for (int m = 0; m < M; ++m) { dl[m] = -dl[m]; lW += lam[m] * W[m]; slope += G[m] * dl[m]; }
-            const double Phi0 = Phi_sum - lW;
-            double alpha = 1.0;
-            for (int ls = 0; ls < 10; ++ls) {
-                double lt[M], ltW = 0.0;
-#pragma unroll
-                for (int m = 0; m < M; ++m) { lt[m] = lam[m] + alpha * dl[m]; ltW += lt[m] * W[m]; }
-                double ph[1] = {0.0};
-                for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                    double v[D], psi[M];
-#pragma unroll
-                    for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
-                    psi_of<D>(v, psi);
-                    double lp = 0.0;
-#pragma unroll
-                    for (int m = 0; m < M; ++m) lp += lt[m] * psi[m];
-                    ph[0] += own.wt[i] * f[i] * exp(lp);
-                }
-                block_reduce<1>(ph, red);
-                if (ph[0] - ltW <= Phi0 + 1e-4 * alpha * slope) break;
-                alpha *= 0.5;
-            }
-#pragma unroll
-            for (int m = 0; m < M; ++m) lam[m] += alpha * dl[m];
-        }
-    }
+    solve_projection<D, K>(own, f, n, np, W, mn, red, lam);
     // ---- projection f_h *= exp(lambda.psi) (:147-149), relaxation towards M[prim_c] + S (:186-187)
     const double tau = us.tau;
     const double ra = tau / (tau + dt), rb = dt / (tau + dt);
@@ -3314,6 +3326,49 @@ __global__ void __launch_bounds__(256) vs_resolution_kernel(DevView g, VsPar par
         const bool fluid = ci.bound_enc >= 0;
         out[2 * c] = fluid ? sensor::mul(dmax, par.cell_weight) : 0.0;
         out[2 * c + 1] = fluid ? sensor::mul(sensor::mul(0.5, emax), par.cell_weight) : 0.0;
+    }
+}
+
+// conserved_I_porjection!(vs_data, ps_data.w), Theory/I-projection.jl:144-159, on a list of cells (the cells a
+// velocity-space adaptation pass regridded, Velocity_space/AMR.jl:120-133): f_h is projected onto the cell's w
+// (2D2F: with the internal energy of b removed).  One CTA per cell; the same Newton iteration as cip_update_kernel.
+template <int D, int K>
+__global__ void __launch_bounds__(256) project_cells_kernel(DevView g, const int* __restrict__ cell_list) {
+    constexpr int M = D + 2, NJ = M * (M + 1) / 2, NV = M + NJ;
+    __shared__ double red[NV * 9];
+    __shared__ CellInfo ci;
+    const int c = cell_list[blockIdx.x];
+    copy_words(g.cells + c, &ci, (int)(sizeof(CellInfo) / sizeof(int)));
+    __syncthreads();
+    const CellPtr<D, K> own(g, ci);
+    const int n = ci.n, np = ci.np;
+    double* f = g.df + ci.doff * K;
+    double W[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) W[m] = g.w[(size_t)c * M + m];
+    double e[1] = {0.0}, mn[2] = {CUDART_INF, CUDART_INF};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x = f[i];
+        if (K > 1) e[0] += own.wt[i] * f[np + i];
+        mn[0] = fmin(mn[0], x);
+        if (x > 0.) mn[1] = fmin(mn[1], x);
+    }
+    if (K > 1) {
+        block_reduce<1>(e, red);
+        W[M - 1] -= e[0] / 2;
+    }
+    block_min<2>(mn, red);
+    double lam[M];
+    solve_projection<D, K>(own, f, n, np, W, mn, red, lam);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v[D], psi[M];
+#pragma unroll
+        for (int t = 0; t < D; ++t) v[t] = own.v[t * np + i];
+        psi_of<D>(v, psi);
+        double lp = 0.0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) lp += lam[m] * psi[m];
+        f[i] *= exp(lp);
     }
 }
 

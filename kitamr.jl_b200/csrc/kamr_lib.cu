@@ -1919,6 +1919,32 @@ void do_vs_resolution(kamr_ctx* c, const kamr_vs_adapt* p, double* out) {
     }
 }
 
+template <int D, int K>
+void do_project_cells(kamr_ctx* c, int n, const int32_t* cells) {
+    if (n <= 0) return;
+    if (!cells) throw Fail("kamr_project_cells: cells is NULL");
+    std::vector<int> list;
+    for (int q = 0; q < n; ++q) {
+        if (cells[q] < 0 || cells[q] >= c->n_local) throw Fail("kamr_project_cells: cell id outside [0, n_local)");
+        if (c->cells[cells[q]].bound_enc >= 0) list.push_back(cells[q]);   // AMR.jl:128
+    }
+    if (list.empty()) return;
+    halo_finish_df(c);
+    halo_join_puts(c);
+    int* d_list = nullptr;
+    CK(cudaMalloc((void**)&d_list, list.size() * sizeof(int)));
+    CK(cudaMemcpyAsync(d_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    {
+        Launch L_(c, KID_UPDATE);
+        project_cells_kernel<D, K><<<(int)list.size(), 256, 0, c->stream>>>(c->dv, d_list);
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_list);
+    CK(e);
+    c->sw_valid = false; c->raw_sdf_valid = false;
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch sequences
 #ifndef KAMR_NT
@@ -2542,6 +2568,9 @@ int kamr_vs_resolution(kamr_ctx* c, const kamr_vs_adapt* par, double* out) {
 }
 int kamr_vs_criterion(kamr_ctx* c, const kamr_vs_adapt* par, uint8_t* refine_flag, uint8_t* coarsen_ok) {
     return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_vs_criterion, c, par, refine_flag, coarsen_ok); });
+}
+int kamr_project_cells(kamr_ctx* c, int32_t n, const int32_t* cells) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_project_cells, c, (int)n, cells); });
 }
 int kamr_flux(kamr_ctx* c, double dt) {
     return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); DISPATCH(c, do_flux, c, dt); });

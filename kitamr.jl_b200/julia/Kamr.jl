@@ -521,6 +521,18 @@ function vs_flags(ctx::Context, ka::KA{DIM}) where {DIM}
 end
 
 """
+    vs_conserved_correction!(ctx, cells)
+
+Drop-in for `vs_conserved_correction!` (Velocity_space/AMR.jl:120-133) after the re-flatten that follows a
+velocity-space adaptation pass: `cells` are the flat ids (0-based) of the cells whose `va_flags` entry is set.
+"""
+function vs_conserved_correction!(ctx::Context, cells::Vector{Int32})
+    check(ctx, ccall((:kamr_project_cells, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}), ctx.h, length(cells), cells))
+    check(ctx, ccall((:kamr_exchange_df, LIB), Cint, (Ptr{Cvoid},), ctx.h))
+    return nothing
+end
+
+"""
 The `solve!`-shaped loop with the device in it (compare Solver/Solver.jl:44-87).  The adapt events keep their cadence;
 each one is bracketed by a download (what it reads) and a re-flatten (what it changed).
 """

@@ -1749,3 +1749,20 @@ int orc_vs_criterion(const kamr_config* cfg, const kamr_mesh* m, const orc_state
     octx_free(&o);
     return rc;
 }
+
+/* vs_conserved_correction!, Velocity_space/AMR.jl:120-133: conserved_I_porjection!(vs_data, ps_data.w) on the listed
+ * local cells (the ones a velocity-space adaptation pass regridded); solid cells are skipped as there */
+int orc_project_cells(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, int n_list, const int32_t* list) {
+    octx o;
+    if (octx_init(&o, cfg, m)) return 1;
+    int rc = 0;
+    for (int q = 0; q < n_list && !rc; ++q) {
+        int c = list[q];
+        if (c < 0 || c >= m->n_local) { rc = 2; break; }
+        if (skip_cell(&o, c)) continue;
+        rc = conserved_I_projection(o.D, o.K, cell_n(&o, c), cell_vmid(&o, c), cell_df(&o, st, c), cell_weight(&o, c),
+                                    st->w + (size_t)c * o.M);
+    }
+    octx_free(&o);
+    return rc;
+}

@@ -49,6 +49,7 @@ int orc_vs_resolution(const kamr_config* cfg, const kamr_mesh* m, const orc_stat
                       double* out);
 int orc_vs_criterion(const kamr_config* cfg, const kamr_mesh* m, const orc_state* st, const kamr_vs_adapt* par,
                      uint8_t* refine_flag, uint8_t* coarsen_ok);
+int orc_project_cells(const kamr_config* cfg, const kamr_mesh* m, orc_state* st, int n_list, const int32_t* list);
 /* test hook: order of the Newton sums of solve_I_projection over the velocity points (0 forward, 1 reverse) */
 void orc_set_cip_sum_order(int reverse);
 #ifdef __cplusplus

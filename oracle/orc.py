@@ -177,6 +177,16 @@ def vs_criterion(cfg, mesh, st, par):
     return rf, co
 
 
+def project_cells(cfg, mesh, st, cells):
+    """vs_conserved_correction! (Velocity_space/AMR.jl:120-133) on the listed local cells, in place"""
+    m = mesh.c_struct(); s = state_struct(st)
+    cells = np.ascontiguousarray(cells, dtype=np.int32)
+    f = lib().orc_project_cells
+    f.restype = C.c_int
+    rc = f(C.byref(cfg), C.byref(m), C.byref(s), len(cells), cells.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0, f"orc_project_cells rc={rc}"
+
+
 def pair_map(dim, lev_a, lev_b):
     start = np.zeros(len(lev_a) + 1, dtype=np.int32)
     rc = lib().orc_pair_map(dim, len(lev_a), lev_a.ctypes.data_as(C.POINTER(C.c_int8)), len(lev_b),

@@ -51,6 +51,8 @@ def _cases():
         "s5_small": lambda: cases.x38like_s5(ps_maxlevel=2, trees=4, vtrees=10, vs_maxlevel=1),
         "euler2d": lambda: cases.amr_case(dim=2, trees=4, maxlevel=1, vtrees=8, vs_maxlevel=1, ragged=True, seed=6,
                                           marching=abi.MARCH_EULER),
+        "euler3d": lambda: cases.amr_case(dim=3, trees=2, maxlevel=1, vtrees=4, vs_maxlevel=1, ragged=True, seed=7,
+                                          marching=abi.MARCH_EULER),
         # big velocity grids: 512-thread CTAs with M[prim_c] recomputed instead of staged (n*(NDF+1)*8 > 32 KB) and,
         # above ~100 KB of staged f, the output array as staging area
         "big2d": lambda: cases.amr_case(dim=2, trees=3, maxlevel=1, vtrees=48, vs_maxlevel=2, ragged=True, seed=11),
@@ -267,6 +269,41 @@ def test_vs_criterion_matches_oracle(setup, mode):
     # a second call reuses the cached neighbour tables
     rf2, co2 = ctx.vs_criterion(par)
     assert np.array_equal(rf2, rf_d) and np.array_equal(co2, co_d)
+
+
+def test_project_cells_matches_oracle(setup):
+    """kamr_project_cells (conserved_I_porjection! of regridded cells, Velocity_space/AMR.jl:120-133) against the
+    oracle: f to the Newton tolerance (the same iteration as CIP_Marching, TOL_CIP_DF), the moments of the projected f
+    equal to w, untouched cells bit-identical."""
+    from kitamr_jl_b200 import abi
+    from oracle import orc
+    from test_vs_adapt_cpu import _moments, perturbed_state
+    case, mesh, st0, cfg, ctx = setup
+    D, K, M = mesh.dim, mesh.ndf, mesh.dim + 2
+    nl = mesh.n_local
+    be = mesh.bound_enc[:nl]
+    fluid = np.flatnonzero(be >= 0)
+    cells = [int(c) for c in fluid[:: max(1, len(fluid) // 9)][:9]]
+    solid = np.flatnonzero(be < 0)
+    if len(solid):
+        cells.append(int(solid[0]))
+    ref = perturbed_state(case, mesh, cfg, cells)
+    ctx.upload_state(ref, aux=False)
+    orc.project_cells(cfg, mesh, ref, cells)
+    ctx.project_cells(cells)
+    out = ctx.download_state(ref.copy(), abi.DL_DF | abi.DL_W)
+    assert rel_l2(local_pts(mesh, out.df, K), local_pts(mesh, ref.df, K)) <= TOL_CIP_DF
+    assert np.array_equal(out.w[: nl * M], ref.w[: nl * M])
+    off = mesh.vs_off()
+    listed = np.zeros(nl, dtype=bool); listed[cells] = True
+    for c in cells:
+        if be[c] >= 0:
+            w = out.w[c * M:(c + 1) * M]
+            assert np.allclose(_moments(mesh, out, c, D, K), w, rtol=0, atol=1e-8 * max(1.0, np.abs(w).max()))
+    for c in np.flatnonzero(~listed | (be < 0)):
+        assert np.array_equal(out.df[off[c] * K: off[c + 1] * K], ref.df[off[c] * K: off[c + 1] * K])
+    with pytest.raises(RuntimeError, match="outside"):
+        ctx.project_cells([nl])
 
 
 def test_pair_maps_bit_exact(setup):

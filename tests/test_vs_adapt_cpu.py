@@ -221,3 +221,64 @@ def test_resolved_maxwellian_wants_no_refinement_and_a_spike_does():
     changed = np.flatnonzero(rf1 != rf0)
     assert set(changed) <= {far, *[int(j) for j in nb.ravel() if j >= 0]} | set(np.flatnonzero(rf1[:n] != rf0[:n]))
     assert (changed < n).all()          # other cells are untouched
+
+
+def _moments(mesh, st, c, D, K):
+    off = mesh.vs_off()
+    g = mesh.cell_grid[c]; a, b = mesh.grid_off[g], mesh.grid_off[g + 1]; n = b - a
+    v = mesh.v_mid[a * D: b * D].reshape(D, n); wt = mesh.v_weight[a:b]
+    df = st.df[off[c] * K: off[c + 1] * K].reshape(K, n)
+    m = [np.sum(wt * df[0])] + [np.sum(wt * v[d] * df[0]) for d in range(D)]
+    e = 0.5 * np.sum(wt * np.sum(v ** 2, axis=0) * df[0]) + (0.5 * np.sum(wt * df[1]) if K == 2 else 0.0)
+    return np.array(m + [e])
+
+
+def perturbed_state(case, mesh, cfg, cells, steps=1):
+    """a stepped state whose listed cells carry a distribution that no longer has the moments w (what a regridded
+    velocity grid leaves behind, Velocity_space/AMR.jl:120-133)"""
+    st = case.init_state(mesh)
+    for _ in range(steps):
+        orc.step(cfg, mesh, st, case.dt())
+    D, K = case.dim, case.ndf
+    off = mesh.vs_off()
+    for c in cells:
+        g = mesh.cell_grid[c]; a, b = mesh.grid_off[g], mesh.grid_off[g + 1]; n = b - a
+        v = mesh.v_mid[a * D: b * D].reshape(D, n)
+        blk = st.df[off[c] * K: off[c + 1] * K].reshape(K, n)
+        blk *= 1.0 + 0.05 * np.sin(v[0]) + 0.02 * np.cos(v[D - 1])
+    return st
+
+
+@pytest.mark.parametrize("name", ["amr2d", "amr3d", "s2_ib"])
+def test_project_cells_restores_the_moments(name):
+    case = _vs_cases()[name]()
+    mesh = case.rank_mesh()
+    cfg = case.config()
+    D, K, M = case.dim, case.ndf, case.dim + 2
+    be = mesh.bound_enc[: mesh.n_local]
+    fluid = np.flatnonzero(be >= 0)
+    cells = list(fluid[:: max(1, len(fluid) // 7)][:7])
+    solid = np.flatnonzero(be < 0)
+    if len(solid):
+        cells.append(int(solid[0]))      # skipped, as vs_conserved_correction! skips it (:128)
+    st = perturbed_state(case, mesh, cfg, cells)
+    before = st.copy()
+    for c in cells:
+        if be[c] >= 0:
+            assert np.abs(_moments(mesh, st, c, D, K) - st.w[c * M:(c + 1) * M]).max() > 1e-4
+    orc.project_cells(cfg, mesh, st, cells)
+    off = mesh.vs_off()
+    for c in cells:
+        if be[c] < 0:
+            assert np.array_equal(st.df[off[c] * K: off[c + 1] * K], before.df[off[c] * K: off[c + 1] * K])
+            continue
+        w = st.w[c * M:(c + 1) * M]
+        assert np.allclose(_moments(mesh, st, c, D, K), w, rtol=0, atol=1e-8 * max(1.0, np.abs(w).max()))
+    touched = np.zeros(mesh.n_local, dtype=bool); touched[cells] = True
+    for c in np.flatnonzero(~touched)[:20]:
+        assert np.array_equal(st.df[off[c] * K: off[c + 1] * K], before.df[off[c] * K: off[c + 1] * K])
+    assert np.array_equal(st.w, before.w)
+    # projecting again changes nothing beyond the Newton tolerance
+    again = st.copy()
+    orc.project_cells(cfg, mesh, again, cells)
+    assert np.allclose(again.df, st.df, rtol=1e-9, atol=1e-12)
