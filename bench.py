@@ -360,6 +360,14 @@ def run_ours(args):
     log(f"[rank {rank}] workload {case.name}: {mesh.n_local} local cells (+{mesh.n_ghost} ghosts), "
         f"{nph_local} phase cells, {mesh.n_grid} velocity grids, generated in {time.time() - t_gen:.1f}s")
 
+    # The synthetic forest leaves many long-lived Python objects behind; a generation-2 collection that happens to start
+    # inside a timed window would walk all of them.  The host this library is written for has no such collector: park
+    # the survivors and keep the collector out of the timed windows.
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc.disable()
+
     stream = torch.cuda.Stream()
     cfg = case.config(device=local, rank=rank, nranks=world, stream=stream.cuda_stream)
     ctx = api.Context(cfg)
@@ -466,19 +474,24 @@ def run_ours(args):
     h2d_win = topo_b + (npts * K + 2 * mesh.n_local * M) * 8
     d2h_win = (npts * K + 2 * mesh.n_local * M) * 8 + args.steps * 2 * M * 8
     out = st
-    barrier()
-    t0 = time.perf_counter()
-    ctx.upload_topology(mesh)            # the amr_recover! event (Solver/AMR.jl:54): re-flatten
-    t_topo = time.perf_counter() - t0
-    ctx.upload_state(st, aux=False)
-    if world > 1:
-        ctx.exchange_df()
-    for _ in range(args.steps):
-        ctx.step(dt, True)  # residual scalars come back to the host every step
-    ctx.download_state(out, abi.DL_DF | abi.DL_W | abi.DL_PRIM)
-    ctx.sync()
-    t_win = reduce_max(time.perf_counter() - t0)
-    reflatten_ms = reduce_max(t_topo * 1e3)
+    # Three windows, the median one reported: driver calls (cudaMalloc / cudaFree / small copies) of the re-flatten
+    # stall sporadically on this pool's boxes (+0.1 ... 1.5 s on a 40-160 ms re-flatten, about one window in three,
+    # in varying phases of kamr_upload_topology; profiles/r02_h_reflatten_outliers.txt); all three are listed.
+    wins = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        ctx.upload_topology(mesh)            # the amr_recover! event (Solver/AMR.jl:54): re-flatten
+        t_topo = time.perf_counter() - t0
+        ctx.upload_state(st, aux=False)
+        if world > 1:
+            ctx.exchange_df()
+        for _ in range(args.steps):
+            ctx.step(dt, True)  # residual scalars come back to the host every step
+        ctx.download_state(out, abi.DL_DF | abi.DL_W | abi.DL_PRIM)
+        ctx.sync()
+        wins.append((reduce_max(time.perf_counter() - t0), reduce_max(t_topo * 1e3)))
+    t_win, reflatten_ms = sorted(wins)[1]
     e2e_val = nph_total * args.steps / t_win
     # window without the re-flatten (state transfers only), for comparison with round 1
     barrier()
@@ -507,6 +520,7 @@ def run_ours(args):
     stats = ctx.stats()
     dev_gb = stats.device_bytes / 1e9
     halo_b = int(stats.halo_bytes_per_step)
+    gc.enable()
 
     # ---- parity, outside every timed region
     parity = None
@@ -562,8 +576,9 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_win / args.steps,
                     "d2h_bytes_per_step": d2h_win / args.steps,
                     "pattern": "one adapt window incl. re-flatten: upload_topology, upload_state, %d x step(+residual "
-                               "to host), download_state" % args.steps,
-                    "window_s": t_win, "upload_topology_ms": reflatten_ms},
+                               "to host), download_state; median of 3 windows" % args.steps,
+                    "window_s": t_win, "upload_topology_ms": reflatten_ms,
+                    "windows_s": [w[0] for w in wins], "upload_topology_ms_all": [w[1] for w in wins]},
             "e2e_window_without_reflatten": {"value": nph_total * args.steps / t_win2, "unit": UNIT},
             "e2e_strict": {"value": strict_val, "unit": UNIT,
                            "h2d_bytes_per_step": (npts * K + 2 * mesh.n_local * M) * 8,
