@@ -191,6 +191,23 @@ int  kamr_download_state(kamr_ctx* ctx, uint32_t mask, double* df, double* sdf, 
 int  kamr_pack_cells(kamr_ctx* ctx, int32_t n, const int32_t* cells, double* df, double* w);
 int  kamr_unpack_cells(kamr_ctx* ctx, int32_t n, const int32_t* cells, const double* df, const double* w);
 
+/* Partition migration device to device (ps_partition!, Parallel/Partition.jl:339-445, 517-610): the w, prim
+ * and df of the cells that change rank (and of the cells that stay) cross the re-flatten without touching the host.
+ * The statics the reference ships beside them (bound_enc, solid_cell_index, vs levels / midpoints) are the host's and
+ * arrive through the new kamr_mesh as before.
+ *   kamr_migrate_begin, on the OLD topology, collective over the ranks that exchange cells: cells[q] (local id) goes
+ *     to rank dest_rank[q] — this rank included, for the cells it keeps.  Per destination the list order is kept.
+ *     src_rank[i] (ascending; this rank included if it keeps cells) announces what arrives: src_cells[i] cells with
+ *     src_points[i] velocity points in total (the receive_nums / vs_nums the reference exchanges first,
+ *     Partition.jl:300-338).  Payloads travel with ncclSend/ncclRecv over NVLink; kept cells are copied on the device.
+ *   kamr_upload_topology of the NEW partition (the staging buffer survives it).
+ *   kamr_migrate_finish: arrival q — sources in ascending rank, the sender's list order within a source — becomes
+ *     local cell recv_cells[q]; its velocity grid must have the size the sender's had.  prim arrives with w (the
+ *     reference recomputes get_prim(w), Partition.jl:639).  Follow with kamr_exchange_df on a mesh with peers. */
+int  kamr_migrate_begin(kamr_ctx* ctx, int32_t n_send, const int32_t* cells, const int32_t* dest_rank, int32_t n_src,
+                        const int32_t* src_rank, const int32_t* src_cells, const int64_t* src_points);
+int  kamr_migrate_finish(kamr_ctx* ctx, int32_t n_recv, const int32_t* recv_cells);
+
 /* update_criterion!(ka), Physical_space/AMR.jl:256-341: the physical-space adaptation sensor on the device.  For every
  * local fluid cell and direction the Löhner estimator of Physical_space/Criteria.jl:25-200 over the primitive state
  * of the two sides (mean of the neighbours' conserved state; ds, 0.75 ds or 1.5 ds by the side's level, AMR.jl:5-157;

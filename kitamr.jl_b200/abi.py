@@ -115,7 +115,7 @@ EXPORTS = [
     "kamr_slope", "kamr_flux", "kamr_iterate", "kamr_step", "kamr_exchange_df", "kamr_sync",
     "kamr_get_stats", "kamr_get_pair_map", "kamr_get_cell_slots", "kamr_profile_enable", "kamr_profile_read", "kamr_set_option",
     "kamr_debug_exp_nonpos", "kamr_pack_cells", "kamr_unpack_cells", "kamr_ps_criterion",
-    "kamr_vs_resolution", "kamr_vs_criterion", "kamr_project_cells",
+    "kamr_vs_resolution", "kamr_vs_criterion", "kamr_project_cells", "kamr_migrate_begin", "kamr_migrate_finish",
 ]
 
 _lib = None
@@ -160,6 +160,8 @@ def load(path: str | None = None):
     lib.kamr_pack_cells.argtypes = [vp, C.c_int32, c_i32p, c_f64p, c_f64p]
     lib.kamr_unpack_cells.argtypes = [vp, C.c_int32, c_i32p, c_f64p, c_f64p]
     lib.kamr_ps_criterion.argtypes = [vp, C.c_double, c_f64p, c_f64p]
+    lib.kamr_migrate_begin.argtypes = [vp, C.c_int32, c_i32p, c_i32p, C.c_int32, c_i32p, c_i32p, C.POINTER(C.c_int64)]
+    lib.kamr_migrate_finish.argtypes = [vp, C.c_int32, c_i32p]
     lib.kamr_project_cells.argtypes = [vp, C.c_int32, c_i32p]
     lib.kamr_vs_resolution.argtypes = [vp, C.POINTER(KamrVsAdapt), c_f64p]
     lib.kamr_vs_criterion.argtypes = [vp, C.POINTER(KamrVsAdapt), C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]

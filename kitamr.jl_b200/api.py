@@ -139,6 +139,20 @@ class Context:
                                             sen.ctypes.data_as(abi.c_f64p)))
         return loh, sen
 
+    def migrate_begin(self, cells, dest_rank, src_rank, src_cells, src_points):
+        """phase 1 of the device-to-device partition migration (old topology); see include/kamr.h"""
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        cells, dest_rank, src_rank, src_cells = i32(cells), i32(dest_rank), i32(src_rank), i32(src_cells)
+        src_points = np.ascontiguousarray(src_points, dtype=np.int64)
+        p = lambda a: a.ctypes.data_as(abi.c_i32p)
+        self._ck(self.lib.kamr_migrate_begin(self.h, len(cells), p(cells), p(dest_rank), len(src_rank), p(src_rank),
+                                             p(src_cells), src_points.ctypes.data_as(C.POINTER(C.c_int64))))
+
+    def migrate_finish(self, recv_cells):
+        """phase 2 (new topology): arrival q becomes local cell recv_cells[q]"""
+        recv_cells = np.ascontiguousarray(recv_cells, dtype=np.int32)
+        self._ck(self.lib.kamr_migrate_finish(self.h, len(recv_cells), recv_cells.ctypes.data_as(abi.c_i32p)))
+
     def project_cells(self, cells):
         """conserved_I_porjection! of the listed local cells (vs_conserved_correction!, Velocity_space/AMR.jl:120-133)"""
         cells = np.ascontiguousarray(cells, dtype=np.int32)

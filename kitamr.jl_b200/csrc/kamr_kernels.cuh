@@ -3372,4 +3372,14 @@ __global__ void __launch_bounds__(256) project_cells_kernel(DevView g, const int
     }
 }
 
+// inverse of gather_rows_kernel: row q of the contiguous buffer goes to row list[q] of the per-cell array
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const int* __restrict__ list, int n, int width,
+                                                           const double* __restrict__ src, double* __restrict__ dst) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)n * width;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(t / width), j = (int)(t - (long long)q * width);
+        dst[(size_t)list[q] * width + j] = src[t];
+    }
+}
+
 }  // namespace kamr

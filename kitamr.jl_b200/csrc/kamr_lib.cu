@@ -241,6 +241,18 @@ struct kamr_ctx {
         int* d_nbt = nullptr;
         long long* d_nb_off = nullptr;
     } vs_cache;
+    // partition migration device to device (kamr_migrate_begin / _finish): the arrived cells wait here across the
+    // re-flatten (plain cudaMalloc, not part of the topology's allocations)
+    struct Migrate {
+        bool pending = false;
+        double *d_df = nullptr, *d_w = nullptr, *d_prim = nullptr;
+        long long points = 0;
+        int cells = 0;
+        void release() {
+            cudaFree(d_df); cudaFree(d_w); cudaFree(d_prim);
+            d_df = d_w = d_prim = nullptr; pending = false; points = 0; cells = 0;
+        }
+    } mig;
     unsigned char* d_vs_flags = nullptr;   // refine_flag | coarsen_ok of the local points (host order)
     double* d_vs_res = nullptr;
     // per-kernel timing (kamr_profile_enable)
@@ -2393,6 +2405,7 @@ int kamr_destroy(kamr_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->cfg.device);
     c->free_topology();
+    c->mig.release();
     for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->comm) nccl().CommDestroy(c->comm);
@@ -2555,6 +2568,155 @@ int kamr_pack_cells(kamr_ctx* c, int32_t n, const int32_t* cells, double* df, do
 }
 int kamr_unpack_cells(kamr_ctx* c, int32_t n, const int32_t* cells, const double* df, const double* w) {
     return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); transfer_cells(c, n, cells, nullptr, df, nullptr, w, true); });
+}
+
+// Partition migration device to device.  Phase 1 on the OLD topology: the listed cells' df, w and prim are packed per
+// destination rank (list order kept within a destination) and exchanged with ncclSend/ncclRecv; cells whose destination
+// is this rank are copied on the device.  The arrivals are kept in a staging buffer in ascending source-rank order.
+static void migrate_begin(kamr_ctx* c, int n_send, const int32_t* cells, const int32_t* dest, int n_src,
+                          const int32_t* src_rank, const int32_t* src_cells, const int64_t* src_points) {
+    if (c->cells.empty()) throw Fail("upload_topology first");
+    if (c->mig.pending) throw Fail("kamr_migrate_begin: a migration is already pending (call kamr_migrate_finish)");
+    if (n_send < 0 || n_src < 0 || (n_send && (!cells || !dest)) || (n_src && (!src_rank || !src_cells || !src_points)))
+        throw Fail("kamr_migrate_begin: bad arguments");
+    const int K = c->K, M = c->M, me = c->cfg.rank, nr = std::max(1, (int)c->cfg.nranks);
+    // ---- sends, grouped by destination (stable)
+    std::vector<int> order(n_send);
+    for (int q = 0; q < n_send; ++q) {
+        if (cells[q] < 0 || cells[q] >= c->n_local) throw Fail("kamr_migrate_begin: cell id outside [0, n_local)");
+        if (dest[q] < 0 || dest[q] >= nr) throw Fail("kamr_migrate_begin: destination rank out of range");
+        order[q] = q;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return dest[a] < dest[b]; });
+    std::vector<int> list(n_send);
+    std::vector<long long> off(n_send + 1, 0);
+    std::vector<long long> d_cells(nr, 0), d_points(nr, 0), d_cell0(nr, 0), d_point0(nr, 0);
+    for (int q = 0; q < n_send; ++q) {
+        const int cell = cells[order[q]], r = dest[order[q]];
+        list[q] = cell;
+        off[q + 1] = off[q] + c->cells[cell].n;
+        if (d_cells[r] == 0) { d_cell0[r] = q; d_point0[r] = off[q]; }
+        d_cells[r] += 1; d_points[r] += c->cells[cell].n;
+    }
+    // ---- arrivals, ascending source rank
+    long long rc = 0, rp = 0;
+    std::vector<long long> s_cell0(n_src), s_point0(n_src);
+    bool remote = false;
+    for (int i = 0; i < n_src; ++i) {
+        if (src_rank[i] < 0 || src_rank[i] >= nr || (i && src_rank[i] <= src_rank[i - 1]))
+            throw Fail("kamr_migrate_begin: src_rank must ascend and lie in [0, nranks)");
+        if (src_cells[i] < 0 || src_points[i] < 0) throw Fail("kamr_migrate_begin: negative source counts");
+        if (src_rank[i] == me && (src_cells[i] != d_cells[me] || src_points[i] != d_points[me]))
+            throw Fail("kamr_migrate_begin: the counts of the cells this rank keeps do not match its own send list");
+        s_cell0[i] = rc; s_point0[i] = rp;
+        rc += src_cells[i]; rp += src_points[i];
+        remote = remote || src_rank[i] != me;
+    }
+    for (int r = 0; r < nr; ++r) remote = remote || (r != me && d_cells[r] > 0);
+    if (remote && !c->comm) throw Fail("kamr_migrate_begin: cells move between ranks but kamr_comm_init was not called");
+    if (d_cells[me] > 0) {
+        bool found = false;
+        for (int i = 0; i < n_src; ++i) found = found || src_rank[i] == me;
+        if (!found) throw Fail("kamr_migrate_begin: cells stay on this rank but src_rank does not list it");
+    }
+    halo_finish_df(c);
+    halo_join_puts(c);
+    double *s_df = nullptr, *s_w = nullptr, *s_prim = nullptr;
+    int* d_list = nullptr; long long* d_off = nullptr;
+    struct Free { double*& a; double*& b; double*& p; int*& l; long long*& o; ~Free() { cudaFree(a); cudaFree(b); cudaFree(p); cudaFree(l); cudaFree(o); } } fr{s_df, s_w, s_prim, d_list, d_off};
+    auto& g = c->mig;
+    try {
+        if (n_send) {
+            CK(cudaMalloc((void**)&s_df, sizeof(double) * std::max<size_t>(1, (size_t)off[n_send] * K)));
+            CK(cudaMalloc((void**)&s_w, sizeof(double) * (size_t)n_send * M));
+            CK(cudaMalloc((void**)&s_prim, sizeof(double) * (size_t)n_send * M));
+            CK(cudaMalloc((void**)&d_list, sizeof(int) * n_send));
+            CK(cudaMalloc((void**)&d_off, sizeof(long long) * (n_send + 1)));
+            CK(cudaMemcpyAsync(d_list, list.data(), sizeof(int) * n_send, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * (n_send + 1), cudaMemcpyHostToDevice, c->stream));
+            Launch L_(c, KID_PACK);
+            repack_list_kernel<<<std::min(n_send, 148 * 16), 256, 0, c->stream>>>(c->dv.cells, d_list, d_off, n_send, K, c->dv.df, s_df, 0);
+            const int gr = (int)std::min<long long>(((long long)n_send * M + 255) / 256, 1024);
+            gather_rows_kernel<<<gr, 256, 0, c->stream>>>(d_list, n_send, M, c->dv.w, s_w);
+            gather_rows_kernel<<<gr, 256, 0, c->stream>>>(d_list, n_send, M, c->dv.prim, s_prim);
+            CK(cudaGetLastError());
+        }
+        CK(cudaMalloc((void**)&g.d_df, sizeof(double) * std::max<size_t>(1, (size_t)rp * K)));
+        CK(cudaMalloc((void**)&g.d_w, sizeof(double) * std::max<size_t>(1, (size_t)rc * M)));
+        CK(cudaMalloc((void**)&g.d_prim, sizeof(double) * std::max<size_t>(1, (size_t)rc * M)));
+        // packed block of a cell: n*K doubles, so a destination's segment starts at point0*K
+        if (remote) NCK(nccl().GroupStart());
+        for (int r = 0; r < nr; ++r) {
+            if (r == me || d_cells[r] == 0) continue;
+            NCK(nccl().Send(s_df + d_point0[r] * K, (size_t)d_points[r] * K, ncclFloat64, r, c->comm, c->stream));
+            NCK(nccl().Send(s_w + d_cell0[r] * M, (size_t)d_cells[r] * M, ncclFloat64, r, c->comm, c->stream));
+            NCK(nccl().Send(s_prim + d_cell0[r] * M, (size_t)d_cells[r] * M, ncclFloat64, r, c->comm, c->stream));
+        }
+        for (int i = 0; i < n_src; ++i) {
+            if (src_rank[i] == me || src_cells[i] == 0) continue;
+            NCK(nccl().Recv(g.d_df + s_point0[i] * K, (size_t)src_points[i] * K, ncclFloat64, src_rank[i], c->comm, c->stream));
+            NCK(nccl().Recv(g.d_w + s_cell0[i] * M, (size_t)src_cells[i] * M, ncclFloat64, src_rank[i], c->comm, c->stream));
+            NCK(nccl().Recv(g.d_prim + s_cell0[i] * M, (size_t)src_cells[i] * M, ncclFloat64, src_rank[i], c->comm, c->stream));
+        }
+        if (remote) NCK(nccl().GroupEnd());
+        for (int i = 0; i < n_src; ++i) {
+            if (src_rank[i] != me || src_cells[i] == 0) continue;
+            CK(cudaMemcpyAsync(g.d_df + s_point0[i] * K, s_df + d_point0[me] * K, sizeof(double) * (size_t)d_points[me] * K, cudaMemcpyDeviceToDevice, c->stream));
+            CK(cudaMemcpyAsync(g.d_w + s_cell0[i] * M, s_w + d_cell0[me] * M, sizeof(double) * (size_t)d_cells[me] * M, cudaMemcpyDeviceToDevice, c->stream));
+            CK(cudaMemcpyAsync(g.d_prim + s_cell0[i] * M, s_prim + d_cell0[me] * M, sizeof(double) * (size_t)d_cells[me] * M, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+    } catch (...) {
+        g.release();
+        throw;
+    }
+    g.pending = true; g.points = rp; g.cells = (int)rc;
+}
+
+// Phase 2, after kamr_upload_topology of the NEW partition: arrival q (ascending source rank, the sender's list order
+// within a source) becomes local cell recv_cells[q].
+static void migrate_finish(kamr_ctx* c, int n_recv, const int32_t* recv_cells) {
+    auto& g = c->mig;
+    if (!g.pending) throw Fail("kamr_migrate_finish: no migration pending");
+    if (c->cells.empty()) throw Fail("upload_topology first");
+    struct Release { kamr_ctx::Migrate& g; ~Release() { g.release(); } } rel{g};
+    if (n_recv != g.cells) throw Fail("kamr_migrate_finish: n_recv differs from the number of cells that arrived");
+    if (n_recv == 0) return;
+    if (!recv_cells) throw Fail("kamr_migrate_finish: recv_cells is NULL");
+    const int K = c->K, M = c->M;
+    std::vector<long long> off(n_recv + 1, 0);
+    for (int q = 0; q < n_recv; ++q) {
+        if (recv_cells[q] < 0 || recv_cells[q] >= c->n_local) throw Fail("kamr_migrate_finish: cell id outside [0, n_local)");
+        off[q + 1] = off[q] + c->cells[recv_cells[q]].n;
+    }
+    if (off[n_recv] != g.points)
+        throw Fail("kamr_migrate_finish: the velocity grids of recv_cells do not add up to the points that arrived");
+    halo_finish_df(c);
+    halo_join_puts(c);
+    int* d_list = nullptr; long long* d_off = nullptr;
+    struct Free { int*& l; long long*& o; ~Free() { cudaFree(l); cudaFree(o); } } fr{d_list, d_off};
+    CK(cudaMalloc((void**)&d_list, sizeof(int) * n_recv));
+    CK(cudaMalloc((void**)&d_off, sizeof(long long) * (n_recv + 1)));
+    CK(cudaMemcpyAsync(d_list, recv_cells, sizeof(int) * n_recv, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * (n_recv + 1), cudaMemcpyHostToDevice, c->stream));
+    {
+        Launch L_(c, KID_UNPACK);
+        repack_list_kernel<<<std::min(n_recv, 148 * 16), 256, 0, c->stream>>>(c->dv.cells, d_list, d_off, n_recv, K, c->dv.df, g.d_df, 1);
+        const int gr = (int)std::min<long long>(((long long)n_recv * M + 255) / 256, 1024);
+        scatter_rows_kernel<<<gr, 256, 0, c->stream>>>(d_list, n_recv, M, g.d_w, c->dv.w);
+        scatter_rows_kernel<<<gr, 256, 0, c->stream>>>(d_list, n_recv, M, g.d_prim, c->dv.prim);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    c->sw_valid = false; c->raw_sdf_valid = false;
+}
+
+int kamr_migrate_begin(kamr_ctx* c, int32_t n_send, const int32_t* cells, const int32_t* dest_rank, int32_t n_src,
+                       const int32_t* src_rank, const int32_t* src_cells, const int64_t* src_points) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); migrate_begin(c, n_send, cells, dest_rank, n_src, src_rank, src_cells, src_points); });
+}
+int kamr_migrate_finish(kamr_ctx* c, int32_t n_recv, const int32_t* recv_cells) {
+    return guarded(c, [&] { CK(cudaSetDevice(c->cfg.device)); migrate_finish(c, n_recv, recv_cells); });
 }
 
 int kamr_slope(kamr_ctx* c) {

@@ -533,6 +533,28 @@ function vs_conserved_correction!(ctx::Context, cells::Vector{Int32})
 end
 
 """
+    migrate_begin!(ctx, dest_rank, src_rank, src_cells, src_points); reflatten!(ctx, p4est, ka); migrate_finish!(ctx, recv_cells)
+
+`ps_partition!` (Parallel/Partition.jl) with the heavy payload moved device to device: `dest_rank[c]` is the new owner
+of flat cell `c` (this rank included), known after `p4est_partition` from the new `global_first_quadrant`; `src_*` are
+the `receive_nums` / `vs_nums` the reference exchanges first (Partition.jl:300-338) with this rank's own kept cells
+listed too; `recv_cells` are the new flat ids in arrival order (ascending source rank, sender's order).  The host
+still ships `bound_enc`, `solid_cell_index`, `vs_levels` and `vs_midpoints` as `transfer_wrap` does — only `w` and `df`
+stay on the devices.
+"""
+function migrate_begin!(ctx::Context, dest_rank::Vector{Int32}, src_rank::Vector{Int32}, src_cells::Vector{Int32},
+                        src_points::Vector{Int64})
+    cells = collect(Int32(0):Int32(length(dest_rank) - 1))
+    check(ctx, ccall((:kamr_migrate_begin, LIB), Cint,
+                     (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}),
+                     ctx.h, length(cells), cells, dest_rank, length(src_rank), src_rank, src_cells, src_points))
+end
+function migrate_finish!(ctx::Context, recv_cells::Vector{Int32})
+    check(ctx, ccall((:kamr_migrate_finish, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}), ctx.h, length(recv_cells), recv_cells))
+    check(ctx, ccall((:kamr_exchange_df, LIB), Cint, (Ptr{Cvoid},), ctx.h))
+end
+
+"""
 The `solve!`-shaped loop with the device in it (compare Solver/Solver.jl:44-87).  The adapt events keep their cadence;
 each one is bracketed by a download (what it reads) and a re-flatten (what it changed).
 """

@@ -249,7 +249,8 @@ def smoke_s0(noise=0.01, trees=16, vtrees=16, tree_order="morton") -> Case:
 
 
 def amr_case(dim=2, trees=4, maxlevel=2, vtrees=6, vs_maxlevel=2, ragged=True, periodic=None, bcs=None,
-             seed=1, name=None, marching=abi.MARCH_CAIDVM, U0=None, quad_half=5.0, refine="ball") -> Case:
+             seed=1, name=None, marching=abi.MARCH_CAIDVM, U0=None, quad_half=5.0, refine="ball",
+             tree_order="morton") -> Case:
     """Small AMR case used by the parity tests: a refined ball/band in physical space (hanging faces,
     coarse/fine slope sweep) and, when `ragged`, Maxwellian-adapted velocity grids that differ from
     cell to cell (pair-list path)."""
@@ -265,7 +266,7 @@ def amr_case(dim=2, trees=4, maxlevel=2, vtrees=6, vs_maxlevel=2, ragged=True, p
             return np.abs(mid[:, 0] + 0.5 * mid[:, 1]) < 0.25 / (l + 1)
         return np.zeros(len(mid), dtype=bool)
 
-    forest = Forest.build(dim, geo, (trees,) * dim, maxlevel, refine_fn, periodic=periodic)
+    forest = Forest.build(dim, geo, (trees,) * dim, maxlevel, refine_fn, periodic=periodic, tree_order=tree_order)
     quad = tuple([-quad_half, quad_half] * dim)
     gas = Gas(K=1.0 if dim == 2 else 0.0, Kn=0.05)
     prim_fn = smooth_prim(dim, geo, U0=U0)

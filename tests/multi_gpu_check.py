@@ -115,10 +115,52 @@ def main():
         loh_o, sen_o, _ = orc.ps_criterion(cfg_r, mesh, dev, thr, ghost_flag=ghost_flag)
         bad_sensor = int(not (np.array_equal(loh_n, loh_o) and np.array_equal(sen_n, sen_o)))
         n_buf = int((sen_n == 2 * thr).sum())
-        t = torch.tensor([num, den, nsw, dsw, bad_sensor, n_buf, int(same_as_one_rank)], dtype=torch.float64, device="cuda")
+        # ps_partition! with the payload moved device to device (kamr_migrate_begin / _finish): a second, skewed split
+        # of the same Morton curve; the cells that change rank travel over NCCL, the others are copied on the device;
+        # three more steps on the new partition against the oracle, which never noticed
+        from kitamr_jl_b200.synth.forest import partition
+        owner_a = case.owner(world)
+        n_of = np.array([g.n for g in case.grids])[case.cell_grid].astype(np.float64)
+        if case.cell_class is not None:
+            n_of = np.where(case.cell_class == -2, 0.0, n_of)
+        owner_b = partition(n_of * np.linspace(0.4, 1.6, len(n_of)), world)
+        moved = int(np.sum((owner_a != owner_b) & (n_of > 0)))
+        meshes_a = [mesh if r == rank else case.rank_mesh(r, world) for r in range(world)]
+        case.owner = lambda nranks, _o=owner_b: _o
+        mesh_b = case.rank_mesh(rank, world)
+        new_id = {int(g): i for i, g in enumerate(mesh_b.global_ids[: mesh_b.n_local])}
+        dest = owner_b[mesh.global_ids[:nl]]
+        src_rank, src_cells, src_points, recv_cells = [], [], [], []
+        nb_of = mesh_b.cell_n()
+        for r in range(world):
+            gids = meshes_a[r].global_ids[: meshes_a[r].n_local]
+            mine = [new_id[int(g)] for g in gids if owner_b[g] == rank]
+            if mine:
+                src_rank.append(r); src_cells.append(len(mine)); src_points.append(int(nb_of[mine].sum()))
+                recv_cells += mine
+        ctx.migrate_begin(np.arange(nl), dest, src_rank, src_cells, src_points)
+        ctx.upload_topology(mesh_b)
+        ctx.migrate_finish(recv_cells)
+        ctx.exchange_df()
+        for _ in range(3):
+            ctx.step(case.dt(), False)
+            orc.step(cfg1, full, ref, case.dt(), False)
+        st_b = case.init_state(mesh_b)
+        out_b = ctx.download_state(st_b, abi.DL_DF)
+        off_b = mesh_b.vs_off()
+        mnum = mden = 0.0
+        for i in range(mesh_b.n_local):
+            g = index_of[int(mesh_b.global_ids[i])]
+            a_, b_ = out_b.df[off_b[i] * K: off_b[i + 1] * K], ref.df[off_g[g] * K: off_g[g + 1] * K]
+            mnum += float(np.sum((a_ - b_) ** 2)); mden += float(np.sum(b_ ** 2))
+        del case.owner
+        t = torch.tensor([num, den, nsw, dsw, bad_sensor, n_buf, int(same_as_one_rank), mnum, mden], dtype=torch.float64,
+                         device="cuda")
         dist.all_reduce(t)
         if t[4] > 0:
             worst = max(worst, 1.0)
+        err_mig = float(torch.sqrt(t[7] / t[8]))
+        worst = max(worst, err_mig / (1e4 if case.marching == abi.MARCH_CIP else 1.0))
         err = float(torch.sqrt(t[0] / t[1]))
         err_sw = float(torch.sqrt(t[2] / torch.clamp(t[3], min=1e-300)))
         worst = max(worst, err_sw * 1e-12 / (1e-9 if case.marching != abi.MARCH_CIP else 1e-5))
@@ -128,7 +170,8 @@ def main():
                   f"rel L2(df) vs single-rank oracle after {steps} steps = {err:.3e}; ghost sw after kamr_slope = {err_sw:.3e}; "
                   f"ps sensor vs per-rank oracle on the device's fields: {'bit-identical' if t[4] == 0 else 'DIFFERS'} "
                   f"({int(t[5])} buffered cells; vs a single-rank device run: "
-                  f"{'bit-identical' if t[6] == world else 'differs (the states do, in the last bits)'})",
+                  f"{'bit-identical' if t[6] == world else 'differs (the states do, in the last bits)'}); "
+                  f"after a device-to-device migration of {moved} cells to a skewed partition + 3 steps: rel L2(df) = {err_mig:.3e}",
                   flush=True)
         ctx.close()
     dist.destroy_process_group()

@@ -521,3 +521,63 @@ def test_pack_and_unpack_cells_round_trip(kamr_lib):
         assert np.array_equal(got.w[: nl * M], want.w[: nl * M])
     finally:
         a.close(); b.close()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_migrate_carries_the_state_across_a_reflatten(kamr_lib, dim):
+    """kamr_migrate_begin / kamr_upload_topology / kamr_migrate_finish on one rank: the same forest flattened in another
+    cell order (p4est's Morton tree order vs. lexicographic).  Every cell's df, w and prim arrive bit for bit in their
+    new places without passing through the host, and the run continues as if nothing had happened."""
+    from kitamr_jl_b200 import abi, api
+    from kitamr_jl_b200.synth import cases
+    from oracle import orc
+    kw = dict(dim=dim, trees=4 if dim == 2 else 3, maxlevel=2 if dim == 2 else 1, vtrees=8 if dim == 2 else 4,
+              vs_maxlevel=2 if dim == 2 else 1, ragged=True, seed=61)
+    ca, cb = cases.amr_case(tree_order="morton", **kw), cases.amr_case(tree_order="lex", **kw)
+    ma, mb = ca.rank_mesh(), cb.rank_mesh()
+    D, K, M = dim, ma.ndf, dim + 2
+    na = ma.n_local
+    assert mb.n_local == na
+    key = lambda m, c: tuple(np.round(m.mid[c * D:(c + 1) * D], 12)) + (int(m.ps_level[c]),)
+    where_b = {key(mb, c): c for c in range(na)}
+    to_b = np.array([where_b[key(ma, c)] for c in range(na)], dtype=np.int32)
+    assert not np.array_equal(to_b, np.arange(na))          # the two orders do differ
+    st = ca.init_state(ma)
+    cfg = ca.config(device=0)
+    dt = ca.dt()
+    ctx = api.Context(cfg)
+    try:
+        ctx.upload_topology(ma)
+        ctx.upload_state(st)
+        ref = st.copy()
+        for _ in range(3):
+            ctx.step(dt)
+            orc.step(cfg, ma, ref, dt)
+        sa = ctx.download_state(st.copy(), abi.DL_DF | abi.DL_W | abi.DL_PRIM)
+        offa, offb = ma.vs_off(), mb.vs_off()
+        npts = int(offa[na])
+        with pytest.raises(RuntimeError, match="no migration pending"):
+            ctx.migrate_finish(to_b)
+        with pytest.raises(RuntimeError, match="do not match"):
+            ctx.migrate_begin(np.arange(na), np.zeros(na), [0], [na - 1], [npts])
+        ctx.migrate_begin(np.arange(na), np.zeros(na), [0], [na], [npts])
+        ctx.upload_topology(mb)
+        ctx.migrate_finish(to_b)
+        sb = ctx.download_state(cb.init_state(mb), abi.DL_DF | abi.DL_W | abi.DL_PRIM)
+        for a in range(na):
+            b = to_b[a]
+            assert np.array_equal(sb.df[offb[b] * K: offb[b + 1] * K], sa.df[offa[a] * K: offa[a + 1] * K])
+            assert np.array_equal(sb.w[b * M:(b + 1) * M], sa.w[a * M:(a + 1) * M])
+            assert np.array_equal(sb.prim[b * M:(b + 1) * M], sa.prim[a * M:(a + 1) * M])
+        for _ in range(3):
+            ctx.step(dt)
+            orc.step(cfg, ma, ref, dt)
+        sb = ctx.download_state(cb.init_state(mb), abi.DL_DF | abi.DL_W)
+        num = den = 0.0
+        for a in range(na):
+            b = to_b[a]
+            x, y = sb.df[offb[b] * K: offb[b + 1] * K], ref.df[offa[a] * K: offa[a + 1] * K]
+            num += float(np.sum((x - y) ** 2)); den += float(np.sum(y ** 2))
+        assert np.sqrt(num / den) <= 1e-12
+    finally:
+        ctx.close()
