@@ -175,8 +175,11 @@ int  kamr_comm_init(kamr_ctx* ctx, const void* id128);
  * schedule and, for the one-sided halo, the CUDA IPC handles and ghost offsets of their arrays); a mesh with peers
  * without a communicator is refused.  All index arrays are range-checked; a malformed mesh is an error, not a crash. */
 int  kamr_upload_topology(kamr_ctx* ctx, const kamr_mesh* mesh);
-/* state in host layout; df for all n_cell cells (ghost / solid-neighbour blocks may be anything),
- * w and prim for local cells [n_local*(DIM+2)].  NULL pointers are skipped. */
+/* state in host layout; df for all n_cell cells (solid-neighbour blocks may be anything), w and prim for local cells
+ * [n_local*(DIM+2)].  NULL pointers are skipped.  On a mesh with peers the ghost blocks of df are copied as well and are
+ * then replaced by the owners' values with kamr_exchange_df; since the one-sided halo has no rendezvous, a peer that is
+ * already past its own upload may have stored its mirrors first — pass the owners' values in the ghost blocks (what
+ * GhostPsData holds after data_exchange!), or separate the ranks' upload and exchange calls by a barrier. */
 int  kamr_upload_state(kamr_ctx* ctx, const double* df, const double* w, const double* prim);
 /* optional: upload sdf / vs flux / macro flux (restart in the middle of a step) */
 int  kamr_upload_aux(kamr_ctx* ctx, const double* sdf, const double* flux, const double* mflux);

@@ -30,6 +30,15 @@ def _case(name):
         c = cases.cylinder_s2(trees=5, ps_maxlevel=4, box_level=2, vtrees=8, vs_maxlevel=2, ib=True)
         c.partition_mode = "cost"
         return c
+    if name in ("s2_skewed", "ib2d_skewed"):   # a skewed split of the Morton curve (what a re-partition moves to)
+        from kitamr_jl_b200.synth.forest import partition
+        c = cases.cylinder_s2(trees=5, ps_maxlevel=4 if name == "s2_skewed" else 5, box_level=2, vtrees=8, vs_maxlevel=2,
+                              ib=name == "ib2d_skewed")
+        n_of = np.array([g.n for g in c.grids])[c.cell_grid].astype(np.float64)
+        if c.cell_class is not None:
+            n_of = np.where(c.cell_class == -2, 0.0, n_of)
+        c.owner = lambda nranks, _w=n_of * np.linspace(0.4, 1.6, len(n_of)): partition(_w, nranks)
+        return c
     if name == "cip2d":       # CIP_Marching: un-fused path, f defined to the Newton tolerance
         from kitamr_jl_b200 import abi
         return cases.amr_case(dim=2, trees=4, maxlevel=2, vtrees=8, vs_maxlevel=1, ragged=True, seed=24,
@@ -64,7 +73,7 @@ def _worker(rank, world, port, name, steps, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["amr2d", "amr3d", "periodic2d", "ib2d", "ib2d_cost", "cip2d"])
+@pytest.mark.parametrize("name", ["amr2d", "amr3d", "periodic2d", "ib2d", "ib2d_cost", "cip2d", "s2_skewed", "ib2d_skewed"])
 def test_two_rank_oracle_equals_single_rank(name):
     from oracle import orc
     steps = 2
@@ -97,7 +106,7 @@ def test_two_rank_oracle_equals_single_rank(name):
             g = index_of[int(g)]
             n = int(off[g + 1] - off[g]) * K
             a, b = df[pos: pos + n], st.df[off[g] * K: off[g] * K + n]
-            assert np.linalg.norm(a - b) <= (1e-8 if name == "cip2d" else 1e-14) * np.linalg.norm(b), (rank, g)
+            assert np.linalg.norm(a - b) <= (1e-8 if name == "cip2d" else 3e-14) * np.linalg.norm(b), (rank, g)
             assert np.allclose(w[i * M:(i + 1) * M], st.w[g * M:(g + 1) * M], rtol=1e-13, atol=1e-15)
             pos += n
             seen += 1
