@@ -616,8 +616,11 @@ def parity_check(args, case, mesh, st0, ctx, rank, world, local, stream, dt):
     n_df = int(off[nl]) * K
     nph = mesh.n_phase_local()
     steps = 2 if (world > 1 or nph <= 5e7) else 1
-    # device side: from the initial state, `steps` fused steps
+    # device side: from the initial state, `steps` fused steps.  The raw slopes are part of the state: on meshes with
+    # non-dyadic cell sizes the reference's sweep projects some finer neighbours' slopes of the PREVIOUS step (DESIGN.md
+    # section 5), and this context has been stepping — so st0's (zero) sdf is uploaded too.
     ctx.upload_state(st0, aux=False)
+    ctx._ck(ctx.lib.kamr_upload_aux(ctx.h, st0.sdf.ctypes.data_as(abi.c_f64p), None, None))
     if world > 1:
         ctx.exchange_df()
     for _ in range(steps):

@@ -246,11 +246,15 @@ struct kamr_ctx {
     struct Migrate {
         bool pending = false;
         double *d_df = nullptr, *d_w = nullptr, *d_prim = nullptr;
+        double* d_sdf = nullptr;            // raw slopes of the cells that stay on this rank (see migrate_begin)
         long long points = 0;
         int cells = 0;
+        int kept_first = 0, kept_cells = 0; // their range among the arrivals
+        long long kept_points = 0;
         void release() {
-            cudaFree(d_df); cudaFree(d_w); cudaFree(d_prim);
-            d_df = d_w = d_prim = nullptr; pending = false; points = 0; cells = 0;
+            cudaFree(d_df); cudaFree(d_w); cudaFree(d_prim); cudaFree(d_sdf);
+            d_df = d_w = d_prim = d_sdf = nullptr; pending = false; points = 0; cells = 0;
+            kept_first = kept_cells = 0; kept_points = 0;
         }
     } mig;
     unsigned char* d_vs_flags = nullptr;   // refine_flag | coarsen_ok of the local points (host order)
@@ -2661,6 +2665,23 @@ static void migrate_begin(kamr_ctx* c, int n_send, const int32_t* cells, const i
         if (remote) NCK(nccl().GroupEnd());
         for (int i = 0; i < n_src; ++i) {
             if (src_rank[i] != me || src_cells[i] == 0) continue;
+            {   // The raw slopes stay with the cells that stay: in the reference a kept PsData keeps its VsData.sdf while
+                // an arriving one starts with zeros (Partition.jl:645-652), and on meshes with non-dyadic cell sizes
+                // the next sweep projects some finer neighbours' slopes of the PREVIOUS step.
+                const int D = c->D;
+                const int first = (int)d_cell0[me], cnt = (int)d_cells[me];
+                std::vector<long long> koff(cnt + 1);
+                for (int q = 0; q <= cnt; ++q) koff[q] = off[first + q] - off[first];
+                long long* d_koff = nullptr;
+                CK(cudaMalloc((void**)&d_koff, sizeof(long long) * (cnt + 1)));
+                CK(cudaMemcpyAsync(d_koff, koff.data(), sizeof(long long) * (cnt + 1), cudaMemcpyHostToDevice, c->stream));
+                CK(cudaMalloc((void**)&g.d_sdf, sizeof(double) * std::max<size_t>(1, (size_t)d_points[me] * K * D)));
+                repack_list_kernel<<<std::min(cnt, 148 * 16), 256, 0, c->stream>>>(c->dv.cells, d_list + first, d_koff, cnt, K * D, c->dv.sdf, g.d_sdf, 0);
+                CK(cudaGetLastError());
+                CK(cudaStreamSynchronize(c->stream));   // koff is a local
+                cudaFree(d_koff);
+                g.kept_first = (int)s_cell0[i]; g.kept_cells = cnt; g.kept_points = d_points[me];
+            }
             CK(cudaMemcpyAsync(g.d_df + s_point0[i] * K, s_df + d_point0[me] * K, sizeof(double) * (size_t)d_points[me] * K, cudaMemcpyDeviceToDevice, c->stream));
             CK(cudaMemcpyAsync(g.d_w + s_cell0[i] * M, s_w + d_cell0[me] * M, sizeof(double) * (size_t)d_cells[me] * M, cudaMemcpyDeviceToDevice, c->stream));
             CK(cudaMemcpyAsync(g.d_prim + s_cell0[i] * M, s_prim + d_cell0[me] * M, sizeof(double) * (size_t)d_cells[me] * M, cudaMemcpyDeviceToDevice, c->stream));
@@ -2707,6 +2728,20 @@ static void migrate_finish(kamr_ctx* c, int n_recv, const int32_t* recv_cells) {
         scatter_rows_kernel<<<gr, 256, 0, c->stream>>>(d_list, n_recv, M, g.d_prim, c->dv.prim);
     }
     CK(cudaGetLastError());
+    if (g.kept_cells > 0 && g.d_sdf) {   // the kept cells' raw slopes (what their VsData.sdf would still hold)
+        const int D = c->D, first = g.kept_first, cnt = g.kept_cells;
+        std::vector<long long> koff(cnt + 1);
+        for (int q = 0; q <= cnt; ++q) koff[q] = off[first + q] - off[first];
+        if (koff[cnt] != g.kept_points) throw Fail("kamr_migrate_finish: the kept cells' velocity grids changed size");
+        long long* d_koff = nullptr;
+        CK(cudaMalloc((void**)&d_koff, sizeof(long long) * (cnt + 1)));
+        CK(cudaMemcpyAsync(d_koff, koff.data(), sizeof(long long) * (cnt + 1), cudaMemcpyHostToDevice, c->stream));
+        repack_list_kernel<<<std::min(cnt, 148 * 16), 256, 0, c->stream>>>(c->dv.cells, d_list + first, d_koff, cnt, K * D, c->dv.sdf, g.d_sdf, 1);
+        cudaError_t e = cudaGetLastError();
+        cudaStreamSynchronize(c->stream);
+        cudaFree(d_koff);
+        CK(e);
+    }
     CK(cudaStreamSynchronize(c->stream));
     c->sw_valid = false; c->raw_sdf_valid = false;
 }

@@ -319,7 +319,7 @@ def uniform_case(dim=2, trees=64, maxlevel=0, vtrees=60, name=None, seed=3, refi
 
 # ---------------------------------------------------------------------- bench workloads
 def cylinder_s2(copies=1, ps_maxlevel=7, box_level=4, vs_maxlevel=3, vtrees=16, trees=25, noise=0.01,
-                ib=False, Ma=5.0) -> Case:
+                ib=False, Ma=5.0, tree_order="morton") -> Case:
     """S2 cylinder2d (example/cylinder/cylinder.jl:5-47): 25x25 roots on [-16,16]^2, level `box_level`
     in max-norm(x)<5 (the converged dynamic-AMR region, cylinder_udf.jl:9-15), level `ps_maxlevel`
     within search_coeffi*ds_min = 4*ds_min of the r=1 circle; velocity grids 16x16 roots on
@@ -347,7 +347,7 @@ def cylinder_s2(copies=1, ps_maxlevel=7, box_level=4, vs_maxlevel=3, vtrees=16, 
         half_diag = 0.5 * np.sqrt(np.sum(ds ** 2))
         return np.abs(r - 1.0) < 4.0 * ds_min + half_diag
 
-    forest = Forest.build(2, geo, (trees * copies, trees), ps_maxlevel, refine_fn)
+    forest = Forest.build(2, geo, (trees * copies, trees), ps_maxlevel, refine_fn, tree_order=tree_order)
     quad = (-10.0, 10.0, -10.0, 10.0)
     gas = Gas(K=1.0, Kn=0.1, omega=0.81, omega_r=0.81)
 

@@ -139,6 +139,12 @@ def main():
                 src_rank.append(r); src_cells.append(len(mine)); src_points.append(int(nb_of[mine].sum()))
                 recv_cells += mine
         ctx.migrate_begin(np.arange(nl), dest, src_rank, src_cells, src_points)
+        # the reference's arriving cells start with zero slopes, its kept cells keep theirs (Partition.jl:645-652), and
+        # on non-dyadic meshes the next sweep reads some finer neighbours' slopes of the previous step
+        off_s = off_g * K * case.dim
+        for g_ in np.flatnonzero((owner_a != owner_b) & (n_of > 0)):
+            if int(g_) in index_of:
+                ref.sdf[off_s[index_of[int(g_)]]: off_s[index_of[int(g_)] + 1]] = 0.0
         ctx.upload_topology(mesh_b)
         ctx.migrate_finish(recv_cells)
         ctx.exchange_df()
@@ -160,9 +166,10 @@ def main():
         if t[4] > 0:
             worst = max(worst, 1.0)
         err_mig = float(torch.sqrt(t[7] / t[8]))
-        # OPEN DEFECT: the migrated state arrives bit for bit (tools/migrate_probe.py), yet on the
-        # cylinder meshes the first step on the new partition differs from the oracle by ~1e-6 at a few interior
-        # level-jump cells; the other meshes continue at rounding level.  Reported, and bounded here at 1e-5 only.
+        # On the cylinder meshes (non-dyadic cell sizes) the step after a partition event depends on the previous step's
+        # slopes: without them the first step differs by 9.9e-7 — on the device and in the oracle
+        # alike.  The library now carries the kept cells' slopes; that path is pinned on one rank
+        # (test_migrate_carries_the_state_across_a_reflatten[s2]); this 2-rank bound stays loose until it has been re-run.
         worst = max(worst, err_mig * 1e-12 / 1e-5)
         err = float(torch.sqrt(t[0] / t[1]))
         err_sw = float(torch.sqrt(t[2] / torch.clamp(t[3], min=1e-300)))
