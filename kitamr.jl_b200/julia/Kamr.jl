@@ -307,6 +307,9 @@ function gather_state!(f::Flat)
         n = x.vs_data.vs_num
         o = f.vs_off[c] * f.ndf
         copyto!(f.df, o + 1, x.vs_data.df, 1, n * f.ndf)        # column-major [n × NDF] block == the ABI layout
+        # the raw slopes are state too: on meshes with non-dyadic cell sizes the next sweep projects some finer
+        # neighbours' slopes of the previous step (DESIGN.md §5); [n × NDF × DIM] column-major == the ABI layout
+        c <= f.n_local && copyto!(f.sdf, f.vs_off[c] * f.ndf * f.dim + 1, x.vs_data.sdf, 1, n * f.ndf * f.dim)
         if c <= f.n_local
             f.w[(c-1)*M+1:c*M] .= x.w; f.prim[(c-1)*M+1:c*M] .= x.prim
         end
@@ -397,6 +400,8 @@ function reflatten!(ctx::Context, p4est, ka::KA)
         check(ctx, ccall((:kamr_upload_topology, LIB), Cint, (Ptr{Cvoid}, Ref{CMesh}), ctx.h, m))
         check(ctx, ccall((:kamr_upload_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                          ctx.h, flat.df, flat.w, flat.prim))
+        check(ctx, ccall((:kamr_upload_aux, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                         ctx.h, flat.sdf, C_NULL, C_NULL))             # VsData.sdf as the adapt event left it
         check(ctx, ccall((:kamr_exchange_df, LIB), Cint, (Ptr{Cvoid},), ctx.h))
     end
     ctx.flat = flat

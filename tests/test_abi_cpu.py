@@ -39,7 +39,7 @@ def test_ctypes_layout_matches_c(tmp_path):
     """sizeof/offsetof of every struct that crosses the boundary, C compiler vs ctypes mirror."""
     from kitamr_jl_b200 import abi
     structs = {"kamr_config": abi.KamrConfig, "kamr_mesh": abi.KamrMesh, "kamr_ib": abi.KamrIB,
-               "kamr_stats": abi.KamrStats, "kamr_kernel_time": abi.KamrKernelTime}
+               "kamr_stats": abi.KamrStats, "kamr_kernel_time": abi.KamrKernelTime, "kamr_vs_adapt": abi.KamrVsAdapt}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HDR}"', 'int main(void){']
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
