@@ -169,7 +169,8 @@ def main():
         # On the cylinder meshes (non-dyadic cell sizes) the step after a partition event depends on the previous step's
         # slopes: without them the first step differs by 9.9e-7 — on the device and in the oracle
         # alike.  The library now carries the kept cells' slopes; that path is pinned on one rank
-        # (test_migrate_carries_the_state_across_a_reflatten[s2]); this 2-rank bound stays loose until it has been re-run.
+        # (test_migrate_carries_the_state_across_a_reflatten[s2]) and the 2-rank semantics by the oracle under gloo
+        # (test_two_rank_repartition_semantics: rounding level); this bound stays loose until the 2-GPU run is repeated.
         worst = max(worst, err_mig * 1e-12 / 1e-5)
         err = float(torch.sqrt(t[0] / t[1]))
         err_sw = float(torch.sqrt(t[2] / torch.clamp(t[3], min=1e-300)))
