@@ -267,3 +267,23 @@ def test_rank_partitions_with_ghost_flags_reproduce_the_single_rank_sensor(world
             loh_no, _, _ = orc.ps_criterion(case.config(rank=r, nranks=world), mesh, sr, thr)
             seen += int(not np.array_equal(loh_no, loh))
     assert seen > 0
+
+
+@pytest.mark.parametrize("name", ["amr2d_ragged", "amr3d_ragged", "s2_ib_small"])
+def test_criteria_reproduce_golden(name):
+    """regression pin of the oracle's adaptation criteria (tests/golden/make_golden_criteria.py): flags bit for bit,
+    Löhner values to rounding"""
+    import os
+    import sys
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    import make_golden_criteria as mgc
+    gold = np.load(os.path.join(gold_dir, "criteria.npz"))
+    got = mgc.evaluate(name)
+    for k, v in got.items():
+        ref = gold[f"{name}.{k}"]
+        if v.dtype == np.uint8:
+            assert np.array_equal(v, ref), k
+        else:
+            assert np.allclose(v, ref, rtol=1e-12, atol=1e-14), k
+    assert got["above"].any() and np.unpackbits(got["refine_lohner"]).any() and np.unpackbits(got["coarsen_lohner"]).any()
