@@ -44,9 +44,10 @@ def _brute_neighbors(grid, quad, trees, maxlevel):
     return out
 
 
-@pytest.mark.parametrize("dim,trees,maxlevel", [(2, (6, 5), 2), (2, (4, 4), 3), (3, (3, 4, 3), 2)])
-def test_face_neighbors_match_a_brute_force_search(dim, trees, maxlevel):
-    rng = np.random.default_rng(11 + dim + maxlevel)
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("dim,trees,maxlevel", [(2, (6, 5), 2), (2, (4, 4), 3), (3, (3, 4, 3), 2), (2, (7, 3), 1)])
+def test_face_neighbors_match_a_brute_force_search(dim, trees, maxlevel, seed):
+    rng = np.random.default_rng(11 + dim + maxlevel + 100 * seed)
     quad = tuple(np.ravel([(-4.0 - d, 5.0 + 0.5 * d) for d in range(dim)]))
     grid = vg.random_grid(quad, trees, maxlevel, rng, p=0.35)
     par = abi.vs_adapt(_Shape(dim, quad, trees, maxlevel))
